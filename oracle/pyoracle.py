@@ -1,0 +1,391 @@
+"""ctypes binding of oracle/liboracle.so -- the CPU restatement of the reference.
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs.  Nothing under bpvo_b200/ imports this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+class OrcParams(C.Structure):
+    _fields_ = [
+        ("numPyramidLevels", C.c_int32), ("minImageDimensionForPyramid", C.c_int32),
+        ("sigmaPriorToCensusTransform", C.c_float), ("sigmaBitPlanes", C.c_float),
+        ("maxIterations", C.c_int32), ("parameterTolerance", C.c_float),
+        ("functionTolerance", C.c_float), ("gradientTolerance", C.c_float),
+        ("relaxTolerancesForCoarseLevels", C.c_int32), ("gradientEstimation", C.c_int32),
+        ("interp", C.c_int32), ("lossFunction", C.c_int32), ("descriptor", C.c_int32),
+        ("verbosity", C.c_int32), ("minTranslationMagToKeyFrame", C.c_float),
+        ("minRotationMagToKeyFrame", C.c_float), ("maxFractionOfGoodPointsToKeyFrame", C.c_float),
+        ("goodPointThreshold", C.c_float), ("minNumPixelsForNonMaximaSuppression", C.c_int32),
+        ("nonMaxSuppRadius", C.c_int32), ("minNumPixelsToWork", C.c_int32),
+        ("minSaliency", C.c_float), ("minValidDisparity", C.c_float),
+        ("maxValidDisparity", C.c_float), ("maxTestLevel", C.c_int32),
+        ("withNormalization", C.c_int32), ("use_rcp", C.c_int32), ("num_threads", C.c_int32),
+    ]
+
+
+class OrcStats(C.Structure):
+    _fields_ = [("numIterations", C.c_int32), ("finalError", C.c_float),
+                ("firstOrderOptimality", C.c_float), ("status", C.c_int32)]
+
+
+class OrcResult(C.Structure):
+    _fields_ = [("pose", C.c_float * 16), ("isKeyFrame", C.c_int32), ("keyFramingReason", C.c_int32),
+                ("numLevels", C.c_int32), ("stats", OrcStats * 16), ("numFunEvals", C.c_int32),
+                ("numPointCloud", C.c_int32)]
+
+
+def build(force: bool = False) -> str:
+    so = os.path.join(_HERE, "liboracle.so")
+    src = os.path.join(_HERE, "bpvo_oracle.cc")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.run(["make", "-C", _HERE, "-s", "-B", "liboracle.so"], check=True)
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    L = C.CDLL(build())
+    vp, fp, u8p, ip = C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_uint8), C.POINTER(C.c_int32)
+    sig = {
+        "orc_default_params": (None, [C.POINTER(OrcParams)]),
+        "orc_pyr_down": (None, [u8p, C.c_int, C.c_int, u8p]),
+        "orc_gaussian_blur5": (None, [fp, C.c_int, C.c_int, C.c_float, fp]),
+        "orc_census": (None, [u8p, C.c_int, C.c_int, u8p]),
+        "orc_descriptor": (C.c_int, [C.POINTER(OrcParams), u8p, C.c_int, C.c_int, fp]),
+        "orc_saliency": (None, [fp, C.c_int, C.c_int, C.c_int, fp]),
+        "orc_median": (C.c_float, [fp, C.c_size_t]),
+        "orc_solve6": (C.c_int, [fp, fp, fp]),
+        "orc_params_to_pose": (None, [fp, fp, fp]),
+        "orc_frame_create": (vp, [fp, C.c_float, C.c_int, C.c_int, C.POINTER(OrcParams)]),
+        "orc_frame_destroy": (None, [vp]),
+        "orc_frame_set_data": (None, [vp, u8p, fp]),
+        "orc_frame_set_template": (C.c_int, [vp]),
+        "orc_frame_num_levels": (C.c_int, [vp]),
+        "orc_frame_level_size": (None, [vp, C.c_int, ip, ip]),
+        "orc_frame_pyramid": (u8p, [vp, C.c_int]),
+        "orc_frame_descriptor": (fp, [vp, C.c_int, ip]),
+        "orc_frame_saliency": (fp, [vp, C.c_int]),
+        "orc_frame_num_points": (C.c_int, [vp, C.c_int]),
+        "orc_frame_points": (fp, [vp, C.c_int]),
+        "orc_frame_pixels": (fp, [vp, C.c_int]),
+        "orc_frame_jacobians": (fp, [vp, C.c_int]),
+        "orc_frame_point_inds": (ip, [vp, C.c_int]),
+        "orc_frame_normalization": (None, [vp, C.c_int, fp]),
+        "orc_estimator_create": (vp, [C.POINTER(OrcParams)]),
+        "orc_estimator_destroy": (None, [vp]),
+        "orc_linearize": (C.c_float, [vp, vp, vp, C.c_int, fp, C.c_int, fp, fp, fp]),
+        "orc_estimator_num_residuals": (C.c_size_t, [vp]),
+        "orc_estimator_residuals": (fp, [vp]),
+        "orc_estimator_weights": (fp, [vp]),
+        "orc_estimator_valid": (C.POINTER(C.c_uint16), [vp]),
+        "orc_estimate_pose": (C.c_int, [vp, vp, vp, fp, fp, C.POINTER(OrcStats)]),
+        "orc_fraction_good": (C.c_float, [vp, C.c_float]),
+        "orc_vo_create": (vp, [fp, C.c_float, C.c_int, C.c_int, C.POINTER(OrcParams)]),
+        "orc_vo_destroy": (None, [vp]),
+        "orc_vo_add_frame": (C.c_int, [vp, u8p, fp, C.POINTER(OrcResult)]),
+        "orc_vo_num_points_at_level": (C.c_int, [vp, C.c_int]),
+        "orc_vo_ref_frame": (vp, [vp]),
+        "orc_vo_estimator": (vp, [vp]),
+        "orc_vo_trajectory": (C.c_int, [vp, fp, C.c_int]),
+        "orc_vo_point_cloud": (C.c_int, [vp, fp, fp, u8p, C.c_int]),
+        "orc_last_error": (C.c_char_p, []),
+    }
+    for name, (res, args) in sig.items():
+        f = getattr(L, name)
+        f.restype, f.argtypes = res, args
+    _LIB = L
+    return L
+
+
+def _fp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def _u8(a):
+    return a.ctypes.data_as(C.POINTER(C.c_uint8))
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _colmajor(M):
+    """row-major numpy matrix -> flat column-major float32 (what crosses the C API)."""
+    return np.ascontiguousarray(np.asarray(M, dtype=np.float32).T).ravel()
+
+
+def _from_colmajor(buf, n):
+    return np.array(buf, dtype=np.float32).reshape(n, n).T.copy()
+
+
+def make_params(p, use_rcp: int = 1, num_threads: int = 1) -> OrcParams:
+    """p: bpvo_b200.types.AlgorithmParameters (duck-typed by field name)."""
+    c = OrcParams()
+    lib().orc_default_params(C.byref(c))
+    for name, _ in OrcParams._fields_[:26]:
+        v = getattr(p, name)
+        setattr(c, name, type(getattr(c, name))(v))
+    c.use_rcp, c.num_threads = int(use_rcp), int(num_threads)
+    return c
+
+
+def _err():
+    return RuntimeError(lib().orc_last_error().decode())
+
+
+# ---- stage functions ---------------------------------------------------------------------------
+def pyr_down(img):
+    img = np.ascontiguousarray(img, dtype=np.uint8)
+    r, c = img.shape
+    out = np.empty(((r + 1) // 2, (c + 1) // 2), dtype=np.uint8)
+    lib().orc_pyr_down(_u8(img), r, c, _u8(out))
+    return out
+
+
+def gaussian_blur5(img, sigma):
+    img = _f32(img)
+    out = np.empty_like(img)
+    lib().orc_gaussian_blur5(_fp(img), img.shape[0], img.shape[1], float(sigma), _fp(out))
+    return out
+
+
+def census(img):
+    img = np.ascontiguousarray(img, dtype=np.uint8)
+    out = np.empty_like(img)
+    lib().orc_census(_u8(img), img.shape[0], img.shape[1], _u8(out))
+    return out
+
+
+def descriptor(params, img):
+    img = np.ascontiguousarray(img, dtype=np.uint8)
+    out = np.empty((8,) + img.shape, dtype=np.float32)
+    cp = make_params(params)
+    n = lib().orc_descriptor(C.byref(cp), _u8(img), img.shape[0], img.shape[1], _fp(out))
+    if n < 0:
+        raise _err()
+    return out[:n].copy()
+
+
+def saliency(planes):
+    planes = _f32(planes)
+    c, r, w = planes.shape
+    out = np.zeros((r, w), dtype=np.float32)
+    lib().orc_saliency(_fp(planes), c, r, w, _fp(out))
+    return out
+
+
+def median(values):
+    buf = _f32(values).copy()
+    return float(lib().orc_median(_fp(buf), buf.size))
+
+
+def solve6(H, G):
+    Hc, Gc = _colmajor(H), _f32(G).ravel()
+    dp = np.zeros(6, dtype=np.float32)
+    ok = lib().orc_solve6(_fp(Hc), _fp(Gc), _fp(dp))
+    return bool(ok), dp
+
+
+def params_to_pose(Tn, p):
+    out = np.zeros(16, dtype=np.float32)
+    lib().orc_params_to_pose(_fp(_colmajor(Tn)), _fp(_f32(p).ravel()), _fp(out))
+    return _from_colmajor(out, 4)
+
+
+# ---- objects -----------------------------------------------------------------------------------
+class Frame:
+    def __init__(self, K, baseline, rows, cols, params, use_rcp=1, num_threads=1, _borrow=None):
+        self._own = _borrow is None
+        if _borrow is not None:
+            self.h = _borrow
+        else:
+            cp = make_params(params, use_rcp, num_threads)
+            self.h = lib().orc_frame_create(_fp(_colmajor(K)), float(baseline), rows, cols, C.byref(cp))
+            if not self.h:
+                raise _err()
+
+    def __del__(self):
+        if getattr(self, "_own", False) and getattr(self, "h", None):
+            lib().orc_frame_destroy(self.h)
+            self.h = None
+
+    def set_data(self, img, disp):
+        img = np.ascontiguousarray(img, dtype=np.uint8)
+        disp = _f32(disp)
+        lib().orc_frame_set_data(self.h, _u8(img), _fp(disp))
+
+    def set_template(self):
+        if lib().orc_frame_set_template(self.h) != 0:
+            raise _err()
+
+    @property
+    def num_levels(self):
+        return lib().orc_frame_num_levels(self.h)
+
+    def level_size(self, l):
+        r, c = C.c_int32(), C.c_int32()
+        lib().orc_frame_level_size(self.h, l, C.byref(r), C.byref(c))
+        return r.value, c.value
+
+    def pyramid(self, l):
+        r, c = self.level_size(l)
+        return np.ctypeslib.as_array(lib().orc_frame_pyramid(self.h, l), shape=(r, c)).copy()
+
+    def descriptor(self, l):
+        r, c = self.level_size(l)
+        ch = C.c_int32()
+        p = lib().orc_frame_descriptor(self.h, l, C.byref(ch))
+        return np.ctypeslib.as_array(p, shape=(ch.value, r, c)).copy()
+
+    def saliency(self, l):
+        r, c = self.level_size(l)
+        return np.ctypeslib.as_array(lib().orc_frame_saliency(self.h, l), shape=(r, c)).copy()
+
+    def num_points(self, l):
+        return lib().orc_frame_num_points(self.h, l)
+
+    def points(self, l):
+        n = self.num_points(l)
+        if n == 0:
+            return np.zeros((0, 4), np.float32)
+        return np.ctypeslib.as_array(lib().orc_frame_points(self.h, l), shape=(n, 4)).copy()
+
+    def num_channels(self, l):
+        ch = C.c_int32()
+        lib().orc_frame_descriptor(self.h, l, C.byref(ch))
+        return ch.value
+
+    def pixels(self, l):
+        n, ch = self.num_points(l), self.num_channels(l)
+        return np.ctypeslib.as_array(lib().orc_frame_pixels(self.h, l), shape=(ch, n)).copy()
+
+    def jacobians(self, l):
+        n, ch = self.num_points(l), self.num_channels(l)
+        return np.ctypeslib.as_array(lib().orc_frame_jacobians(self.h, l), shape=(ch * n + 1, 6))[:ch * n].reshape(ch, n, 6).copy()
+
+    def point_inds(self, l):
+        n = self.num_points(l)
+        return np.ctypeslib.as_array(lib().orc_frame_point_inds(self.h, l), shape=(n,)).copy()
+
+    def normalization(self, l):
+        out = np.zeros(16, dtype=np.float32)
+        lib().orc_frame_normalization(self.h, l, _fp(out))
+        return _from_colmajor(out, 4)
+
+
+class Estimator:
+    def __init__(self, params, num_threads=1, _borrow=None):
+        self._own = _borrow is None
+        if _borrow is not None:
+            self.h = _borrow
+        else:
+            cp = make_params(params, 1, num_threads)
+            self.h = lib().orc_estimator_create(C.byref(cp))
+
+    def __del__(self):
+        if getattr(self, "_own", False) and getattr(self, "h", None):
+            lib().orc_estimator_destroy(self.h)
+            self.h = None
+
+    def linearize(self, ref, cur, level, T, reset_scale=True):
+        H = np.zeros(36, np.float32)
+        G = np.zeros(6, np.float32)
+        s = C.c_float()
+        f = lib().orc_linearize(self.h, ref.h, cur.h, level, _fp(_colmajor(T)), int(reset_scale), _fp(H), _fp(G), C.byref(s))
+        if f < 0:
+            raise _err()
+        return dict(f_norm=float(f), H=_from_colmajor(H, 6), G=G.copy(), sigma=float(s.value),
+                    residuals=self.residuals(), weights=self.weights(), valid=self.valid())
+
+    def residuals(self):
+        n = lib().orc_estimator_num_residuals(self.h)
+        return np.ctypeslib.as_array(lib().orc_estimator_residuals(self.h), shape=(n,)).copy()
+
+    def weights(self):
+        n = lib().orc_estimator_num_residuals(self.h)
+        return np.ctypeslib.as_array(lib().orc_estimator_weights(self.h), shape=(n,)).copy()
+
+    def valid(self):
+        n = lib().orc_estimator_num_residuals(self.h)
+        return np.ctypeslib.as_array(lib().orc_estimator_valid(self.h), shape=(n,)).copy()
+
+    def estimate_pose(self, ref, cur, T_init):
+        L = ref.num_levels
+        stats = (OrcStats * L)()
+        T = np.zeros(16, np.float32)
+        n = lib().orc_estimate_pose(self.h, ref.h, cur.h, _fp(_colmajor(T_init)), _fp(T), stats)
+        if n < 0:
+            raise _err()
+        return _from_colmajor(T, 4), [dict(numIterations=s.numIterations, finalError=s.finalError,
+                                          firstOrderOptimality=s.firstOrderOptimality, status=s.status) for s in stats], n
+
+    def fraction_good(self, thresh):
+        return float(lib().orc_fraction_good(self.h, float(thresh)))
+
+
+class VisualOdometry:
+    """restated bpvo::VisualOdometry (bpvo/vo.cc)."""
+
+    def __init__(self, K, baseline, image_size, params, use_rcp=1, num_threads=1):
+        rows, cols = image_size
+        cp = make_params(params, use_rcp, num_threads)
+        self.h = lib().orc_vo_create(_fp(_colmajor(K)), float(baseline), rows, cols, C.byref(cp))
+        if not self.h:
+            raise _err()
+        self.rows, self.cols = rows, cols
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_vo_destroy(self.h)
+            self.h = None
+
+    def add_frame(self, img, disp):
+        img = np.ascontiguousarray(img, dtype=np.uint8)
+        disp = _f32(disp)
+        r = OrcResult()
+        if lib().orc_vo_add_frame(self.h, _u8(img), _fp(disp), C.byref(r)) != 0:
+            raise _err()
+        return dict(pose=_from_colmajor(r.pose, 4), isKeyFrame=bool(r.isKeyFrame), keyFramingReason=r.keyFramingReason,
+                    stats=[dict(numIterations=s.numIterations, finalError=s.finalError,
+                                firstOrderOptimality=s.firstOrderOptimality, status=s.status) for s in r.stats[:r.numLevels]],
+                    numFunEvals=r.numFunEvals, numPointCloud=r.numPointCloud)
+
+    def add_frame_raw(self, img_ptr, disp_ptr, result):
+        """no-copy call for timing loops: img_ptr/disp_ptr are ctypes pointers, result an OrcResult."""
+        return lib().orc_vo_add_frame(self.h, img_ptr, disp_ptr, C.byref(result))
+
+    def num_points_at_level(self, level=-1):
+        return lib().orc_vo_num_points_at_level(self.h, level)
+
+    def ref_frame(self):
+        return Frame(None, 0, 0, 0, None, _borrow=lib().orc_vo_ref_frame(self.h))
+
+    def estimator(self):
+        return Estimator(None, _borrow=lib().orc_vo_estimator(self.h))
+
+    def trajectory(self):
+        n = lib().orc_vo_trajectory(self.h, None, 0)
+        buf = np.zeros((n, 16), np.float32)
+        lib().orc_vo_trajectory(self.h, _fp(buf), n)
+        return np.stack([b.reshape(4, 4).T for b in buf]) if n else np.zeros((0, 4, 4), np.float32)
+
+    def point_cloud(self):
+        n = lib().orc_vo_point_cloud(self.h, None, None, None, 0)
+        xyzw = np.zeros((n, 4), np.float32)
+        w = np.zeros(n, np.float32)
+        g = np.zeros(n, np.uint8)
+        if n:
+            lib().orc_vo_point_cloud(self.h, _fp(xyzw), _fp(w), _u8(g), n)
+        return xyzw, w, g
