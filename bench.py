@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""bench.py -- frames/sec and GN-iterations/sec of the per-frame Gauss-Newton dense-alignment path
+(bpvo's VisualOdometry::addFrame) on synthetic KITTI-sized bit-planes streams.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload kitti|vga|kitti_dense|1080p]
+
+A "step" is one addFrame() = image+disparity in -> pose out (pyramid, bit-planes descriptors, the whole
+coarse-to-fine GN solve, key-frame work when it triggers).  Prints ONE JSON line (rank 0).
+
+  value : frames/s with the step's inputs already resident in HBM when the timed region starts
+  e2e   : frames/s through the same public call with PINNED HOST buffers (H2D inside the timed region)
+  roofline : the dominant kernel (the persistent on-device GN solve) against the measured HBM peak
+  cpu_baseline : the CPU restatement of the reference (oracle/) timed on this box's host cores
+
+--impl reference times the reference's own CPU implementation of the path.  The reference cannot be
+built in this image (needs Eigen + OpenCV 2.4 + Boost), so that arm runs the oracle
+port with all the host threads the path can use.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # BASELINE.json configs[2]: KITTI 1241x376 bit-planes (8 ch), 4 levels, Tukey IRLS
+    "kitti": dict(scene="kitti", descriptor="bitplanes", levels=4, loss="tukey", nms=1,
+                  name="kitti_1241x376_bitplanes_8ch_4levels_tukey"),
+    "kitti_dense": dict(scene="kitti", descriptor="bitplanes", levels=4, loss="tukey", nms=-1,
+                        name="kitti_1241x376_bitplanes_8ch_4levels_tukey_dense"),
+    "vga": dict(scene="vga", descriptor="intensity", levels=4, loss="huber", nms=1,
+                name="vga_640x480_intensity_4levels_huber"),
+    "1080p": dict(scene="1080p", descriptor="bitplanes", levels=5, loss="tukey", nms=1,
+                  name="1080p_bitplanes_8ch_5levels_tukey"),
+}
+
+
+def make_scene(w, seed):
+    from bpvo_b200 import synth
+    return {"kitti": synth.scene_kitti, "vga": synth.scene_vga, "1080p": synth.scene_1080p}[w["scene"]](seed=seed)
+
+
+def make_params(w):
+    from bpvo_b200.types import AlgorithmParameters, DescriptorType, LossFunctionType, VerbosityType
+    return AlgorithmParameters(
+        descriptor={"intensity": DescriptorType.kIntensity, "bitplanes": DescriptorType.kBitPlanes}[w["descriptor"]],
+        numPyramidLevels=w["levels"],
+        lossFunction={"tukey": LossFunctionType.kTukey, "huber": LossFunctionType.kHuber, "l2": LossFunctionType.kL2}[w["loss"]],
+        nonMaxSuppRadius=w["nms"], verbosity=VerbosityType.kSilent)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """samples nvidia-smi clocks / throttle reasons DURING the timed region"""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower() == "active"})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def algorithmic_bytes_per_iter(N, C, rows, cols):
+    """points + (J + I0) + descriptor footprint touched + (r + w written), reference data model"""
+    return 16 * N + (24 + 4) * N * C + min(16 * N * C, 4 * C * rows * cols) + 8 * N * C
+
+
+# --------------------------------------------------------------------------------------------------
+def run_reference(args, w, rank, world):
+    """CPU arm: the restated reference (oracle port), all host threads the path can use, rank 0 only."""
+    if rank != 0:
+        return
+    from oracle import pyoracle as po
+    sc = make_scene(w, 0xB200)
+    p = make_params(w)
+    ncpu = os.cpu_count() or 1
+    nthreads = max(1, min(ncpu, 8))          # parallel_for over the 8 descriptor channels + range-split reduction
+    vo = po.VisualOdometry(sc.K, sc.baseline, (sc.rows, sc.cols), p, use_rcp=1, num_threads=nthreads)
+    nframes = args.steps + args.warmup + 1
+    frames = [sc.render(k) for k in range(nframes)]
+    res = po.OrcResult()
+    ptrs = [(f[0].ctypes.data_as(C.POINTER(C.c_uint8)), f[1].ctypes.data_as(C.POINTER(C.c_float))) for f in frames]
+    evals = 0
+    for k in range(args.warmup + 1):
+        vo.add_frame_raw(ptrs[k][0], ptrs[k][1], res)
+    t0 = time.perf_counter()
+    for k in range(args.warmup + 1, nframes):
+        vo.add_frame_raw(ptrs[k][0], ptrs[k][1], res)
+        evals += res.numFunEvals
+    dt = time.perf_counter() - t0
+    fps = args.steps / dt
+    line = {
+        "impl": "reference", "metric": "frames_per_sec", "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "gn_iters_per_sec": evals / dt,
+        "config": {"workload": w["name"], "streams": 1, "rows": sc.rows, "cols": sc.cols, "note": "restated reference (oracle port, CPU); the reference binary cannot be built here"},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": nthreads, "kind": "port",
+                         "sample": f"{args.steps} consecutive addFrame calls of the same stream, {nthreads} OpenMP threads standing in for TBB"},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+def timed_stream(vo, ptr_pairs, warmup, steps, dist, torch, sampler=None):
+    """W untimed + K timed addFrame calls; returns (device ms, wall ms, GN evals, key-frames) for the K steps."""
+    ctx = vo.ctx
+    evals = kfs = 0
+    for k in range(warmup):
+        vo.addFrameRaw(ptr_pairs[k][0], ptr_pairs[k][1], want_cloud=False)
+    ctx.synchronize()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    if sampler:
+        sampler.start()
+    t0 = time.perf_counter()
+    ctx.timer_start()
+    for k in range(warmup, warmup + steps):
+        r = vo.addFrameRaw(ptr_pairs[k][0], ptr_pairs[k][1], want_cloud=False)
+        evals += r.numFunEvals
+        kfs += int(r.isKeyFrame)
+    ms = ctx.timer_stop()
+    torch.cuda.synchronize()
+    wall = (time.perf_counter() - t0) * 1e3
+    clocks = sampler.stop() if sampler else None
+    return ms, wall, evals, kfs, clocks
+
+
+def run_ours(args, w, rank, world, local_rank):
+    import torch
+    from bpvo_b200 import VisualOdometry
+    from bpvo_b200.engine import PinnedBuffer
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    else:
+        torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+
+    # one independent stream per GPU (BASELINE.json configs[4]: seeds 0xB200 + g), weak scaling, no data-path collective
+    sc = make_scene(w, 0xB200 + rank)
+    p = make_params(w)
+    n_roof = 8
+    n_total = args.warmup + args.steps + 1 + n_roof
+    frames = [sc.render(k) for k in range(n_total)]
+    npx = sc.rows * sc.cols
+
+    # (1) inputs resident in HBM
+    d_img = [torch.from_numpy(f[0]).to(dev) for f in frames]
+    d_dsp = [torch.from_numpy(f[1]).to(dev) for f in frames]
+    torch.cuda.synchronize()
+    dev_ptrs = [(a.data_ptr(), b.data_ptr()) for a, b in zip(d_img, d_dsp)]
+    # (2) inputs in pinned host memory
+    pin_img = PinnedBuffer((n_total, sc.rows, sc.cols), np.uint8)
+    pin_dsp = PinnedBuffer((n_total, sc.rows, sc.cols), np.float32)
+    for k, f in enumerate(frames):
+        pin_img.array[k] = f[0]
+        pin_dsp.array[k] = f[1]
+    host_ptrs = [(pin_img.ptr + k * npx, pin_dsp.ptr + k * npx * 4) for k in range(n_total)]
+
+    def fresh_vo():
+        v = VisualOdometry(sc.K, sc.baseline, (sc.rows, sc.cols), p, device_id=local_rank)
+        v.addFrameRaw(host_ptrs[0][0], host_ptrs[0][1], want_cloud=False)    # frame 0 = first key-frame (template only)
+        return v
+
+    # ---- device-resident run -> `value` -----------------------------------------------------------
+    vo = fresh_vo()
+    vo.ctx.reset_counters()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ms, wall, evals, kfs, clocks = timed_stream(vo, dev_ptrs[1:], args.warmup, args.steps, dist, torch, sampler)
+    cnt = vo.ctx.counters()
+    launches_total = cnt["launches"]
+    launches_timed = int(round(launches_total * args.steps / float(args.steps + args.warmup)))
+    vo.close()
+
+    # ---- host-buffer run -> `e2e` -----------------------------------------------------------------
+    vo = fresh_vo()
+    vo.ctx.reset_counters()
+    ms_e, wall_e, evals_e, kfs_e, _ = timed_stream(vo, host_ptrs[1:], args.warmup, args.steps, dist, torch)
+    cnt_e = vo.ctx.counters()
+    h2d = cnt_e["h2d_bytes"] / float(args.steps + args.warmup)
+    d2h = cnt_e["d2h_bytes"] / float(args.steps + args.warmup)
+
+    # ---- roofline of the dominant kernel (persistent GN solve), measured live with CUDA events -----
+    roof = None
+    if rank == 0:
+        ctx = vo.ctx
+        ctx.set_profiling(True)
+        ctx.reset_counters()
+        ref = vo.ref_frame()
+        alg_bytes, ms_lin, n_solves = 0.0, 0.0, 0
+        phase = {k2: 0.0 for k2 in ("ms_upload", "ms_pyramid", "ms_descriptor", "ms_template", "ms_linearize")}
+        Cch = ctx.channels
+        sizes = [ref.level_size(l) for l in range(p.numPyramidLevels)]
+        for k in range(args.warmup + args.steps, args.warmup + args.steps + n_roof):
+            npts = [vo.ref_frame().numPoints(l) for l in range(p.numPyramidLevels)]    # template the solve runs against
+            c0 = ctx.counters()
+            r = vo.addFrameRaw(host_ptrs[1 + k][0], host_ptrs[1 + k][1], want_cloud=False)
+            c1 = ctx.counters()
+            ev = ctx.last_level_evals()
+            for k2 in phase:
+                phase[k2] += c1[k2] - c0[k2]
+            if r.isKeyFrame:
+                continue      # key-frames run two solves against two templates; keep the byte accounting exact by skipping them
+            ms_lin += c1["ms_linearize"] - c0["ms_linearize"]
+            n_solves += c1["solve_calls"] - c0["solve_calls"]
+            for l in range(p.numPyramidLevels):
+                alg_bytes += ev[l] * algorithmic_bytes_per_iter(npts[l], Cch, sizes[l][0], sizes[l][1])
+        n_solves = max(1, n_solves)
+        peak, how = peaks()
+        achieved = alg_bytes / (ms_lin * 1e-3) / 1e9 if ms_lin > 0 else 0.0
+        roof = {"bound": "hbm", "kernel": "k_estimate_pose<8> (persistent on-device GN solve, all levels/iterations in one launch)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": how, "ms_per_launch": ms_lin / n_solves,
+                "algorithmic_bytes_per_launch": alg_bytes / n_solves,
+                "phase_ms_per_frame": {k2: v / float(n_roof) for k2, v in phase.items()}}
+        ctx.set_profiling(False)
+    vo.close()
+
+    # ---- reduce over ranks: max time, total work ----------------------------------------------------
+    t = torch.tensor([ms, ms_e, float(evals), float(evals_e)], dtype=torch.float64, device=dev)
+    if dist is not None:
+        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        ms, ms_e = float(tmax[0]), float(tmax[1])
+        evals, evals_e = float(tsum[2]), float(tsum[3])
+    frames_total = args.steps * world
+    value = frames_total / (ms * 1e-3)
+    e2e = frames_total / (ms_e * 1e-3)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline(w, args)
+
+    if rank == 0:
+        line = {
+            "metric": "frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 (fp64 projection + bilinear blend, as the reference)", "data": "synthetic",
+            "gn_iters_per_sec": evals / (ms * 1e-3), "gn_iters_per_frame": evals / frames_total, "keyframes_in_timed_region": kfs,
+            "config": {"workload": w["name"], "rows": sc.rows, "cols": sc.cols, "streams": world, "parallelism": f"replicas x{world} (one independent stream per GPU)",
+                       "l2_policy": "each step consumes a NEW frame (2.3 MB input, 20 MB of fresh descriptors); working set is L2-resident by nature, no artificial flush",
+                       "timing": "cudaEvents on the engine stream around K addFrame calls, max over ranks", "wall_ms": wall},
+            "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "gn_iters_per_sec": evals_e / (ms_e * 1e-3), "ms_per_step": ms_e / args.steps},
+            "gpu_launches": launches_timed,
+            "clocks": clocks,
+            "roofline": roof,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    pin_img.free(); pin_dsp.free()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def cpu_baseline(w, args):
+    """the oracle port, 1 thread (= the reference's default build, WITH_TBB off), on a bounded sample"""
+    from oracle import pyoracle as po
+    sc = make_scene(w, 0xB200)
+    p = make_params(w)
+    vo = po.VisualOdometry(sc.K, sc.baseline, (sc.rows, sc.cols), p, use_rcp=1, num_threads=1)
+    budget_s = 15.0
+    res = po.OrcResult()
+    k = 0
+    img, d = sc.render(0)
+    vo.add_frame(img, d)
+    t_used, n, evals = 0.0, 0, 0
+    while t_used < budget_s and n < 48:
+        k += 1
+        img, d = sc.render(k)
+        t0 = time.perf_counter()
+        vo.add_frame_raw(img.ctypes.data_as(C.POINTER(C.c_uint8)), d.ctypes.data_as(C.POINTER(C.c_float)), res)
+        t_used += time.perf_counter() - t0
+        n += 1
+        evals += res.numFunEvals
+    return {"value": n / t_used, "unit": "frames/s", "cores": 1, "kind": "port", "gn_iters_per_sec": evals / t_used,
+            "sample": f"first {n} addFrame calls of the same synthetic stream ({t_used:.1f} s of CPU work), single thread = reference default build"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=64)
+    ap.add_argument("--warmup", type=int, default=4)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="kitti", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    w = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, w, rank, world)
+    else:
+        run_ours(args, w, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

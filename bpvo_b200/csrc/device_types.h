@@ -1,0 +1,108 @@
+// device_types.h -- structures shared between the host engine and the sm_100a kernels.
+#pragma once
+
+#include <stdint.h>
+#include <cuda_runtime.h>
+#include "host_math.h"
+
+namespace bp {
+
+constexpr int kMaxLevels = 16;
+constexpr int kHist1Bins = 2048;   // |r| float bits [30:20]
+constexpr int kHist2Bins = 2048;   // bits [19:9]
+constexpr int kHist3Bins = 512;    // bits [8:0]
+constexpr int kHistBins = kHist1Bins + 2 * kHist2Bins + 2 * kHist3Bins;
+constexpr int kHistWords = kHistBins + 4;   // one histogram set; word [kHistBins] = max(~i) over valid points i
+constexpr int kPartialStride = 32; // doubles per block partial (21 H + 6 G + f + n_good + pad)
+constexpr int kLinThreads = 512;   // threads per CTA of the linearize phases (1 CTA per SM)
+
+// Per-level template ("TemplateData", bpvo/template_data.h) in the device layout:
+//   pts   [N]      float4 (X, Y, Z, 1)                                  (reference: _points)
+//   gx    [N][C]   fx * Ix of every channel, point-major                (reference: folded into _jacobians)
+//   gy    [N][C]   fy * Iy
+//   i0    [N][C]   template pixel values                                (reference: _pixels, channel-major)
+// The 1x6 Jacobian of a residual is gx*A(X) + gy*B(X) with A, B the rows of the 2x6 warp Jacobian at
+// identity (rigid_body_warp.h:94-106); A, B are recomputed in registers from (X,Y,Z).
+struct TemplateMeta {     // device-resident header of a level's template (written by the build kernels)
+  int n_raw;              // pixels that passed saliency + NMS + disparity gate
+  int n;                  // points held by THIS rank (multiple of 16)
+  int n_total;            // points kept globally (== n when unsharded)
+  int first;              // global scan-order index of this rank's first point
+  float s, c1, c2, c3;    // Hartley normalisation: Tn = [sI, -s c; 0 1]  (warps.cc:27-48)
+};
+
+struct LevelTemplate {
+  const float4* pts;
+  const float* gx;
+  const float* gy;
+  const float* i0;
+  const TemplateMeta* meta;   // n and the normalisation live on the device: set_template never syncs
+  float fx, fy, cx, cy;
+};
+
+// Per-level dense descriptor of the moving frame: channel-interleaved f32 [rows][cols][C]
+struct LevelImage {
+  const float* desc;
+  int rows, cols;
+};
+
+struct ScaleState {      // AutoScaleEstimator state (mestimator.h:62-83)
+  float scale;
+  float delta;
+};
+
+// result of one linearize, written by the last CTA of the reduce phase
+struct LinOut {
+  float H[36];           // column-major, symmetric
+  float G[6];
+  float f_norm;          // sqrt(sum w r^2)
+  float sigma;
+  int   n_valid;         // valid POINTS
+  int   n_good;          // weights > goodPointThreshold over all C*N entries (invalid entries count as weight 1, Q6)
+  int   pad[2];
+};
+
+// scratch owned by a ctx
+struct Work {
+  float* res;            // [N][C] residuals of the last linearize (point-major; 0 for invalid points)
+  uint8_t* valid;        // [N]
+  unsigned* hist;        // 2 sets x kHistWords (double-buffered across iterations)
+  double* partials;      // [grid][kPartialStride]
+  ScaleState* scale;
+  LinOut* out;
+  unsigned* ticket;      // last-CTA-done counter
+};
+
+struct SolverParams {    // PoseEstimatorParameters (pose_estimator_params.h) + loss
+  int   max_iterations;
+  int   max_fun_evals;   // 1200
+  float parameter_tolerance, function_tolerance, gradient_tolerance;
+  int   loss;            // 0x10 huber, 0x11 tukey, 0x12 L2
+  float good_threshold;
+  int   max_test_level;
+  int   num_levels;
+};
+
+struct LevelStats {      // OptimizerStatistics (types.h:444-482)
+  int   num_iterations;
+  float final_error;
+  float first_order_optimality;
+  int   status;
+  int   num_evals;       // linearize() calls at this level
+};
+
+// everything the on-device GN loop needs for one estimatePose
+struct SolveArgs {
+  LevelTemplate tmpl[kMaxLevels];
+  LevelImage img[kMaxLevels];
+  SolverParams sp;
+  Work work;
+  M44 T_init;
+  // outputs (device memory)
+  M44* T_out;
+  LevelStats* stats;     // [num_levels]
+  int* num_fun_evals;
+  long long* prof;       // optional: per-phase cycle counters of CTA 0 (nullptr = off)
+};
+
+}  // namespace bp

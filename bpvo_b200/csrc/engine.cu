@@ -1,0 +1,787 @@
+// engine.cu -- host side of the seam-level C ABI (include/bpvo_b200.h): device buffers, stream,
+// kernel launches, the host-driven and the on-device Gauss-Newton drivers.
+//
+// Mirrors, method for method, what bpvo/vo.cc calls on VisualOdometryFrame (bpvo/vo_frame.{h,cc}) and
+// VisualOdometryPoseEstimator (bpvo/vo_pose_estimator.{h,cc}); the state machine of vo.cc itself
+// lives in host/vo_shim.cpp on top of these entry points.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/bpvo_b200.h"
+#include "device_types.h"
+#include "kernels_image.cuh"
+#include "kernels_template.cuh"
+#include "kernels_linearize.cuh"
+#include "engine_internal.h"
+
+using namespace bp;
+
+namespace {
+thread_local std::string g_err;
+}
+
+int bp_fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                         \
+  do {                                                                                         \
+    cudaError_t _e = (expr);                                                                   \
+    if (_e != cudaSuccess)                                                                     \
+      return bp_fail(BPVO_B200_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+#define LAUNCH_CHECK(ctx)                                                                      \
+  do {                                                                                         \
+    (ctx)->counters.launches++;                                                                \
+    cudaError_t _e = cudaGetLastError();                                                       \
+    if (_e != cudaSuccess)                                                                     \
+      return bp_fail(BPVO_B200_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// -------------------------------------------------------------------------------------------------
+// phase timers (cudaEvent pairs, only when profiling is on)
+// -------------------------------------------------------------------------------------------------
+struct PhaseTimer {
+  bpvo_b200_ctx* c; double* acc; bool on;
+  PhaseTimer(bpvo_b200_ctx* ctx, double* a) : c(ctx), acc(a), on(ctx->profiling) {
+    if (on) cudaEventRecord(c->ev0, c->stream);
+  }
+  ~PhaseTimer() {
+    if (on) {
+      cudaEventRecord(c->ev1, c->stream);
+      cudaEventSynchronize(c->ev1);
+      float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+      *acc += ms; c->counters.ms_total += ms;
+    }
+  }
+};
+
+extern "C" {
+
+int bpvo_b200_version(void) { return BPVO_B200_VERSION; }
+const char* bpvo_b200_last_error(void) { return g_err.c_str(); }
+
+void bpvo_b200_default_params(bpvo_b200_params* p) {     // bpvo/types.cc:31-66
+  p->numPyramidLevels = -1; p->minImageDimensionForPyramid = 40;
+  p->sigmaPriorToCensusTransform = -1.0f; p->sigmaBitPlanes = 0.5f;
+  p->maxIterations = 50; p->parameterTolerance = 1e-7f; p->functionTolerance = 1e-6f; p->gradientTolerance = 1e-8f;
+  p->relaxTolerancesForCoarseLevels = 1; p->gradientEstimation = BPVO_B200_CD3; p->interp = BPVO_B200_LINEAR;
+  p->lossFunction = BPVO_B200_TUKEY; p->descriptor = BPVO_B200_INTENSITY; p->verbosity = 0x20;
+  p->minTranslationMagToKeyFrame = 0.15f; p->minRotationMagToKeyFrame = 5.0f;
+  p->maxFractionOfGoodPointsToKeyFrame = 0.6f; p->goodPointThreshold = 0.85f;
+  p->minNumPixelsForNonMaximaSuppression = 320 * 240; p->nonMaxSuppRadius = 1; p->minNumPixelsToWork = 256;
+  p->minSaliency = 0.1f; p->minValidDisparity = 0.001f; p->maxValidDisparity = 512.0f;
+  p->maxTestLevel = 0; p->withNormalization = 1;
+  p->device_id = 0; p->flags = 0;
+}
+
+int bpvo_b200_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+void* bpvo_b200_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return p;
+}
+void bpvo_b200_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+// -------------------------------------------------------------------------------------------------
+// ctx
+// -------------------------------------------------------------------------------------------------
+int bpvo_b200_create(bpvo_b200_ctx** out, const float K[9], float baseline, int rows, int cols, const bpvo_b200_params* p) {
+  if (!out || !K || !p) return bp_fail(BPVO_B200_ERR_INVALID_ARG, "null argument");
+  *out = nullptr;
+  if (p->numPyramidLevels <= 0 || p->numPyramidLevels > kMaxLevels)
+    return bp_fail(BPVO_B200_ERR_INVALID_ARG, "invalid number of pyramid levels");          // dense_descriptor_pyramid.cc:37
+  if (p->maxTestLevel < 0 || p->maxTestLevel >= p->numPyramidLevels)
+    return bp_fail(BPVO_B200_ERR_INVALID_ARG, "invalid maxTestLevel");                       // dense_descriptor_pyramid.cc:38
+  if (rows < 16 || cols < 24) return bp_fail(BPVO_B200_ERR_INVALID_ARG, "image too small");
+  if (p->descriptor != BPVO_B200_INTENSITY && p->descriptor != BPVO_B200_BITPLANES)
+    return bp_fail(BPVO_B200_ERR_UNSUPPORTED, "DescriptorType 0x%x is not on the accelerated path (Intensity, BitPlanes only)", p->descriptor);
+  if (p->interp != BPVO_B200_LINEAR)
+    return bp_fail(BPVO_B200_ERR_UNSUPPORTED, "only InterpolationType::kLinear is implemented");
+  if (p->descriptor == BPVO_B200_BITPLANES && p->sigmaPriorToCensusTransform > 0.0f)
+    return bp_fail(BPVO_B200_ERR_UNSUPPORTED, "sigmaPriorToCensusTransform > 0 (third-party u8 3x3 GaussianBlur) is not implemented");
+  if (p->lossFunction != BPVO_B200_HUBER && p->lossFunction != BPVO_B200_TUKEY && p->lossFunction != BPVO_B200_L2)
+    return bp_fail(BPVO_B200_ERR_INVALID_ARG, "unknown RobustFunction");
+  if (p->gradientEstimation != BPVO_B200_CD3 && p->gradientEstimation != BPVO_B200_CD5)
+    return bp_fail(BPVO_B200_ERR_INVALID_ARG, "unknown GradientEstimationType");
+  // K is column-major: K[0]=fx K[4]=fy K[6]=cx K[7]=cy K[8]=1; skew / lower entries must be 0
+  if (K[1] != 0.0f || K[2] != 0.0f || K[3] != 0.0f || K[5] != 0.0f || K[8] != 1.0f)
+    return bp_fail(BPVO_B200_ERR_UNSUPPORTED, "K must be [fx 0 cx; 0 fy cy; 0 0 1]");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return bp_fail(BPVO_B200_ERR_CUDA, "no CUDA device: bpvo_b200 has no CPU fallback");
+  }
+  if (p->device_id < 0 || p->device_id >= ndev) return bp_fail(BPVO_B200_ERR_INVALID_ARG, "device_id %d out of range (%d devices)", p->device_id, ndev);
+  CUDA_TRY(cudaSetDevice(p->device_id));
+
+  bpvo_b200_ctx* c = new bpvo_b200_ctx();
+  c->p = *p; c->rows = rows; c->cols = cols; c->L = p->numPyramidLevels; c->baseline = baseline;
+  c->C = (p->descriptor == BPVO_B200_BITPLANES) ? 8 : 1;
+  memcpy(c->K, K, sizeof(c->K));
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, p->device_id));
+  c->sm_count = prop.multiProcessorCount;
+  c->coop = prop.cooperativeLaunch != 0;
+  // per-level geometry: K halves (K(2,2) = 1), baseline doubles (vo_frame.cc:24-28); pyrDown sizes
+  float fx = K[0], fy = K[4], cx = K[6], cy = K[7], b = baseline; int r = rows, cl = cols;
+  for (int l = 0; l < c->L; ++l) {
+    if (l > 0) { fx *= 0.5f; fy *= 0.5f; cx *= 0.5f; cy *= 0.5f; b *= 2.0f; r = (r + 1) / 2; cl = (cl + 1) / 2; }
+    LevelGeom& g = c->geom[l];
+    g.rows = r; g.cols = cl; g.fx = fx; g.fy = fy; g.cx = cx; g.cy = cy; g.Bf = b * fx;
+    const int border = std::max(p->nonMaxSuppRadius, 3);
+    g.capacity = std::max(0, r - 2 * border - 1) * std::max(0, cl - 2 * border - 1);
+    g.capacity = (g.capacity + 15) & ~15;
+    if (g.capacity == 0) g.capacity = 16;
+  }
+  CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CUDA_TRY(cudaEventCreate(&c->ev0)); CUDA_TRY(cudaEventCreate(&c->ev1));
+  CUDA_TRY(cudaEventCreate(&c->tm0)); CUDA_TRY(cudaEventCreate(&c->tm1));
+  CUDA_TRY(cudaEventCreateWithFlags(&c->stage_free, cudaEventDisableTiming));
+  const size_t cap0 = (size_t) c->geom[c->p.maxTestLevel].capacity;
+  size_t capmax = 0; for (int l = c->p.maxTestLevel; l < c->L; ++l) capmax = std::max(capmax, (size_t) c->geom[l].capacity);
+  (void) cap0;
+  CUDA_TRY(cudaMalloc(&c->work.res, capmax * c->C * sizeof(float)));
+  CUDA_TRY(cudaMalloc(&c->work.valid, capmax));
+  CUDA_TRY(cudaMalloc(&c->work.hist, 2 * kHistWords * sizeof(unsigned)));
+  CUDA_TRY(cudaMalloc(&c->work.partials, (size_t) 1024 * kPartialStride * sizeof(double)));
+  CUDA_TRY(cudaMalloc(&c->work.scale, sizeof(ScaleState)));
+  CUDA_TRY(cudaMalloc(&c->work.out, sizeof(LinOut)));
+  CUDA_TRY(cudaMalloc(&c->work.ticket, 4 * sizeof(unsigned)));
+  CUDA_TRY(cudaMalloc(&c->sel, sizeof(Sel)));
+  CUDA_TRY(cudaMalloc(&c->export_buf, capmax * c->C * 6 * sizeof(float)));
+  CUDA_TRY(cudaMemsetAsync(c->work.hist, 0, 2 * kHistWords * sizeof(unsigned), c->stream));
+  CUDA_TRY(cudaMemsetAsync(c->work.ticket, 0, 4 * sizeof(unsigned), c->stream));
+  CUDA_TRY(cudaMemsetAsync(c->work.out, 0, sizeof(LinOut), c->stream));
+  CUDA_TRY(cudaMemsetAsync(c->sel, 0, sizeof(Sel), c->stream));
+  k_reset_scale<<<1, 1, 0, c->stream>>>(c->work.scale);
+  // template-build scratch (sized for level maxTestLevel = the largest one built)
+  const int r0 = c->geom[c->p.maxTestLevel].rows, c0 = c->geom[c->p.maxTestLevel].cols;
+  CUDA_TRY(cudaMalloc(&c->flags, (size_t) r0 * c0));
+  CUDA_TRY(cudaMalloc(&c->block_counts, (size_t) (ceil_div(r0 * c0, kSelPerBlock) + 1) * sizeof(int)));
+  CUDA_TRY(cudaMalloc(&c->hpartials, 1024 * 4 * sizeof(double)));
+  // device outputs of estimate_pose + pinned mailboxes
+  CUDA_TRY(cudaMalloc(&c->d_T, sizeof(M44)));
+  CUDA_TRY(cudaMalloc(&c->d_stats, kMaxLevels * sizeof(LevelStats)));
+  CUDA_TRY(cudaMalloc(&c->d_evals, sizeof(int)));
+  CUDA_TRY(cudaMalloc(&c->d_prof, 16 * sizeof(long long)));
+  CUDA_TRY(cudaMemsetAsync(c->d_prof, 0, 16 * sizeof(long long), c->stream));
+  CUDA_TRY(cudaHostAlloc(&c->h_mail, sizeof(Mailbox), cudaHostAllocDefault));
+  memset(c->h_mail, 0, sizeof(Mailbox));
+  CUDA_TRY(cudaHostAlloc(&c->stage_img, (size_t) rows * cols, cudaHostAllocDefault));
+  CUDA_TRY(cudaHostAlloc(&c->stage_disp, (size_t) rows * cols * sizeof(float), cudaHostAllocDefault));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  *out = c;
+  return BPVO_B200_OK;
+}
+
+int bpvo_b200_destroy(bpvo_b200_ctx* c) {
+  if (!c) return BPVO_B200_OK;
+  cudaSetDevice(c->p.device_id);
+  cudaStreamSynchronize(c->stream);
+  bp_comm_destroy(c);
+  cudaFree(c->work.res); cudaFree(c->work.valid); cudaFree(c->work.hist); cudaFree(c->work.partials);
+  cudaFree(c->work.scale); cudaFree(c->work.out); cudaFree(c->work.ticket); cudaFree(c->sel); cudaFree(c->export_buf);
+  cudaFree(c->flags); cudaFree(c->block_counts); cudaFree(c->hpartials);
+  cudaFree(c->d_T); cudaFree(c->d_stats); cudaFree(c->d_evals); cudaFree(c->d_prof);
+  cudaFreeHost(c->h_mail); cudaFreeHost(c->stage_img); cudaFreeHost(c->stage_disp);
+  if (c->flush_buf) cudaFree(c->flush_buf);
+  cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->tm0); cudaEventDestroy(c->tm1); cudaEventDestroy(c->stage_free);
+  cudaStreamDestroy(c->stream);
+  delete c;
+  return BPVO_B200_OK;
+}
+
+int bpvo_b200_synchronize(bpvo_b200_ctx* c) {
+  if (!c) return bp_fail(BPVO_B200_ERR_INVALID_ARG, "null ctx");
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  return BPVO_B200_OK;
+}
+int bpvo_b200_timer_start(bpvo_b200_ctx* c) {
+  if (!c) return bp_fail(BPVO_B200_ERR_INVALID_ARG, "null ctx");
+  CUDA_TRY(cudaEventRecord(c->tm0, c->stream));
+  return BPVO_B200_OK;
+}
+int bpvo_b200_timer_stop(bpvo_b200_ctx* c, float* ms) {
+  if (!c || !ms) return bp_fail(BPVO_B200_ERR_INVALID_ARG, "null argument");
+  CUDA_TRY(cudaEventRecord(c->tm1, c->stream));
+  CUDA_TRY(cudaEventSynchronize(c->tm1));
+  CUDA_TRY(cudaEventElapsedTime(ms, c->tm0, c->tm1));
+  return BPVO_B200_OK;
+}
+int bpvo_b200_last_level_evals(bpvo_b200_ctx* c, int* evals) {
+  if (!c || !evals) return bp_fail(BPVO_B200_ERR_INVALID_ARG, "null argument");
+  for (int l = 0; l < c->L; ++l) evals[l] = c->level_evals[l];
+  return BPVO_B200_OK;
+}
+int bpvo_b200_get_phase_cycles(bpvo_b200_ctx* c, long long cycles[16], int reset) {
+  if (!c || !cycles) return bp_fail(BPVO_B200_ERR_INVALID_ARG, "null argument");
+  CUDA_TRY(cudaSetDevice(c->p.device_id));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  CUDA_TRY(cudaMemcpy(cycles, c->d_prof, 16 * sizeof(long long), cudaMemcpyDeviceToHost));
+  if (reset) CUDA_TRY(cudaMemset(c->d_prof, 0, 16 * sizeof(long long)));
+  return BPVO_B200_OK;
+}
+int bpvo_b200_set_profiling(bpvo_b200_ctx* c, int enable) { if (!c) return bp_fail(BPVO_B200_ERR_INVALID_ARG, "null ctx"); c->profiling = enable != 0; return BPVO_B200_OK; }
+int bpvo_b200_get_counters(bpvo_b200_ctx* c, bpvo_b200_counters* out) { if (!c || !out) return bp_fail(BPVO_B200_ERR_INVALID_ARG, "null"); *out = c->counters; return BPVO_B200_OK; }
+int bpvo_b200_reset_counters(bpvo_b200_ctx* c) { if (!c) return bp_fail(BPVO_B200_ERR_INVALID_ARG, "null ctx"); memset(&c->counters, 0, sizeof(c->counters)); return BPVO_B200_OK; }
+
+// -------------------------------------------------------------------------------------------------
+// frame
+// -------------------------------------------------------------------------------------------------
+int bpvo_b200_frame_create(bpvo_b200_ctx* c, bpvo_b200_frame** out) {
+  if (!c || !out) return bp_fail(BPVO_B200_ERR_INVALID_ARG, "null argument");
+  CUDA_TRY(cudaSetDevice(c->p.device_id));
+  bpvo_b200_frame* f = new bpvo_b200_frame();
+  f->ctx = c;
+  CUDA_TRY(cudaMalloc(&f->disp, (size_t) c->rows * c->cols * sizeof(float)));
+  for (int l = 0; l < c->L; ++l) {
+    const LevelGeom& g = c->geom[l];
+    CUDA_TRY(cudaMalloc(&f->pyr[l], (size_t) g.rows * g.cols));
+    if (l < c->p.maxTestLevel) continue;
+    const size_t npx = (size_t) g.rows * g.cols, cap = (size_t) g.capacity;
+    CUDA_TRY(cudaMalloc(&f->desc[l], (npx + 1) * c->C * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&f->saliency[l], npx * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&f->pts[l], cap * sizeof(float4)));
+    CUDA_TRY(cudaMalloc(&f->gx[l], cap * c->C * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&f->gy[l], cap * c->C * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&f->i0[l], cap * c->C * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&f->inds[l], cap * sizeof(int)));
+  }
+  CUDA_TRY(cudaMalloc(&f->d_meta, kMaxLevels * sizeof(TemplateMeta)));
+  CUDA_TRY(cudaMemsetAsync(f->d_meta, 0, kMaxLevels * sizeof(TemplateMeta), c->stream));
+  CUDA_TRY(cudaHostAlloc(&f->h_meta, kMaxLevels * sizeof(TemplateMeta), cudaHostAllocDefault));
+  memset(f->h_meta, 0, kMaxLevels * sizeof(TemplateMeta));
+  CUDA_TRY(cudaEventCreateWithFlags(&f->meta_ready, cudaEventDisableTiming));
+  *out = f;
+  return BPVO_B200_OK;
+}
+
+int bpvo_b200_frame_destroy(bpvo_b200_frame* f) {
+  if (!f) return BPVO_B200_OK;
+  bpvo_b200_ctx* c = f->ctx;
+  cudaSetDevice(c->p.device_id);
+  cudaStreamSynchronize(c->stream);
+  cudaFree(f->disp);
+  for (int l = 0; l < c->L; ++l) {
+    cudaFree(f->pyr[l]); cudaFree(f->desc[l]); cudaFree(f->saliency[l]); cudaFree(f->pts[l]);
+    cudaFree(f->gx[l]); cudaFree(f->gy[l]); cudaFree(f->i0[l]); cudaFree(f->inds[l]);
+  }
+  cudaFree(f->d_meta); cudaFreeHost(f->h_meta); cudaEventDestroy(f->meta_ready);
+  if (c->last_ref == f) c->last_ref = nullptr;
+  delete f;
+  return BPVO_B200_OK;
+}
+
+// true if the DMA engine can read p directly: page-locked host memory or device / managed memory
+static bool is_dma_able(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+// setData (vo_frame.cc:48-55) -> DenseDescriptorPyramid::init (dense_descriptor_pyramid.cc:67-78)
+int bpvo_b200_frame_set_data(bpvo_b200_frame* f, const uint8_t* image, const float* disparity) {
+  if (!f) return bp_fail(BPVO_B200_ERR_INVALID_ARG, "null frame");
+  if (!image || !disparity) return bp_fail(BPVO_B200_ERR_INVALID_ARG, "nullptr image/disparity");     // vo.cc:68
+  bpvo_b200_ctx* c = f->ctx;
+  CUDA_TRY(cudaSetDevice(c->p.device_id));
+  const size_t npx = (size_t) c->rows * c->cols;
+  {
+    PhaseTimer t(c, &c->counters.ms_upload);
+    const uint8_t* src_i = image; const float* src_d = disparity;
+    if (!(is_dma_able(image) && is_dma_able(disparity))) {
+      CUDA_TRY(cudaEventSynchronize(c->stage_free));
+      memcpy(c->stage_img, image, npx); memcpy(c->stage_disp, disparity, npx * sizeof(float));
+      src_i = c->stage_img; src_d = c->stage_disp;
+    }
+    CUDA_TRY(cudaMemcpyAsync(f->pyr[0], src_i, npx, cudaMemcpyDefault, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(f->disp, src_d, npx * sizeof(float), cudaMemcpyDefault, c->stream));
+    CUDA_TRY(cudaEventRecord(c->stage_free, c->stream));
+    c->counters.h2d_bytes += (int64_t) (npx * 5);
+  }
+  {
+    PhaseTimer t(c, &c->counters.ms_pyramid);
+    for (int l = 1; l < c->L; ++l) {
+      const LevelGeom& s = c->geom[l - 1]; const LevelGeom& d = c->geom[l];
+      pyr_down_kernel<<<dim3(ceil_div(d.cols, 32), ceil_div(d.rows, 8)), 256, 0, c->stream>>>(f->pyr[l - 1], s.rows, s.cols, f->pyr[l], d.rows, d.cols);
+      LAUNCH_CHECK(c);
+    }
+  }
+  {
+    PhaseTimer t(c, &c->counters.ms_descriptor);
+    for (int l = c->L - 1; l >= c->p.maxTestLevel; --l) {
+      const LevelGeom& g = c->geom[l];
+      if (c->C == 1) {
+        intensity_kernel<<<ceil_div(g.rows * g.cols, 256), 256, 0, c->stream>>>(f->pyr[l], f->desc[l], g.rows * g.cols);
+      } else {
+        float k[5]; double sum = 0; const double sg = c->p.sigmaBitPlanes > 0 ? (double) c->p.sigmaBitPlanes : 1.1;
+        // cv::getGaussianKernel(5, sigma, CV_32F): exp in double -> float taps, normalised by the double sum of the float taps
+        for (int i = 0; i < 5; ++i) { const double x = i - 2.0; k[i] = (float) exp(-0.5 / (sg * sg) * x * x); sum += k[i]; }
+        for (int i = 0; i < 5; ++i) k[i] = (float) (k[i] * (1.0 / sum));
+        bitplanes_kernel<<<dim3(ceil_div(g.cols, kBpTW), ceil_div(g.rows, kBpTH)), 256, 0, c->stream>>>(
+            f->pyr[l], g.rows, g.cols, k[2], k[3], k[4], c->p.sigmaBitPlanes > 0.0f ? 1 : 0, f->desc[l]);
+      }
+      LAUNCH_CHECK(c);
+    }
+  }
+  f->has_data = true;
+  return BPVO_B200_OK;
+}
+
+static LevelTemplate make_level_template(const bpvo_b200_frame* f, int l) {
+  const LevelGeom& g = f->ctx->geom[l];
+  LevelTemplate t;
+  t.pts = f->pts[l]; t.gx = f->gx[l]; t.gy = f->gy[l]; t.i0 = f->i0[l]; t.meta = f->d_meta + l;
+  t.fx = g.fx; t.fy = g.fy; t.cx = g.cx; t.cy = g.cy;
+  return t;
+}
+
+// setTemplate (vo_frame.cc:61-93) -> TemplateData::setData per level (template_data.cc:37-142); fully asynchronous
+int bpvo_b200_frame_set_template(bpvo_b200_frame* f) {
+  if (!f) return bp_fail(BPVO_B200_ERR_INVALID_ARG, "null frame");
+  if (!f->has_data) return bp_fail(BPVO_B200_ERR_NO_DATA, "no data in frame");                       // vo_frame.cc:63
+  bpvo_b200_ctx* c = f->ctx;
+  CUDA_TRY(cudaSetDevice(c->p.device_id));
+  PhaseTimer t(c, &c->counters.ms_template);
+  for (int l = c->L - 1; l >= c->p.maxTestLevel; --l) {
+    const LevelGeom& g = c->geom[l];
+    const int npx = g.rows * g.cols;
+    if (c->C == 1) saliency_kernel<1><<<ceil_div(npx, 256), 256, 0, c->stream>>>(f->desc[l], g.rows, g.cols, f->saliency[l]);
+    else saliency_kernel<8><<<ceil_div(npx, 256), 256, 0, c->stream>>>(f->desc[l], g.rows, g.cols, f->saliency[l]);
+    LAUNCH_CHECK(c);
+    SelectArgs sa;
+    sa.S = f->saliency[l]; sa.D = f->disp; sa.rows = g.rows; sa.cols = g.cols; sa.Dcols = c->cols; sa.level = l;
+    sa.nms_radius = (npx >= c->p.minNumPixelsForNonMaximaSuppression) ? c->p.nonMaxSuppRadius : -1;   // template_data.cc:43-49
+    sa.border = std::max(c->p.nonMaxSuppRadius, 3);
+    sa.min_saliency = c->p.minSaliency; sa.min_disp = c->p.minValidDisparity; sa.max_disp = c->p.maxValidDisparity;
+    const int nb = ceil_div(npx, kSelPerBlock);
+    select_flags_kernel<<<nb, kSelThreads, 0, c->stream>>>(sa, c->flags, c->block_counts);
+    LAUNCH_CHECK(c);
+    select_scan_kernel<<<1, 1024, 0, c->stream>>>(c->block_counts, nb, f->d_meta + l, c->shard_rank, c->shard_size);
+    LAUNCH_CHECK(c);
+    PointArgs pa; pa.rows = g.rows; pa.cols = g.cols; pa.Dcols = c->cols; pa.level = l;
+    pa.fx = g.fx; pa.fy = g.fy; pa.cx = g.cx; pa.cy = g.cy; pa.Bf = g.Bf;
+    select_scatter_kernel<<<nb, kSelThreads, 0, c->stream>>>(pa, f->disp, c->flags, c->block_counts, f->d_meta + l, f->inds[l], f->pts[l]);
+    LAUNCH_CHECK(c);
+    if (c->p.withNormalization) {
+      int rc = bp_hartley(c, f, l);
+      if (rc != BPVO_B200_OK) return rc;
+    } else {
+      set_identity_normalization_kernel<<<1, 1, 0, c->stream>>>(f->d_meta + l);
+      LAUNCH_CHECK(c);
+    }
+    const int rb = std::max(1, std::min(ceil_div(g.capacity * c->C, 256), c->sm_count * 8));
+    const int cd5 = c->p.gradientEstimation == BPVO_B200_CD5;
+    if (c->C == 1) template_records_kernel<1><<<rb, 256, 0, c->stream>>>(f->desc[l], g.cols, f->inds[l], f->d_meta + l, g.fx, g.fy, cd5, f->gx[l], f->gy[l], f->i0[l]);
+    else template_records_kernel<8><<<rb, 256, 0, c->stream>>>(f->desc[l], g.cols, f->inds[l], f->d_meta + l, g.fx, g.fy, cd5, f->gx[l], f->gy[l], f->i0[l]);
+    LAUNCH_CHECK(c);
+  }
+  CUDA_TRY(cudaMemcpyAsync(f->h_meta, f->d_meta, kMaxLevels * sizeof(TemplateMeta), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaEventRecord(f->meta_ready, c->stream));
+  c->counters.d2h_bytes += kMaxLevels * sizeof(TemplateMeta);
+  f->has_template = true;
+  return BPVO_B200_OK;
+}
+
+int bpvo_b200_frame_has_template(const bpvo_b200_frame* f) { return f && f->has_template; }
+int bpvo_b200_frame_empty(const bpvo_b200_frame* f) { return !f || !f->has_data; }
+int bpvo_b200_frame_clear(bpvo_b200_frame* f) { if (!f) return bp_fail(BPVO_B200_ERR_INVALID_ARG, "null frame"); f->has_data = false; f->has_template = false; return BPVO_B200_OK; }
+int bpvo_b200_frame_num_levels(const bpvo_b200_frame* f) { return f ? f->ctx->L : 0; }
+int bpvo_b200_frame_level_size(const bpvo_b200_frame* f, int level, int* rows, int* cols) {
+  if (!f || level < 0 || level >= f->ctx->L) return bp_fail(BPVO_B200_ERR_INVALID_ARG, "bad level");
+  *rows = f->ctx->geom[level].rows; *cols = f->ctx->geom[level].cols;
+  return BPVO_B200_OK;
+}
+
+static int wait_meta(const bpvo_b200_frame* f) {
+  CUDA_TRY(cudaEventSynchronize(f->meta_ready));
+  return BPVO_B200_OK;
+}
+#define CHECK_LEVEL(f, level)                                                                                           \
+  if (!(f) || (level) < (f)->ctx->p.maxTestLevel || (level) >= (f)->ctx->L) return bp_fail(BPVO_B200_ERR_INVALID_ARG, "bad frame/level")
+
+int bpvo_b200_frame_num_points(const bpvo_b200_frame* f, int level, int* n) {
+  CHECK_LEVEL(f, level);
+  if (!f->has_template) { *n = 0; return BPVO_B200_OK; }
+  int rc = wait_meta(f); if (rc) return rc;
+  *n = f->h_meta[level].n;
+  return BPVO_B200_OK;
+}
+int bpvo_b200_frame_get_points(const bpvo_b200_frame* f, int level, float* xyzw) {
+  CHECK_LEVEL(f, level);
+  if (!f->has_template) return bp_fail(BPVO_B200_ERR_NO_DATA, "frame has no template");
+  int rc = wait_meta(f); if (rc) return rc;
+  bpvo_b200_ctx* c = f->ctx;
+  CUDA_TRY(cudaSetDevice(c->p.device_id));
+  CUDA_TRY(cudaMemcpyAsync(xyzw, f->pts[level], (size_t) f->h_meta[level].n * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  c->counters.d2h_bytes += (int64_t) f->h_meta[level].n * 16;
+  return BPVO_B200_OK;
+}
+int bpvo_b200_frame_get_pyramid(const bpvo_b200_frame* f, int level, uint8_t* out) {
+  if (!f || level < 0 || level >= f->ctx->L) return bp_fail(BPVO_B200_ERR_INVALID_ARG, "bad frame/level");
+  bpvo_b200_ctx* c = f->ctx; const LevelGeom& g = c->geom[level];
+  CUDA_TRY(cudaSetDevice(c->p.device_id));
+  CUDA_TRY(cudaMemcpyAsync(out, f->pyr[level], (size_t) g.rows * g.cols, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  return BPVO_B200_OK;
+}
+int bpvo_b200_frame_get_descriptor(const bpvo_b200_frame* f, int level, float* planes, int* channels) {
+  CHECK_LEVEL(f, level);
+  bpvo_b200_ctx* c = f->ctx; const LevelGeom& g = c->geom[level];
+  CUDA_TRY(cudaSetDevice(c->p.device_id));
+  const int npx = g.rows * g.cols;
+  float* tmp = nullptr;
+  CUDA_TRY(cudaMalloc(&tmp, (size_t) npx * c->C * sizeof(float)));
+  deinterleave_kernel<<<ceil_div(npx, 256), 256, 0, c->stream>>>(f->desc[level], npx, c->C, tmp);
+  cudaError_t e = cudaMemcpyAsync(planes, tmp, (size_t) npx * c->C * sizeof(float), cudaMemcpyDeviceToHost, c->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  cudaFree(tmp);
+  if (e != cudaSuccess) return bp_fail(BPVO_B200_ERR_CUDA, "descriptor download failed: %s", cudaGetErrorString(e));
+  if (channels) *channels = c->C;
+  return BPVO_B200_OK;
+}
+int bpvo_b200_frame_get_saliency(const bpvo_b200_frame* f, int level, float* out) {
+  CHECK_LEVEL(f, level);
+  bpvo_b200_ctx* c = f->ctx; const LevelGeom& g = c->geom[level];
+  CUDA_TRY(cudaSetDevice(c->p.device_id));
+  CUDA_TRY(cudaMemcpyAsync(out, f->saliency[level], (size_t) g.rows * g.cols * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  return BPVO_B200_OK;
+}
+static int export_template(const bpvo_b200_frame* f, int level, float* pixels_out, float* J_out) {
+  CHECK_LEVEL(f, level);
+  if (!f->has_template) return bp_fail(BPVO_B200_ERR_NO_DATA, "frame has no template");
+  int rc = wait_meta(f); if (rc) return rc;
+  bpvo_b200_ctx* c = f->ctx;
+  CUDA_TRY(cudaSetDevice(c->p.device_id));
+  const int n = f->h_meta[level].n;
+  if (n == 0) return BPVO_B200_OK;
+  float* tmp = nullptr;
+  CUDA_TRY(cudaMalloc(&tmp, (size_t) n * c->C * 7 * sizeof(float)));
+  float* dJ = tmp; float* dP = tmp + (size_t) n * c->C * 6;
+  LevelTemplate t = make_level_template(f, level);
+  if (c->C == 1) export_template_kernel<1><<<ceil_div(n, 256), 256, 0, c->stream>>>(t, dP, dJ);
+  else export_template_kernel<8><<<ceil_div(n * 8, 256), 256, 0, c->stream>>>(t, dP, dJ);
+  cudaError_t e = cudaSuccess;
+  if (pixels_out) e = cudaMemcpyAsync(pixels_out, dP, (size_t) n * c->C * sizeof(float), cudaMemcpyDeviceToHost, c->stream);
+  if (e == cudaSuccess && J_out) e = cudaMemcpyAsync(J_out, dJ, (size_t) n * c->C * 6 * sizeof(float), cudaMemcpyDeviceToHost, c->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  cudaFree(tmp);
+  if (e != cudaSuccess) return bp_fail(BPVO_B200_ERR_CUDA, "template export failed: %s", cudaGetErrorString(e));
+  return BPVO_B200_OK;
+}
+int bpvo_b200_frame_get_pixels(const bpvo_b200_frame* f, int level, float* out) { return export_template(f, level, out, nullptr); }
+int bpvo_b200_frame_get_jacobians(const bpvo_b200_frame* f, int level, float* out) { return export_template(f, level, nullptr, out); }
+int bpvo_b200_frame_get_point_inds(const bpvo_b200_frame* f, int level, int32_t* out) {
+  CHECK_LEVEL(f, level);
+  if (!f->has_template) return bp_fail(BPVO_B200_ERR_NO_DATA, "frame has no template");
+  int rc = wait_meta(f); if (rc) return rc;
+  bpvo_b200_ctx* c = f->ctx;
+  CUDA_TRY(cudaSetDevice(c->p.device_id));
+  CUDA_TRY(cudaMemcpyAsync(out, f->inds[level], (size_t) f->h_meta[level].n * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  return BPVO_B200_OK;
+}
+int bpvo_b200_frame_get_normalization(const bpvo_b200_frame* f, int level, float Tn[16]) {
+  CHECK_LEVEL(f, level);
+  if (!f->has_template) return bp_fail(BPVO_B200_ERR_NO_DATA, "frame has no template");
+  int rc = wait_meta(f); if (rc) return rc;
+  const TemplateMeta& m = f->h_meta[level];
+  M44 T = identity44();
+  T(0, 0) = T(1, 1) = T(2, 2) = m.s; T(0, 3) = -m.s * m.c1; T(1, 3) = -m.s * m.c2; T(2, 3) = -m.s * m.c3;
+  memcpy(Tn, T.m, sizeof(T.m));
+  return BPVO_B200_OK;
+}
+
+}  // extern "C"
+
+// Hartley normalisation of one level (two tiny grid reductions with last-CTA finish)
+int bp_hartley(bpvo_b200_ctx* c, bpvo_b200_frame* f, int l) {
+  const int nb = std::max(1, std::min(ceil_div(c->geom[l].capacity, 256 * 8), c->sm_count * 2));
+  hartley_sum_kernel<<<nb, 256, 0, c->stream>>>(f->pts[l], f->d_meta + l, c->hpartials, c->work.ticket + 1, 0);
+  LAUNCH_CHECK(c);
+  hartley_sum_kernel<<<nb, 256, 0, c->stream>>>(f->pts[l], f->d_meta + l, c->hpartials, c->work.ticket + 1, 1);
+  LAUNCH_CHECK(c);
+  return BPVO_B200_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+// linearize (fine seam) and estimate_pose (coarse seam)
+// -------------------------------------------------------------------------------------------------
+static int lin_grid(const bpvo_b200_ctx* c, int level) {
+  // one CTA of 512 threads per SM at most; fewer when the level cannot hold that many points
+  const int need = ceil_div(c->geom[level].capacity, kLinThreads);
+  return std::max(1, std::min(c->sm_count, need));
+}
+
+template <int C>
+static int launch_linearize(bpvo_b200_ctx* c, const bpvo_b200_frame* ref, const bpvo_b200_frame* cur, int level, const M44& T) {
+  LinArgs a;
+  a.tmpl = make_level_template(ref, level);
+  a.img.desc = cur->desc[level]; a.img.rows = c->geom[level].rows; a.img.cols = c->geom[level].cols;
+  a.work = c->work; a.loss = c->p.lossFunction; a.good_thr = c->p.goodPointThreshold;
+  a.hset = c->work.hist; a.sel = c->sel;
+  make_projection(a.tmpl, T, a.P);
+  const int grid = lin_grid(c, level);
+  const bool robust = c->p.lossFunction != BPVO_B200_L2;
+  if (robust) CUDA_TRY(cudaMemsetAsync(c->work.hist, 0, kHistWords * sizeof(unsigned), c->stream));
+  k_residuals<C><<<grid, kLinThreads, 0, c->stream>>>(a); LAUNCH_CHECK(c);
+  if (robust) {
+    k_select<C, 2><<<grid, kLinThreads, 0, c->stream>>>(a); LAUNCH_CHECK(c);
+    k_select<C, 3><<<grid, kLinThreads, 0, c->stream>>>(a); LAUNCH_CHECK(c);
+  }
+  k_reduce<C><<<grid, kLinThreads, 0, c->stream>>>(a); LAUNCH_CHECK(c);
+  c->counters.linearize_calls++;
+  c->last_ref = ref; c->last_level = level;
+  return BPVO_B200_OK;
+}
+
+static int check_pair(bpvo_b200_ctx* c, const bpvo_b200_frame* ref, const bpvo_b200_frame* cur) {
+  if (!c || !ref || !cur) return bp_fail(BPVO_B200_ERR_INVALID_ARG, "null argument");
+  if (ref->ctx != c || cur->ctx != c) return bp_fail(BPVO_B200_ERR_INVALID_ARG, "frames belong to another ctx");
+  if (!ref->has_template) return bp_fail(BPVO_B200_ERR_NO_POINTS, "you should call setData before calling computeResiduals");
+  if (!cur->has_data) return bp_fail(BPVO_B200_ERR_NO_DATA, "no data in frame");
+  return BPVO_B200_OK;
+}
+
+extern "C" int bpvo_b200_linearize(bpvo_b200_ctx* c, const bpvo_b200_frame* ref, const bpvo_b200_frame* cur, int level,
+                                    const float T[16], int first_call_of_level, float H[36], float G[6], float* f_norm, float* sigma, int* n_valid) {
+  int rc = check_pair(c, ref, cur); if (rc) return rc;
+  if (level < c->p.maxTestLevel || level >= c->L || !T) return bp_fail(BPVO_B200_ERR_INVALID_ARG, "bad level / pose");
+  CUDA_TRY(cudaSetDevice(c->p.device_id));
+  {
+    PhaseTimer t(c, &c->counters.ms_linearize);
+    if (first_call_of_level) { k_reset_scale<<<1, 1, 0, c->stream>>>(c->work.scale); LAUNCH_CHECK(c); }
+    M44 Tm; memcpy(Tm.m, T, sizeof(Tm.m));
+    rc = (c->C == 1) ? launch_linearize<1>(c, ref, cur, level, Tm) : launch_linearize<8>(c, ref, cur, level, Tm);
+    if (rc) return rc;
+    rc = bp_comm_allreduce_linout(c);
+    if (rc) return rc;
+  }
+  CUDA_TRY(cudaMemcpyAsync(&c->h_mail->lin, c->work.out, sizeof(LinOut), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  c->counters.d2h_bytes += sizeof(LinOut);
+  const LinOut& o = c->h_mail->lin;
+  if (H) memcpy(H, o.H, sizeof(o.H));
+  if (G) memcpy(G, o.G, sizeof(o.G));
+  if (f_norm) *f_norm = o.f_norm;
+  if (sigma) *sigma = o.sigma;
+  if (n_valid) *n_valid = o.n_valid;
+  if (ref->h_meta[level].n_total == 0 && cudaEventQuery(ref->meta_ready) == cudaSuccess)
+    return bp_fail(BPVO_B200_ERR_NO_POINTS, "you should call setData before calling computeResiduals");   // template_data.cc:177
+  return BPVO_B200_OK;
+}
+
+// PoseEstimatorBase::run driven from the host on top of the fine seam (pose_estimator_base.h:324-407)
+static int host_run_level(bpvo_b200_ctx* c, const bpvo_b200_frame* ref, const bpvo_b200_frame* cur, int level, M44& T, bpvo_b200_stats& st, int& evals) {
+  int rc = wait_meta(ref); if (rc) return rc;
+  const TemplateMeta& m = ref->h_meta[level];
+  if (m.n_total == 0) return bp_fail(BPVO_B200_ERR_NO_POINTS, "you should call setData before calling computeResiduals");
+  M44 Tn = identity44();
+  Tn(0, 0) = Tn(1, 1) = Tn(2, 2) = m.s; Tn(0, 3) = -m.s * m.c1; Tn(1, 3) = -m.s * m.c2; Tn(2, 3) = -m.s * m.c3;
+  const M44 Tn_inv = inverse44(Tn);
+  const float sqrt_eps = sqrtf(FLT_EPSILON);
+  st.numIterations = 0; st.firstOrderOptimality = 0; st.status = BPVO_B200_MAX_ITERS; st.finalError = -1.0f;
+  float H[36], G[6], dp[6], ndp[6], f_norm = 0, g_norm = 0;
+  int n_evals = 0;
+  auto gnorm = [&]() { float g = 0; for (int k = 0; k < 6; ++k) g = std::max(g, fabsf(G[k])); return g; };
+  M44 Td = T;
+  rc = bpvo_b200_linearize(c, ref, cur, level, Td.m, 1, H, G, &f_norm, nullptr, nullptr); if (rc) return rc;
+  ++n_evals;
+  g_norm = gnorm();
+  const float g_tol = c->p.gradientTolerance * std::max(g_norm, sqrt_eps);
+  if (g_norm < g_tol) { st.status = BPVO_B200_GRAD_TOL; st.finalError = f_norm; st.numIterations = 1; st.firstOrderOptimality = g_norm; evals += n_evals; c->level_evals[level] = n_evals; return BPVO_B200_OK; }
+  if (!solve6(H, G, dp)) { st.status = BPVO_B200_SOLVER_ERROR; st.finalError = f_norm; evals += n_evals; c->level_evals[level] = n_evals; return BPVO_B200_OK; }
+  float f_prev = 0.0f, dp_prev = 0.0f; bool conv = false;
+  for (int k = 0; k < 6; ++k) ndp[k] = -dp[k];
+  Td = mul44(Td, params_to_pose(Tn, Tn_inv, ndp));
+  do {
+    float dpn = 0; for (int k = 0; k < 6; ++k) dpn += dp[k] * dp[k]; dpn = sqrtf(dpn);
+    g_norm = gnorm();
+    if (dpn < c->p.parameterTolerance || dpn < c->p.parameterTolerance * (sqrt_eps + dp_prev)) { st.status = BPVO_B200_PARAM_TOL; conv = true; }
+    else if (f_norm < c->p.functionTolerance || f_norm < c->p.functionTolerance * (sqrt_eps + f_prev) ||
+             fabsf(f_norm - f_prev) < c->p.functionTolerance) { st.status = BPVO_B200_FUNC_TOL; conv = true; }
+    else if (g_norm < g_tol) { st.status = BPVO_B200_GRAD_TOL; conv = true; }
+    dp_prev = dpn; f_prev = f_norm;
+    if (!conv) {
+      rc = bpvo_b200_linearize(c, ref, cur, level, Td.m, 0, H, G, &f_norm, nullptr, nullptr); if (rc) return rc;
+      ++n_evals;
+      if (!solve6(H, G, dp)) { st.status = BPVO_B200_SOLVER_ERROR; break; }
+    }
+    for (int k = 0; k < 6; ++k) ndp[k] = -dp[k];
+    Td = mul44(Td, params_to_pose(Tn, Tn_inv, ndp));       // also on the converged pass (Q1)
+  } while (st.numIterations++ < c->p.maxIterations && !conv && n_evals < 1200);
+  if (st.status != BPVO_B200_SOLVER_ERROR) T = Td;
+  st.numIterations -= 1; st.finalError = f_norm; st.firstOrderOptimality = g_norm;
+  evals += n_evals; c->level_evals[level] = n_evals;
+  return BPVO_B200_OK;
+}
+
+template <int C>
+static int launch_estimate_pose(bpvo_b200_ctx* c, const bpvo_b200_frame* ref, const bpvo_b200_frame* cur, const M44& T_init) {
+  SolveArgs a;
+  memset(&a, 0, sizeof(a));
+  for (int l = c->p.maxTestLevel; l < c->L; ++l) {
+    a.tmpl[l] = make_level_template(ref, l);
+    a.img[l].desc = cur->desc[l]; a.img[l].rows = c->geom[l].rows; a.img[l].cols = c->geom[l].cols;
+  }
+  a.sp.max_iterations = c->p.maxIterations; a.sp.max_fun_evals = 1200;
+  a.sp.parameter_tolerance = c->p.parameterTolerance; a.sp.function_tolerance = c->p.functionTolerance; a.sp.gradient_tolerance = c->p.gradientTolerance;
+  a.sp.loss = c->p.lossFunction; a.sp.good_threshold = c->p.goodPointThreshold;
+  a.sp.max_test_level = c->p.maxTestLevel; a.sp.num_levels = c->L;
+  a.work = c->work; a.T_init = T_init; a.T_out = c->d_T; a.stats = c->d_stats; a.num_fun_evals = c->d_evals;
+  a.prof = c->profiling ? c->d_prof : nullptr;
+  Sel* sel = c->sel; int parity = 0;
+  // both histogram sets must be zero on entry (the kernel leaves them zeroed for the next call, but the
+  // host-driven path may have dirtied set 0 in between)
+  CUDA_TRY(cudaMemsetAsync(c->work.hist, 0, 2 * kHistWords * sizeof(unsigned), c->stream));
+  void* args[] = {&a, &sel, &parity};
+  int grid = c->sm_count;
+  CUDA_TRY(cudaLaunchCooperativeKernel((void*) k_estimate_pose<C>, dim3(grid), dim3(kLinThreads), args, 0, c->stream));
+  c->counters.launches++;
+  return BPVO_B200_OK;
+}
+
+extern "C" int bpvo_b200_estimate_pose(bpvo_b200_ctx* c, const bpvo_b200_frame* ref, const bpvo_b200_frame* cur,
+                                        const float T_init[16], float T_est[16], bpvo_b200_stats* stats, int* num_fun_evals) {
+  int rc = check_pair(c, ref, cur); if (rc) return rc;
+  if (!T_init || !T_est || !stats) return bp_fail(BPVO_B200_ERR_INVALID_ARG, "null argument");
+  CUDA_TRY(cudaSetDevice(c->p.device_id));
+  for (int l = 0; l < c->L; ++l) { stats[l].numIterations = 0; stats[l].finalError = -1.0f; stats[l].firstOrderOptimality = -1.0f; stats[l].status = BPVO_B200_SOLVER_ERROR; }   // types.cc:306-310
+  M44 T; memcpy(T.m, T_init, sizeof(T.m));
+  int evals = 0;
+  c->counters.solve_calls++;
+  const bool host_loop = (c->p.flags & BPVO_B200_FLAG_HOST_SOLVE) || !c->coop || c->shard_size > 1;
+  if (host_loop) {
+    for (int l = c->L - 1; l >= c->p.maxTestLevel; --l) {              // vo_pose_estimator.cc:76-84
+      rc = host_run_level(c, ref, cur, l, T, stats[l], evals);
+      if (rc) return rc;
+    }
+  } else {
+    {
+      PhaseTimer t(c, &c->counters.ms_linearize);
+      rc = (c->C == 1) ? launch_estimate_pose<1>(c, ref, cur, T) : launch_estimate_pose<8>(c, ref, cur, T);
+      if (rc) return rc;
+    }
+    Mailbox* mb = c->h_mail;
+    CUDA_TRY(cudaMemcpyAsync(&mb->T, c->d_T, sizeof(M44), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(mb->stats, c->d_stats, kMaxLevels * sizeof(LevelStats), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(&mb->evals, c->d_evals, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(&mb->lin, c->work.out, sizeof(LinOut), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    c->counters.d2h_bytes += sizeof(M44) + kMaxLevels * sizeof(LevelStats) + sizeof(int) + sizeof(LinOut);
+    T = mb->T; evals = mb->evals;
+    c->counters.linearize_calls += evals;
+    for (int l = c->p.maxTestLevel; l < c->L; ++l) {
+      if (mb->stats[l].status == -3) return bp_fail(BPVO_B200_ERR_NO_POINTS, "you should call setData before calling computeResiduals");
+      stats[l].numIterations = mb->stats[l].num_iterations; stats[l].finalError = mb->stats[l].final_error;
+      stats[l].firstOrderOptimality = mb->stats[l].first_order_optimality; stats[l].status = mb->stats[l].status;
+      c->level_evals[l] = mb->stats[l].num_evals;
+    }
+    c->last_ref = ref; c->last_level = c->p.maxTestLevel;
+  }
+  memcpy(T_est, T.m, sizeof(T.m));
+  if (num_fun_evals) *num_fun_evals = evals;
+  return BPVO_B200_OK;
+}
+
+// getWeights / residuals / valid of the last linearize, in the reference's channel-major layout
+static int export_last(bpvo_b200_ctx* c, float* w, float* r, size_t* count) {
+  if (!c || !count) return bp_fail(BPVO_B200_ERR_INVALID_ARG, "null argument");
+  if (!c->last_ref) { *count = 0; return BPVO_B200_OK; }
+  int rc = wait_meta(c->last_ref); if (rc) return rc;
+  const int n = c->last_ref->h_meta[c->last_level].n;
+  *count = (size_t) n * c->C;
+  if ((!w && !r) || n == 0) return BPVO_B200_OK;
+  CUDA_TRY(cudaSetDevice(c->p.device_id));
+  // sigma of the last linearize
+  CUDA_TRY(cudaMemcpyAsync(&c->h_mail->lin, c->work.out, sizeof(LinOut), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  const float sigma = c->h_mail->lin.sigma;
+  float* dw = w ? c->export_buf : nullptr;
+  float* dr = r ? c->export_buf + (size_t) n * c->C : nullptr;
+  if (c->C == 1) k_export_weights<1><<<ceil_div(n, 256), 256, 0, c->stream>>>(c->work.res, n, sigma, c->p.lossFunction, dw, dr);
+  else k_export_weights<8><<<ceil_div(n * 8, 256), 256, 0, c->stream>>>(c->work.res, n, sigma, c->p.lossFunction, dw, dr);
+  LAUNCH_CHECK(c);
+  if (w) CUDA_TRY(cudaMemcpyAsync(w, dw, *count * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  if (r) CUDA_TRY(cudaMemcpyAsync(r, dr, *count * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  c->counters.d2h_bytes += (int64_t) (*count * sizeof(float) * ((w ? 1 : 0) + (r ? 1 : 0)));
+  return BPVO_B200_OK;
+}
+extern "C" int bpvo_b200_get_weights(bpvo_b200_ctx* c, float* w, size_t* count) { return export_last(c, w, nullptr, count); }
+extern "C" int bpvo_b200_get_residuals(bpvo_b200_ctx* c, float* r, size_t* count) { return export_last(c, nullptr, r, count); }
+extern "C" int bpvo_b200_get_valid(bpvo_b200_ctx* c, uint8_t* v, size_t* count) {
+  if (!c || !count) return bp_fail(BPVO_B200_ERR_INVALID_ARG, "null argument");
+  if (!c->last_ref) { *count = 0; return BPVO_B200_OK; }
+  int rc = wait_meta(c->last_ref); if (rc) return rc;
+  *count = (size_t) c->last_ref->h_meta[c->last_level].n;
+  if (!v || *count == 0) return BPVO_B200_OK;
+  CUDA_TRY(cudaSetDevice(c->p.device_id));
+  CUDA_TRY(cudaMemcpyAsync(v, c->work.valid, *count, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  return BPVO_B200_OK;
+}
+
+// getFractionOfGoodPoints (vo_pose_estimator.cc:101-107): counted inside the reduce phase, no bulk D2H
+extern "C" int bpvo_b200_fraction_good(bpvo_b200_ctx* c, float thresh, float* frac) {
+  if (!c || !frac) return bp_fail(BPVO_B200_ERR_INVALID_ARG, "null argument");
+  if (!c->last_ref) { *frac = 0.0f; return BPVO_B200_OK; }
+  int rc = wait_meta(c->last_ref); if (rc) return rc;
+  const size_t total = (size_t) c->last_ref->h_meta[c->last_level].n_total * c->C;
+  if (total == 0) { *frac = 0.0f; return BPVO_B200_OK; }
+  if (thresh == c->p.goodPointThreshold) {
+    // h_mail->lin is the LinOut of the last linearize / estimate_pose
+    *frac = (float) c->h_mail->lin.n_good / static_cast<float>(total);
+    return BPVO_B200_OK;
+  }
+  std::vector<float> w(total); size_t cnt = 0;
+  rc = export_last(c, w.data(), nullptr, &cnt); if (rc) return rc;
+  size_t n = 0; for (size_t i = 0; i < cnt; ++i) n += (w[i] > thresh);
+  *frac = n / static_cast<float>(cnt);
+  return BPVO_B200_OK;
+}
+
+// device-time of back-to-back linearize launches (no host round trip), for the roofline figure
+extern "C" int bpvo_b200_time_linearize(bpvo_b200_ctx* c, const bpvo_b200_frame* ref, const bpvo_b200_frame* cur, int level,
+                                         const float T[16], int iters, int flush_l2, float* ms_per_iter) {
+  int rc = check_pair(c, ref, cur); if (rc) return rc;
+  if (!T || !ms_per_iter || iters <= 0) return bp_fail(BPVO_B200_ERR_INVALID_ARG, "bad argument");
+  CUDA_TRY(cudaSetDevice(c->p.device_id));
+  M44 Tm; memcpy(Tm.m, T, sizeof(Tm.m));
+  const size_t flush_bytes = (size_t) 256 << 20;
+  if (flush_l2 && !c->flush_buf) CUDA_TRY(cudaMalloc(&c->flush_buf, flush_bytes));
+  double total = 0;
+  for (int i = 0; i < iters; ++i) {
+    if (flush_l2) CUDA_TRY(cudaMemsetAsync(c->flush_buf, i & 0xff, flush_bytes, c->stream));
+    k_reset_scale<<<1, 1, 0, c->stream>>>(c->work.scale);
+    CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
+    rc = (c->C == 1) ? launch_linearize<1>(c, ref, cur, level, Tm) : launch_linearize<8>(c, ref, cur, level, Tm);
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
+    CUDA_TRY(cudaEventSynchronize(c->ev1));
+    float ms = 0; CUDA_TRY(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    total += ms;
+  }
+  *ms_per_iter = (float) (total / iters);
+  return BPVO_B200_OK;
+}

@@ -1,0 +1,73 @@
+// engine_internal.h -- the opaque objects behind include/bpvo_b200.h
+#pragma once
+
+#include <stdarg.h>
+#include <cuda_runtime.h>
+#include "../../include/bpvo_b200.h"
+#include "device_types.h"
+
+namespace bp { struct Sel; }
+
+struct LevelGeom {
+  int rows, cols;
+  float fx, fy, cx, cy;   // K_l = K / 2^l with K(2,2) = 1 (vo_frame.cc:24-28)
+  float Bf;               // b_l * fx_l (level invariant: baseline doubles as fx halves)
+  int capacity;           // upper bound of template points at this level (selection window)
+};
+
+struct Mailbox {          // pinned host memory the device results land in
+  bp::LinOut lin;
+  bp::M44 T;
+  bp::LevelStats stats[bp::kMaxLevels];
+  int evals;
+};
+
+struct bpvo_b200_frame;
+
+struct bpvo_b200_ctx {
+  bpvo_b200_params p;
+  int rows = 0, cols = 0, L = 0, C = 1;
+  float K[9]; float baseline = 0;
+  LevelGeom geom[bp::kMaxLevels];
+  int sm_count = 0; bool coop = false;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, stage_free = nullptr, tm0 = nullptr, tm1 = nullptr;
+  int level_evals[bp::kMaxLevels] = {};
+  bp::Work work{};
+  bp::Sel* sel = nullptr;
+  float* export_buf = nullptr;
+  uint8_t* flags = nullptr; int* block_counts = nullptr; double* hpartials = nullptr;
+  bp::M44* d_T = nullptr; bp::LevelStats* d_stats = nullptr; int* d_evals = nullptr; long long* d_prof = nullptr;
+  Mailbox* h_mail = nullptr;
+  uint8_t* stage_img = nullptr; float* stage_disp = nullptr;
+  void* flush_buf = nullptr;
+  const bpvo_b200_frame* last_ref = nullptr; int last_level = 0;
+  bool profiling = false;
+  bpvo_b200_counters counters{};
+  // multi-GPU
+  int shard_rank = 0, shard_size = 1;
+  void* comm = nullptr;          // ncclComm_t
+  double* comm_buf = nullptr;    // device staging for the exchanges
+};
+
+struct bpvo_b200_frame {
+  bpvo_b200_ctx* ctx = nullptr;
+  bool has_data = false, has_template = false;
+  uint8_t* pyr[bp::kMaxLevels] = {};
+  float* desc[bp::kMaxLevels] = {};
+  float* saliency[bp::kMaxLevels] = {};
+  float* disp = nullptr;
+  float4* pts[bp::kMaxLevels] = {};
+  float* gx[bp::kMaxLevels] = {};
+  float* gy[bp::kMaxLevels] = {};
+  float* i0[bp::kMaxLevels] = {};
+  int* inds[bp::kMaxLevels] = {};
+  bp::TemplateMeta* d_meta = nullptr;
+  bp::TemplateMeta* h_meta = nullptr;   // pinned mirror, valid after meta_ready
+  cudaEvent_t meta_ready = nullptr;
+};
+
+int bp_fail(int code, const char* fmt, ...);
+int bp_hartley(bpvo_b200_ctx* c, bpvo_b200_frame* f, int level);
+int bp_comm_destroy(bpvo_b200_ctx* c);
+int bp_comm_allreduce_linout(bpvo_b200_ctx* c);

@@ -1,0 +1,153 @@
+// kernels_image.cuh -- per-frame image work: pyramid and dense descriptors (sm_100a).
+//
+// Replaces (reference file:line):
+//   cv::pyrDown chain                       bpvo/image_pyramid.cc:43-50
+//   census + 8 bit-planes + 5x5 Gaussian    bpvo/census.cc:42-91, bpvo/bitplanes_descriptor.cc:37-91
+//   u8 -> f32 intensity                     bpvo/intensity_descriptor.cc:31-43
+//
+// All of it is HBM/L2-bound byte work (33 B per pixel for bit-planes): one pass, results written once
+// in the channel-interleaved layout the alignment kernels gather from.
+#pragma once
+
+#include "device_types.h"
+
+namespace bp {
+
+__device__ __forceinline__ int reflect101(int i, int n) {
+  // BORDER_REFLECT_101: ... 2 1 | 0 1 2 ... n-1 | n-2 n-3 ...
+  while (i < 0 || i >= n) {
+    if (n == 1) return 0;
+    i = (i < 0) ? -i : 2 * (n - 1) - i;
+  }
+  return i;
+}
+
+// ---------------------------------------------------------------------------------------------
+// pyrDown: 5x5 [1 4 6 4 1]^2 / 256, reflect-101, dst = ((C+1)/2, (R+1)/2), u8 result (sum+128)>>8.
+// One thread per output pixel; rows of the 5x5 window come from L1/L2 (each source byte is read by
+// ~6 threads of neighbouring lanes).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pyr_down_kernel(const uint8_t* __restrict__ src, int rows, int cols,
+                                                       uint8_t* __restrict__ dst, int drows, int dcols) {
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (x >= dcols || y >= drows) return;
+  int xs[5];
+#pragma unroll
+  for (int k = 0; k < 5; ++k) xs[k] = reflect101(2 * x - 2 + k, cols);
+  int acc = 0;
+#pragma unroll
+  for (int ky = 0; ky < 5; ++ky) {
+    const uint8_t* s = src + (size_t) reflect101(2 * y - 2 + ky, rows) * cols;
+    const int row = (int) __ldg(s + xs[0]) + 4 * (int) __ldg(s + xs[1]) + 6 * (int) __ldg(s + xs[2]) +
+                    4 * (int) __ldg(s + xs[3]) + (int) __ldg(s + xs[4]);
+    const int wy = (ky == 0 || ky == 4) ? 1 : ((ky == 2) ? 6 : 4);
+    acc += wy * row;
+  }
+  dst[(size_t) y * dcols + x] = (uint8_t) ((acc + 128) >> 8);
+}
+
+// ---------------------------------------------------------------------------------------------
+// intensity descriptor: f32(u8), one channel
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) intensity_kernel(const uint8_t* __restrict__ src, float* __restrict__ dst, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = (float) src[i];
+}
+
+// ---------------------------------------------------------------------------------------------
+// bit-planes descriptor, fused: census (3x3, neighbour >= centre, border rows/cols = 0) ->
+// 8 bit channels -> separable 5x5 Gaussian (f32, reflect-101 on the census image) -> interleaved
+// [rows][cols][8] f32 store (32 B per pixel, two 16-B stores per thread, fully coalesced).
+//
+// Tile: 32 x 8 output pixels per CTA of 256 threads.
+//   stage 1: census bytes of the (8+4) x (32+4) halo tile -> smem            (u8 reads via L1/L2)
+//   stage 2: horizontal pass of all 8 bits for (8+4) x 32 -> smem [row][bit][col]  (conflict-free)
+//   stage 3: vertical pass, 8 floats per thread -> global
+// Evaluation order of the taps follows OpenCV's symmetric row/column filters,
+// (s0*k0 + (s-1+s1)*k1) + (s-2+s2)*k2, with separate mul/add roundings (no FMA).
+// ---------------------------------------------------------------------------------------------
+constexpr int kBpTW = 32, kBpTH = 8;
+
+__device__ __forceinline__ uint8_t census_at(const uint8_t* __restrict__ img, int rows, int cols, int y, int x) {
+  if (y <= 0 || y >= rows - 1 || x <= 0 || x >= cols - 1) return 0;
+  const uint8_t* p = img + (size_t) y * cols + x;
+  const uint8_t c = __ldg(p);
+  unsigned v = 0;
+  v |= (unsigned) (__ldg(p - cols - 1) >= c) << 0;
+  v |= (unsigned) (__ldg(p - cols) >= c) << 1;
+  v |= (unsigned) (__ldg(p - cols + 1) >= c) << 2;
+  v |= (unsigned) (__ldg(p - 1) >= c) << 3;
+  v |= (unsigned) (__ldg(p + 1) >= c) << 4;
+  v |= (unsigned) (__ldg(p + cols - 1) >= c) << 5;
+  v |= (unsigned) (__ldg(p + cols) >= c) << 6;
+  v |= (unsigned) (__ldg(p + cols + 1) >= c) << 7;
+  return (uint8_t) v;
+}
+
+__global__ void __launch_bounds__(256) bitplanes_kernel(const uint8_t* __restrict__ img, int rows, int cols,
+                                                        float k0, float k1, float k2, int do_blur,
+                                                        float* __restrict__ out) {
+  __shared__ uint8_t s_census[kBpTH + 4][kBpTW + 4];
+  __shared__ float s_h[kBpTH + 4][8][kBpTW];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int x0 = blockIdx.x * kBpTW, y0 = blockIdx.y * kBpTH;
+
+  for (int i = threadIdx.x; i < (kBpTH + 4) * (kBpTW + 4); i += 256) {
+    const int r = i / (kBpTW + 4), c = i % (kBpTW + 4);
+    const int gy = reflect101(y0 + r - 2, rows), gx = reflect101(x0 + c - 2, cols);
+    s_census[r][c] = census_at(img, rows, cols, gy, gx);
+  }
+  __syncthreads();
+
+  const int gx = x0 + tx, gy = y0 + ty;
+  if (!do_blur) {
+    if (gx < cols && gy < rows) {
+      const unsigned v = s_census[ty + 2][tx + 2];
+      float4* o = reinterpret_cast<float4*>(out + ((size_t) gy * cols + gx) * 8);
+      o[0] = make_float4((float) (v & 1), (float) ((v >> 1) & 1), (float) ((v >> 2) & 1), (float) ((v >> 3) & 1));
+      o[1] = make_float4((float) ((v >> 4) & 1), (float) ((v >> 5) & 1), (float) ((v >> 6) & 1), (float) ((v >> 7) & 1));
+    }
+    return;
+  }
+
+  for (int i = threadIdx.x; i < (kBpTH + 4) * kBpTW; i += 256) {
+    const int r = i / kBpTW, c = i % kBpTW;
+    const unsigned m2 = s_census[r][c], m1 = s_census[r][c + 1], c0 = s_census[r][c + 2],
+                   p1 = s_census[r][c + 3], p2 = s_census[r][c + 4];
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+      const float s0 = (float) ((c0 >> b) & 1);
+      const float a = __fadd_rn((float) ((m1 >> b) & 1), (float) ((p1 >> b) & 1));
+      const float bb = __fadd_rn((float) ((m2 >> b) & 1), (float) ((p2 >> b) & 1));
+      float v = __fmul_rn(s0, k0);
+      v = __fadd_rn(v, __fmul_rn(a, k1));
+      v = __fadd_rn(v, __fmul_rn(bb, k2));
+      s_h[r][b][c] = v;
+    }
+  }
+  __syncthreads();
+
+  if (gx < cols && gy < rows) {
+    float o[8];
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+      float v = __fmul_rn(k0, s_h[ty + 2][b][tx]);
+      v = __fadd_rn(v, __fmul_rn(k1, __fadd_rn(s_h[ty + 3][b][tx], s_h[ty + 1][b][tx])));
+      v = __fadd_rn(v, __fmul_rn(k2, __fadd_rn(s_h[ty + 4][b][tx], s_h[ty][b][tx])));
+      o[b] = v;
+    }
+    float4* dst = reinterpret_cast<float4*>(out + ((size_t) gy * cols + gx) * 8);
+    dst[0] = make_float4(o[0], o[1], o[2], o[3]);
+    dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+  }
+}
+
+// interleaved [rows][cols][C] -> planar C x rows x cols (parity dumps only)
+__global__ void __launch_bounds__(256) deinterleave_kernel(const float* __restrict__ src, int n, int C, float* __restrict__ dst) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  for (int c = 0; c < C; ++c) dst[(size_t) c * n + i] = src[(size_t) i * C + c];
+}
+
+}  // namespace bp

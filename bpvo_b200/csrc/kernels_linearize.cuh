@@ -1,0 +1,580 @@
+// kernels_linearize.cuh -- the per-iteration hot path: one PoseEstimatorGN::linearize on the device,
+// and the whole coarse-to-fine Gauss-Newton loop as ONE persistent cooperative kernel (sm_100a).
+//
+// Replaces (reference file:line):
+//   RigidBodyWarp::setPose + PhotoError::init/run (fp64 projection, bilinear)   rigid_body_warp.h:111-114, photo_error.cc:344-389
+//   replicateValidFlags                                                         pose_estimator_base.h:307-320
+//   AutoScaleEstimator::estimateScale (exact median of |r| over valid)          mestimator.cc:452-490, utils.h:224-252
+//   MEstimator::ComputeWeights (Huber / Tukey / L2)                             mestimator.cc:242-415
+//   LinearSystemBuilder::Run (H = sum w J'J, G = sum w r J, sqrt(sum w r^2))    linear_system_builder.cc:140-284, 334-350
+//   PoseEstimatorBase::run + solve + testConvergence (device loop)              pose_estimator_base.h:90-148, 258-282, 324-407
+//   VisualOdometryPoseEstimator::estimatePose (level loop)                      vo_pose_estimator.cc:63-93
+//
+// Structure of one linearize (4 phases; kernel boundaries in the host-driven path, grid syncs in
+// the persistent path):
+//   P1 residuals : thread per point: fp64 project -> floor -> valid -> 4 bilinear taps x C channels
+//                  (one 32-B sector per tap for C = 8) -> r = f32(Iw - I0) ; level-1 radix histogram of |r|
+//   P2 select-2  : every CTA scans the 2048-bin histogram, then histograms bits [19:9] of the two median bins
+//   P3 select-3  : same for bits [8:0]  -> the two middle order statistics, exactly
+//   P4 reduce    : sigma -> weight -> rank-2 per-point update of the 21+6+1 normal-equation scalars
+//                  (J = gx*A + gy*B) -> fp64 warp shuffle -> CTA partial -> fixed-order final sum
+// HBM/L2-bound gather-and-reduce: no tensor cores (no dense contraction on this path).
+#pragma once
+
+#include <cooperative_groups.h>
+#include "device_types.h"
+
+namespace bp {
+namespace cg = cooperative_groups;
+
+template <int C> struct VecC;
+template <> struct VecC<8> {
+  float v[8];
+  __device__ __forceinline__ void load(const float* __restrict__ p) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+  __device__ __forceinline__ void load_plain(const float* p) {   // data written earlier in the same kernel
+    const float4 a = *reinterpret_cast<const float4*>(p);
+    const float4 b = *(reinterpret_cast<const float4*>(p) + 1);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+  __device__ __forceinline__ void store(float* p) const {
+    reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
+    reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+  }
+};
+template <> struct VecC<1> {
+  float v[1];
+  __device__ __forceinline__ void load(const float* __restrict__ p) { v[0] = __ldg(p); }
+  __device__ __forceinline__ void load_plain(const float* p) { v[0] = *p; }
+  __device__ __forceinline__ void store(float* p) const { *p = v[0]; }
+};
+
+struct Sel {            // radix-select bookkeeping of one linearize (global, written by CTA 0)
+  unsigned n;           // number of valid residuals (C * valid points)
+  unsigned b1[2], rem1[2];
+  unsigned b2[2], rem2[2];
+};
+
+struct LinShared {      // static shared memory of the linearize phases
+  unsigned hist[2 * kHist2Bins];          // 16 KB, reused by every phase
+  double red[kLinThreads / 32][kPartialStride];
+  unsigned scan[kLinThreads / 32];
+  unsigned found[8];
+};
+
+// ---------------------------------------------------------------------------------------------
+// CTA-wide: locate the bins holding ranks ra and rb in a histogram of NB bins (NB multiple of blockDim).
+// Returns (bin, rank inside bin) for both, and the total count.  All threads get the results.
+// ---------------------------------------------------------------------------------------------
+template <int NB>
+__device__ __forceinline__ void block_find2(const unsigned* __restrict__ hist, unsigned ra, unsigned rb, LinShared& sh,
+                                            unsigned& bin_a, unsigned& rem_a, unsigned& bin_b, unsigned& rem_b, unsigned& total) {
+  constexpr int PER = (NB + kLinThreads - 1) / kLinThreads;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  unsigned loc[PER], sum = 0;
+#pragma unroll
+  for (int k = 0; k < PER; ++k) { const int b = tid * PER + k; loc[k] = (b < NB) ? hist[b] : 0u; sum += loc[k]; }
+  unsigned incl = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+  __syncthreads();                       // protects sh.scan / sh.found reuse across calls
+  if (lane == 31) sh.scan[warp] = incl;
+  if (tid < 8) sh.found[tid] = 0;
+  __syncthreads();
+  unsigned woff = 0, tot = 0;
+#pragma unroll
+  for (int w = 0; w < kLinThreads / 32; ++w) { const unsigned v = sh.scan[w]; if (w < warp) woff += v; tot += v; }
+  unsigned excl = woff + incl - sum;
+#pragma unroll
+  for (int k = 0; k < PER; ++k) {
+    const unsigned lo = excl, hi = excl + loc[k];
+    if (ra >= lo && ra < hi) { sh.found[0] = tid * PER + k; sh.found[1] = ra - lo; }
+    if (rb >= lo && rb < hi) { sh.found[2] = tid * PER + k; sh.found[3] = rb - lo; }
+    excl = hi;
+  }
+  __syncthreads();
+  bin_a = sh.found[0]; rem_a = sh.found[1]; bin_b = sh.found[2]; rem_b = sh.found[3]; total = tot;
+}
+
+// projection matrix P = K * T[0:3,:] in fp32 (rigid_body_warp.h:111-114), column-major 3x4
+__host__ __device__ __forceinline__ void make_projection(const LevelTemplate& L, const M44& T, float P[12]) {
+  for (int j = 0; j < 4; ++j) {
+    // K = [fx 0 cx; 0 fy cy; 0 0 1]; the zero terms are kept so that the rounding matches a dense 3x3 * 3x4 product
+    float r0 = L.fx * T(0, j); r0 += 0.0f * T(1, j); r0 += L.cx * T(2, j);
+    float r1 = 0.0f * T(0, j); r1 += L.fy * T(1, j); r1 += L.cy * T(2, j);
+    float r2 = 0.0f * T(0, j); r2 += 0.0f * T(1, j); r2 += 1.0f * T(2, j);
+    P[j * 3 + 0] = r0; P[j * 3 + 1] = r1; P[j * 3 + 2] = r2;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// P1: residuals (+ level-1 histogram when the scale is to be re-estimated)
+// ---------------------------------------------------------------------------------------------
+template <int C>
+__device__ __forceinline__ void phase_residuals(const LevelTemplate& L, const LevelImage& I, const float* P, const Work& W,
+                                                unsigned* __restrict__ hist1, bool do_hist, LinShared& sh, int block, int nblocks) {
+  const int tid = threadIdx.x;
+  if (do_hist) { for (int b = tid; b < kHist1Bins; b += kLinThreads) sh.hist[b] = 0; }
+  __syncthreads();
+  const double P00 = P[0], P10 = P[1], P20 = P[2], P01 = P[3], P11 = P[4], P21 = P[5],
+               P02 = P[6], P12 = P[7], P22 = P[8], P03 = P[9], P13 = P[10], P23 = P[11];
+  const int cols = I.cols, rows = I.rows;
+  const int n_pts = L.meta->n;
+  int my_first = 0x7fffffff;
+  for (int i = block * kLinThreads + tid; i < n_pts; i += nblocks * kLinThreads) {
+    const float4 X = __ldg(L.pts + i);
+    const double X0 = X.x, X1 = X.y, X2 = X.z, X3 = X.w;
+    const double h0 = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(P00, X0), __dmul_rn(P01, X1)), __dmul_rn(P02, X2)), __dmul_rn(P03, X3));
+    const double h1 = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(P10, X0), __dmul_rn(P11, X1)), __dmul_rn(P12, X2)), __dmul_rn(P13, X3));
+    const double h2 = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(P20, X0), __dmul_rn(P21, X1)), __dmul_rn(P22, X2)), __dmul_rn(P23, X3));
+    const double w = __ddiv_rn(1.0, h2);
+    const double u = __dmul_rn(w, h0), v = __dmul_rn(w, h1);
+    bool ok = isfinite(u) && isfinite(v) && fabs(u) < 1e9 && fabs(v) < 1e9;
+    int xi = 0, yi = 0;
+    if (ok) {
+      xi = (int) u; xi -= (xi > u);      // Floor(double), photo_error.cc:261-265
+      yi = (int) v; yi -= (yi > v);
+      ok = xi >= 0 && xi < cols - 1 && yi >= 0 && yi < rows - 1;
+    }
+    VecC<C> r;
+    if (ok) {
+      const double xf = __dsub_rn(u, (double) xi), yf = __dsub_rn(v, (double) yi);
+      const double wx = __dsub_rn(1.0, xf), wy = __dsub_rn(1.0, yf);
+      const float* tap = I.desc + ((size_t) yi * cols + xi) * C;
+      VecC<C> t00, t01, t10, t11, i0;
+      t00.load(tap); t01.load(tap + C); t10.load(tap + (size_t) cols * C); t11.load(tap + (size_t) cols * C + C);
+      i0.load(L.i0 + (size_t) i * C);
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const double top = __dadd_rn(__dmul_rn((double) t00.v[c], wx), __dmul_rn((double) t01.v[c], xf));
+        const double bot = __dadd_rn(__dmul_rn((double) t10.v[c], wx), __dmul_rn((double) t11.v[c], xf));
+        const double Iw = __dadd_rn(__dmul_rn(wy, top), __dmul_rn(yf, bot));
+        r.v[c] = (float) __dsub_rn(Iw, (double) i0.v[c]);
+      }
+      if (do_hist) {
+#pragma unroll
+        for (int c = 0; c < C; ++c) atomicAdd(&sh.hist[__float_as_uint(fabsf(r.v[c])) >> 20], 1u);
+        my_first = min(my_first, i);
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < C; ++c) r.v[c] = 0.0f;
+    }
+    r.store(W.res + (size_t) i * C);
+    W.valid[i] = ok ? 1 : 0;
+  }
+  if (do_hist) {
+    __syncthreads();
+    for (int b = tid; b < kHist1Bins; b += kLinThreads) { const unsigned v = sh.hist[b]; if (v) atomicAdd(hist1 + b, v); }
+    for (int o = 16; o > 0; o >>= 1) my_first = min(my_first, __shfl_xor_sync(0xffffffffu, my_first, o));
+    if ((tid & 31) == 0 && my_first != 0x7fffffff) atomicMax(hist1 + kHistBins, ~(unsigned) my_first);   // word zero-initialised
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// P2 / P3: refine the radix select by 11 then 9 more bits.  level == 2: input hist1, output hist2 sets;
+// level == 3: input hist2 sets, output hist3 sets.  slot 0 = rank n/2-1 ("lo"), slot 1 = rank n/2 ("hi").
+// ---------------------------------------------------------------------------------------------
+template <int C, int LEVEL>
+__device__ __forceinline__ void phase_select(const LevelTemplate& L, const Work& W, unsigned* __restrict__ hset, Sel* __restrict__ sel,
+                                             LinShared& sh, int block, int nblocks) {
+  const int tid = threadIdx.x;
+  unsigned* hist1 = hset;
+  unsigned* hist2 = hset + kHist1Bins;               // [2][kHist2Bins]
+  unsigned* hist3 = hset + kHist1Bins + 2 * kHist2Bins;   // [2][kHist3Bins]
+  unsigned pa, pb;                                   // prefixes to match
+  constexpr int NBOUT = (LEVEL == 2) ? kHist2Bins : kHist3Bins;
+  if (LEVEL == 2) {
+    unsigned ba, ra, bb, rb, n;
+    // total first (ranks depend on n): scan with dummy ranks, then the real ones
+    block_find2<kHist1Bins>(hist1, 0u, 0u, sh, ba, ra, bb, rb, n);
+    const unsigned t_hi = n / 2, t_lo = (n >= 1) ? ((n / 2) - ((n % 2 == 0 && n >= 2) ? 1u : 0u)) : 0u;
+    block_find2<kHist1Bins>(hist1, t_lo, t_hi, sh, ba, ra, bb, rb, n);
+    pa = ba; pb = bb;
+    if (block == 0 && tid == 0) { sel->n = n; sel->b1[0] = ba; sel->rem1[0] = ra; sel->b1[1] = bb; sel->rem1[1] = rb; }
+    if (n < 3) return;                               // median rule for tiny n needs no refinement
+  } else {
+    const unsigned n = sel->n;
+    if (n < 3) return;
+    unsigned ba, ra, bb, rb, tot;
+    block_find2<kHist2Bins>(hist2, sel->rem1[0], 0xffffffffu, sh, ba, ra, bb, rb, tot);
+    unsigned bb2, rb2, dummy0, dummy1;
+    block_find2<kHist2Bins>(hist2 + kHist2Bins, sel->rem1[1], 0xffffffffu, sh, bb2, rb2, dummy0, dummy1, tot);
+    if (block == 0 && tid == 0) { sel->b2[0] = ba; sel->rem2[0] = ra; sel->b2[1] = bb2; sel->rem2[1] = rb2; }
+    pa = (sel->b1[0] << 11) | ba; pb = (sel->b1[1] << 11) | bb2;
+  }
+  for (int b = tid; b < 2 * NBOUT; b += kLinThreads) sh.hist[b] = 0;
+  __syncthreads();
+  constexpr int SHIFT_MATCH = (LEVEL == 2) ? 20 : 9;
+  constexpr int SHIFT_BIN = (LEVEL == 2) ? 9 : 0;
+  const int n_pts = L.meta->n;
+  for (int i = block * kLinThreads + tid; i < n_pts; i += nblocks * kLinThreads) {
+    if (!W.valid[i]) continue;
+    VecC<C> r; r.load_plain(W.res + (size_t) i * C);
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const unsigned bits = __float_as_uint(fabsf(r.v[c]));
+      const unsigned pre = bits >> SHIFT_MATCH, bin = (bits >> SHIFT_BIN) & (NBOUT - 1);
+      if (pre == pa) atomicAdd(&sh.hist[bin], 1u);
+      if (pre == pb) atomicAdd(&sh.hist[NBOUT + bin], 1u);
+    }
+  }
+  __syncthreads();
+  unsigned* out = (LEVEL == 2) ? hist2 : hist3;
+  for (int b = tid; b < 2 * NBOUT; b += kLinThreads) { const unsigned v = sh.hist[b]; if (v) atomicAdd(out + b, v); }
+}
+
+// sigma from the finished select (every CTA, identical result): median rule of utils.h:224-252 and
+// scale = 1.4826 (1 + 5/(n-6)) median, "< 1e-6 -> 1" (mestimator.cc:452-482)
+template <int C>
+__device__ __forceinline__ float finish_scale(const Work& W, const unsigned* __restrict__ hset, const Sel* __restrict__ sel, LinShared& sh) {
+  const unsigned n = sel->n;
+  float med;
+  if (n == 0) {
+    med = 0.0f;
+  } else if (n < 3) {
+    med = fabsf(W.res[(size_t) (~hset[kHistBins]) * C]);         // data[0]: channel 0 of the first valid point
+  } else {
+    const unsigned* hist3 = hset + kHist1Bins + 2 * kHist2Bins;
+    unsigned ba, ra, bb, rb, t0, d0, d1;
+    block_find2<kHist3Bins>(hist3, sel->rem2[0], 0xffffffffu, sh, ba, ra, d0, d1, t0);
+    block_find2<kHist3Bins>(hist3 + kHist3Bins, sel->rem2[1], 0xffffffffu, sh, bb, rb, d0, d1, t0);
+    const float lo = __uint_as_float((sel->b1[0] << 20) | (sel->b2[0] << 9) | ba);
+    const float hi = __uint_as_float((sel->b1[1] << 20) | (sel->b2[1] << 9) | bb);
+    med = (n % 2 != 0) ? hi : (float) ((double) __fadd_rn(lo, hi) / 2.0);
+  }
+  const float denom = (n >= 6) ? (float) (n - 6) : 1.8446744073709552e19f;     // size_t wrap-around of `size()-6`
+  float s = __fmul_rn(__fmul_rn(1.4826f, __fadd_rn(1.0f, __fdiv_rn(5.0f, denom))), med);
+  if ((double) s < 1e-6) s = 1.0f;
+  return s;
+}
+
+__device__ __forceinline__ float robust_weight(int loss, float r, float sigma_inv) {
+  if (loss == 0x12) return 1.0f;
+  const float x = __fmul_rn(r, sigma_inv);
+  if (loss == 0x10) {                                    // huber_simd: k / max(|x|, k)
+    const float k = 1.345f;
+    return __fdiv_rn(k, fmaxf(fabsf(x), k));
+  }
+  const float t = 4.685f, t_i = (float) (1.0 / 4.685f);  // tukey_simd: (|x| < t) ? (1 - (x/t)^2)^2 : 0
+  float q = __fmul_rn(x, t_i);
+  q = __fsub_rn(1.0f, __fmul_rn(q, q));
+  q = __fmul_rn(q, q);
+  return (fabsf(x) < t) ? q : 0.0f;
+}
+
+// ---------------------------------------------------------------------------------------------
+// P4: weights + normal equations.  Per point: channel sums -> rank-2 update with A, B.
+// Partial layout (kPartialStride doubles): [0..20] upper triangle of H row-major, [21..26] G, [27] sum w r^2,
+// [28] count(w > good_threshold), [29] valid points.
+// ---------------------------------------------------------------------------------------------
+template <int C>
+__device__ __forceinline__ void phase_reduce(const LevelTemplate& L, const Work& W, float sigma, int loss, float good_thr,
+                                             LinShared& sh, int block, int nblocks) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float acc[30];
+#pragma unroll
+  for (int k = 0; k < 30; ++k) acc[k] = 0.0f;
+  const float sigma_inv = __fdiv_rn(1.0f, sigma);
+  const TemplateMeta m = *L.meta;
+  const float is = 1.0f / m.s;
+  const float w_invalid_good = (1.0f > good_thr) ? (float) C : 0.0f;   // invalid entries carry weight 1 in getWeights() (Q6)
+  for (int i = block * kLinThreads + tid; i < m.n; i += nblocks * kLinThreads) {
+    if (!W.valid[i]) { acc[28] += w_invalid_good; continue; }
+    const float4 X = __ldg(L.pts + i);
+    VecC<C> r, gx, gy;
+    r.load_plain(W.res + (size_t) i * C);
+    gx.load(L.gx + (size_t) i * C); gy.load(L.gy + (size_t) i * C);
+    float sxx = 0, sxy = 0, syy = 0, bx = 0, by = 0, e = 0, good = 0;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const float w = robust_weight(loss, r.v[c], sigma_inv);
+      const float wr = w * r.v[c];
+      const float wgx = w * gx.v[c], wgy = w * gy.v[c];
+      sxx += wgx * gx.v[c]; sxy += wgx * gy.v[c]; syy += wgy * gy.v[c];
+      bx += wr * gx.v[c]; by += wr * gy.v[c]; e += wr * r.v[c];
+      good += (w > good_thr) ? 1.0f : 0.0f;
+    }
+    const float iz = 1.0f / X.z, iz2 = iz * iz;
+    const float xc = X.x - m.c1, yc = X.y - m.c2, zc = (X.z - m.c3) * iz;
+    float A[6], B[6];
+    A[0] = -X.x * yc * iz2;        B[0] = -X.y * yc * iz2 - zc;
+    A[1] = X.x * xc * iz2 + zc;    B[1] = X.y * xc * iz2;
+    A[2] = -yc * iz;               B[2] = xc * iz;
+    A[3] = iz * is;                B[3] = 0.0f;
+    A[4] = 0.0f;                   B[4] = iz * is;
+    A[5] = -X.x * iz2 * is;        B[5] = -X.y * iz2 * is;
+    int k = 0;
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+      const float pa = sxx * A[a] + sxy * B[a], qa = sxy * A[a] + syy * B[a];
+#pragma unroll
+      for (int b = a; b < 6; ++b) acc[k++] += pa * A[b] + qa * B[b];
+    }
+#pragma unroll
+    for (int a = 0; a < 6; ++a) acc[21 + a] += bx * A[a] + by * B[a];
+    acc[27] += e; acc[28] += good; acc[29] += 1.0f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 30; ++k) {
+    double v = (double) acc[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) sh.red[warp][k] = v;
+  }
+  __syncthreads();
+  if (tid < 30) {
+    double v = 0.0;
+#pragma unroll
+    for (int w = 0; w < kLinThreads / 32; ++w) v += sh.red[w][tid];
+    W.partials[(size_t) block * kPartialStride + tid] = v;
+    __threadfence();
+  }
+}
+
+// fixed-order sum of the CTA partials -> LinOut (whole CTA participates; result valid in `out` for thread 0
+// after the trailing __syncthreads, and broadcast through shared memory by the caller if needed)
+__device__ __forceinline__ void final_sum(const Work& W, int nblocks, float sigma, LinShared& sh, LinOut& out /* shared or global */) {
+  const int tid = threadIdx.x, k = tid & 31, g = tid >> 5;
+  constexpr int G = kLinThreads / 32;
+  double v = 0.0;
+  for (int b = g; b < nblocks; b += G) v += W.partials[(size_t) b * kPartialStride + k];
+  __syncthreads();
+  sh.red[g][k] = v;
+  __syncthreads();
+  if (tid < 30) {
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < G; ++w) t += sh.red[w][tid];
+    sh.red[0][tid] = t;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int q = 0;
+    for (int a = 0; a < 6; ++a)
+      for (int b = a; b < 6; ++b) { const float h = (float) sh.red[0][q++]; out.H[b * 6 + a] = h; out.H[a * 6 + b] = h; }
+    for (int a = 0; a < 6; ++a) out.G[a] = (float) sh.red[0][21 + a];
+    out.f_norm = sqrtf((float) sh.red[0][27]);
+    out.n_good = (int) (sh.red[0][28] + 0.5);
+    out.n_valid = (int) (sh.red[0][29] + 0.5);
+    out.sigma = sigma;
+  }
+  __syncthreads();
+}
+
+// =============================================================================================
+// host-driven path: four kernels per linearize (fine seam, bpvo_b200_linearize)
+// =============================================================================================
+struct LinArgs {
+  LevelTemplate tmpl;
+  LevelImage img;
+  Work work;
+  float P[12];
+  int loss;
+  float good_thr;
+  unsigned* hset;     // histogram set (zeroed by the host before K1)
+  Sel* sel;
+};
+
+template <int C> __global__ void __launch_bounds__(kLinThreads, 1) k_residuals(LinArgs a) {
+  __shared__ LinShared sh;
+  const bool do_hist = (a.loss != 0x12) && (a.work.scale->delta > 1e-6f);
+  phase_residuals<C>(a.tmpl, a.img, a.P, a.work, a.hset, do_hist, sh, blockIdx.x, gridDim.x);
+}
+template <int C, int LEVEL> __global__ void __launch_bounds__(kLinThreads, 1) k_select(LinArgs a) {
+  __shared__ LinShared sh;
+  const bool do_hist = (a.loss != 0x12) && (a.work.scale->delta > 1e-6f);
+  if (!do_hist) return;
+  phase_select<C, LEVEL>(a.tmpl, a.work, a.hset, a.sel, sh, blockIdx.x, gridDim.x);
+}
+template <int C> __global__ void __launch_bounds__(kLinThreads, 1) k_reduce(LinArgs a) {
+  __shared__ LinShared sh;
+  __shared__ bool s_last;
+  const bool do_hist = (a.loss != 0x12) && (a.work.scale->delta > 1e-6f);
+  float sigma = a.work.scale->scale;
+  if (do_hist) sigma = finish_scale<C>(a.work, a.hset, a.sel, sh);
+  phase_reduce<C>(a.tmpl, a.work, sigma, a.loss, a.good_thr, sh, blockIdx.x, gridDim.x);
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(a.work.ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    final_sum(a.work, gridDim.x, sigma, sh, *a.work.out);
+    if (threadIdx.x == 0) {
+      if (do_hist) { a.work.scale->delta = fabsf(sigma - a.work.scale->scale); a.work.scale->scale = sigma; }
+      *a.work.ticket = 0;
+    }
+  }
+}
+
+__global__ void k_reset_scale(ScaleState* s) { s->scale = 1.0f; s->delta = 1e10f; }
+
+// weights of the last linearize in the reference's channel-major layout (getWeights(), Q6: invalid -> f(0))
+template <int C>
+__global__ void __launch_bounds__(256) k_export_weights(const float* __restrict__ res, int n, float sigma, int loss,
+                                                        float* __restrict__ w_out, float* __restrict__ r_out) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * C) return;
+  const int i = t / C, c = t - i * C;
+  const float r = res[t];
+  if (w_out) w_out[(size_t) c * n + i] = robust_weight(loss, r, __fdiv_rn(1.0f, sigma));
+  if (r_out) r_out[(size_t) c * n + i] = r;
+}
+
+// =============================================================================================
+// persistent path: the whole estimatePose (all levels, all GN iterations, 6x6 solves, convergence
+// tests, pose updates) in ONE cooperative launch; the host sees only T_est and the statistics.
+// Every CTA carries the (tiny) solver state redundantly in shared memory and computes identical
+// values, so only histograms and CTA partials travel through global memory; 4 grid syncs / iteration.
+// =============================================================================================
+// optional in-kernel phase profile (CTA 0, thread 0): cycles accumulated per phase of the GN loop
+#define BP_PROF(slot)                                                                       \
+  do { if (a.prof && blockIdx.x == 0 && threadIdx.x == 0) { const long long _t = clock64(); a.prof[slot] += _t - ss.t_last; ss.t_last = _t; } } while (0)
+enum { PROF_P1 = 0, PROF_SYNC1, PROF_P2, PROF_SYNC2, PROF_P3, PROF_SYNC3, PROF_SCALE, PROF_P4, PROF_SYNC4, PROF_FINAL, PROF_SOLVE, PROF_OTHER, PROF_COUNT };
+
+struct SolveShared {
+  long long t_last;
+  LinOut lin;
+  M44 T, Td;
+  float P[12];
+  float dp[6];
+  float scale, delta;
+};
+
+template <int C>
+__device__ __forceinline__ void device_linearize(const SolveArgs& a, int lvl, const M44& T, SolveShared& ss, LinShared& sh,
+                                                 cg::grid_group& grid, int& parity, Sel* sel) {
+  const LevelTemplate& L = a.tmpl[lvl];
+  const LevelImage& I = a.img[lvl];
+  const int nb = gridDim.x, blk = blockIdx.x, tid = threadIdx.x;
+  unsigned* hset = a.work.hist + (size_t) parity * kHistWords;
+  unsigned* hother = a.work.hist + (size_t) (parity ^ 1) * kHistWords;
+  if (tid == 0) make_projection(L, T, ss.P);
+  __syncthreads();
+  const bool do_hist = (a.sp.loss != 0x12) && (ss.delta > 1e-6f);
+  BP_PROF(PROF_OTHER);
+  phase_residuals<C>(L, I, ss.P, a.work, hset, do_hist, sh, blk, nb);
+  BP_PROF(PROF_P1);
+  float sigma = ss.scale;
+  if (do_hist) {
+    grid.sync();
+    BP_PROF(PROF_SYNC1);
+    phase_select<C, 2>(L, a.work, hset, sel, sh, blk, nb);
+    BP_PROF(PROF_P2);
+    grid.sync();
+    BP_PROF(PROF_SYNC2);
+    phase_select<C, 3>(L, a.work, hset, sel, sh, blk, nb);
+    BP_PROF(PROF_P3);
+    grid.sync();
+    BP_PROF(PROF_SYNC3);
+    sigma = finish_scale<C>(a.work, hset, sel, sh);
+    BP_PROF(PROF_SCALE);
+  }   // else: P4 reads only what the SAME thread wrote in P1, no grid-wide dependency
+  phase_reduce<C>(L, a.work, sigma, a.sp.loss, a.sp.good_threshold, sh, blk, nb);
+  // zero the histogram set of the NEXT linearize (nobody touches it during this phase)
+  for (int b = blk * kLinThreads + tid; b < kHistWords; b += nb * kLinThreads) hother[b] = 0;
+  __threadfence();
+  BP_PROF(PROF_P4);
+  grid.sync();
+  BP_PROF(PROF_SYNC4);
+  final_sum(a.work, nb, sigma, sh, ss.lin);
+  if (tid == 0 && do_hist) { ss.delta = fabsf(sigma - ss.scale); ss.scale = sigma; }
+  __syncthreads();
+  BP_PROF(PROF_FINAL);
+  parity ^= 1;
+}
+
+template <int C>
+__global__ void __launch_bounds__(kLinThreads, 1) k_estimate_pose(SolveArgs a, Sel* sel, int first_parity) {
+  __shared__ LinShared sh;
+  __shared__ SolveShared ss;
+  cg::grid_group grid = cg::this_grid();
+  const int tid = threadIdx.x;
+  int parity = first_parity;
+  int total_evals = 0;
+  if (tid == 0) { ss.T = a.T_init; ss.t_last = clock64(); }
+  __syncthreads();
+  const float sqrt_eps = sqrtf(FLT_EPSILON);
+  for (int lvl = a.sp.num_levels - 1; lvl >= a.sp.max_test_level; --lvl) {
+    const LevelTemplate& L = a.tmpl[lvl];
+    // PoseEstimatorBase::run (pose_estimator_base.h:324-407); all control flow below is CTA-uniform AND grid-uniform
+    if (tid == 0) { ss.scale = 1.0f; ss.delta = 1e10f; }                      // reset() :287-293
+    __syncthreads();
+    int n_evals = 0, it = 0, status = 0x33;
+    float f_prev = 0.0f, g_tol = 0.0f, dp_prev = 0.0f, f_norm, g_norm;
+    bool solver_error = false, early = false;
+    const TemplateMeta meta = *L.meta;
+    M44 Tn = identity44(), Tn_inv = identity44();
+    Tn(0, 0) = Tn(1, 1) = Tn(2, 2) = meta.s; Tn(0, 3) = -meta.s * meta.c1; Tn(1, 3) = -meta.s * meta.c2; Tn(2, 3) = -meta.s * meta.c3;
+    Tn_inv = inverse44(Tn);
+    if (meta.n_total == 0) {                              // "you should call setData before calling computeResiduals" (template_data.cc:177)
+      if (blockIdx.x == 0 && tid == 0) { LevelStats st; st.num_iterations = 0; st.final_error = -1.0f; st.first_order_optimality = -1.0f; st.status = -3; st.num_evals = 0; a.stats[lvl] = st; }
+      continue;
+    }
+
+    device_linearize<C>(a, lvl, ss.T, ss, sh, grid, parity, sel); ++n_evals;
+    f_norm = ss.lin.f_norm;
+    g_norm = 0.0f; for (int k = 0; k < 6; ++k) g_norm = fmaxf(g_norm, fabsf(ss.lin.G[k]));
+    g_tol = a.sp.gradient_tolerance * fmaxf(g_norm, sqrt_eps);
+    if (g_norm < g_tol) {                                                      // :346-357
+      status = 0x32; it = 1; early = true;
+    } else {
+      if (tid == 0) { const bool ok = solve6(ss.lin.H, ss.lin.G, ss.dp); ss.lin.pad[0] = ok ? 1 : 0; }
+      __syncthreads();
+      if (!ss.lin.pad[0]) {                                                    // :359-365
+        status = 0x34; solver_error = true; early = true; it = 0; g_norm = 0.0f;
+      }
+    }
+    if (!early) {
+      if (tid == 0) {
+        float ndp[6]; for (int k = 0; k < 6; ++k) ndp[k] = -ss.dp[k];
+        ss.Td = mul44(ss.T, params_to_pose(Tn, Tn_inv, ndp));                  // :371
+      }
+      __syncthreads();
+      bool conv = false;
+      do {
+        float dpn = 0.0f; for (int k = 0; k < 6; ++k) dpn += ss.dp[k] * ss.dp[k];
+        dpn = sqrtf(dpn);
+        g_norm = 0.0f; for (int k = 0; k < 6; ++k) g_norm = fmaxf(g_norm, fabsf(ss.lin.G[k]));
+        // testConvergence (:258-282)
+        if (dpn < a.sp.parameter_tolerance || dpn < a.sp.parameter_tolerance * (sqrt_eps + dp_prev)) { status = 0x30; conv = true; }
+        else if (f_norm < a.sp.function_tolerance || f_norm < a.sp.function_tolerance * (sqrt_eps + f_prev) ||
+                 fabsf(f_norm - f_prev) < a.sp.function_tolerance) { status = 0x31; conv = true; }
+        else if (g_norm < g_tol) { status = 0x32; conv = true; }
+        dp_prev = dpn; f_prev = f_norm;
+        if (!conv) {                                                           // runIteration (pose_estimator_gn.h:83-100)
+          device_linearize<C>(a, lvl, ss.Td, ss, sh, grid, parity, sel); ++n_evals;
+          f_norm = ss.lin.f_norm;
+          if (tid == 0) { const bool ok = solve6(ss.lin.H, ss.lin.G, ss.dp); ss.lin.pad[0] = ok ? 1 : 0; }
+          __syncthreads();
+          if (!ss.lin.pad[0]) { status = 0x34; solver_error = true; break; }
+        }
+        if (tid == 0) {                                                        // also when converged (Q1)
+          float ndp[6]; for (int k = 0; k < 6; ++k) ndp[k] = -ss.dp[k];
+          ss.Td = mul44(ss.Td, params_to_pose(Tn, Tn_inv, ndp));
+        }
+        __syncthreads();
+        BP_PROF(PROF_SOLVE);
+      } while (it++ < a.sp.max_iterations && !conv && n_evals < a.sp.max_fun_evals);
+      if (!solver_error && tid == 0) ss.T = ss.Td;                             // :395-396
+      __syncthreads();
+      it -= 1;                                                                 // :398
+    }
+    total_evals += n_evals;
+    if (blockIdx.x == 0 && tid == 0) {
+      LevelStats st; st.num_iterations = it; st.final_error = f_norm; st.first_order_optimality = g_norm; st.status = status; st.num_evals = n_evals;
+      a.stats[lvl] = st;
+    }
+  }
+  if (blockIdx.x == 0 && tid == 0) {
+    *a.T_out = ss.T; *a.num_fun_evals = total_evals;
+    *a.work.out = ss.lin;
+    a.work.scale->scale = ss.scale; a.work.scale->delta = ss.delta;
+  }
+}
+
+}  // namespace bp

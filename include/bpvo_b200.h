@@ -1,0 +1,256 @@
+/*
+ * bpvo_b200.h -- C ABI of the B200-native dense-alignment engine that sits under
+ * bpvo::VisualOdometry::addFrame() (reference: halismai/bpvo @ 343d9da).
+ *
+ * The reference has no FFI of its own; its seam is the pair of internal C++ classes that bpvo/vo.cc
+ * drives (VisualOdometryFrame, VisualOdometryPoseEstimator) plus the public VisualOdometry class that
+ * apps/*.cc and matlab/vo_mex.cc:204-208 bind.  Every entry point below names the reference
+ * interface it replaces (file:line relative to the reference root).  INTEGRATION.md shows the
+ * reference-side shim a maintainer would add.
+ *
+ * Conventions
+ *  - plain C, no C++/torch types; all matrices are explicit float arrays in COLUMN-MAJOR order
+ *    (Eigen's default storage: pass Matrix44::data() straight through);
+ *  - images are row-major, contiguous: uint8 gray `rows x cols`, float32 disparity `rows x cols`;
+ *  - every function returns 0 on success, a negative bpvo_b200_status otherwise (the reference throws
+ *    bpvo::Error, bpvo/utils.h:211-220; the C++ shim in bpvo_b200/csrc/host re-throws) and never
+ *    calls exit(); bpvo_b200_last_error() returns the message of the calling thread's last failure;
+ *  - the caller owns every host pointer it passes; the library copies what it keeps
+ *    (reference: vo_frame.cc:50-51);
+ *  - one ctx = one CUDA device + one stream; a ctx is NOT thread-safe (neither is
+ *    bpvo::VisualOdometry), different ctxs may be driven from different threads.
+ *  - there is NO CPU fallback: without a CUDA device bpvo_b200_create / bpvo_b200_vo_create fail.
+ */
+#ifndef BPVO_B200_H
+#define BPVO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BPVO_B200_VERSION 100
+#define BPVO_B200_MAX_LEVELS 16
+
+typedef enum {
+  BPVO_B200_OK = 0,
+  BPVO_B200_ERR_INVALID_ARG = -1,   /* nullptr image/disparity (vo.cc:68), bad params (dense_descriptor_pyramid.cc:37-38) */
+  BPVO_B200_ERR_NO_DATA = -2,       /* "no data in frame" (vo_frame.cc:63) */
+  BPVO_B200_ERR_NO_POINTS = -3,     /* "you should call setData before calling computeResiduals" (template_data.cc:177) */
+  BPVO_B200_ERR_CUDA = -4,          /* no device / CUDA runtime failure */
+  BPVO_B200_ERR_UNSUPPORTED = -5,   /* a DescriptorType / option outside the hot path */
+  BPVO_B200_ERR_COMM = -6           /* multi-GPU exchange failure */
+} bpvo_b200_status;
+
+/* numeric values are the reference's (bpvo/types.h:125-166, 399-418) */
+enum { BPVO_B200_HUBER = 0x10, BPVO_B200_TUKEY = 0x11, BPVO_B200_L2 = 0x12 };
+enum { BPVO_B200_INTENSITY = 0x30, BPVO_B200_BITPLANES = 0x37 };
+enum { BPVO_B200_CD3 = 0, BPVO_B200_CD5 = 1 };
+enum { BPVO_B200_LINEAR = 0 };
+enum { BPVO_B200_PARAM_TOL = 0x30, BPVO_B200_FUNC_TOL = 0x31, BPVO_B200_GRAD_TOL = 0x32,
+       BPVO_B200_MAX_ITERS = 0x33, BPVO_B200_SOLVER_ERROR = 0x34 };
+enum { BPVO_B200_KF_LARGE_TRANSLATION = 0x40, BPVO_B200_KF_LARGE_ROTATION = 0x41,
+       BPVO_B200_KF_SMALL_FRAC_GOOD = 0x42, BPVO_B200_KF_NONE = 0x43, BPVO_B200_KF_FIRST_FRAME = 0x44 };
+
+/* flags */
+#define BPVO_B200_FLAG_HOST_SOLVE   1  /* estimate_pose drives the GN loop from the host (one sync per iteration)
+                                          instead of the on-device loop; same results, used for parity tests */
+
+/* POD mirror of the hot-path fields of bpvo::AlgorithmParameters (bpvo/types.h:171-397,
+ * defaults bpvo/types.cc:31-66 via bpvo_b200_default_params). */
+typedef struct {
+  int32_t numPyramidLevels;               /* <=0: auto (vo.cc:101-104) */
+  int32_t minImageDimensionForPyramid;
+  float   sigmaPriorToCensusTransform;    /* > 0 is UNSUPPORTED (third-party u8 blur) */
+  float   sigmaBitPlanes;
+  int32_t maxIterations;
+  float   parameterTolerance;
+  float   functionTolerance;
+  float   gradientTolerance;
+  int32_t relaxTolerancesForCoarseLevels; /* unused by the reference too (no reader) */
+  int32_t gradientEstimation;             /* BPVO_B200_CD3 / CD5 (template_data.cc:117-130) */
+  int32_t interp;                         /* only kLinear (photo_error.cc:381-389) */
+  int32_t lossFunction;
+  int32_t descriptor;                     /* kIntensity / kBitPlanes */
+  int32_t verbosity;                      /* ignored: the engine never prints */
+  float   minTranslationMagToKeyFrame;
+  float   minRotationMagToKeyFrame;
+  float   maxFractionOfGoodPointsToKeyFrame;
+  float   goodPointThreshold;
+  int32_t minNumPixelsForNonMaximaSuppression;
+  int32_t nonMaxSuppRadius;
+  int32_t minNumPixelsToWork;             /* unused by the reference too */
+  float   minSaliency;
+  float   minValidDisparity;
+  float   maxValidDisparity;
+  int32_t maxTestLevel;
+  int32_t withNormalization;
+  /* engine options (not in the reference) */
+  int32_t device_id;                      /* CUDA device ordinal */
+  int32_t flags;                          /* BPVO_B200_FLAG_* */
+} bpvo_b200_params;
+
+/* bpvo::OptimizerStatistics (bpvo/types.h:444-482) */
+typedef struct {
+  int32_t numIterations;
+  float   finalError;
+  float   firstOrderOptimality;
+  int32_t status;
+} bpvo_b200_stats;
+
+/* bpvo::Result (bpvo/types.h:496-566) minus the point cloud, which is fetched separately */
+typedef struct {
+  float   pose[16];                       /* column-major */
+  int32_t isKeyFrame;
+  int32_t keyFramingReason;
+  int32_t numLevels;
+  bpvo_b200_stats optimizerStatistics[BPVO_B200_MAX_LEVELS];
+  int32_t numFunEvals;                    /* linearize() calls (= GN iterations) inside this addFrame */
+  int32_t numPointCloud;                  /* size of Result::pointCloud, 0 if none */
+} bpvo_b200_result;
+
+/* per-phase device-time / launch counters (cudaEvent based; enable with bpvo_b200_set_profiling) */
+typedef struct {
+  double  ms_upload, ms_pyramid, ms_descriptor, ms_template, ms_linearize, ms_total;
+  int64_t launches;                       /* kernels launched by this ctx since creation / reset */
+  int64_t linearize_calls;                /* GN iterations (linearize evaluations) */
+  int64_t h2d_bytes, d2h_bytes;
+  int64_t solve_calls;                    /* estimate_pose calls (= launches of the persistent solve kernel) */
+} bpvo_b200_counters;
+
+typedef struct bpvo_b200_ctx   bpvo_b200_ctx;    /* VisualOdometryPoseEstimator + device/stream binding */
+typedef struct bpvo_b200_frame bpvo_b200_frame;  /* VisualOdometryFrame */
+typedef struct bpvo_b200_vo    bpvo_b200_vo;     /* VisualOdometry */
+
+int  bpvo_b200_version(void);
+const char* bpvo_b200_last_error(void);
+/* AlgorithmParameters::AlgorithmParameters() (bpvo/types.cc:31-66) */
+void bpvo_b200_default_params(bpvo_b200_params* p);
+/* number of CUDA devices visible (0 => every create fails with BPVO_B200_ERR_CUDA) */
+int  bpvo_b200_device_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * VisualOdometry level -- what apps/vo_perf.cc:84-87 and matlab/vo_mex.cc:204-208 bind
+ * ------------------------------------------------------------------------------------------- */
+/* VisualOdometry(const Matrix33& K, float baseline, ImageSize, const AlgorithmParameters&)  (bpvo/vo.h:42-43, vo.cc:94-110) */
+int bpvo_b200_vo_create(bpvo_b200_vo** out, const float K[9], float baseline, int rows, int cols, const bpvo_b200_params* p);
+int bpvo_b200_vo_destroy(bpvo_b200_vo* vo);
+/* Result addFrame(const uint8_t* image, const float* disparity)  (bpvo/vo.h:75, vo.cc:66-72, 125-197) */
+int bpvo_b200_vo_add_frame(bpvo_b200_vo* vo, const uint8_t* image, const float* disparity, bpvo_b200_result* result);
+/* int numPointsAtLevel(int level = -1) const  (bpvo/vo.h:83, vo.cc:226-238) */
+int bpvo_b200_vo_num_points_at_level(const bpvo_b200_vo* vo, int level, int* n);
+/* const PointVector& pointsAtLevel(int level = -1) const  (bpvo/vo.h:88, vo.cc:240-247): xyzw, 4*n floats */
+int bpvo_b200_vo_points_at_level(const bpvo_b200_vo* vo, int level, float* xyzw, int max_points);
+/* const Trajectory& trajectory() const  (bpvo/vo.h:93, trajectory.cc:42-50): 16 floats per pose; returns count in *n */
+int bpvo_b200_vo_trajectory(const bpvo_b200_vo* vo, float* poses, int max_poses, int* n);
+/* Result::pointCloud of the last addFrame (vo.cc:260-281): xyzw / weight / gray per point */
+int bpvo_b200_vo_point_cloud(const bpvo_b200_vo* vo, float* xyzw, float* weights, uint8_t* gray, int max_points, int* n);
+/* the engine ctx / reference frame behind a vo (for counters, parity dumps) */
+bpvo_b200_ctx* bpvo_b200_vo_ctx(bpvo_b200_vo* vo);
+const bpvo_b200_frame* bpvo_b200_vo_ref_frame(const bpvo_b200_vo* vo);
+
+/* ---------------------------------------------------------------------------------------------
+ * seam level -- what bpvo/vo.cc calls on VisualOdometryFrame / VisualOdometryPoseEstimator
+ * ------------------------------------------------------------------------------------------- */
+/* VisualOdometryPoseEstimator(const AlgorithmParameters&)  (vo_pose_estimator.cc:55-59) + device binding.
+ * numPyramidLevels must already be resolved (> 0), as at vo.cc:101-104. */
+int bpvo_b200_create(bpvo_b200_ctx** out, const float K[9], float baseline, int rows, int cols, const bpvo_b200_params* p);
+int bpvo_b200_destroy(bpvo_b200_ctx* ctx);
+/* VisualOdometryFrame(const Matrix33& K, float b, const AlgorithmParameters&)  (vo_frame.cc:13-30) */
+int bpvo_b200_frame_create(bpvo_b200_ctx* ctx, bpvo_b200_frame** out);
+int bpvo_b200_frame_destroy(bpvo_b200_frame* f);
+/* void setData(const cv::Mat& image, const cv::Mat& disparity)  (vo_frame.h:39, vo_frame.cc:48-55):
+ * copies both, builds the image pyramid and the dense descriptors of levels >= maxTestLevel.
+ * Pageable pointers are staged; pinned (cudaHostAlloc/Register'd) host pointers and device pointers are
+ * DMA'd directly and stay borrowed until the next synchronising call on this ctx (bpvo_b200_vo_add_frame
+ * always synchronises before it returns). */
+int bpvo_b200_frame_set_data(bpvo_b200_frame* f, const uint8_t* image, const float* disparity);
+/* void setTemplate()  (vo_frame.h:48, vo_frame.cc:61-93) -> TemplateData::setData (template_data.cc:37-142) */
+int bpvo_b200_frame_set_template(bpvo_b200_frame* f);
+/* hasTemplate() / empty() / clear()  (vo_frame.h:50-53) */
+int bpvo_b200_frame_has_template(const bpvo_b200_frame* f);
+int bpvo_b200_frame_empty(const bpvo_b200_frame* f);
+int bpvo_b200_frame_clear(bpvo_b200_frame* f);
+/* numLevels()  (vo_frame.cc:46) and per-level image size */
+int bpvo_b200_frame_num_levels(const bpvo_b200_frame* f);
+int bpvo_b200_frame_level_size(const bpvo_b200_frame* f, int level, int* rows, int* cols);
+/* getTemplateDataAtLevel(l)->numPoints() / points()  (template_data.h:68-71) */
+int bpvo_b200_frame_num_points(const bpvo_b200_frame* f, int level, int* n);
+int bpvo_b200_frame_get_points(const bpvo_b200_frame* f, int level, float* xyzw /* 4n */);
+/* parity dumps in the REFERENCE's layouts (device layouts differ):
+ *   pyramid level (ImagePyramid::operator[], image_pyramid.h)          u8  rows x cols
+ *   descriptor   (DenseDescriptor::getChannel(c), dense_descriptor.h)  f32 planar channels x rows x cols
+ *   saliency     (DenseDescriptor::computeSaliencyMap)                 f32 rows x cols (of the last set_template)
+ *   pixels       (TemplateData::pixels())                              f32 channel-major C*N
+ *   jacobians    (TemplateData::jacobians())                           f32 channel-major C*N x 6
+ *   point_inds   (valid_inds of template_data.cc:69-83)                i32 N  (y*cols + x)
+ *   normalization (RigidBodyWarp::_T, warps.cc:27-48)                  f32 4x4 column-major */
+int bpvo_b200_frame_get_pyramid(const bpvo_b200_frame* f, int level, uint8_t* out);
+int bpvo_b200_frame_get_descriptor(const bpvo_b200_frame* f, int level, float* planes, int* channels);
+int bpvo_b200_frame_get_saliency(const bpvo_b200_frame* f, int level, float* out);
+int bpvo_b200_frame_get_pixels(const bpvo_b200_frame* f, int level, float* out);
+int bpvo_b200_frame_get_jacobians(const bpvo_b200_frame* f, int level, float* out);
+int bpvo_b200_frame_get_point_inds(const bpvo_b200_frame* f, int level, int32_t* out);
+int bpvo_b200_frame_get_normalization(const bpvo_b200_frame* f, int level, float Tn[16]);
+
+/* fine seam: one PoseEstimatorGN::linearize (pose_estimator_gn.h:70-81) = residuals -> robust scale ->
+ * weights -> normal equations.  The host keeps solve() / convergence (pose_estimator_base.h:324-407).
+ * first_call_of_level != 0 resets the scale-estimator state (reset(), pose_estimator_base.h:287-293). */
+int bpvo_b200_linearize(bpvo_b200_ctx* ctx, const bpvo_b200_frame* ref, const bpvo_b200_frame* cur, int level,
+                        const float T[16], int first_call_of_level,
+                        float H[36], float G[6], float* f_norm, float* sigma, int* n_valid);
+/* coarse seam: std::vector<OptimizerStatistics> estimatePose(ref, cur, T_init, T_est)
+ * (vo_pose_estimator.h:48-52, vo_pose_estimator.cc:63-93); stats has numLevels entries; *num_fun_evals
+ * (optional) receives the number of linearize() evaluations. */
+int bpvo_b200_estimate_pose(bpvo_b200_ctx* ctx, const bpvo_b200_frame* ref, const bpvo_b200_frame* cur,
+                            const float T_init[16], float T_est[16], bpvo_b200_stats* stats, int* num_fun_evals);
+/* const WeightsVector& getWeights()  (vo_pose_estimator.cc:95-99): C*N weights of the last linearize,
+ * channel-major; pass w == NULL to query *count only.  Same for residuals / valid flags
+ * (PoseEstimatorBase::residuals()/getValidFlags(), pose_estimator_base.h:189-223). */
+int bpvo_b200_get_weights(bpvo_b200_ctx* ctx, float* w, size_t* count);
+int bpvo_b200_get_residuals(bpvo_b200_ctx* ctx, float* r, size_t* count);
+int bpvo_b200_get_valid(bpvo_b200_ctx* ctx, uint8_t* v, size_t* count);   /* per point, N entries */
+/* float getFractionOfGoodPoints(float thresh)  (vo_pose_estimator.cc:101-107), counted on the device */
+int bpvo_b200_fraction_good(bpvo_b200_ctx* ctx, float thresh, float* frac);
+
+/* ---------------------------------------------------------------------------------------------
+ * multi-GPU: template points sharded across ranks, 28-scalar exchange per GN iteration
+ * (no reference counterpart: the reference is single-process)
+ * ------------------------------------------------------------------------------------------- */
+/* 128-byte rendezvous token created on rank 0 and distributed by the caller (e.g. torch.distributed) */
+int bpvo_b200_comm_unique_id(uint8_t id[128]);
+/* join: after this, set_template keeps this rank's contiguous scan-order block of points and
+ * linearize / estimate_pose all-reduce the normal equations and the median histograms */
+int bpvo_b200_comm_init(bpvo_b200_ctx* ctx, int rank, int nranks, const uint8_t id[128]);
+int bpvo_b200_comm_destroy(bpvo_b200_ctx* ctx);
+
+/* ---------------------------------------------------------------------------------------------
+ * measurement helpers
+ * ------------------------------------------------------------------------------------------- */
+int bpvo_b200_set_profiling(bpvo_b200_ctx* ctx, int enable);   /* cudaEvent pairs around each phase */
+int bpvo_b200_get_counters(bpvo_b200_ctx* ctx, bpvo_b200_counters* out);
+/* SM-cycle counters of the phases of the on-device GN loop (CTA 0), accumulated while profiling is on:
+ * P1, sync, P2, sync, P3, sync, scale, P4, sync, final-sum, solve, other, ... */
+int bpvo_b200_get_phase_cycles(bpvo_b200_ctx* ctx, long long cycles[16], int reset);
+int bpvo_b200_reset_counters(bpvo_b200_ctx* ctx);
+int bpvo_b200_synchronize(bpvo_b200_ctx* ctx);
+/* cudaEvent pair on the ctx stream: start records an event, stop records another, waits for it and returns
+ * the device time between them (what bench.py times its steps with) */
+int bpvo_b200_timer_start(bpvo_b200_ctx* ctx);
+int bpvo_b200_timer_stop(bpvo_b200_ctx* ctx, float* ms);
+/* linearize() evaluations per pyramid level of the last estimate_pose (numLevels ints) */
+int bpvo_b200_last_level_evals(bpvo_b200_ctx* ctx, int* evals);
+/* pinned host allocation for zero-staging uploads (cudaHostAlloc / cudaFreeHost) */
+void* bpvo_b200_host_alloc(size_t bytes);
+void  bpvo_b200_host_free(void* p);
+/* time `iters` back-to-back linearize() launches at a fixed pose on the ctx stream with cudaEvents
+ * (device time only, no host round trip per iteration); returns the average ms per linearize */
+int bpvo_b200_time_linearize(bpvo_b200_ctx* ctx, const bpvo_b200_frame* ref, const bpvo_b200_frame* cur, int level,
+                             const float T[16], int iters, int flush_l2, float* ms_per_iter);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BPVO_B200_H */

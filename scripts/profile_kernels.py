@@ -1,0 +1,67 @@
+"""Small driver for ncu captures and per-kernel device timing of the linearize path.
+
+    python scripts/profile_kernels.py [--workload kitti|kitti_dense] [--iters 20]
+
+Prints the cudaEvent time of one host-driven linearize (4 kernels) at level 0 with and without an L2 flush,
+its algorithmic bytes and the resulting fraction of the measured HBM peak; then runs one
+on-device estimate_pose so that `ncu -k regex:k_estimate_pose` has something to capture."""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--workload", default="kitti_dense")
+    ap.add_argument("--iters", type=int, default=20)
+    args = ap.parse_args()
+    from bpvo_b200.engine import Context
+    w = bench.WORKLOADS[args.workload]
+    sc = bench.make_scene(w, 0xB200)
+    p = bench.make_params(w)
+    ctx = Context(sc.K, sc.baseline, (sc.rows, sc.cols), p)
+    a, b = ctx.frame(), ctx.frame()
+    i0, d0 = sc.render(0)
+    i1, d1 = sc.render(1)
+    a.setData(i0, d0); a.setTemplate(); b.setData(i1, d1)
+    T = np.eye(4, dtype=np.float32)
+    peak, how = bench.peaks()
+    out = {"workload": w["name"], "peak_gbs": peak, "peak_source": how, "levels": []}
+    for l in range(p.numPyramidLevels):
+        N = a.numPoints(l)
+        r, c = a.level_size(l)
+        B = bench.algorithmic_bytes_per_iter(N, ctx.channels, r, c)
+        ms_cold = ctx.time_linearize(a, b, l, T, iters=args.iters, flush_l2=True)
+        ms_warm = ctx.time_linearize(a, b, l, T, iters=args.iters, flush_l2=False)
+        out["levels"].append({"level": l, "N": N, "algorithmic_bytes": B, "ms_cold_l2": ms_cold, "ms_warm_l2": ms_warm,
+                              "gbs_cold": B / ms_cold / 1e6, "gbs_warm": B / ms_warm / 1e6,
+                              "frac_cold": B / ms_cold / 1e6 / peak, "frac_warm": B / ms_warm / 1e6 / peak})
+    Tg, stats, evals = ctx.estimatePose(a, b, T)
+    out["estimate_pose_evals"] = evals
+    # in-kernel phase profile of the persistent solve (CTA 0 cycle counters)
+    ctx.set_profiling(True)
+    ctx.phase_cycles(reset=True)
+    ctx.reset_counters()
+    tot_ev = 0
+    for _ in range(5):
+        Tg, stats, evals = ctx.estimatePose(a, b, T)
+        tot_ev += evals
+    cyc = ctx.phase_cycles()
+    ms = ctx.counters()["ms_linearize"]
+    tot = float(sum(cyc.values())) or 1.0
+    out["solve_profile"] = {"evals": tot_ev, "ms": ms, "us_per_eval": 1e3 * ms / max(tot_ev, 1),
+                            "phase_share": {k: round(v / tot, 4) for k, v in cyc.items()},
+                            "phase_us_per_eval": {k: round(1e3 * ms * (v / tot) / max(tot_ev, 1), 3) for k, v in cyc.items()},
+                            "level_evals": ctx.last_level_evals()}
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()
