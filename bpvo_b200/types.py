@@ -106,7 +106,7 @@ class AlgorithmParameters:
 
 
 class CParams(ctypes.Structure):
-    """`bpvo_b200_params` of include/bpvo_b200.h (first 26 fields) -- also the oracle's layout."""
+    """`bpvo_b200_params` of include/bpvo_b200.h."""
     _fields_ = [
         ("numPyramidLevels", ctypes.c_int32), ("minImageDimensionForPyramid", ctypes.c_int32),
         ("sigmaPriorToCensusTransform", ctypes.c_float), ("sigmaBitPlanes", ctypes.c_float),
@@ -121,8 +121,7 @@ class CParams(ctypes.Structure):
         ("minSaliency", ctypes.c_float), ("minValidDisparity", ctypes.c_float),
         ("maxValidDisparity", ctypes.c_float), ("maxTestLevel", ctypes.c_int32),
         ("withNormalization", ctypes.c_int32),
-        # two trailing int32 whose meaning depends on the library:
-        #   libbpvo_b200.so : device_id, flags        liboracle.so : use_rcp, num_threads
+        # engine options: x0 = device_id, x1 = flags (BPVO_B200_FLAG_*)
         ("x0", ctypes.c_int32), ("x1", ctypes.c_int32),
     ]
 

@@ -1,0 +1,97 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads, exports exactly what include/bpvo_b200.h declares,
+mirrors the reference's defaults, and fails LOUDLY (no CPU fallback) when there is no CUDA device."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import HAS_GPU, ROOT, make_params
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "bpvo_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(bpvo_b200_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from bpvo_b200 import _capi
+    lib = _capi.lib()
+    declared = _declared_symbols()
+    assert len(declared) >= 45
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/bpvo_b200.h but not exported"
+    assert sorted(_capi.SIGNATURES) == declared, "python binding and header disagree"
+    assert lib.bpvo_b200_version() == 100
+
+
+def test_default_params_are_the_reference_defaults():
+    from bpvo_b200 import _capi
+    from bpvo_b200.types import AlgorithmParameters, CParams, fill_cparams
+    c = CParams()
+    _capi.lib().bpvo_b200_default_params(C.byref(c))
+    py = fill_cparams(AlgorithmParameters())
+    for name, _ in CParams._fields_[:26]:
+        assert getattr(c, name) == getattr(py, name), name
+    # bpvo/types.cc:31-66
+    assert (c.numPyramidLevels, c.sigmaBitPlanes, c.maxIterations, c.lossFunction, c.descriptor) == (-1, 0.5, 50, 0x11, 0x30)
+    assert (c.minNumPixelsForNonMaximaSuppression, c.nonMaxSuppRadius, c.withNormalization) == (76800, 1, 1)
+    assert abs(c.parameterTolerance - 1e-7) < 1e-12 and abs(c.minSaliency - 0.1) < 1e-7
+    assert C.sizeof(CParams) == 28 * 4
+
+
+def test_auto_pyramid_levels_rule():
+    from bpvo_b200.types import AlgorithmParameters
+    p = AlgorithmParameters()
+    assert p.resolved_num_levels(480, 640) == 5        # 1 + round(log2(480/40)) (vo.cc:101-104)
+    assert p.resolved_num_levels(376, 1241) == 4
+    assert p.resolved_num_levels(1080, 1920) == 6
+
+
+@pytest.mark.skipif(HAS_GPU, reason="checks the no-device behaviour")
+def test_no_cpu_fallback():
+    from bpvo_b200 import Error, VisualOdometry, _capi
+    from bpvo_b200.engine import Context
+    assert _capi.lib().bpvo_b200_device_count() == 0
+    with pytest.raises(Error, match="no CUDA device"):
+        VisualOdometry(np.eye(3), 0.1, (96, 128), make_params("intensity", 2))
+    with pytest.raises(Error, match="no CUDA device"):
+        Context(np.eye(3), 0.1, (96, 128), make_params("bitplanes", 2))
+
+
+def test_argument_validation_happens_before_touching_the_device():
+    from bpvo_b200 import Error
+    from bpvo_b200.engine import Context
+    from bpvo_b200.types import DescriptorType
+    with pytest.raises(Error, match="pyramid"):
+        Context(np.eye(3), 0.1, (96, 128), make_params("intensity", 40))
+    bad = make_params("intensity", 2); bad.descriptor = DescriptorType.kLatch
+    with pytest.raises(Error, match="not on the accelerated path"):
+        Context(np.eye(3), 0.1, (96, 128), bad)
+    K = np.eye(3); K[0, 1] = 0.5
+    with pytest.raises(Error, match="K must be"):
+        Context(K, 0.1, (96, 128), make_params("intensity", 2))
+
+
+def test_product_does_not_import_the_oracle():
+    """the oracle is test infrastructure: nothing under bpvo_b200/ may reference it"""
+    pkg = os.path.join(ROOT, "bpvo_b200")
+    for root, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                src = open(os.path.join(root, f), errors="ignore").read()
+                assert "pyoracle" not in src and "liboracle" not in src and "bpvo_oracle" not in src, os.path.join(root, f)
+
+
+def test_synthetic_scene_is_deterministic():
+    from bpvo_b200 import synth
+    a = synth.scene_small(48, 64).render(1)
+    b = synth.scene_small(48, 64).render(1)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    assert a[0].dtype == np.uint8 and a[1].dtype == np.float32 and a[1].min() > 0
+    sc = synth.scene_small(48, 64, hole_fraction=0.2)
+    assert 0.1 < (sc.render(0)[1] == 0).mean() < 0.3
+    T = sc.relative_pose(0, 1)
+    assert np.abs(T[:3, :3] @ T[:3, :3].T - np.eye(3)).max() < 1e-12
