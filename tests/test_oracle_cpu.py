@@ -182,9 +182,11 @@ def test_vo_recovers_synthetic_motion(oracle, desc, levels, loss):
             assert r["isKeyFrame"] and r["keyFramingReason"] == 0x44 and np.array_equal(r["pose"], np.eye(4, dtype=np.float32))
         else:
             gt = sc.relative_pose(k - 1, k)
-            # sanity only: the 120x160 toy scene carries ~1k points at its top level
-            assert np.abs(r["pose"][:3, 3] - gt[:3, 3]).max() < 1.5e-2
-            assert np.abs(r["pose"][:3, :3] - gt[:3, :3]).max() < 5e-3
+            # sanity only: on the 120x160 toy scene the motion is ~0.5 px per frame; census bit-planes resolve that
+            # coarsely, intensity resolves it well
+            tol_t, tol_r = (5e-3, 2e-3) if desc == "intensity" else (3e-2, 1e-2)
+            assert np.abs(r["pose"][:3, 3] - gt[:3, 3]).max() < tol_t
+            assert np.abs(r["pose"][:3, :3] - gt[:3, :3]).max() < tol_r
     assert evals > 0 and vo.trajectory().shape == (5, 4, 4)
 
 
