@@ -12,7 +12,9 @@ constexpr int kHist1Bins = 2048;   // |r| float bits [30:20]
 constexpr int kHist2Bins = 2048;   // bits [19:9]
 constexpr int kHist3Bins = 512;    // bits [8:0]
 constexpr int kHistBins = kHist1Bins + 2 * kHist2Bins + 2 * kHist3Bins;
-constexpr int kHistWords = kHistBins + 4;   // one histogram set; word [kHistBins] = max(~i) over valid points i
+constexpr int kHistWords = kHistBins + 8;   // one histogram set + bookkeeping words:
+//   [kHistBins+0] max(~i) over valid points i   [+1] valid points   [+2] residuals below the bracket   [+3] residuals inside it
+constexpr int kCandCap = 512;               // capacity of the bracketed-median candidate buffer
 constexpr int kPartialStride = 32; // doubles per block partial (21 H + 6 G + f + n_good + pad)
 constexpr int kLinThreads = 512;   // threads per CTA of the linearize phases (1 CTA per SM)
 
@@ -71,6 +73,7 @@ struct Work {
   ScaleState* scale;
   LinOut* out;
   unsigned* ticket;      // last-CTA-done counter
+  float* cand;           // [kCandCap] |r| values inside the median bracket (on-device GN loop)
 };
 
 struct SolverParams {    // PoseEstimatorParameters (pose_estimator_params.h) + loss

@@ -165,6 +165,7 @@ int bpvo_b200_create(bpvo_b200_ctx** out, const float K[9], float baseline, int 
   CUDA_TRY(cudaMalloc(&c->work.scale, sizeof(ScaleState)));
   CUDA_TRY(cudaMalloc(&c->work.out, sizeof(LinOut)));
   CUDA_TRY(cudaMalloc(&c->work.ticket, 4 * sizeof(unsigned)));
+  CUDA_TRY(cudaMalloc(&c->work.cand, kCandCap * sizeof(float)));
   CUDA_TRY(cudaMalloc(&c->sel, sizeof(Sel)));
   CUDA_TRY(cudaMalloc(&c->export_buf, capmax * c->C * 6 * sizeof(float)));
   CUDA_TRY(cudaMemsetAsync(c->work.hist, 0, 2 * kHistWords * sizeof(unsigned), c->stream));
@@ -198,7 +199,7 @@ int bpvo_b200_destroy(bpvo_b200_ctx* c) {
   cudaStreamSynchronize(c->stream);
   bp_comm_destroy(c);
   cudaFree(c->work.res); cudaFree(c->work.valid); cudaFree(c->work.hist); cudaFree(c->work.partials);
-  cudaFree(c->work.scale); cudaFree(c->work.out); cudaFree(c->work.ticket); cudaFree(c->sel); cudaFree(c->export_buf);
+  cudaFree(c->work.scale); cudaFree(c->work.out); cudaFree(c->work.ticket); cudaFree(c->work.cand); cudaFree(c->sel); cudaFree(c->export_buf);
   cudaFree(c->flags); cudaFree(c->block_counts); cudaFree(c->hpartials);
   cudaFree(c->d_T); cudaFree(c->d_stats); cudaFree(c->d_evals); cudaFree(c->d_prof);
   cudaFreeHost(c->h_mail); cudaFreeHost(c->stage_img); cudaFreeHost(c->stage_disp);

@@ -23,9 +23,17 @@
 
 #include <cooperative_groups.h>
 #include "device_types.h"
+#include "device_solve.cuh"
 
 namespace bp {
 namespace cg = cooperative_groups;
+
+// Point -> thread mapping of every linearize phase: warp g = warp_in_cta * nblocks + cta owns points
+// [32 g, 32 g + 32) (+ multiples of the grid size).  Small levels therefore spread one or two warps onto EVERY
+// SM instead of filling a few CTAs, and a thread meets the same points in every phase (no cross-CTA hand-over).
+__device__ __forceinline__ int first_point(int block, int nblocks) {
+  return (((int) (threadIdx.x >> 5)) * nblocks + block) * 32 + (int) (threadIdx.x & 31);
+}
 
 template <int C> struct VecC;
 template <> struct VecC<8> {
@@ -113,18 +121,25 @@ __host__ __device__ __forceinline__ void make_projection(const LevelTemplate& L,
 // ---------------------------------------------------------------------------------------------
 // P1: residuals (+ level-1 histogram when the scale is to be re-estimated)
 // ---------------------------------------------------------------------------------------------
+struct Bracket {       // median bracket carried from the previous GN iteration (on-device loop only)
+  bool on;
+  float lo, hi;        // candidates are the valid |r| with lo <= |r| <= hi
+};
+
 template <int C>
 __device__ __forceinline__ void phase_residuals(const LevelTemplate& L, const LevelImage& I, const float* P, const Work& W,
-                                                unsigned* __restrict__ hist1, bool do_hist, LinShared& sh, int block, int nblocks) {
+                                                unsigned* __restrict__ hist1, bool do_hist, Bracket br, LinShared& sh, int block, int nblocks) {
   const int tid = threadIdx.x;
   if (do_hist) { for (int b = tid; b < kHist1Bins; b += kLinThreads) sh.hist[b] = 0; }
+  if (tid < 4) sh.found[4 + tid] = 0;        // CTA-level counters: [4] valid points, [5] below bracket
   __syncthreads();
+  unsigned cnt_valid = 0, cnt_below = 0;
   const double P00 = P[0], P10 = P[1], P20 = P[2], P01 = P[3], P11 = P[4], P21 = P[5],
                P02 = P[6], P12 = P[7], P22 = P[8], P03 = P[9], P13 = P[10], P23 = P[11];
   const int cols = I.cols, rows = I.rows;
   const int n_pts = L.meta->n;
   int my_first = 0x7fffffff;
-  for (int i = block * kLinThreads + tid; i < n_pts; i += nblocks * kLinThreads) {
+  for (int i = first_point(block, nblocks); i < n_pts; i += nblocks * kLinThreads) {
     const float4 X = __ldg(L.pts + i);
     const double X0 = X.x, X1 = X.y, X2 = X.z, X3 = X.w;
     const double h0 = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(P00, X0), __dmul_rn(P01, X1)), __dmul_rn(P02, X2)), __dmul_rn(P03, X3));
@@ -158,6 +173,18 @@ __device__ __forceinline__ void phase_residuals(const LevelTemplate& L, const Le
 #pragma unroll
         for (int c = 0; c < C; ++c) atomicAdd(&sh.hist[__float_as_uint(fabsf(r.v[c])) >> 20], 1u);
         my_first = min(my_first, i);
+        ++cnt_valid;
+        if (br.on) {
+#pragma unroll
+          for (int c = 0; c < C; ++c) {
+            const float a = fabsf(r.v[c]);
+            cnt_below += (a < br.lo) ? 1u : 0u;
+            if (a >= br.lo && a <= br.hi) {
+              const unsigned slot = atomicAdd(hist1 + kHistBins + 3, 1u);
+              if (slot < (unsigned) kCandCap) W.cand[slot] = a;
+            }
+          }
+        }
       }
     } else {
 #pragma unroll
@@ -169,8 +196,21 @@ __device__ __forceinline__ void phase_residuals(const LevelTemplate& L, const Le
   if (do_hist) {
     __syncthreads();
     for (int b = tid; b < kHist1Bins; b += kLinThreads) { const unsigned v = sh.hist[b]; if (v) atomicAdd(hist1 + b, v); }
-    for (int o = 16; o > 0; o >>= 1) my_first = min(my_first, __shfl_xor_sync(0xffffffffu, my_first, o));
-    if ((tid & 31) == 0 && my_first != 0x7fffffff) atomicMax(hist1 + kHistBins, ~(unsigned) my_first);   // word zero-initialised
+    for (int o = 16; o > 0; o >>= 1) {
+      my_first = min(my_first, __shfl_xor_sync(0xffffffffu, my_first, o));
+      cnt_valid += __shfl_xor_sync(0xffffffffu, cnt_valid, o);
+      cnt_below += __shfl_xor_sync(0xffffffffu, cnt_below, o);
+    }
+    if ((tid & 31) == 0 && my_first != 0x7fffffff) {
+      atomicMax(hist1 + kHistBins, ~(unsigned) my_first);   // word zero-initialised
+      atomicAdd(&sh.found[4], cnt_valid);
+      if (cnt_below) atomicAdd(&sh.found[5], cnt_below);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      if (sh.found[4]) atomicAdd(hist1 + kHistBins + 1, sh.found[4]);
+      if (sh.found[5]) atomicAdd(hist1 + kHistBins + 2, sh.found[5]);
+    }
   }
 }
 
@@ -211,7 +251,7 @@ __device__ __forceinline__ void phase_select(const LevelTemplate& L, const Work&
   constexpr int SHIFT_MATCH = (LEVEL == 2) ? 20 : 9;
   constexpr int SHIFT_BIN = (LEVEL == 2) ? 9 : 0;
   const int n_pts = L.meta->n;
-  for (int i = block * kLinThreads + tid; i < n_pts; i += nblocks * kLinThreads) {
+  for (int i = first_point(block, nblocks); i < n_pts; i += nblocks * kLinThreads) {
     if (!W.valid[i]) continue;
     VecC<C> r; r.load_plain(W.res + (size_t) i * C);
 #pragma unroll
@@ -227,29 +267,69 @@ __device__ __forceinline__ void phase_select(const LevelTemplate& L, const Work&
   for (int b = tid; b < 2 * NBOUT; b += kLinThreads) { const unsigned v = sh.hist[b]; if (v) atomicAdd(out + b, v); }
 }
 
+// scale = 1.4826 (1 + 5/(n-6)) median with the reference's size_t arithmetic and the "< 1e-6 -> 1" rule
+__device__ __forceinline__ float scale_from_median(unsigned n, float med) {
+  const float denom = (n >= 6) ? (float) (n - 6) : 1.8446744073709552e19f;     // size_t wrap-around of `size()-6`
+  float s = __fmul_rn(__fmul_rn(1.4826f, __fadd_rn(1.0f, __fdiv_rn(5.0f, denom))), med);
+  if ((double) s < 1e-6) s = 1.0f;
+  return s;
+}
+
 // sigma from the finished select (every CTA, identical result): median rule of utils.h:224-252 and
 // scale = 1.4826 (1 + 5/(n-6)) median, "< 1e-6 -> 1" (mestimator.cc:452-482)
 template <int C>
-__device__ __forceinline__ float finish_scale(const Work& W, const unsigned* __restrict__ hset, const Sel* __restrict__ sel, LinShared& sh) {
+__device__ __forceinline__ float finish_scale(const Work& W, const unsigned* __restrict__ hset, const Sel* __restrict__ sel, LinShared& sh,
+                                              float* lo_out = nullptr, float* hi_out = nullptr) {
   const unsigned n = sel->n;
-  float med;
+  float med, lo = 0.0f, hi = 0.0f;
   if (n == 0) {
     med = 0.0f;
   } else if (n < 3) {
     med = fabsf(W.res[(size_t) (~hset[kHistBins]) * C]);         // data[0]: channel 0 of the first valid point
+    lo = hi = med;
   } else {
     const unsigned* hist3 = hset + kHist1Bins + 2 * kHist2Bins;
     unsigned ba, ra, bb, rb, t0, d0, d1;
     block_find2<kHist3Bins>(hist3, sel->rem2[0], 0xffffffffu, sh, ba, ra, d0, d1, t0);
     block_find2<kHist3Bins>(hist3 + kHist3Bins, sel->rem2[1], 0xffffffffu, sh, bb, rb, d0, d1, t0);
-    const float lo = __uint_as_float((sel->b1[0] << 20) | (sel->b2[0] << 9) | ba);
-    const float hi = __uint_as_float((sel->b1[1] << 20) | (sel->b2[1] << 9) | bb);
+    lo = __uint_as_float((sel->b1[0] << 20) | (sel->b2[0] << 9) | ba);
+    hi = __uint_as_float((sel->b1[1] << 20) | (sel->b2[1] << 9) | bb);
     med = (n % 2 != 0) ? hi : (float) ((double) __fadd_rn(lo, hi) / 2.0);
+    if (n % 2 != 0) lo = hi;
   }
-  const float denom = (n >= 6) ? (float) (n - 6) : 1.8446744073709552e19f;     // size_t wrap-around of `size()-6`
-  float s = __fmul_rn(__fmul_rn(1.4826f, __fadd_rn(1.0f, __fdiv_rn(5.0f, denom))), med);
-  if ((double) s < 1e-6) s = 1.0f;
-  return s;
+  if (lo_out) { *lo_out = lo; *hi_out = hi; }
+  return scale_from_median(n, med);
+}
+
+// Bracketed exact median (on-device loop): P1 counted the valid residuals below the bracket and appended the ones
+// inside it to W.cand.  If both middle ranks fall inside and the buffer did not overflow, the two order statistics
+// are found by rank counting among <= kCandCap candidates in shared memory -- no further pass over the residuals,
+// no further grid sync.  Returns false when the bracket missed (caller falls back to the 3-level radix select).
+template <int C>
+__device__ __forceinline__ bool bracket_select(const Work& W, const unsigned* __restrict__ hset, LinShared& sh,
+                                               unsigned& n_out, float& lo_out, float& hi_out) {
+  const int tid = threadIdx.x;
+  const unsigned nv = hset[kHistBins + 1], below = hset[kHistBins + 2], ncand = hset[kHistBins + 3];
+  const unsigned n = nv * (unsigned) C;
+  n_out = n;
+  if (n < 3) return false;
+  const unsigned t_hi = n / 2, t_lo = (n % 2 == 0) ? t_hi - 1 : t_hi;
+  if (ncand > (unsigned) kCandCap || below > t_lo || t_hi >= below + ncand) return false;
+  float* cand = reinterpret_cast<float*>(sh.hist);
+  __syncthreads();
+  if (tid < (int) ncand) cand[tid] = W.cand[tid];
+  if (tid < 2) sh.found[6 + tid] = 0;
+  __syncthreads();
+  if (tid < (int) ncand) {
+    const float v = cand[tid];
+    unsigned rank = 0;
+    for (unsigned j = 0; j < ncand; ++j) { const float u = cand[j]; rank += (u < v || (u == v && j < (unsigned) tid)) ? 1u : 0u; }
+    if (rank == t_lo - below) sh.found[6] = __float_as_uint(v);
+    if (rank == t_hi - below) sh.found[7] = __float_as_uint(v);
+  }
+  __syncthreads();
+  lo_out = __uint_as_float(sh.found[6]); hi_out = __uint_as_float(sh.found[7]);
+  return true;
 }
 
 __device__ __forceinline__ float robust_weight(int loss, float r, float sigma_inv) {
@@ -273,7 +353,7 @@ __device__ __forceinline__ float robust_weight(int loss, float r, float sigma_in
 // ---------------------------------------------------------------------------------------------
 template <int C>
 __device__ __forceinline__ void phase_reduce(const LevelTemplate& L, const Work& W, float sigma, int loss, float good_thr,
-                                             LinShared& sh, int block, int nblocks) {
+                                             LinShared& sh, int block, int nblocks, bool fence = true) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   float acc[30];
 #pragma unroll
@@ -282,7 +362,7 @@ __device__ __forceinline__ void phase_reduce(const LevelTemplate& L, const Work&
   const TemplateMeta m = *L.meta;
   const float is = 1.0f / m.s;
   const float w_invalid_good = (1.0f > good_thr) ? (float) C : 0.0f;   // invalid entries carry weight 1 in getWeights() (Q6)
-  for (int i = block * kLinThreads + tid; i < m.n; i += nblocks * kLinThreads) {
+  for (int i = first_point(block, nblocks); i < m.n; i += nblocks * kLinThreads) {
     if (!W.valid[i]) { acc[28] += w_invalid_good; continue; }
     const float4 X = __ldg(L.pts + i);
     VecC<C> r, gx, gy;
@@ -318,21 +398,33 @@ __device__ __forceinline__ void phase_reduce(const LevelTemplate& L, const Work&
     for (int a = 0; a < 6; ++a) acc[21 + a] += bx * A[a] + by * B[a];
     acc[27] += e; acc[28] += good; acc[29] += 1.0f;
   }
+  // warp reduction of the 30 scalars as a transposing butterfly: 16+8+4+2+1 = 31 shuffles instead of 30 x 5;
+  // afterwards lane l holds the warp total of scalar l.  Warps that own no point skip it altogether.
+  const int n_active_warps = min(kLinThreads / 32, max(0, ((m.n + 31) / 32 - block + nblocks - 1) / nblocks));
   __syncthreads();
+  if (warp < n_active_warps) {
+    float v[32];
 #pragma unroll
-  for (int k = 0; k < 30; ++k) {
-    double v = (double) acc[k];
+    for (int k = 0; k < 32; ++k) v[k] = (k < 30) ? acc[k] : 0.0f;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (lane == 0) sh.red[warp][k] = v;
+    for (int step = 0; step < 5; ++step) {
+      const int off = 16 >> step;
+      const bool upper = (lane & off) != 0;
+#pragma unroll
+      for (int k = 0; k < (16 >> step); ++k) {
+        const float send = upper ? v[k] : v[k + off];
+        const float keep = upper ? v[k + off] : v[k];
+        v[k] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+      }
+    }
+    sh.red[warp][lane] = (double) v[0];
   }
   __syncthreads();
   if (tid < 30) {
     double v = 0.0;
-#pragma unroll
-    for (int w = 0; w < kLinThreads / 32; ++w) v += sh.red[w][tid];
+    for (int w = 0; w < n_active_warps; ++w) v += sh.red[w][tid];
     W.partials[(size_t) block * kPartialStride + tid] = v;
-    __threadfence();
+    if (fence) __threadfence();     // last-CTA pattern of the host-driven path; the persistent path relies on grid.sync()
   }
 }
 
@@ -342,7 +434,13 @@ __device__ __forceinline__ void final_sum(const Work& W, int nblocks, float sigm
   const int tid = threadIdx.x, k = tid & 31, g = tid >> 5;
   constexpr int G = kLinThreads / 32;
   double v = 0.0;
-  for (int b = g; b < nblocks; b += G) v += W.partials[(size_t) b * kPartialStride + k];
+  for (int b0 = g; b0 < nblocks; b0 += 10 * G) {     // up to 10 independent L2 loads in flight per thread, fixed summation order
+    double p[10];
+#pragma unroll
+    for (int j = 0; j < 10; ++j) { const int b = b0 + j * G; p[j] = (b < nblocks) ? W.partials[(size_t) b * kPartialStride + k] : 0.0; }
+#pragma unroll
+    for (int j = 0; j < 10; ++j) v += p[j];
+  }
   __syncthreads();
   sh.red[g][k] = v;
   __syncthreads();
@@ -383,7 +481,7 @@ struct LinArgs {
 template <int C> __global__ void __launch_bounds__(kLinThreads, 1) k_residuals(LinArgs a) {
   __shared__ LinShared sh;
   const bool do_hist = (a.loss != 0x12) && (a.work.scale->delta > 1e-6f);
-  phase_residuals<C>(a.tmpl, a.img, a.P, a.work, a.hset, do_hist, sh, blockIdx.x, gridDim.x);
+  phase_residuals<C>(a.tmpl, a.img, a.P, a.work, a.hset, do_hist, Bracket{false, 0.0f, 0.0f}, sh, blockIdx.x, gridDim.x);
 }
 template <int C, int LEVEL> __global__ void __launch_bounds__(kLinThreads, 1) k_select(LinArgs a) {
   __shared__ LinShared sh;
@@ -443,6 +541,10 @@ struct SolveShared {
   float P[12];
   float dp[6];
   float scale, delta;
+  // bracketed-median state of the current level (identical in every CTA)
+  int br_on;           // a previous median exists
+  float br_lo, br_hi;  // previous middle order statistics
+  float br_rel;        // relative half-width of the next bracket
 };
 
 template <int C>
@@ -457,27 +559,55 @@ __device__ __forceinline__ void device_linearize(const SolveArgs& a, int lvl, co
   __syncthreads();
   const bool do_hist = (a.sp.loss != 0x12) && (ss.delta > 1e-6f);
   BP_PROF(PROF_OTHER);
-  phase_residuals<C>(L, I, ss.P, a.work, hset, do_hist, sh, blk, nb);
+  Bracket br;
+  br.on = do_hist && ss.br_on;
+  br.lo = ss.br_lo * (1.0f - ss.br_rel); br.hi = ss.br_hi * (1.0f + ss.br_rel);
+  phase_residuals<C>(L, I, ss.P, a.work, hset, do_hist, br, sh, blk, nb);
   BP_PROF(PROF_P1);
   float sigma = ss.scale;
   if (do_hist) {
     grid.sync();
     BP_PROF(PROF_SYNC1);
-    phase_select<C, 2>(L, a.work, hset, sel, sh, blk, nb);
-    BP_PROF(PROF_P2);
-    grid.sync();
-    BP_PROF(PROF_SYNC2);
-    phase_select<C, 3>(L, a.work, hset, sel, sh, blk, nb);
-    BP_PROF(PROF_P3);
-    grid.sync();
-    BP_PROF(PROF_SYNC3);
-    sigma = finish_scale<C>(a.work, hset, sel, sh);
-    BP_PROF(PROF_SCALE);
+    unsigned n = 0; float lo = 0.0f, hi = 0.0f;
+    bool hit = false;
+    if (br.on) hit = bracket_select<C>(a.work, hset, sh, n, lo, hi);
+    if (hit) {
+      const float med = (n % 2 != 0) ? hi : (float) ((double) __fadd_rn(lo, hi) / 2.0);
+      sigma = scale_from_median(n, med);
+      BP_PROF(PROF_SCALE);
+    } else {
+      phase_select<C, 2>(L, a.work, hset, sel, sh, blk, nb);
+      BP_PROF(PROF_P2);
+      grid.sync();
+      BP_PROF(PROF_SYNC2);
+      phase_select<C, 3>(L, a.work, hset, sel, sh, blk, nb);
+      BP_PROF(PROF_P3);
+      grid.sync();
+      BP_PROF(PROF_SYNC3);
+      sigma = finish_scale<C>(a.work, hset, sel, sh, &lo, &hi);
+      n = sel->n;
+      BP_PROF(PROF_SCALE);
+    }
+    // next bracket: centred on this median, half-width from how far the median just moved (every CTA computes the same)
+    if (tid == 0) {
+      const float mid_new = 0.5f * (lo + hi), mid_old = 0.5f * (ss.br_lo + ss.br_hi);
+      float rel = 0.004f;
+      if (ss.br_on && mid_new > 0.0f) {
+        const float moved = fabsf(mid_new - mid_old) / mid_new;
+        rel = fminf(fmaxf(2.0f * moved, 2e-4f), 0.02f);
+        if (!hit && br.on) {
+          const unsigned nc = hset[kHistBins + 3];
+          rel = (nc > (unsigned) kCandCap) ? fmaxf(0.25f * ss.br_rel, 1e-4f) : fminf(4.0f * fmaxf(ss.br_rel, moved), 0.05f);
+        }
+      }
+      ss.br_rel = rel; ss.br_lo = lo; ss.br_hi = hi; ss.br_on = (n >= 3) ? 1 : 0;
+      if (a.prof && blk == 0) { a.prof[12] += hit ? 1 : 0; a.prof[13] += 1; }
+    }
+    __syncthreads();
   }   // else: P4 reads only what the SAME thread wrote in P1, no grid-wide dependency
-  phase_reduce<C>(L, a.work, sigma, a.sp.loss, a.sp.good_threshold, sh, blk, nb);
+  phase_reduce<C>(L, a.work, sigma, a.sp.loss, a.sp.good_threshold, sh, blk, nb, false);
   // zero the histogram set of the NEXT linearize (nobody touches it during this phase)
   for (int b = blk * kLinThreads + tid; b < kHistWords; b += nb * kLinThreads) hother[b] = 0;
-  __threadfence();
   BP_PROF(PROF_P4);
   grid.sync();
   BP_PROF(PROF_SYNC4);
@@ -502,15 +632,12 @@ __global__ void __launch_bounds__(kLinThreads, 1) k_estimate_pose(SolveArgs a, S
   for (int lvl = a.sp.num_levels - 1; lvl >= a.sp.max_test_level; --lvl) {
     const LevelTemplate& L = a.tmpl[lvl];
     // PoseEstimatorBase::run (pose_estimator_base.h:324-407); all control flow below is CTA-uniform AND grid-uniform
-    if (tid == 0) { ss.scale = 1.0f; ss.delta = 1e10f; }                      // reset() :287-293
+    if (tid == 0) { ss.scale = 1.0f; ss.delta = 1e10f; ss.br_on = 0; ss.br_lo = ss.br_hi = 0.0f; ss.br_rel = 0.004f; }   // reset() :287-293
     __syncthreads();
     int n_evals = 0, it = 0, status = 0x33;
     float f_prev = 0.0f, g_tol = 0.0f, dp_prev = 0.0f, f_norm, g_norm;
     bool solver_error = false, early = false;
     const TemplateMeta meta = *L.meta;
-    M44 Tn = identity44(), Tn_inv = identity44();
-    Tn(0, 0) = Tn(1, 1) = Tn(2, 2) = meta.s; Tn(0, 3) = -meta.s * meta.c1; Tn(1, 3) = -meta.s * meta.c2; Tn(2, 3) = -meta.s * meta.c3;
-    Tn_inv = inverse44(Tn);
     if (meta.n_total == 0) {                              // "you should call setData before calling computeResiduals" (template_data.cc:177)
       if (blockIdx.x == 0 && tid == 0) { LevelStats st; st.num_iterations = 0; st.final_error = -1.0f; st.first_order_optimality = -1.0f; st.status = -3; st.num_evals = 0; a.stats[lvl] = st; }
       continue;
@@ -523,17 +650,14 @@ __global__ void __launch_bounds__(kLinThreads, 1) k_estimate_pose(SolveArgs a, S
     if (g_norm < g_tol) {                                                      // :346-357
       status = 0x32; it = 1; early = true;
     } else {
-      if (tid == 0) { const bool ok = solve6(ss.lin.H, ss.lin.G, ss.dp); ss.lin.pad[0] = ok ? 1 : 0; }
+      if (tid == 0) { bool ok = solve6_fp32_registers(ss.lin.H, ss.lin.G, ss.dp); if (!ok) ok = solve6(ss.lin.H, ss.lin.G, ss.dp); ss.lin.pad[0] = ok ? 1 : 0; }
       __syncthreads();
       if (!ss.lin.pad[0]) {                                                    // :359-365
         status = 0x34; solver_error = true; early = true; it = 0; g_norm = 0.0f;
       }
     }
     if (!early) {
-      if (tid == 0) {
-        float ndp[6]; for (int k = 0; k < 6; ++k) ndp[k] = -ss.dp[k];
-        ss.Td = mul44(ss.T, params_to_pose(Tn, Tn_inv, ndp));                  // :371
-      }
+      if (tid == 0) { ss.Td = ss.T; apply_update(ss.Td, ss.dp, meta.s, meta.c1, meta.c2, meta.c3); }   // :371
       __syncthreads();
       bool conv = false;
       do {
@@ -549,14 +673,11 @@ __global__ void __launch_bounds__(kLinThreads, 1) k_estimate_pose(SolveArgs a, S
         if (!conv) {                                                           // runIteration (pose_estimator_gn.h:83-100)
           device_linearize<C>(a, lvl, ss.Td, ss, sh, grid, parity, sel); ++n_evals;
           f_norm = ss.lin.f_norm;
-          if (tid == 0) { const bool ok = solve6(ss.lin.H, ss.lin.G, ss.dp); ss.lin.pad[0] = ok ? 1 : 0; }
+          if (tid == 0) { bool ok = solve6_fp32_registers(ss.lin.H, ss.lin.G, ss.dp); if (!ok) ok = solve6(ss.lin.H, ss.lin.G, ss.dp); ss.lin.pad[0] = ok ? 1 : 0; }
           __syncthreads();
           if (!ss.lin.pad[0]) { status = 0x34; solver_error = true; break; }
         }
-        if (tid == 0) {                                                        // also when converged (Q1)
-          float ndp[6]; for (int k = 0; k < 6; ++k) ndp[k] = -ss.dp[k];
-          ss.Td = mul44(ss.Td, params_to_pose(Tn, Tn_inv, ndp));
-        }
+        if (tid == 0) apply_update(ss.Td, ss.dp, meta.s, meta.c1, meta.c2, meta.c3);   // also when converged (Q1)
         __syncthreads();
         BP_PROF(PROF_SOLVE);
       } while (it++ < a.sp.max_iterations && !conv && n_evals < a.sp.max_fun_evals);

@@ -143,7 +143,9 @@ class Context:
     def phase_cycles(self, reset=True):
         buf = (C.c_longlong * 16)()
         _check(self._lib.bpvo_b200_get_phase_cycles(self.h, buf, int(reset)))
-        return dict(zip(self.PHASES, list(buf)[:len(self.PHASES)]))
+        out = dict(zip(self.PHASES, list(buf)[:len(self.PHASES)]))
+        out["_bracket_hits"], out["_scale_estimates"] = buf[12], buf[13]
+        return out
 
     def reset_counters(self):
         _check(self._lib.bpvo_b200_reset_counters(self.h))

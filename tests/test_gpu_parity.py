@@ -114,9 +114,17 @@ def _cmp_linearize(ctx, gref, gcur, oref, ocur, oest, level, T, first, tol_hg):
     if ctx.params.lossFunction != 0x12:    # kL2: the reference estimates a scale it never uses; the engine skips it
         assert abs(g["sigma"] - o["sigma"]) <= 1e-6 * max(1.0, abs(o["sigma"])), m
     assert m["w_err"] <= 1e-5, m
-    # the oracle (like the reference) sums C*N terms sequentially in fp32; the engine sums per-thread fp32 then fp64
-    assert m["H_rel"] < tol_hg, m
-    assert m["G_rel"] < tol_hg * 10, m      # G suffers cancellation near the optimum
+    # The oracle (like the reference) accumulates C*N rank-1 terms sequentially in fp32 (error grows with C*N, ~1e-4 at
+    # 2e5 terms); the engine sums per-thread fp32, then tree/fp64.  Loose bound against the oracle, tight bound against an
+    # fp64 evaluation of the SAME J, r, w, valid (the engine must be the closer one).
+    assert m["H_rel"] < 5 * tol_hg, m
+    assert m["G_rel"] < 50 * tol_hg, m      # G suffers cancellation near the optimum
+    J = oref.jacobians(level).reshape(C * N, 6).astype(np.float64)
+    wv = w_o.astype(np.float64) * np.tile(v_o, C).astype(np.float64)
+    H64 = (J * wv[:, None]).T @ J
+    G64 = J.T @ (wv * r_o.astype(np.float64))
+    assert rel_err(g["H"], H64) < tol_hg, (m, rel_err(g["H"], H64), rel_err(o["H"], H64))
+    assert np.abs(g["G"] - G64).max() <= tol_hg * np.abs(J * (wv * np.abs(r_o))[:, None]).sum(axis=0).max(), m
     # f_norm: the oracle accumulates sum(w r^2) sequentially in fp32 like the reference (error grows with C*N);
     # check both against an fp64 evaluation of the same (bit-identical) r, w, valid: the engine must be the closer one
     f_exact = float(np.sqrt(np.sum(w_o.astype(np.float64) * np.tile(v_o, C).astype(np.float64) * r_o.astype(np.float64) ** 2)))
