@@ -306,28 +306,65 @@ __device__ __forceinline__ float finish_scale(const Work& W, const unsigned* __r
 // are found by rank counting among <= kCandCap candidates in shared memory -- no further pass over the residuals,
 // no further grid sync.  Returns false when the bracket missed (caller falls back to the 3-level radix select).
 template <int C>
-__device__ __forceinline__ bool bracket_select(const Work& W, const unsigned* __restrict__ hset, LinShared& sh,
-                                               unsigned& n_out, float& lo_out, float& hi_out) {
+__device__ __forceinline__ bool bracket_select(const Work& W, const unsigned* __restrict__ hset, LinShared& sh, float bl, float bh,
+                                               unsigned& n_out, unsigned& ncand_out, float& lo_out, float& hi_out) {
   const int tid = threadIdx.x;
   const unsigned nv = hset[kHistBins + 1], below = hset[kHistBins + 2], ncand = hset[kHistBins + 3];
   const unsigned n = nv * (unsigned) C;
-  n_out = n;
+  n_out = n; ncand_out = ncand;
   if (n < 3) return false;
   const unsigned t_hi = n / 2, t_lo = (n % 2 == 0) ? t_hi - 1 : t_hi;
   if (ncand > (unsigned) kCandCap || below > t_lo || t_hi >= below + ncand) return false;
-  float* cand = reinterpret_cast<float*>(sh.hist);
+  const unsigned ra = t_lo - below, rb = t_hi - below;
+  // shared-memory carve-up of the 16 KB histogram area
+  float* cand = reinterpret_cast<float*>(sh.hist);                 // [kCandCap]
+  unsigned* bins = sh.hist + kCandCap;                             // [1024]
+  float* list = reinterpret_cast<float*>(sh.hist + kCandCap + 1024);   // [256]
+  constexpr int kList = 256, kBins = 1024;
   __syncthreads();
-  if (tid < (int) ncand) cand[tid] = W.cand[tid];
-  if (tid < 2) sh.found[6 + tid] = 0;
+  for (unsigned j = tid; j < ncand; j += kLinThreads) cand[j] = W.cand[j];
+  if (tid < 4) sh.found[4 + tid] = 0;       // [4] list length, [6] lo bits, [7] hi bits
   __syncthreads();
-  if (tid < (int) ncand) {
-    const float v = cand[tid];
-    unsigned rank = 0;
-    for (unsigned j = 0; j < ncand; ++j) { const float u = cand[j]; rank += (u < v || (u == v && j < (unsigned) tid)) ? 1u : 0u; }
-    if (rank == t_lo - below) sh.found[6] = __float_as_uint(v);
-    if (rank == t_hi - below) sh.found[7] = __float_as_uint(v);
+  if (ncand <= 128u) {
+    if (tid < (int) ncand) {
+      const float v = cand[tid];
+      unsigned rank = 0;
+      for (unsigned j = 0; j < ncand; ++j) { const float u = cand[j]; rank += (u < v || (u == v && j < (unsigned) tid)) ? 1u : 0u; }
+      if (rank == ra) sh.found[6] = __float_as_uint(v);
+      if (rank == rb) sh.found[7] = __float_as_uint(v);
+    }
+    __syncthreads();
+  } else {
+    // candidates live in [bl, bh]: a linear (monotone) binning puts the wanted ranks into bins holding a handful of values
+    const float inv_w = (bh > bl) ? (float) kBins / (bh - bl) : 0.0f;
+    for (int b = tid; b < kBins; b += kLinThreads) bins[b] = 0;
+    __syncthreads();
+    for (unsigned j = tid; j < ncand; j += kLinThreads) atomicAdd(&bins[min(kBins - 1, (int) ((cand[j] - bl) * inv_w))], 1u);
+    __syncthreads();
+    unsigned bin_a, rem_a, bin_b, rem_b, tot;
+    block_find2<kBins>(bins, ra, rb, sh, bin_a, rem_a, bin_b, rem_b, tot);      // resets sh.found[0..7]
+    for (unsigned j = tid; j < ncand; j += kLinThreads) {
+      const float v = cand[j];
+      const unsigned b = (unsigned) min(kBins - 1, (int) ((v - bl) * inv_w));
+      if (b == bin_a || b == bin_b) { const unsigned slot = atomicAdd(&sh.found[4], 1u); if (slot < (unsigned) kList) list[slot] = v; }
+    }
+    __syncthreads();
+    const unsigned nl = sh.found[4];
+    if (nl > (unsigned) kList) return false;       // pathological pile-up of equal values: let the radix select handle it
+    if (tid < (int) nl) {
+      const float v = list[tid];
+      const unsigned bj = (unsigned) min(kBins - 1, (int) ((v - bl) * inv_w));
+      unsigned rank = 0;
+      for (unsigned j = 0; j < nl; ++j) {
+        const float u = list[j];
+        const unsigned bu = (unsigned) min(kBins - 1, (int) ((u - bl) * inv_w));
+        rank += (bu == bj && (u < v || (u == v && j < (unsigned) tid))) ? 1u : 0u;
+      }
+      if (bj == bin_a && rank == rem_a) sh.found[6] = __float_as_uint(v);
+      if (bj == bin_b && rank == rem_b) sh.found[7] = __float_as_uint(v);
+    }
+    __syncthreads();
   }
-  __syncthreads();
   lo_out = __uint_as_float(sh.found[6]); hi_out = __uint_as_float(sh.found[7]);
   return true;
 }
@@ -545,6 +582,7 @@ struct SolveShared {
   int br_on;           // a previous median exists
   float br_lo, br_hi;  // previous middle order statistics
   float br_rel;        // relative half-width of the next bracket
+  float br_density;    // candidates per unit of relative half-width, from the last bracketed pass
 };
 
 template <int C>
@@ -568,9 +606,9 @@ __device__ __forceinline__ void device_linearize(const SolveArgs& a, int lvl, co
   if (do_hist) {
     grid.sync();
     BP_PROF(PROF_SYNC1);
-    unsigned n = 0; float lo = 0.0f, hi = 0.0f;
+    unsigned n = 0, ncand = 0; float lo = 0.0f, hi = 0.0f;
     bool hit = false;
-    if (br.on) hit = bracket_select<C>(a.work, hset, sh, n, lo, hi);
+    if (br.on) hit = bracket_select<C>(a.work, hset, sh, br.lo, br.hi, n, ncand, lo, hi);
     if (hit) {
       const float med = (n % 2 != 0) ? hi : (float) ((double) __fadd_rn(lo, hi) / 2.0);
       sigma = scale_from_median(n, med);
@@ -588,20 +626,20 @@ __device__ __forceinline__ void device_linearize(const SolveArgs& a, int lvl, co
       n = sel->n;
       BP_PROF(PROF_SCALE);
     }
-    // next bracket: centred on this median, half-width from how far the median just moved (every CTA computes the same)
+    // Next bracket, centred on this median (every CTA computes the same).  Half-width: at least twice the distance
+    // the median just moved; otherwise sized from the measured candidate density so that ~600 values fall inside.
     if (tid == 0) {
       const float mid_new = 0.5f * (lo + hi), mid_old = 0.5f * (ss.br_lo + ss.br_hi);
-      float rel = 0.004f;
+      float rel = 0.002f;
       if (ss.br_on && mid_new > 0.0f) {
         const float moved = fabsf(mid_new - mid_old) / mid_new;
-        rel = fminf(fmaxf(2.0f * moved, 2e-4f), 0.02f);
-        if (!hit && br.on) {
-          const unsigned nc = hset[kHistBins + 3];
-          rel = (nc > (unsigned) kCandCap) ? fmaxf(0.25f * ss.br_rel, 1e-4f) : fminf(4.0f * fmaxf(ss.br_rel, moved), 0.05f);
-        }
+        if (br.on && ncand > 0) ss.br_density = (float) ncand / fmaxf(ss.br_rel, 1e-6f);       // candidates per unit of rel
+        const float rel_density = (ss.br_density > 0.0f) ? 600.0f / ss.br_density : 0.002f;
+        rel = fmaxf(2.0f * moved, fminf(rel_density, 0.02f));
+        rel = fminf(fmaxf(rel, 1e-5f), 0.05f);
       }
       ss.br_rel = rel; ss.br_lo = lo; ss.br_hi = hi; ss.br_on = (n >= 3) ? 1 : 0;
-      if (a.prof && blk == 0) { a.prof[12] += hit ? 1 : 0; a.prof[13] += 1; }
+      if (a.prof && blk == 0) { a.prof[12] += hit ? 1 : 0; a.prof[13] += 1; a.prof[14] += (br.on && !hit && ncand > (unsigned) kCandCap) ? 1 : 0; a.prof[15] += (br.on && !hit && ncand <= (unsigned) kCandCap) ? 1 : 0; }
     }
     __syncthreads();
   }   // else: P4 reads only what the SAME thread wrote in P1, no grid-wide dependency
@@ -632,7 +670,7 @@ __global__ void __launch_bounds__(kLinThreads, 1) k_estimate_pose(SolveArgs a, S
   for (int lvl = a.sp.num_levels - 1; lvl >= a.sp.max_test_level; --lvl) {
     const LevelTemplate& L = a.tmpl[lvl];
     // PoseEstimatorBase::run (pose_estimator_base.h:324-407); all control flow below is CTA-uniform AND grid-uniform
-    if (tid == 0) { ss.scale = 1.0f; ss.delta = 1e10f; ss.br_on = 0; ss.br_lo = ss.br_hi = 0.0f; ss.br_rel = 0.004f; }   // reset() :287-293
+    if (tid == 0) { ss.scale = 1.0f; ss.delta = 1e10f; ss.br_on = 0; ss.br_lo = ss.br_hi = 0.0f; ss.br_rel = 0.002f; ss.br_density = 0.0f; }   // reset() :287-293
     __syncthreads();
     int n_evals = 0, it = 0, status = 0x33;
     float f_prev = 0.0f, g_tol = 0.0f, dp_prev = 0.0f, f_norm, g_norm;

@@ -145,6 +145,7 @@ class Context:
         _check(self._lib.bpvo_b200_get_phase_cycles(self.h, buf, int(reset)))
         out = dict(zip(self.PHASES, list(buf)[:len(self.PHASES)]))
         out["_bracket_hits"], out["_scale_estimates"] = buf[12], buf[13]
+        out["_bracket_overflows"], out["_bracket_misses"] = buf[14], buf[15]
         return out
 
     def reset_counters(self):

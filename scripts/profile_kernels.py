@@ -57,6 +57,7 @@ def main():
     ms = ctx.counters()["ms_linearize"]
     hits, ests = cyc.pop("_bracket_hits"), cyc.pop("_scale_estimates")
     out["bracket_hit_rate"] = hits / max(ests, 1)
+    out["bracket_overflows"], out["bracket_misses"] = cyc.pop("_bracket_overflows"), cyc.pop("_bracket_misses")
     tot = float(sum(cyc.values())) or 1.0
     out["solve_profile"] = {"evals": tot_ev, "ms": ms, "us_per_eval": 1e3 * ms / max(tot_ev, 1),
                             "phase_share": {k: round(v / tot, 4) for k, v in cyc.items()},
