@@ -2,9 +2,12 @@
  * bpvo_oracle.cc -- dependency-free CPU restatement of halismai/bpvo's per-frame Gauss-Newton
  * dense-alignment path (reference @ 343d9da).  TEST INFRASTRUCTURE ONLY (see bpvo_oracle.h).
  *
- * "parity unpinned": the reference ships no golden vectors for this path and cannot be built in
- * this image (Eigen/OpenCV/Boost absent).  What IS pinned: cv::pyrDown and cv::GaussianBlur
- * restatements against cv2 4.13 golden vectors (tests/golden/).
+ * "parity unpinned" by the reference's own tests: it ships no golden vectors for this path and cannot be
+ * built as a whole in this image (Eigen/OpenCV/Boost absent).  What IS pinned:
+ *   - census, saliency (incl. its bugs), IsLocalMax selection, median, Huber/Tukey weights, the scale estimator and
+ *     the rank-1 linear-system builder: BIT-EXACT against the reference's own .cc files compiled from
+ *     /root/reference against header stand-ins (oracle/_ref, tests/test_oracle_vs_reference.py);
+ *   - cv::pyrDown / cv::GaussianBlur restatements against cv2 4.13 golden vectors (tests/golden/).
  *
  * Each function cites the reference file:line it follows (paths relative to /root/reference).
  * The reference's SSE/AVX intrinsics are kept where it has them; its documented quirks

@@ -389,3 +389,47 @@ class VisualOdometry:
         if n:
             lib().orc_vo_point_cloud(self.h, _fp(xyzw), _fp(w), _u8(g), n)
         return xyzw, w, g
+
+
+# ---- oracle/_ref: the REAL reference code (leaf files) built against header stand-ins; pins the restatement ------
+_REF = None
+
+
+def build_ref() -> str:
+    """builds oracle/_ref/libbpvo_ref.so when the reference sources are present (build container); the GPU box
+    uses the prebuilt file that travels with the repo snapshot.  Returns the path or '' when unavailable."""
+    so = os.path.join(_HERE, "_ref", "libbpvo_ref.so")
+    ref_root = os.environ.get("BPVO_REFERENCE", "/root/reference")
+    if os.path.isdir(os.path.join(ref_root, "bpvo")):
+        stale = (not os.path.exists(so)) or os.path.getmtime(so) < os.path.getmtime(os.path.join(_HERE, "ref_shim.cc"))
+        if stale:
+            subprocess.run(["make", "-C", _HERE, "-s", "ref", f"REF={ref_root}"], check=True)
+    return so if os.path.exists(so) else ""
+
+
+def ref_lib():
+    global _REF
+    if _REF is not None:
+        return _REF
+    so = build_ref()
+    if not so:
+        return None
+    L = C.CDLL(so)
+    fp, u8p, u16p = C.POINTER(C.c_float), C.POINTER(C.c_uint8), C.POINTER(C.c_uint16)
+    sig = {
+        "ref_census": (None, [u8p, C.c_int, C.c_int, u8p]),
+        "ref_saliency": (None, [fp, C.c_int, C.c_int, C.c_int, fp]),
+        "ref_local_max": (None, [fp, C.c_int, C.c_int, C.c_int, C.c_int, u8p]),
+        "ref_median": (C.c_float, [fp, C.c_size_t]),
+        "ref_compute_weights": (None, [C.c_int, fp, u16p, C.c_size_t, C.c_float, fp]),
+        "ref_scale_create": (C.c_void_p, []),
+        "ref_scale_destroy": (None, [C.c_void_p]),
+        "ref_scale_reset": (None, [C.c_void_p]),
+        "ref_scale_estimate": (C.c_float, [C.c_void_p, fp, u16p, C.c_size_t]),
+        "ref_linear_system": (C.c_float, [fp, fp, fp, u16p, C.c_size_t, fp, fp]),
+    }
+    for name, (res, args) in sig.items():
+        f = getattr(L, name)
+        f.restype, f.argtypes = res, args
+    _REF = L
+    return L

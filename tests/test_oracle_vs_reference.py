@@ -1,0 +1,140 @@
+"""Pins the oracle against the REAL reference code: oracle/_ref/libbpvo_ref.so is compiled from the reference's own
+mestimator.cc, census.cc, imgproc.cc, linear_system_builder.cc, utils.cc (+ header-only IsLocalMax / median) where they
+lie under /root/reference, against small header stand-ins for Eigen/OpenCV (oracle/refstub).  These are exactly the
+quirk-laden SIMD pieces (saliency store bug, 3x4 NMS window, weights ignoring `valid`, packed rank-1 update, size_t
+arithmetic in the scale).  Everything here must match BIT FOR BIT.  Runs on CPU; skipped if the library is absent."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from conftest import make_params
+
+
+@pytest.fixture(scope="module")
+def ref(oracle):
+    L = oracle.ref_lib()
+    if L is None:
+        pytest.skip("oracle/_ref/libbpvo_ref.so not available (reference sources absent and no prebuilt library)")
+    return L
+
+
+def _fp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def _u8(a):
+    return a.ctypes.data_as(C.POINTER(C.c_uint8))
+
+
+def _u16(a):
+    return a.ctypes.data_as(C.POINTER(C.c_uint16))
+
+
+@pytest.mark.parametrize("shape", [(20, 33), (37, 64), (40, 18), (94, 311)])
+def test_census_bit_exact(oracle, ref, shape):
+    rng = np.random.RandomState(shape[1])
+    img = rng.randint(0, 256, size=shape).astype(np.uint8)
+    img[5:9, 4:12] = 100
+    out = np.zeros_like(img)
+    ref.ref_census(_u8(img), shape[0], shape[1], _u8(out))
+    assert np.array_equal(oracle.census(img), out)
+
+
+@pytest.mark.parametrize("shape", [(12, 16), (11, 19), (9, 22), (47, 156), (94, 311), (60, 80)])
+@pytest.mark.parametrize("channels", [1, 8])
+def test_saliency_bit_exact_including_the_bugs(oracle, ref, shape, channels):
+    rng = np.random.RandomState(7 * channels + shape[1])
+    planes = rng.rand(channels, *shape).astype(np.float32)
+    out = np.zeros(shape, np.float32)
+    ref.ref_saliency(_fp(planes), channels, shape[0], shape[1], _fp(out))
+    assert np.array_equal(oracle.saliency(planes), out)
+
+
+def test_saliency_on_a_real_descriptor(oracle, ref):
+    from bpvo_b200 import synth
+    img, _ = synth.scene_small(96, 128).render(0)
+    planes = oracle.descriptor(make_params("bitplanes", 1), img)
+    out = np.zeros(img.shape, np.float32)
+    ref.ref_saliency(_fp(planes), 8, img.shape[0], img.shape[1], _fp(out))
+    mine = oracle.saliency(planes)
+    assert np.array_equal(mine, out)
+    assert mine[:, 4:-4].max() <= 2.0          # columns >= 4 only ever see channel 0 (store-to-dst bug, Q3)
+
+
+@pytest.mark.parametrize("radius", [1, 2])
+def test_selection_matches_reference_local_max(oracle, ref, radius):
+    """TemplateData::setData's candidate scan with the reference's IsLocalMax vs the oracle's selected pixel list"""
+    from bpvo_b200 import synth
+    sc = synth.scene_small(96, 128)
+    img, d = sc.render(0)
+    p = make_params("intensity", 1, nonMaxSuppRadius=radius, minNumPixelsForNonMaximaSuppression=1, minSaliency=1.0)
+    f = oracle.Frame(sc.K, sc.baseline, sc.rows, sc.cols, p)
+    f.set_data(img, d); f.set_template()
+    S = f.saliency(0)
+    flags = np.zeros(S.shape, np.uint8)
+    border = max(radius, 3)
+    ref.ref_local_max(_fp(S), S.shape[0], S.shape[1], radius, border, _u8(flags))
+    expect = np.flatnonzero((flags.ravel() == 1) & (S.ravel() >= p.minSaliency))
+    expect = expect[: len(expect) // 16 * 16]
+    assert np.array_equal(f.point_inds(0), expect.astype(np.int32))
+
+
+def test_median_bit_exact(oracle, ref):
+    rng = np.random.RandomState(11)
+    for n in [1, 2, 3, 4, 5, 16, 101, 1000, 4097]:
+        v = rng.rand(n).astype(np.float32)
+        assert oracle.median(v) == ref.ref_median(_fp(v), n)
+
+
+@pytest.mark.parametrize("loss", [0x10, 0x11, 0x12])
+def test_weights_bit_exact(oracle, ref, loss):
+    """through the oracle's linearize (weights are an output of it) vs MEstimator::ComputeWeights on the same r, valid, sigma"""
+    from bpvo_b200 import synth
+    sc = synth.scene_small(96, 128)
+    name = {0x10: "huber", 0x11: "tukey", 0x12: "l2"}[loss]
+    p = make_params("bitplanes", 2, name)
+    a = oracle.Frame(sc.K, sc.baseline, sc.rows, sc.cols, p); b = oracle.Frame(sc.K, sc.baseline, sc.rows, sc.cols, p)
+    i0, d0 = sc.render(0); i1, d1 = sc.render(1)
+    a.set_data(i0, d0); a.set_template(); b.set_data(i1, d1)
+    T = np.eye(4, dtype=np.float32); T[0, 3] = 0.3          # pushes some points out: invalid entries keep weight f(0) (Q6)
+    o = oracle.Estimator(p).linearize(a, b, 0, T)
+    r, v = np.ascontiguousarray(o["residuals"]), np.ascontiguousarray(o["valid"])
+    assert 0 < v.sum() < v.size
+    w = np.zeros_like(r)
+    ref.ref_compute_weights(loss, _fp(r), _u16(v), r.size, C.c_float(o["sigma"]), _fp(w))
+    assert np.array_equal(w, o["weights"])
+    # scale: AutoScaleEstimator::estimateScale on the same vectors, fresh state
+    h = ref.ref_scale_create()
+    s = ref.ref_scale_estimate(h, _fp(r), _u16(v), r.size)
+    ref.ref_scale_destroy(h)
+    assert s == o["sigma"]
+    # normal equations: LinearSystemBuilder::Run on the oracle's Jacobians / residuals / weights
+    J = np.ascontiguousarray(a.jacobians(0).reshape(-1, 6))
+    H = np.zeros(36, np.float32); G = np.zeros(6, np.float32)
+    f = ref.ref_linear_system(_fp(J), _fp(r), _fp(w), _u16(v), r.size, _fp(H), _fp(G))
+    assert f == o["f_norm"]
+    assert np.array_equal(H.reshape(6, 6).T, o["H"]) and np.array_equal(G, o["G"])
+
+
+def test_scale_estimator_state_machine(oracle, ref):
+    """delta-scale gate across successive calls (mestimator.cc:467-490): same sequence of sigmas"""
+    from bpvo_b200 import synth
+    sc = synth.scene_small(96, 128)
+    p = make_params("intensity", 2, "huber")
+    a = oracle.Frame(sc.K, sc.baseline, sc.rows, sc.cols, p); b = oracle.Frame(sc.K, sc.baseline, sc.rows, sc.cols, p)
+    i0, d0 = sc.render(0); i1, d1 = sc.render(1)
+    a.set_data(i0, d0); a.set_template(); b.set_data(i1, d1)
+    est = oracle.Estimator(p)
+    h = ref.ref_scale_create()
+    T = np.eye(4, dtype=np.float32)
+    for it in range(4):
+        o = est.linearize(a, b, 1, T, reset_scale=(it == 0))
+        r, v = np.ascontiguousarray(o["residuals"]), np.ascontiguousarray(o["valid"])
+        if it == 0:
+            ref.ref_scale_reset(h)
+        s = ref.ref_scale_estimate(h, _fp(r), _u16(v), r.size)
+        assert s == o["sigma"], it
+        if it == 1:
+            T = T.copy(); T[0, 3] = 0.01
+    ref.ref_scale_destroy(h)
