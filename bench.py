@@ -280,8 +280,11 @@ def run_ours(args, w, rank, world, local_rank):
     e2e = frames_total / (ms_e * 1e-3)
 
     cpu = None
+    dense = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline(w, args)
+    if rank == 0 and world == 1 and args.workload == "kitti" and not args.no_dense:
+        dense = dense_variant_roofline(local_rank)
 
     if rank == 0:
         line = {
@@ -298,12 +301,49 @@ def run_ours(args, w, rank, world, local_rank):
             "clocks": clocks,
             "roofline": roof,
             "cpu_baseline": cpu,
+            "roofline_dense_variant": dense,
         }
         print(json.dumps(line), flush=True)
     pin_img.free(); pin_dsp.free()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def dense_variant_roofline(local_rank):
+    """the same persistent kernel on the DENSE selection of the same frames (nonMaxSuppRadius = -1, ~400k points at
+    level 0, 137 MB algorithmic per GN iteration): shows what the kernel does when it is bandwidth- rather than
+    latency-bound.  A handful of frames, cudaEvent time of the solve launches only."""
+    from bpvo_b200 import VisualOdometry
+    w = WORKLOADS["kitti_dense"]
+    sc = make_scene(w, 0xB200)
+    p = make_params(w)
+    vo = VisualOdometry(sc.K, sc.baseline, (sc.rows, sc.cols), p, device_id=local_rank)
+    ctx = vo.ctx
+    frames = [sc.render(k) for k in range(6)]
+    vo.addFrame(*frames[0])
+    vo.addFrame(*frames[1])
+    ctx.set_profiling(True)
+    sizes = [vo.ref_frame().level_size(l) for l in range(p.numPyramidLevels)]
+    alg, ms, evals, solves = 0.0, 0.0, 0, 0
+    for k in range(2, 6):
+        npts = [vo.ref_frame().numPoints(l) for l in range(p.numPyramidLevels)]
+        c0 = ctx.counters()
+        r = vo.addFrame(*frames[k])
+        c1 = ctx.counters()
+        if r.isKeyFrame:
+            continue
+        ev = ctx.last_level_evals()
+        ms += c1["ms_linearize"] - c0["ms_linearize"]
+        solves += c1["solve_calls"] - c0["solve_calls"]
+        evals += sum(ev)
+        for l in range(p.numPyramidLevels):
+            alg += ev[l] * algorithmic_bytes_per_iter(npts[l], 8, sizes[l][0], sizes[l][1])
+    vo.close()
+    peak, how = peaks()
+    ach = alg / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+    return {"workload": w["name"], "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+            "peak_source": how, "gn_iters": evals, "us_per_gn_iter": 1e3 * ms / max(evals, 1), "solve_launches": solves}
 
 
 def cpu_baseline(w, args):
@@ -338,6 +378,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="kitti", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-dense", action="store_true", help="skip the dense-selection roofline variant")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
