@@ -1,20 +1,103 @@
-// comm.cu -- multi-GPU exchange for the point-sharded mode.
-// Round-1 state: the rendezvous API is in place; the sharded exchange itself is not wired yet,
-// so comm_init with nranks > 1 reports BPVO_B200_ERR_UNSUPPORTED (replica mode -- one independent
-// ctx per GPU, no exchange -- is what bench.py --gpus N runs).
+// comm.cu -- multi-GPU exchange for the point-sharded mode (no reference counterpart).
+//
+// Every rank holds the full moving-frame descriptors and a contiguous scan-order block of the template points.
+// Per GN iteration the ranks exchange: the level-1/2/3 radix histograms of |r| (exact global median) and the
+// 30 fp64 normal-equation sums.  All of it goes through NCCL all-reduce on the ctx stream (NVLink 5 / NVSwitch).
+// NCCL is bound at run time (dlopen "libnccl.so.2": the copy torch already loaded, or the system one), so the
+// library has no link-time dependency on it and single-GPU users never touch it.
+#include <dlfcn.h>
 #include <string.h>
+
 #include "engine_internal.h"
 
-int bp_comm_destroy(bpvo_b200_ctx* c) { (void) c; return BPVO_B200_OK; }
-int bp_comm_allreduce_linout(bpvo_b200_ctx* c) { (void) c; return BPVO_B200_OK; }
+namespace {
+
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+typedef int ncclResult_t;                       // ncclSuccess == 0
+enum { ncclUint32 = 3, ncclFloat64 = 8 };        // ncclDataType_t values of nccl.h (2.x ABI)
+enum { ncclSum = 0 };
+
+struct NcclApi {
+  void* handle = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  bool ok = false;
+};
+
+NcclApi& nccl() {
+  static NcclApi api;
+  if (api.handle) return api;
+  const char* names[] = {"libnccl.so.2", "libnccl.so", "/usr/lib/x86_64-linux-gnu/libnccl.so.2"};
+  for (const char* n : names) { api.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (api.handle) break; }
+  if (!api.handle) return api;
+  api.GetUniqueId = (decltype(api.GetUniqueId)) dlsym(api.handle, "ncclGetUniqueId");
+  api.CommInitRank = (decltype(api.CommInitRank)) dlsym(api.handle, "ncclCommInitRank");
+  api.CommDestroy = (decltype(api.CommDestroy)) dlsym(api.handle, "ncclCommDestroy");
+  api.AllReduce = (decltype(api.AllReduce)) dlsym(api.handle, "ncclAllReduce");
+  api.GetErrorString = (decltype(api.GetErrorString)) dlsym(api.handle, "ncclGetErrorString");
+  api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllReduce && api.GetErrorString;
+  return api;
+}
+
+int nccl_fail(const char* what, ncclResult_t r) {
+  return bp_fail(BPVO_B200_ERR_COMM, "%s failed: %s", what, nccl().GetErrorString ? nccl().GetErrorString(r) : "?");
+}
+
+}  // namespace
+
+int bp_comm_destroy(bpvo_b200_ctx* c) {
+  if (c->comm) { nccl().CommDestroy((ncclComm_t) c->comm); c->comm = nullptr; }
+  if (c->comm_buf) { cudaFree(c->comm_buf); c->comm_buf = nullptr; }
+  c->shard_rank = 0; c->shard_size = 1;
+  return BPVO_B200_OK;
+}
+
+int bp_comm_allreduce_u32(bpvo_b200_ctx* c, unsigned* buf, size_t count) {
+  if (c->shard_size <= 1) return BPVO_B200_OK;
+  ncclResult_t r = nccl().AllReduce(buf, buf, count, ncclUint32, ncclSum, (ncclComm_t) c->comm, c->stream);
+  if (r != 0) return nccl_fail("ncclAllReduce(u32)", r);
+  return BPVO_B200_OK;
+}
+
+int bp_comm_allreduce_f64(bpvo_b200_ctx* c, double* buf, size_t count) {
+  if (c->shard_size <= 1) return BPVO_B200_OK;
+  ncclResult_t r = nccl().AllReduce(buf, buf, count, ncclFloat64, ncclSum, (ncclComm_t) c->comm, c->stream);
+  if (r != 0) return nccl_fail("ncclAllReduce(f64)", r);
+  return BPVO_B200_OK;
+}
 
 extern "C" {
-int bpvo_b200_comm_unique_id(uint8_t id[128]) { if (!id) return bp_fail(BPVO_B200_ERR_INVALID_ARG, "null id"); memset(id, 0, 128); return BPVO_B200_OK; }
+
+int bpvo_b200_comm_unique_id(uint8_t id[128]) {
+  if (!id) return bp_fail(BPVO_B200_ERR_INVALID_ARG, "null id");
+  if (!nccl().ok) return bp_fail(BPVO_B200_ERR_COMM, "libnccl.so.2 could not be loaded");
+  ncclUniqueId u;
+  ncclResult_t r = nccl().GetUniqueId(&u);
+  if (r != 0) return nccl_fail("ncclGetUniqueId", r);
+  memcpy(id, u.internal, 128);
+  return BPVO_B200_OK;
+}
+
 int bpvo_b200_comm_init(bpvo_b200_ctx* c, int rank, int nranks, const uint8_t id[128]) {
-  (void) id;
   if (!c || rank < 0 || nranks < 1 || rank >= nranks) return bp_fail(BPVO_B200_ERR_INVALID_ARG, "bad rank / nranks");
-  if (nranks == 1) { c->shard_rank = 0; c->shard_size = 1; return BPVO_B200_OK; }
-  return bp_fail(BPVO_B200_ERR_UNSUPPORTED, "point-sharded exchange is not wired yet; run one independent ctx per GPU");
+  bp_comm_destroy(c);
+  if (nranks == 1) return BPVO_B200_OK;
+  if (!id) return bp_fail(BPVO_B200_ERR_INVALID_ARG, "null id");
+  if (!nccl().ok) return bp_fail(BPVO_B200_ERR_COMM, "libnccl.so.2 could not be loaded");
+  if (cudaSetDevice(c->p.device_id) != cudaSuccess) return bp_fail(BPVO_B200_ERR_CUDA, "cudaSetDevice failed");
+  ncclUniqueId u; memcpy(u.internal, id, 128);
+  ncclComm_t comm = nullptr;
+  ncclResult_t r = nccl().CommInitRank(&comm, nranks, u, rank);
+  if (r != 0) return nccl_fail("ncclCommInitRank", r);
+  c->comm = comm; c->shard_rank = rank; c->shard_size = nranks;
+  if (cudaMalloc(&c->comm_buf, 64 * sizeof(double)) != cudaSuccess) return bp_fail(BPVO_B200_ERR_CUDA, "cudaMalloc(comm_buf) failed");
+  return BPVO_B200_OK;
 }
+
 int bpvo_b200_comm_destroy(bpvo_b200_ctx* c) { if (!c) return bp_fail(BPVO_B200_ERR_INVALID_ARG, "null ctx"); return bp_comm_destroy(c); }
-}
+
+}  // extern "C"

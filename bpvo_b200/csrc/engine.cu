@@ -178,6 +178,7 @@ int bpvo_b200_create(bpvo_b200_ctx** out, const float K[9], float baseline, int 
   CUDA_TRY(cudaMalloc(&c->flags, (size_t) r0 * c0));
   CUDA_TRY(cudaMalloc(&c->block_counts, (size_t) (ceil_div(r0 * c0, kSelPerBlock) + 1) * sizeof(int)));
   CUDA_TRY(cudaMalloc(&c->hpartials, 1024 * 4 * sizeof(double)));
+  CUDA_TRY(cudaMalloc(&c->hsums, 4 * sizeof(double)));
   // device outputs of estimate_pose + pinned mailboxes
   CUDA_TRY(cudaMalloc(&c->d_T, sizeof(M44)));
   CUDA_TRY(cudaMalloc(&c->d_stats, kMaxLevels * sizeof(LevelStats)));
@@ -200,7 +201,7 @@ int bpvo_b200_destroy(bpvo_b200_ctx* c) {
   bp_comm_destroy(c);
   cudaFree(c->work.res); cudaFree(c->work.valid); cudaFree(c->work.hist); cudaFree(c->work.partials);
   cudaFree(c->work.scale); cudaFree(c->work.out); cudaFree(c->work.ticket); cudaFree(c->work.cand); cudaFree(c->sel); cudaFree(c->export_buf);
-  cudaFree(c->flags); cudaFree(c->block_counts); cudaFree(c->hpartials);
+  cudaFree(c->flags); cudaFree(c->block_counts); cudaFree(c->hpartials); cudaFree(c->hsums);
   cudaFree(c->d_T); cudaFree(c->d_stats); cudaFree(c->d_evals); cudaFree(c->d_prof);
   cudaFreeHost(c->h_mail); cudaFreeHost(c->stage_img); cudaFreeHost(c->stage_disp);
   if (c->flush_buf) cudaFree(c->flush_buf);
@@ -515,13 +516,18 @@ int bpvo_b200_frame_get_normalization(const bpvo_b200_frame* f, int level, float
 
 }  // extern "C"
 
-// Hartley normalisation of one level (two tiny grid reductions with last-CTA finish)
+// Hartley normalisation of one level: two tiny grid reductions (last-CTA fold) each followed by a one-thread finish;
+// in the point-sharded mode the phase totals are all-reduced across ranks in between
 int bp_hartley(bpvo_b200_ctx* c, bpvo_b200_frame* f, int l) {
   const int nb = std::max(1, std::min(ceil_div(c->geom[l].capacity, 256 * 8), c->sm_count * 2));
-  hartley_sum_kernel<<<nb, 256, 0, c->stream>>>(f->pts[l], f->d_meta + l, c->hpartials, c->work.ticket + 1, 0);
-  LAUNCH_CHECK(c);
-  hartley_sum_kernel<<<nb, 256, 0, c->stream>>>(f->pts[l], f->d_meta + l, c->hpartials, c->work.ticket + 1, 1);
-  LAUNCH_CHECK(c);
+  for (int phase = 0; phase < 2; ++phase) {
+    hartley_sum_kernel<<<nb, 256, 0, c->stream>>>(f->pts[l], f->d_meta + l, c->hpartials, c->work.ticket + 1, c->hsums, phase);
+    LAUNCH_CHECK(c);
+    int rc = bp_comm_allreduce_f64(c, c->hsums, 3);
+    if (rc) return rc;
+    hartley_finish_kernel<<<1, 1, 0, c->stream>>>(f->d_meta + l, c->hsums, phase);
+    LAUNCH_CHECK(c);
+  }
   return BPVO_B200_OK;
 }
 
@@ -546,11 +552,22 @@ static int launch_linearize(bpvo_b200_ctx* c, const bpvo_b200_frame* ref, const 
   const bool robust = c->p.lossFunction != BPVO_B200_L2;
   if (robust) CUDA_TRY(cudaMemsetAsync(c->work.hist, 0, kHistWords * sizeof(unsigned), c->stream));
   k_residuals<C><<<grid, kLinThreads, 0, c->stream>>>(a); LAUNCH_CHECK(c);
+  const bool sharded = c->shard_size > 1;
+  int rc;
   if (robust) {
+    if (sharded && (rc = bp_comm_allreduce_u32(c, a.hset, kHist1Bins))) return rc;                       // global level-1 histogram
     k_select<C, 2><<<grid, kLinThreads, 0, c->stream>>>(a); LAUNCH_CHECK(c);
+    if (sharded && (rc = bp_comm_allreduce_u32(c, a.hset + kHist1Bins, 2 * kHist2Bins))) return rc;
     k_select<C, 3><<<grid, kLinThreads, 0, c->stream>>>(a); LAUNCH_CHECK(c);
+    if (sharded && (rc = bp_comm_allreduce_u32(c, a.hset + kHist1Bins + 2 * kHist2Bins, 2 * kHist3Bins))) return rc;
   }
-  k_reduce<C><<<grid, kLinThreads, 0, c->stream>>>(a); LAUNCH_CHECK(c);
+  if (!sharded) {
+    k_reduce<C><<<grid, kLinThreads, 0, c->stream>>>(a); LAUNCH_CHECK(c);
+  } else {
+    k_reduce_sharded<C><<<grid, kLinThreads, 0, c->stream>>>(a, c->comm_buf); LAUNCH_CHECK(c);
+    if ((rc = bp_comm_allreduce_f64(c, c->comm_buf, 32))) return rc;                                     // the 30 normal-equation sums
+    k_finalize_sums<<<1, 32, 0, c->stream>>>(c->comm_buf, c->work.out); LAUNCH_CHECK(c);
+  }
   c->counters.linearize_calls++;
   c->last_ref = ref; c->last_level = level;
   return BPVO_B200_OK;
@@ -574,8 +591,6 @@ extern "C" int bpvo_b200_linearize(bpvo_b200_ctx* c, const bpvo_b200_frame* ref,
     if (first_call_of_level) { k_reset_scale<<<1, 1, 0, c->stream>>>(c->work.scale); LAUNCH_CHECK(c); }
     M44 Tm; memcpy(Tm.m, T, sizeof(Tm.m));
     rc = (c->C == 1) ? launch_linearize<1>(c, ref, cur, level, Tm) : launch_linearize<8>(c, ref, cur, level, Tm);
-    if (rc) return rc;
-    rc = bp_comm_allreduce_linout(c);
     if (rc) return rc;
   }
   CUDA_TRY(cudaMemcpyAsync(&c->h_mail->lin, c->work.out, sizeof(LinOut), cudaMemcpyDeviceToHost, c->stream));

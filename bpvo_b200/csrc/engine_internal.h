@@ -47,7 +47,8 @@ struct bpvo_b200_ctx {
   // multi-GPU
   int shard_rank = 0, shard_size = 1;
   void* comm = nullptr;          // ncclComm_t
-  double* comm_buf = nullptr;    // device staging for the exchanges
+  double* comm_buf = nullptr;    // device staging for the exchanges (sharded mode)
+  double* hsums = nullptr;       // [4] Hartley phase totals
 };
 
 struct bpvo_b200_frame {
@@ -70,4 +71,5 @@ struct bpvo_b200_frame {
 int bp_fail(int code, const char* fmt, ...);
 int bp_hartley(bpvo_b200_ctx* c, bpvo_b200_frame* f, int level);
 int bp_comm_destroy(bpvo_b200_ctx* c);
-int bp_comm_allreduce_linout(bpvo_b200_ctx* c);
+int bp_comm_allreduce_u32(bpvo_b200_ctx* c, unsigned* buf, size_t count);
+int bp_comm_allreduce_f64(bpvo_b200_ctx* c, double* buf, size_t count);

@@ -526,6 +526,42 @@ template <int C, int LEVEL> __global__ void __launch_bounds__(kLinThreads, 1) k_
   if (!do_hist) return;
   phase_select<C, LEVEL>(a.tmpl, a.work, a.hset, a.sel, sh, blockIdx.x, gridDim.x);
 }
+// point-sharded mode: the last CTA leaves this rank's 30 fp64 sums in a.sums (all-reduced by the host over NCCL),
+// k_finalize_sums then builds the LinOut every rank sees identically.
+template <int C> __global__ void __launch_bounds__(kLinThreads, 1) k_reduce_sharded(LinArgs a, double* __restrict__ sums) {
+  __shared__ LinShared sh;
+  __shared__ bool s_last;
+  const bool do_hist = (a.loss != 0x12) && (a.work.scale->delta > 1e-6f);
+  float sigma = a.work.scale->scale;
+  if (do_hist) sigma = finish_scale<C>(a.work, a.hset, a.sel, sh);
+  phase_reduce<C>(a.tmpl, a.work, sigma, a.loss, a.good_thr, sh, blockIdx.x, gridDim.x);
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(a.work.ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    LinOut dummy;
+    final_sum(a.work, gridDim.x, sigma, sh, dummy);       // leaves the fp64 totals in sh.red[0][0..29]
+    if (threadIdx.x < 32) sums[threadIdx.x] = (threadIdx.x < 30) ? sh.red[0][threadIdx.x] : 0.0;
+    if (threadIdx.x == 0) {
+      a.work.out->sigma = sigma;
+      if (do_hist) { a.work.scale->delta = fabsf(sigma - a.work.scale->scale); a.work.scale->scale = sigma; }
+      *a.work.ticket = 0;
+    }
+  }
+}
+
+__global__ void k_finalize_sums(const double* __restrict__ sums, LinOut* __restrict__ out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  int q = 0;
+  for (int a = 0; a < 6; ++a)
+    for (int b = a; b < 6; ++b) { const float h = (float) sums[q++]; out->H[b * 6 + a] = h; out->H[a * 6 + b] = h; }
+  for (int a = 0; a < 6; ++a) out->G[a] = (float) sums[21 + a];
+  out->f_norm = sqrtf((float) sums[27]);
+  out->n_good = (int) (sums[28] + 0.5);
+  out->n_valid = (int) (sums[29] + 0.5);
+}
+
 template <int C> __global__ void __launch_bounds__(kLinThreads, 1) k_reduce(LinArgs a) {
   __shared__ LinShared sh;
   __shared__ bool s_last;

@@ -212,10 +212,11 @@ __global__ void __launch_bounds__(kSelThreads) select_scatter_kernel(PointArgs a
 // Hartley normalisation (warps.cc:27-48): c = mean(p), m = mean ||p - c||, s = sqrt(3)/max(m, 1e-6).
 // The reference accumulates sequentially in fp32; here fp64 tree sums (deterministic order) -- c and s
 // agree with the reference to ~1e-6 relative, which only rescales the (self-consistent) parametrisation.
-// Two phases in ONE launch of a single CTA would serialise 2M points at 1080p-dense; instead: a small
-// grid writes per-block partial sums and the last CTA (ticket) finishes.
-__global__ void __launch_bounds__(256) hartley_sum_kernel(const float4* __restrict__ pts, TemplateMeta* __restrict__ meta,
-                                                          double* __restrict__ partials, unsigned* __restrict__ ticket, int phase) {
+// A small grid writes per-CTA partial sums, the last CTA (ticket) folds them into `sums[0..2]`; a one-thread
+// kernel then finishes the phase.  In the point-sharded multi-GPU mode `sums` is all-reduced in between.
+__global__ void __launch_bounds__(256) hartley_sum_kernel(const float4* __restrict__ pts, const TemplateMeta* __restrict__ meta,
+                                                          double* __restrict__ partials, unsigned* __restrict__ ticket,
+                                                          double* __restrict__ sums, int phase) {
   __shared__ double s_red[8][4];
   __shared__ bool s_last;
   const int n = meta->n;
@@ -247,14 +248,19 @@ __global__ void __launch_bounds__(256) hartley_sum_kernel(const float4* __restri
     __threadfence();
     double t0 = 0, t1 = 0, t2 = 0;
     for (unsigned b = 0; b < gridDim.x; ++b) { t0 += partials[b * 4]; t1 += partials[b * 4 + 1]; t2 += partials[b * 4 + 2]; }
-    if (phase == 0) {
-      const double inv = n > 0 ? 1.0 / (double) n : 0.0;
-      meta->c1 = (float) (t0 * inv); meta->c2 = (float) (t1 * inv); meta->c3 = (float) (t2 * inv);
-    } else {
-      const float m = n > 0 ? (float) (t0 / (double) n) : 0.0f;
-      meta->s = (float) (sqrt(3.0) / (double) fmaxf(m, 1e-6f));
-    }
+    sums[0] = t0; sums[1] = t1; sums[2] = t2;
     *ticket = 0;
+  }
+}
+
+__global__ void hartley_finish_kernel(TemplateMeta* __restrict__ meta, const double* __restrict__ sums, int phase) {
+  const int n = meta->n_total;             // == n when unsharded
+  if (phase == 0) {
+    const double inv = n > 0 ? 1.0 / (double) n : 0.0;
+    meta->c1 = (float) (sums[0] * inv); meta->c2 = (float) (sums[1] * inv); meta->c3 = (float) (sums[2] * inv);
+  } else {
+    const float m = n > 0 ? (float) (sums[0] / (double) n) : 0.0f;
+    meta->s = (float) (sqrt(3.0) / (double) fmaxf(m, 1e-6f));
   }
 }
 

@@ -128,6 +128,20 @@ class Context:
         _check(self._lib.bpvo_b200_fraction_good(self.h, float(thresh), C.byref(f)))
         return f.value
 
+    # -- multi-GPU (point-sharded mode) ----------------------------------------------------------------
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        buf = (C.c_uint8 * 128)()
+        _check(_capi.lib().bpvo_b200_comm_unique_id(buf))
+        return bytes(buf)
+
+    def comm_init(self, rank: int, nranks: int, unique_id: bytes):
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id) if unique_id is not None else None
+        _check(self._lib.bpvo_b200_comm_init(self.h, int(rank), int(nranks), buf))
+
+    def comm_destroy(self):
+        _check(self._lib.bpvo_b200_comm_destroy(self.h))
+
     # -- measurement --------------------------------------------------------------------------------
     def set_profiling(self, on: bool):
         _check(self._lib.bpvo_b200_set_profiling(self.h, int(on)))

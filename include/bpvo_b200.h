@@ -219,10 +219,14 @@ int bpvo_b200_fraction_good(bpvo_b200_ctx* ctx, float thresh, float* frac);
  * multi-GPU: template points sharded across ranks, 28-scalar exchange per GN iteration
  * (no reference counterpart: the reference is single-process)
  * ------------------------------------------------------------------------------------------- */
-/* 128-byte rendezvous token created on rank 0 and distributed by the caller (e.g. torch.distributed) */
+/* 128-byte rendezvous token (an ncclUniqueId) created on rank 0 and distributed by the caller (e.g. torch.distributed,
+ * MPI, a file).  NCCL is bound at run time (libnccl.so.2); BPVO_B200_ERR_COMM if it cannot be loaded. */
 int bpvo_b200_comm_unique_id(uint8_t id[128]);
-/* join: after this, set_template keeps this rank's contiguous scan-order block of points and
- * linearize / estimate_pose all-reduce the normal equations and the median histograms */
+/* join (collective over all ranks): afterwards set_template keeps this rank's contiguous scan-order block of points
+ * (multiples of 16; every rank must feed the SAME frames), the Hartley sums, the radix-select histograms of the exact
+ * median and the 30 fp64 normal-equation sums are all-reduced over NCCL, and estimate_pose runs the host-driven loop:
+ * every rank computes bit-identical H, G, sigma and therefore identical poses and key-frame decisions.
+ * frame_num_points / get_points / get_weights / get_residuals then refer to the local shard. */
 int bpvo_b200_comm_init(bpvo_b200_ctx* ctx, int rank, int nranks, const uint8_t id[128]);
 int bpvo_b200_comm_destroy(bpvo_b200_ctx* ctx);
 

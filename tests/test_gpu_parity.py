@@ -286,3 +286,19 @@ def test_full_size_properties():
     assert np.abs(T02 @ T20 - np.eye(4)).max() < 5e-3
     gt = sc.relative_pose(0, 2)
     assert np.abs(T02[:3, 3] - gt[:3, 3]).max() < 0.02 and np.abs(T02[:3, :3] - gt[:3, :3]).max() < 2e-3
+
+
+def test_point_sharded_two_gpus():
+    """point-sharded mode (NCCL exchange of the median histograms and the 30 normal-equation sums) on 2 GPUs of one box:
+    scripts/shard_check.py under torchrun; skipped when the box has a single GPU"""
+    import os
+    import subprocess
+    import sys
+    from bpvo_b200 import _capi
+    from conftest import ROOT
+    if _capi.lib().bpvo_b200_device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29517", os.path.join(ROOT, "scripts", "shard_check.py")]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0 and "SHARD_CHECK_OK" in res.stdout, res.stdout[-3000:] + res.stderr[-3000:]
