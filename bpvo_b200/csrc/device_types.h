@@ -14,7 +14,9 @@ constexpr int kHist3Bins = 512;    // bits [8:0]
 constexpr int kHistBins = kHist1Bins + 2 * kHist2Bins + 2 * kHist3Bins;
 constexpr int kHistWords = kHistBins + 8;   // one histogram set + bookkeeping words:
 //   [kHistBins+0] max(~i) over valid points i   [+1] valid points   [+2] residuals below the bracket   [+3] residuals inside it
-constexpr int kCandCap = 2048;               // capacity of the bracketed-median candidate buffer
+constexpr int kCandCap = 8192;               // capacity of the bracketed-median candidate buffer
+constexpr int kCtaCandCap = 2048;            // per-CTA staging of candidates in shared memory
+constexpr int kScratchBytes = (kCandCap + 1024 + 256) * 4;   // dynamic-smem scratch of the bracketed select
 constexpr int kPartialStride = 32; // doubles per block partial (21 H + 6 G + f + n_good + pad)
 constexpr int kLinThreads = 512;   // threads per CTA of the linearize phases (1 CTA per SM)
 

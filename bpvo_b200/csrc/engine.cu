@@ -140,6 +140,7 @@ int bpvo_b200_create(bpvo_b200_ctx** out, const float K[9], float baseline, int 
   CUDA_TRY(cudaGetDeviceProperties(&prop, p->device_id));
   c->sm_count = prop.multiProcessorCount;
   c->coop = prop.cooperativeLaunch != 0;
+  c->smem_optin = (int) prop.sharedMemPerBlockOptin;
   // per-level geometry: K halves (K(2,2) = 1), baseline doubles (vo_frame.cc:24-28); pyrDown sizes
   float fx = K[0], fy = K[4], cx = K[6], cy = K[7], b = baseline; int r = rows, cl = cols;
   for (int l = 0; l < c->L; ++l) {
@@ -670,9 +671,19 @@ static int launch_estimate_pose(bpvo_b200_ctx* c, const bpvo_b200_frame* ref, co
   // both histogram sets must be zero on entry (the kernel leaves them zeroed for the next call, but the
   // host-driven path may have dirtied set 0 in between)
   CUDA_TRY(cudaMemsetAsync(c->work.hist, 0, 2 * kHistWords * sizeof(unsigned), c->stream));
-  void* args[] = {&a, &sel, &parity};
+  // dynamic shared memory: candidate scratch + as many template-cache slots per thread as fit (1 CTA per SM)
+  const int per_slot = tpl_cache_bytes_per_slot<C>();
+  int slots = (c->smem_optin - 24 * 1024 - kScratchBytes) / per_slot;
+  slots = std::max(0, std::min(slots, 8));
+  const size_t dyn = (size_t) kScratchBytes + (size_t) slots * per_slot;
+  static thread_local size_t configured[2] = {0, 0};
+  if (configured[C == 8] != dyn) {
+    CUDA_TRY(cudaFuncSetAttribute((const void*) k_estimate_pose<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) dyn));
+    configured[C == 8] = dyn;
+  }
+  void* args[] = {&a, &sel, &parity, &slots};
   int grid = c->sm_count;
-  CUDA_TRY(cudaLaunchCooperativeKernel((void*) k_estimate_pose<C>, dim3(grid), dim3(kLinThreads), args, 0, c->stream));
+  CUDA_TRY(cudaLaunchCooperativeKernel((void*) k_estimate_pose<C>, dim3(grid), dim3(kLinThreads), args, dyn, c->stream));
   c->counters.launches++;
   return BPVO_B200_OK;
 }

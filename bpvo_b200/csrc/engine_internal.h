@@ -29,7 +29,7 @@ struct bpvo_b200_ctx {
   int rows = 0, cols = 0, L = 0, C = 1;
   float K[9]; float baseline = 0;
   LevelGeom geom[bp::kMaxLevels];
-  int sm_count = 0; bool coop = false;
+  int sm_count = 0; bool coop = false; int smem_optin = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, stage_free = nullptr, tm0 = nullptr, tm1 = nullptr;
   int level_evals[bp::kMaxLevels] = {};

@@ -60,6 +60,43 @@ template <> struct VecC<1> {
   __device__ __forceinline__ void store(float* p) const { *p = v[0]; }
 };
 
+// Shared-memory copy of the template records (and residuals) of the points THIS CTA's threads own.  The on-device GN
+// loop visits the same points ~50 times per level: staging (X,Y,Z), I0, gx, gy once per level and keeping r between the
+// phases removes every per-iteration global load except the four bilinear taps.  Slot k of thread t holds point
+// first_point + k * gridsize.  Layout (all conflict-free): float4 pts[K][512] | float f[K][4 fields][C][512] | u8 valid[K][512].
+struct TplCache {
+  float4* pts;
+  float* f;
+  uint8_t* valid;
+  int K;                 // slots per thread resident (0 = cache off: host-driven kernels, or the level does not fit)
+};
+enum { TC_I0 = 0, TC_GX = 1, TC_GY = 2, TC_R = 3 };
+
+template <int C> __host__ __device__ constexpr int tpl_cache_bytes_per_slot() { return kLinThreads * (16 + 16 * C + 1); }
+
+template <int C> __device__ __forceinline__ void tc_get(const TplCache& tc, int k, int field, VecC<C>& v) {
+  const float* p = tc.f + ((size_t) (k * 4 + field) * C) * kLinThreads + threadIdx.x;
+#pragma unroll
+  for (int c = 0; c < C; ++c) v.v[c] = p[c * kLinThreads];
+}
+template <int C> __device__ __forceinline__ void tc_put(const TplCache& tc, int k, int field, const VecC<C>& v) {
+  float* p = tc.f + ((size_t) (k * 4 + field) * C) * kLinThreads + threadIdx.x;
+#pragma unroll
+  for (int c = 0; c < C; ++c) p[c * kLinThreads] = v.v[c];
+}
+
+// stage this CTA's points of level L into the cache (thread-private slots: no barrier needed afterwards)
+template <int C> __device__ __forceinline__ void tc_fill(const TplCache& tc, const LevelTemplate& L, int n, int block, int nblocks) {
+  int k = 0;
+  for (int i = first_point(block, nblocks); i < n && k < tc.K; i += nblocks * kLinThreads, ++k) {
+    tc.pts[k * kLinThreads + threadIdx.x] = __ldg(L.pts + i);
+    VecC<C> v;
+    v.load(L.i0 + (size_t) i * C); tc_put<C>(tc, k, TC_I0, v);
+    v.load(L.gx + (size_t) i * C); tc_put<C>(tc, k, TC_GX, v);
+    v.load(L.gy + (size_t) i * C); tc_put<C>(tc, k, TC_GY, v);
+  }
+}
+
 struct Sel {            // radix-select bookkeeping of one linearize (global, written by CTA 0)
   unsigned n;           // number of valid residuals (C * valid points)
   unsigned b1[2], rem1[2];
@@ -128,19 +165,22 @@ struct Bracket {       // median bracket carried from the previous GN iteration 
 
 template <int C>
 __device__ __forceinline__ void phase_residuals(const LevelTemplate& L, const LevelImage& I, const float* P, const Work& W,
-                                                unsigned* __restrict__ hist1, bool do_hist, Bracket br, LinShared& sh, int block, int nblocks) {
+                                                unsigned* __restrict__ hist1, bool do_hist, Bracket br, const TplCache& tc,
+                                                const TemplateMeta& m, unsigned* scratch, LinShared& sh, int block, int nblocks) {
   const int tid = threadIdx.x;
   if (do_hist) { for (int b = tid; b < kHist1Bins; b += kLinThreads) sh.hist[b] = 0; }
-  if (tid < 4) sh.found[4 + tid] = 0;        // CTA-level counters: [4] valid points, [5] below bracket
+  if (tid < 4) sh.found[4 + tid] = 0;        // CTA-level counters: [4] valid points, [5] below bracket, [6] candidates of this CTA
+  float* cta_cand = reinterpret_cast<float*>(scratch);    // CTA-local candidate list (bracket on), flushed with ONE global atomic
   __syncthreads();
   unsigned cnt_valid = 0, cnt_below = 0;
   const double P00 = P[0], P10 = P[1], P20 = P[2], P01 = P[3], P11 = P[4], P21 = P[5],
                P02 = P[6], P12 = P[7], P22 = P[8], P03 = P[9], P13 = P[10], P23 = P[11];
   const int cols = I.cols, rows = I.rows;
-  const int n_pts = L.meta->n;
+  const int n_pts = m.n;
   int my_first = 0x7fffffff;
-  for (int i = first_point(block, nblocks); i < n_pts; i += nblocks * kLinThreads) {
-    const float4 X = __ldg(L.pts + i);
+  int k = 0;
+  for (int i = first_point(block, nblocks); i < n_pts; i += nblocks * kLinThreads, ++k) {
+    const float4 X = tc.K ? tc.pts[k * kLinThreads + tid] : __ldg(L.pts + i);
     const double X0 = X.x, X1 = X.y, X2 = X.z, X3 = X.w;
     const double h0 = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(P00, X0), __dmul_rn(P01, X1)), __dmul_rn(P02, X2)), __dmul_rn(P03, X3));
     const double h1 = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(P10, X0), __dmul_rn(P11, X1)), __dmul_rn(P12, X2)), __dmul_rn(P13, X3));
@@ -161,7 +201,7 @@ __device__ __forceinline__ void phase_residuals(const LevelTemplate& L, const Le
       const float* tap = I.desc + ((size_t) yi * cols + xi) * C;
       VecC<C> t00, t01, t10, t11, i0;
       t00.load(tap); t01.load(tap + C); t10.load(tap + (size_t) cols * C); t11.load(tap + (size_t) cols * C + C);
-      i0.load(L.i0 + (size_t) i * C);
+      if (tc.K) tc_get<C>(tc, k, TC_I0, i0); else i0.load(L.i0 + (size_t) i * C);
 #pragma unroll
       for (int c = 0; c < C; ++c) {
         const double top = __dadd_rn(__dmul_rn((double) t00.v[c], wx), __dmul_rn((double) t01.v[c], xf));
@@ -180,8 +220,8 @@ __device__ __forceinline__ void phase_residuals(const LevelTemplate& L, const Le
             const float a = fabsf(r.v[c]);
             cnt_below += (a < br.lo) ? 1u : 0u;
             if (a >= br.lo && a <= br.hi) {
-              const unsigned slot = atomicAdd(hist1 + kHistBins + 3, 1u);
-              if (slot < (unsigned) kCandCap) W.cand[slot] = a;
+              const unsigned slot = atomicAdd(&sh.found[6], 1u);        // shared-memory append; overflow is only counted
+              if (slot < (unsigned) kCtaCandCap) cta_cand[slot] = a;
             }
           }
         }
@@ -192,6 +232,7 @@ __device__ __forceinline__ void phase_residuals(const LevelTemplate& L, const Le
     }
     r.store(W.res + (size_t) i * C);
     W.valid[i] = ok ? 1 : 0;
+    if (tc.K) { tc_put<C>(tc, k, TC_R, r); tc.valid[k * kLinThreads + tid] = ok ? 1 : 0; }
   }
   if (do_hist) {
     __syncthreads();
@@ -210,6 +251,15 @@ __device__ __forceinline__ void phase_residuals(const LevelTemplate& L, const Le
     if (tid == 0) {
       if (sh.found[4]) atomicAdd(hist1 + kHistBins + 1, sh.found[4]);
       if (sh.found[5]) atomicAdd(hist1 + kHistBins + 2, sh.found[5]);
+      // reserve this CTA's range in the global candidate buffer; a CTA-local overflow poisons the global count so that
+      // the select falls back to the radix path (correctness never depends on the bracket)
+      const unsigned nc = sh.found[6];
+      sh.found[7] = nc ? atomicAdd(hist1 + kHistBins + 3, nc > (unsigned) kCtaCandCap ? (unsigned) (2 * kCandCap) : nc) : 0u;
+    }
+    if (br.on) {
+      __syncthreads();
+      const unsigned nc = min(sh.found[6], (unsigned) kCtaCandCap), base = sh.found[7];
+      for (unsigned j = tid; j < nc; j += kLinThreads) if (base + j < (unsigned) kCandCap) W.cand[base + j] = cta_cand[j];
     }
   }
 }
@@ -220,7 +270,7 @@ __device__ __forceinline__ void phase_residuals(const LevelTemplate& L, const Le
 // ---------------------------------------------------------------------------------------------
 template <int C, int LEVEL>
 __device__ __forceinline__ void phase_select(const LevelTemplate& L, const Work& W, unsigned* __restrict__ hset, Sel* __restrict__ sel,
-                                             LinShared& sh, int block, int nblocks) {
+                                             const TplCache& tc, const TemplateMeta& m, LinShared& sh, int block, int nblocks) {
   const int tid = threadIdx.x;
   unsigned* hist1 = hset;
   unsigned* hist2 = hset + kHist1Bins;               // [2][kHist2Bins]
@@ -250,10 +300,12 @@ __device__ __forceinline__ void phase_select(const LevelTemplate& L, const Work&
   __syncthreads();
   constexpr int SHIFT_MATCH = (LEVEL == 2) ? 20 : 9;
   constexpr int SHIFT_BIN = (LEVEL == 2) ? 9 : 0;
-  const int n_pts = L.meta->n;
-  for (int i = first_point(block, nblocks); i < n_pts; i += nblocks * kLinThreads) {
-    if (!W.valid[i]) continue;
-    VecC<C> r; r.load_plain(W.res + (size_t) i * C);
+  const int n_pts = m.n;
+  int k = 0;
+  for (int i = first_point(block, nblocks); i < n_pts; i += nblocks * kLinThreads, ++k) {
+    if (!(tc.K ? tc.valid[k * kLinThreads + tid] : W.valid[i])) continue;
+    VecC<C> r;
+    if (tc.K) tc_get<C>(tc, k, TC_R, r); else r.load_plain(W.res + (size_t) i * C);
 #pragma unroll
     for (int c = 0; c < C; ++c) {
       const unsigned bits = __float_as_uint(fabsf(r.v[c]));
@@ -306,23 +358,29 @@ __device__ __forceinline__ float finish_scale(const Work& W, const unsigned* __r
 // are found by rank counting among <= kCandCap candidates in shared memory -- no further pass over the residuals,
 // no further grid sync.  Returns false when the bracket missed (caller falls back to the 3-level radix select).
 template <int C>
-__device__ __forceinline__ bool bracket_select(const Work& W, const unsigned* __restrict__ hset, LinShared& sh, float bl, float bh,
-                                               unsigned& n_out, unsigned& ncand_out, float& lo_out, float& hi_out) {
+__device__ __forceinline__ bool bracket_select(const Work& W, const unsigned* __restrict__ hset, LinShared& sh, unsigned* scratch,
+                                               float bl, float bh, unsigned& n_out, unsigned& ncand_out, float& lo_out, float& hi_out) {
   const int tid = threadIdx.x;
-  const unsigned nv = hset[kHistBins + 1], below = hset[kHistBins + 2], ncand = hset[kHistBins + 3];
+  // one L2 round trip: the three counters and (speculatively) the first 4 candidates of every thread are requested together
+  float pre[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) pre[q] = __ldcg(W.cand + tid + q * kLinThreads);
+  const unsigned nv = __ldcg(hset + kHistBins + 1), below = __ldcg(hset + kHistBins + 2), ncand = __ldcg(hset + kHistBins + 3);
   const unsigned n = nv * (unsigned) C;
   n_out = n; ncand_out = ncand;
   if (n < 3) return false;
   const unsigned t_hi = n / 2, t_lo = (n % 2 == 0) ? t_hi - 1 : t_hi;
   if (ncand > (unsigned) kCandCap || below > t_lo || t_hi >= below + ncand) return false;
   const unsigned ra = t_lo - below, rb = t_hi - below;
-  // shared-memory carve-up of the 16 KB histogram area
-  float* cand = reinterpret_cast<float*>(sh.hist);                 // [kCandCap]
-  unsigned* bins = sh.hist + kCandCap;                             // [1024]
-  float* list = reinterpret_cast<float*>(sh.hist + kCandCap + 1024);   // [256]
+  // carve-up of the dynamic-shared-memory scratch area (kScratchBytes)
+  float* cand = reinterpret_cast<float*>(scratch);                 // [kCandCap]
+  unsigned* bins = scratch + kCandCap;                             // [1024]
+  float* list = reinterpret_cast<float*>(scratch + kCandCap + 1024);   // [256]
   constexpr int kList = 256, kBins = 1024;
   __syncthreads();
-  for (unsigned j = tid; j < ncand; j += kLinThreads) cand[j] = W.cand[j];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) { const unsigned j = tid + q * kLinThreads; if (j < ncand) cand[j] = pre[q]; }
+  for (unsigned j = tid + 4 * kLinThreads; j < ncand; j += kLinThreads) cand[j] = __ldcg(W.cand + j);
   if (tid < 4) sh.found[4 + tid] = 0;       // [4] list length, [6] lo bits, [7] hi bits
   __syncthreads();
   if (ncand <= 128u) {
@@ -390,21 +448,21 @@ __device__ __forceinline__ float robust_weight(int loss, float r, float sigma_in
 // ---------------------------------------------------------------------------------------------
 template <int C>
 __device__ __forceinline__ void phase_reduce(const LevelTemplate& L, const Work& W, float sigma, int loss, float good_thr,
-                                             LinShared& sh, int block, int nblocks, bool fence = true) {
+                                             const TplCache& tc, const TemplateMeta& m, LinShared& sh, int block, int nblocks, bool fence = true) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   float acc[30];
 #pragma unroll
   for (int k = 0; k < 30; ++k) acc[k] = 0.0f;
   const float sigma_inv = __fdiv_rn(1.0f, sigma);
-  const TemplateMeta m = *L.meta;
   const float is = 1.0f / m.s;
   const float w_invalid_good = (1.0f > good_thr) ? (float) C : 0.0f;   // invalid entries carry weight 1 in getWeights() (Q6)
-  for (int i = first_point(block, nblocks); i < m.n; i += nblocks * kLinThreads) {
-    if (!W.valid[i]) { acc[28] += w_invalid_good; continue; }
-    const float4 X = __ldg(L.pts + i);
+  int ks = 0;
+  for (int i = first_point(block, nblocks); i < m.n; i += nblocks * kLinThreads, ++ks) {
+    if (!(tc.K ? tc.valid[ks * kLinThreads + tid] : W.valid[i])) { acc[28] += w_invalid_good; continue; }
+    const float4 X = tc.K ? tc.pts[ks * kLinThreads + tid] : __ldg(L.pts + i);
     VecC<C> r, gx, gy;
-    r.load_plain(W.res + (size_t) i * C);
-    gx.load(L.gx + (size_t) i * C); gy.load(L.gy + (size_t) i * C);
+    if (tc.K) { tc_get<C>(tc, ks, TC_R, r); tc_get<C>(tc, ks, TC_GX, gx); tc_get<C>(tc, ks, TC_GY, gy); }
+    else { r.load_plain(W.res + (size_t) i * C); gx.load(L.gx + (size_t) i * C); gy.load(L.gy + (size_t) i * C); }
     float sxx = 0, sxy = 0, syy = 0, bx = 0, by = 0, e = 0, good = 0;
 #pragma unroll
     for (int c = 0; c < C; ++c) {
@@ -518,13 +576,13 @@ struct LinArgs {
 template <int C> __global__ void __launch_bounds__(kLinThreads, 1) k_residuals(LinArgs a) {
   __shared__ LinShared sh;
   const bool do_hist = (a.loss != 0x12) && (a.work.scale->delta > 1e-6f);
-  phase_residuals<C>(a.tmpl, a.img, a.P, a.work, a.hset, do_hist, Bracket{false, 0.0f, 0.0f}, sh, blockIdx.x, gridDim.x);
+  phase_residuals<C>(a.tmpl, a.img, a.P, a.work, a.hset, do_hist, Bracket{false, 0.0f, 0.0f}, TplCache{nullptr, nullptr, nullptr, 0}, *a.tmpl.meta, nullptr, sh, blockIdx.x, gridDim.x);
 }
 template <int C, int LEVEL> __global__ void __launch_bounds__(kLinThreads, 1) k_select(LinArgs a) {
   __shared__ LinShared sh;
   const bool do_hist = (a.loss != 0x12) && (a.work.scale->delta > 1e-6f);
   if (!do_hist) return;
-  phase_select<C, LEVEL>(a.tmpl, a.work, a.hset, a.sel, sh, blockIdx.x, gridDim.x);
+  phase_select<C, LEVEL>(a.tmpl, a.work, a.hset, a.sel, TplCache{nullptr, nullptr, nullptr, 0}, *a.tmpl.meta, sh, blockIdx.x, gridDim.x);
 }
 // point-sharded mode: the last CTA leaves this rank's 30 fp64 sums in a.sums (all-reduced by the host over NCCL),
 // k_finalize_sums then builds the LinOut every rank sees identically.
@@ -534,7 +592,7 @@ template <int C> __global__ void __launch_bounds__(kLinThreads, 1) k_reduce_shar
   const bool do_hist = (a.loss != 0x12) && (a.work.scale->delta > 1e-6f);
   float sigma = a.work.scale->scale;
   if (do_hist) sigma = finish_scale<C>(a.work, a.hset, a.sel, sh);
-  phase_reduce<C>(a.tmpl, a.work, sigma, a.loss, a.good_thr, sh, blockIdx.x, gridDim.x);
+  phase_reduce<C>(a.tmpl, a.work, sigma, a.loss, a.good_thr, TplCache{nullptr, nullptr, nullptr, 0}, *a.tmpl.meta, sh, blockIdx.x, gridDim.x);
   __syncthreads();
   if (threadIdx.x == 0) s_last = (atomicAdd(a.work.ticket, 1u) == gridDim.x - 1);
   __syncthreads();
@@ -568,7 +626,7 @@ template <int C> __global__ void __launch_bounds__(kLinThreads, 1) k_reduce(LinA
   const bool do_hist = (a.loss != 0x12) && (a.work.scale->delta > 1e-6f);
   float sigma = a.work.scale->scale;
   if (do_hist) sigma = finish_scale<C>(a.work, a.hset, a.sel, sh);
-  phase_reduce<C>(a.tmpl, a.work, sigma, a.loss, a.good_thr, sh, blockIdx.x, gridDim.x);
+  phase_reduce<C>(a.tmpl, a.work, sigma, a.loss, a.good_thr, TplCache{nullptr, nullptr, nullptr, 0}, *a.tmpl.meta, sh, blockIdx.x, gridDim.x);
   __syncthreads();
   if (threadIdx.x == 0) s_last = (atomicAdd(a.work.ticket, 1u) == gridDim.x - 1);
   __syncthreads();
@@ -607,6 +665,9 @@ __global__ void __launch_bounds__(256) k_export_weights(const float* __restrict_
   do { if (a.prof && blockIdx.x == 0 && threadIdx.x == 0) { const long long _t = clock64(); a.prof[slot] += _t - ss.t_last; ss.t_last = _t; } } while (0)
 enum { PROF_P1 = 0, PROF_SYNC1, PROF_P2, PROF_SYNC2, PROF_P3, PROF_SYNC3, PROF_SCALE, PROF_P4, PROF_SYNC4, PROF_FINAL, PROF_SOLVE, PROF_OTHER, PROF_COUNT };
 
+// the damped fp64 retry of solve6() is rare: keep it out of line so that it does not bloat the hot loop
+__device__ __noinline__ bool solve6_fallback(const float* H, const float* G, float* dp) { return solve6(H, G, dp); }
+
 struct SolveShared {
   long long t_last;
   LinOut lin;
@@ -623,7 +684,8 @@ struct SolveShared {
 
 template <int C>
 __device__ __forceinline__ void device_linearize(const SolveArgs& a, int lvl, const M44& T, SolveShared& ss, LinShared& sh,
-                                                 cg::grid_group& grid, int& parity, Sel* sel) {
+                                                 const TplCache& tc, const TemplateMeta& meta, unsigned* scratch, cg::grid_group& grid,
+                                                 int& parity, Sel* sel) {
   const LevelTemplate& L = a.tmpl[lvl];
   const LevelImage& I = a.img[lvl];
   const int nb = gridDim.x, blk = blockIdx.x, tid = threadIdx.x;
@@ -636,7 +698,7 @@ __device__ __forceinline__ void device_linearize(const SolveArgs& a, int lvl, co
   Bracket br;
   br.on = do_hist && ss.br_on;
   br.lo = ss.br_lo * (1.0f - ss.br_rel); br.hi = ss.br_hi * (1.0f + ss.br_rel);
-  phase_residuals<C>(L, I, ss.P, a.work, hset, do_hist, br, sh, blk, nb);
+  phase_residuals<C>(L, I, ss.P, a.work, hset, do_hist, br, tc, meta, scratch, sh, blk, nb);
   BP_PROF(PROF_P1);
   float sigma = ss.scale;
   if (do_hist) {
@@ -644,17 +706,17 @@ __device__ __forceinline__ void device_linearize(const SolveArgs& a, int lvl, co
     BP_PROF(PROF_SYNC1);
     unsigned n = 0, ncand = 0; float lo = 0.0f, hi = 0.0f;
     bool hit = false;
-    if (br.on) hit = bracket_select<C>(a.work, hset, sh, br.lo, br.hi, n, ncand, lo, hi);
+    if (br.on) hit = bracket_select<C>(a.work, hset, sh, scratch, br.lo, br.hi, n, ncand, lo, hi);
     if (hit) {
       const float med = (n % 2 != 0) ? hi : (float) ((double) __fadd_rn(lo, hi) / 2.0);
       sigma = scale_from_median(n, med);
       BP_PROF(PROF_SCALE);
     } else {
-      phase_select<C, 2>(L, a.work, hset, sel, sh, blk, nb);
+      phase_select<C, 2>(L, a.work, hset, sel, tc, meta, sh, blk, nb);
       BP_PROF(PROF_P2);
       grid.sync();
       BP_PROF(PROF_SYNC2);
-      phase_select<C, 3>(L, a.work, hset, sel, sh, blk, nb);
+      phase_select<C, 3>(L, a.work, hset, sel, tc, meta, sh, blk, nb);
       BP_PROF(PROF_P3);
       grid.sync();
       BP_PROF(PROF_SYNC3);
@@ -679,7 +741,7 @@ __device__ __forceinline__ void device_linearize(const SolveArgs& a, int lvl, co
     }
     __syncthreads();
   }   // else: P4 reads only what the SAME thread wrote in P1, no grid-wide dependency
-  phase_reduce<C>(L, a.work, sigma, a.sp.loss, a.sp.good_threshold, sh, blk, nb, false);
+  phase_reduce<C>(L, a.work, sigma, a.sp.loss, a.sp.good_threshold, tc, meta, sh, blk, nb, false);
   // zero the histogram set of the NEXT linearize (nobody touches it during this phase)
   for (int b = blk * kLinThreads + tid; b < kHistWords; b += nb * kLinThreads) hother[b] = 0;
   BP_PROF(PROF_P4);
@@ -693,9 +755,17 @@ __device__ __forceinline__ void device_linearize(const SolveArgs& a, int lvl, co
 }
 
 template <int C>
-__global__ void __launch_bounds__(kLinThreads, 1) k_estimate_pose(SolveArgs a, Sel* sel, int first_parity) {
+__global__ void __launch_bounds__(kLinThreads, 1) k_estimate_pose(const __grid_constant__ SolveArgs a, Sel* sel, int first_parity, int cache_slots) {
   __shared__ LinShared sh;
   __shared__ SolveShared ss;
+  extern __shared__ __align__(16) unsigned char dyn_smem[];
+  // dynamic shared memory: [candidate scratch kScratchBytes][template cache cache_slots * bytes_per_slot]
+  unsigned* scratch = reinterpret_cast<unsigned*>(dyn_smem);
+  TplCache tc_full;
+  tc_full.pts = reinterpret_cast<float4*>(dyn_smem + kScratchBytes);
+  tc_full.f = reinterpret_cast<float*>(dyn_smem + kScratchBytes + (size_t) cache_slots * kLinThreads * 16);
+  tc_full.valid = dyn_smem + kScratchBytes + (size_t) cache_slots * kLinThreads * (16 + 16 * C);
+  tc_full.K = cache_slots;
   cg::grid_group grid = cg::this_grid();
   const int tid = threadIdx.x;
   int parity = first_parity;
@@ -712,19 +782,23 @@ __global__ void __launch_bounds__(kLinThreads, 1) k_estimate_pose(SolveArgs a, S
     float f_prev = 0.0f, g_tol = 0.0f, dp_prev = 0.0f, f_norm, g_norm;
     bool solver_error = false, early = false;
     const TemplateMeta meta = *L.meta;
+    // template cache for this level: on when every thread's points fit into the resident slots
+    TplCache tc = tc_full;
+    if ((meta.n + (int) gridDim.x * kLinThreads - 1) / ((int) gridDim.x * kLinThreads) > cache_slots) tc.K = 0;
+    if (tc.K) tc_fill<C>(tc, L, meta.n, blockIdx.x, gridDim.x);
     if (meta.n_total == 0) {                              // "you should call setData before calling computeResiduals" (template_data.cc:177)
       if (blockIdx.x == 0 && tid == 0) { LevelStats st; st.num_iterations = 0; st.final_error = -1.0f; st.first_order_optimality = -1.0f; st.status = -3; st.num_evals = 0; a.stats[lvl] = st; }
       continue;
     }
 
-    device_linearize<C>(a, lvl, ss.T, ss, sh, grid, parity, sel); ++n_evals;
+    device_linearize<C>(a, lvl, ss.T, ss, sh, tc, meta, scratch, grid, parity, sel); ++n_evals;
     f_norm = ss.lin.f_norm;
     g_norm = 0.0f; for (int k = 0; k < 6; ++k) g_norm = fmaxf(g_norm, fabsf(ss.lin.G[k]));
     g_tol = a.sp.gradient_tolerance * fmaxf(g_norm, sqrt_eps);
     if (g_norm < g_tol) {                                                      // :346-357
       status = 0x32; it = 1; early = true;
     } else {
-      if (tid == 0) { bool ok = solve6_fp32_registers(ss.lin.H, ss.lin.G, ss.dp); if (!ok) ok = solve6(ss.lin.H, ss.lin.G, ss.dp); ss.lin.pad[0] = ok ? 1 : 0; }
+      if (tid == 0) { bool ok = solve6_fp32_registers(ss.lin.H, ss.lin.G, ss.dp); if (!ok) ok = solve6_fallback(ss.lin.H, ss.lin.G, ss.dp); ss.lin.pad[0] = ok ? 1 : 0; }
       __syncthreads();
       if (!ss.lin.pad[0]) {                                                    // :359-365
         status = 0x34; solver_error = true; early = true; it = 0; g_norm = 0.0f;
@@ -745,9 +819,9 @@ __global__ void __launch_bounds__(kLinThreads, 1) k_estimate_pose(SolveArgs a, S
         else if (g_norm < g_tol) { status = 0x32; conv = true; }
         dp_prev = dpn; f_prev = f_norm;
         if (!conv) {                                                           // runIteration (pose_estimator_gn.h:83-100)
-          device_linearize<C>(a, lvl, ss.Td, ss, sh, grid, parity, sel); ++n_evals;
+          device_linearize<C>(a, lvl, ss.Td, ss, sh, tc, meta, scratch, grid, parity, sel); ++n_evals;
           f_norm = ss.lin.f_norm;
-          if (tid == 0) { bool ok = solve6_fp32_registers(ss.lin.H, ss.lin.G, ss.dp); if (!ok) ok = solve6(ss.lin.H, ss.lin.G, ss.dp); ss.lin.pad[0] = ok ? 1 : 0; }
+          if (tid == 0) { bool ok = solve6_fp32_registers(ss.lin.H, ss.lin.G, ss.dp); if (!ok) ok = solve6_fallback(ss.lin.H, ss.lin.G, ss.dp); ss.lin.pad[0] = ok ? 1 : 0; }
           __syncthreads();
           if (!ss.lin.pad[0]) { status = 0x34; solver_error = true; break; }
         }
