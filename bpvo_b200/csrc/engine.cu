@@ -184,8 +184,8 @@ int bpvo_b200_create(bpvo_b200_ctx** out, const float K[9], float baseline, int 
   CUDA_TRY(cudaMalloc(&c->d_T, sizeof(M44)));
   CUDA_TRY(cudaMalloc(&c->d_stats, kMaxLevels * sizeof(LevelStats)));
   CUDA_TRY(cudaMalloc(&c->d_evals, sizeof(int)));
-  CUDA_TRY(cudaMalloc(&c->d_prof, 16 * sizeof(long long)));
-  CUDA_TRY(cudaMemsetAsync(c->d_prof, 0, 16 * sizeof(long long), c->stream));
+  CUDA_TRY(cudaMalloc(&c->d_prof, 32 * sizeof(long long)));
+  CUDA_TRY(cudaMemsetAsync(c->d_prof, 0, 32 * sizeof(long long), c->stream));
   CUDA_TRY(cudaHostAlloc(&c->h_mail, sizeof(Mailbox), cudaHostAllocDefault));
   memset(c->h_mail, 0, sizeof(Mailbox));
   CUDA_TRY(cudaHostAlloc(&c->stage_img, (size_t) rows * cols, cudaHostAllocDefault));
@@ -234,12 +234,12 @@ int bpvo_b200_last_level_evals(bpvo_b200_ctx* c, int* evals) {
   for (int l = 0; l < c->L; ++l) evals[l] = c->level_evals[l];
   return BPVO_B200_OK;
 }
-int bpvo_b200_get_phase_cycles(bpvo_b200_ctx* c, long long cycles[16], int reset) {
+int bpvo_b200_get_phase_cycles(bpvo_b200_ctx* c, long long cycles[32], int reset) {
   if (!c || !cycles) return bp_fail(BPVO_B200_ERR_INVALID_ARG, "null argument");
   CUDA_TRY(cudaSetDevice(c->p.device_id));
   CUDA_TRY(cudaStreamSynchronize(c->stream));
-  CUDA_TRY(cudaMemcpy(cycles, c->d_prof, 16 * sizeof(long long), cudaMemcpyDeviceToHost));
-  if (reset) CUDA_TRY(cudaMemset(c->d_prof, 0, 16 * sizeof(long long)));
+  CUDA_TRY(cudaMemcpy(cycles, c->d_prof, 32 * sizeof(long long), cudaMemcpyDeviceToHost));
+  if (reset) CUDA_TRY(cudaMemset(c->d_prof, 0, 32 * sizeof(long long)));
   return BPVO_B200_OK;
 }
 int bpvo_b200_set_profiling(bpvo_b200_ctx* c, int enable) { if (!c) return bp_fail(BPVO_B200_ERR_INVALID_ARG, "null ctx"); c->profiling = enable != 0; return BPVO_B200_OK; }

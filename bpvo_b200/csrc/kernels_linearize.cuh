@@ -97,6 +97,19 @@ template <int C> __device__ __forceinline__ void tc_fill(const TplCache& tc, con
   }
 }
 
+// fine-grained in-kernel profile (debug aid, compile with -DBP_FINE_PROFILE): CTA 0 / thread 0 accumulates the cycles
+// between consecutive marks into prof[16 + ...]
+#ifdef BP_FINE_PROFILE
+__device__ long long* g_fine_prof = nullptr;
+__device__ long long g_fine_last = 0;
+#define BP_FINE(slot)                                                                                          \
+  do { if (g_fine_prof && blockIdx.x == 0 && threadIdx.x == 0) { const long long _t = clock64(); g_fine_prof[slot] += _t - g_fine_last; g_fine_last = _t; } } while (0)
+#define BP_FINE_INIT(ptr) do { if (blockIdx.x == 0) { g_fine_prof = (ptr); g_fine_last = clock64(); } } while (0)
+#else
+#define BP_FINE(slot) do { } while (0)
+#define BP_FINE_INIT(ptr) do { } while (0)
+#endif
+
 struct Sel {            // radix-select bookkeeping of one linearize (global, written by CTA 0)
   unsigned n;           // number of valid residuals (C * valid points)
   unsigned b1[2], rem1[2];
@@ -172,6 +185,7 @@ __device__ __forceinline__ void phase_residuals(const LevelTemplate& L, const Le
   if (tid < 4) sh.found[4 + tid] = 0;        // CTA-level counters: [4] valid points, [5] below bracket, [6] candidates of this CTA
   float* cta_cand = reinterpret_cast<float*>(scratch);    // CTA-local candidate list (bracket on), flushed with ONE global atomic
   __syncthreads();
+  BP_FINE(16);
   unsigned cnt_valid = 0, cnt_below = 0;
   const double P00 = P[0], P10 = P[1], P20 = P[2], P01 = P[3], P11 = P[4], P21 = P[5],
                P02 = P[6], P12 = P[7], P22 = P[8], P03 = P[9], P13 = P[10], P23 = P[11];
@@ -234,8 +248,10 @@ __device__ __forceinline__ void phase_residuals(const LevelTemplate& L, const Le
     W.valid[i] = ok ? 1 : 0;
     if (tc.K) { tc_put<C>(tc, k, TC_R, r); tc.valid[k * kLinThreads + tid] = ok ? 1 : 0; }
   }
+  BP_FINE(17);
   if (do_hist) {
     __syncthreads();
+    BP_FINE(18);
     for (int b = tid; b < kHist1Bins; b += kLinThreads) { const unsigned v = sh.hist[b]; if (v) atomicAdd(hist1 + b, v); }
     for (int o = 16; o > 0; o >>= 1) {
       my_first = min(my_first, __shfl_xor_sync(0xffffffffu, my_first, o));
@@ -262,6 +278,7 @@ __device__ __forceinline__ void phase_residuals(const LevelTemplate& L, const Le
       for (unsigned j = tid; j < nc; j += kLinThreads) if (base + j < (unsigned) kCandCap) W.cand[base + j] = cta_cand[j];
     }
   }
+  BP_FINE(19);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -496,7 +513,9 @@ __device__ __forceinline__ void phase_reduce(const LevelTemplate& L, const Work&
   // warp reduction of the 30 scalars as a transposing butterfly: 16+8+4+2+1 = 31 shuffles instead of 30 x 5;
   // afterwards lane l holds the warp total of scalar l.  Warps that own no point skip it altogether.
   const int n_active_warps = min(kLinThreads / 32, max(0, ((m.n + 31) / 32 - block + nblocks - 1) / nblocks));
+  BP_FINE(20);
   __syncthreads();
+  BP_FINE(21);
   if (warp < n_active_warps) {
     float v[32];
 #pragma unroll
@@ -514,13 +533,16 @@ __device__ __forceinline__ void phase_reduce(const LevelTemplate& L, const Work&
     }
     sh.red[warp][lane] = (double) v[0];
   }
+  BP_FINE(22);
   __syncthreads();
+  BP_FINE(23);
   if (tid < 30) {
     double v = 0.0;
     for (int w = 0; w < n_active_warps; ++w) v += sh.red[w][tid];
     W.partials[(size_t) block * kPartialStride + tid] = v;
     if (fence) __threadfence();     // last-CTA pattern of the host-driven path; the persistent path relies on grid.sync()
   }
+  BP_FINE(24);
 }
 
 // fixed-order sum of the CTA partials -> LinOut (whole CTA participates; result valid in `out` for thread 0
@@ -770,7 +792,7 @@ __global__ void __launch_bounds__(kLinThreads, 1) k_estimate_pose(const __grid_c
   const int tid = threadIdx.x;
   int parity = first_parity;
   int total_evals = 0;
-  if (tid == 0) { ss.T = a.T_init; ss.t_last = clock64(); }
+  if (tid == 0) { ss.T = a.T_init; ss.t_last = clock64(); BP_FINE_INIT(a.prof); }
   __syncthreads();
   const float sqrt_eps = sqrtf(FLT_EPSILON);
   for (int lvl = a.sp.num_levels - 1; lvl >= a.sp.max_test_level; --lvl) {
@@ -821,12 +843,17 @@ __global__ void __launch_bounds__(kLinThreads, 1) k_estimate_pose(const __grid_c
         if (!conv) {                                                           // runIteration (pose_estimator_gn.h:83-100)
           device_linearize<C>(a, lvl, ss.Td, ss, sh, tc, meta, scratch, grid, parity, sel); ++n_evals;
           f_norm = ss.lin.f_norm;
+          BP_FINE(25);
           if (tid == 0) { bool ok = solve6_fp32_registers(ss.lin.H, ss.lin.G, ss.dp); if (!ok) ok = solve6_fallback(ss.lin.H, ss.lin.G, ss.dp); ss.lin.pad[0] = ok ? 1 : 0; }
+          BP_FINE(26);
           __syncthreads();
+          BP_FINE(27);
           if (!ss.lin.pad[0]) { status = 0x34; solver_error = true; break; }
         }
         if (tid == 0) apply_update(ss.Td, ss.dp, meta.s, meta.c1, meta.c2, meta.c3);   // also when converged (Q1)
+        BP_FINE(28);
         __syncthreads();
+        BP_FINE(29);
         BP_PROF(PROF_SOLVE);
       } while (it++ < a.sp.max_iterations && !conv && n_evals < a.sp.max_fun_evals);
       if (!solver_error && tid == 0) ss.T = ss.Td;                             // :395-396

@@ -55,6 +55,7 @@ def main():
         tot_ev += evals
     cyc = ctx.phase_cycles()
     ms = ctx.counters()["ms_linearize"]
+    fine = cyc.pop("_fine")
     hits, ests = cyc.pop("_bracket_hits"), cyc.pop("_scale_estimates")
     out["bracket_hit_rate"] = hits / max(ests, 1)
     out["bracket_overflows"], out["bracket_misses"] = cyc.pop("_bracket_overflows"), cyc.pop("_bracket_misses")
@@ -63,6 +64,9 @@ def main():
                             "phase_share": {k: round(v / tot, 4) for k, v in cyc.items()},
                             "phase_us_per_eval": {k: round(1e3 * ms * (v / tot) / max(tot_ev, 1), 3) for k, v in cyc.items()},
                             "level_evals": ctx.last_level_evals()}
+    names = ["P1:zero+sync", "P1:loop", "P1:sync", "P1:flush", "P4:loop", "P4:sync", "P4:butterfly", "P4:sync2", "P4:cta-sum", "pre-solve", "LDLT", "sync", "update", "sync"]
+    fine_tot = float(sum(fine)) or 1.0
+    out["fine_cycles_share"] = {n: round(f / fine_tot, 4) for n, f in zip(names, fine)}
     print(json.dumps(out))
 
 
