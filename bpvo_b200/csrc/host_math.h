@@ -76,8 +76,10 @@ BP_HD M44 twist_to_matrix(const float p[6]) {
   M44 ret = identity44();
   const float theta = sqrtf(p[0]*p[0] + p[1]*p[1] + p[2]*p[2]);
   if (theta > 1e-8) {
-    const float a = (float) sin((double) theta);
-    const float b = (float) (1.0 - cos((double) theta));
+    // `T a = ::sin(theta)` with T = float resolves to the float overloads in a libstdc++ >= 6 build of the reference
+    // (checked against the reference's own code in oracle/_ref); `1.0 - ::cos(theta)` and `1.0 / theta` go through double
+    const float a = sinf(theta);
+    const float b = (float) (1.0 - (double) cosf(theta));
     const float t_i = (float) (1.0 / (double) theta);
     float S[3][3], S2[3][3];
     S[0][0] = 0.0f;           S[0][1] = t_i * (-p[2]);  S[0][2] = t_i * p[1];

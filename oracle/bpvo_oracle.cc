@@ -2,12 +2,11 @@
  * bpvo_oracle.cc -- dependency-free CPU restatement of halismai/bpvo's per-frame Gauss-Newton
  * dense-alignment path (reference @ 343d9da).  TEST INFRASTRUCTURE ONLY (see bpvo_oracle.h).
  *
- * "parity unpinned" by the reference's own tests: it ships no golden vectors for this path and cannot be
- * built as a whole in this image (Eigen/OpenCV/Boost absent).  What IS pinned:
- *   - census, saliency (incl. its bugs), IsLocalMax selection, median, Huber/Tukey weights, the scale estimator and
- *     the rank-1 linear-system builder: BIT-EXACT against the reference's own .cc files compiled from
- *     /root/reference against header stand-ins (oracle/_ref, tests/test_oracle_vs_reference.py);
- *   - cv::pyrDown / cv::GaussianBlur restatements against cv2 4.13 golden vectors (tests/golden/).
+ * PARITY STATUS: pinned bit-exact against the reference's own hot-path sources (23 .cc files compiled from
+ * /root/reference against the stand-in Eigen/OpenCV headers of oracle/refstub -> oracle/_ref/libbpvo_ref.so):
+ * every stage, PoseEstimatorGN::linearize, and whole VisualOdometry::addFrame streams incl. per-level iteration
+ * counts and key-frame decisions (tests/test_oracle_vs_reference.py).  cv::pyrDown / cv::GaussianBlur are
+ * pinned against cv2 4.13 golden vectors (tests/golden/).  The reference's own tests pin nothing here.
  *
  * Each function cites the reference file:line it follows (paths relative to /root/reference).
  * The reference's SSE/AVX intrinsics are kept where it has them; its documented quirks
@@ -122,9 +121,12 @@ static M44 twist_to_matrix(const float p[6]) {
   M44 ret = M44::Identity();
   const float theta = std::sqrt(p[0]*p[0] + p[1]*p[1] + p[2]*p[2]);
   if (theta > 1e-8) {
-    float a = (float) ::sin((double) theta);
-    float b = (float) (1.0 - ::cos((double) theta));
-    float t_i = (float) (1.0 / theta);
+    // `T a = ::sin(theta)` with T = float: with libstdc++ >= 6 and <math.h> included (OpenCV's types_c.h does) the global
+    // ::sin / ::cos resolve to the float overloads; `1.0 - ::cos(theta)` and `1.0 / theta` are evaluated in double and
+    // narrowed.  (A pre-GCC-6 toolchain would call the double versions: <= 1 ulp difference in a, b.)
+    float a = sinf(theta);
+    float b = (float) (1.0 - (double) cosf(theta));
+    float t_i = (float) (1.0 / (double) theta);
     // S = t_i * skew(w)
     float S[3][3] = {{0, -p[2]*t_i, p[1]*t_i}, {p[2]*t_i, 0, -p[0]*t_i}, {-p[1]*t_i, p[0]*t_i, 0}};
     S[0][1] = t_i * (-p[2]); S[0][2] = t_i * p[1]; S[1][0] = t_i * p[2];

@@ -6,10 +6,11 @@
  * cpu_baseline / --impl reference legs of bench.py may load it.  The product (bpvo_b200/) never
  * links, imports or calls anything in oracle/.
  *
- * PARITY STATUS: "parity unpinned" by the reference's own tests -- the reference has no golden
- * vectors / assertion tests for this path and cannot be compiled in this image
- * (needs Eigen + OpenCV 2.4 + Boost, none installed).  The third-party image ops it calls
- * (cv::pyrDown, cv::GaussianBlur) are pinned against cv2 4.13 golden vectors in tests/golden/.
+ * PARITY STATUS: pinned BIT-EXACT against the reference's own sources compiled from /root/reference
+ * against stand-in Eigen/OpenCV headers (oracle/_ref, tests/test_oracle_vs_reference.py): every stage
+ * up to whole addFrame streams (poses, per-level iteration counts, key-frame decisions).  The reference's
+ * own tests pin nothing on this path (no golden vectors / assertions); the third-party
+ * image ops (cv::pyrDown, cv::GaussianBlur) are pinned against cv2 4.13 golden vectors in tests/golden/.
  *
  * All matrices cross this API column-major (Eigen's default storage).
  * Every function cites the reference file:line it restates in bpvo_oracle.cc.

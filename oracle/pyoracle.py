@@ -401,7 +401,9 @@ def build_ref() -> str:
     so = os.path.join(_HERE, "_ref", "libbpvo_ref.so")
     ref_root = os.environ.get("BPVO_REFERENCE", "/root/reference")
     if os.path.isdir(os.path.join(ref_root, "bpvo")):
-        stale = (not os.path.exists(so)) or os.path.getmtime(so) < os.path.getmtime(os.path.join(_HERE, "ref_shim.cc"))
+        deps = [os.path.join(_HERE, f) for f in ("ref_shim.cc", "ref_other_descriptors.cc", "bpvo_oracle.h", os.path.join("refstub", "cv_stub_impl.cc"),
+                                                 os.path.join("refstub", "Eigen", "Core"), os.path.join("refstub", "opencv2", "core", "core.hpp"))]
+        stale = (not os.path.exists(so)) or os.path.getmtime(so) < max(os.path.getmtime(d) for d in deps)
         if stale:
             subprocess.run(["make", "-C", _HERE, "-s", "ref", f"REF={ref_root}"], check=True)
     return so if os.path.exists(so) else ""
@@ -427,9 +429,169 @@ def ref_lib():
         "ref_scale_reset": (None, [C.c_void_p]),
         "ref_scale_estimate": (C.c_float, [C.c_void_p, fp, u16p, C.c_size_t]),
         "ref_linear_system": (C.c_float, [fp, fp, fp, u16p, C.c_size_t, fp, fp]),
+        "ref_last_error": (C.c_char_p, []),
+        "ref_set_num_threads": (None, [C.c_int]),
+        "ref_get_num_threads": (C.c_int, []),
+        "ref_frame_create": (C.c_void_p, [fp, C.c_float, C.c_int, C.c_int, C.POINTER(OrcParams)]),
+        "ref_frame_destroy": (None, [C.c_void_p]),
+        "ref_frame_set_data": (C.c_int, [C.c_void_p, u8p, fp]),
+        "ref_frame_set_template": (C.c_int, [C.c_void_p]),
+        "ref_frame_num_points": (C.c_int, [C.c_void_p, C.c_int]),
+        "ref_frame_level_size": (None, [C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+        "ref_frame_descriptor": (C.c_int, [C.c_void_p, C.c_int, fp]),
+        "ref_frame_points": (None, [C.c_void_p, C.c_int, fp]),
+        "ref_frame_pixels": (None, [C.c_void_p, C.c_int, fp]),
+        "ref_frame_jacobians": (None, [C.c_void_p, C.c_int, fp]),
+        "ref_frame_num_pixels": (C.c_int, [C.c_void_p, C.c_int]),
+        "ref_estimator_create": (C.c_void_p, [C.POINTER(OrcParams)]),
+        "ref_estimator_destroy": (None, [C.c_void_p]),
+        "ref_linearize": (C.c_float, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, fp, C.c_int, fp, fp]),
+        "ref_estimator_num_residuals": (C.c_size_t, [C.c_void_p]),
+        "ref_estimator_vectors": (None, [C.c_void_p, fp, fp, u16p]),
+        "ref_run_level": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, fp, C.POINTER(OrcStats)]),
+        "ref_vo_create": (C.c_void_p, [fp, C.c_float, C.c_int, C.c_int, C.POINTER(OrcParams)]),
+        "ref_vo_destroy": (None, [C.c_void_p]),
+        "ref_vo_add_frame": (C.c_int, [C.c_void_p, u8p, fp, C.POINTER(OrcResult)]),
+        "ref_vo_num_points_at_level": (C.c_int, [C.c_void_p, C.c_int]),
+        "ref_vo_trajectory": (C.c_int, [C.c_void_p, fp, C.c_int]),
+        "ref_vo_point_cloud": (C.c_int, [C.c_void_p, fp, fp, u8p, C.c_int]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)
         f.restype, f.argtypes = res, args
     _REF = L
     return L
+
+
+class RefFrame:
+    """the reference's own VisualOdometryFrame (compiled from /root/reference against the stand-in headers)"""
+
+    def __init__(self, K, baseline, rows, cols, params):
+        L = ref_lib()
+        cp = make_params(params)
+        self.L, self.params = L, params
+        self.h = L.ref_frame_create(_fp(_colmajor(K)), float(baseline), rows, cols, C.byref(cp))
+        if not self.h:
+            raise RuntimeError(L.ref_last_error().decode())
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.ref_frame_destroy(self.h)
+            self.h = None
+
+    def set_data(self, img, disp):
+        img = np.ascontiguousarray(img, dtype=np.uint8)
+        disp = _f32(disp)
+        if self.L.ref_frame_set_data(self.h, _u8(img), _fp(disp)) != 0:
+            raise RuntimeError(self.L.ref_last_error().decode())
+
+    def set_template(self):
+        if self.L.ref_frame_set_template(self.h) != 0:
+            raise RuntimeError(self.L.ref_last_error().decode())
+
+    def level_size(self, l):
+        r, c = C.c_int32(), C.c_int32()
+        self.L.ref_frame_level_size(self.h, l, C.byref(r), C.byref(c))
+        return r.value, c.value
+
+    def num_points(self, l):
+        return self.L.ref_frame_num_points(self.h, l)
+
+    def descriptor(self, l):
+        r, c = self.level_size(l)
+        out = np.zeros((8, r, c), np.float32)
+        n = self.L.ref_frame_descriptor(self.h, l, _fp(out))
+        return out[:n].copy()
+
+    def points(self, l):
+        out = np.zeros((self.num_points(l), 4), np.float32)
+        self.L.ref_frame_points(self.h, l, _fp(out))
+        return out
+
+    def pixels(self, l):
+        n, tot = self.num_points(l), self.L.ref_frame_num_pixels(self.h, l)
+        out = np.zeros(tot, np.float32)
+        self.L.ref_frame_pixels(self.h, l, _fp(out))
+        return out.reshape(tot // max(n, 1), n)
+
+    def jacobians(self, l):
+        n, tot = self.num_points(l), self.L.ref_frame_num_pixels(self.h, l)
+        out = np.zeros((tot, 6), np.float32)
+        self.L.ref_frame_jacobians(self.h, l, _fp(out))
+        return out.reshape(tot // max(n, 1), n, 6)
+
+
+class RefEstimator:
+    """the reference's own PoseEstimatorGN<TemplateData>"""
+
+    def __init__(self, params):
+        self.L = ref_lib()
+        cp = make_params(params)
+        self.h = self.L.ref_estimator_create(C.byref(cp))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.ref_estimator_destroy(self.h)
+            self.h = None
+
+    def linearize(self, ref, cur, level, T, reset=True):
+        H = np.zeros(36, np.float32); G = np.zeros(6, np.float32)
+        f = self.L.ref_linearize(self.h, ref.h, cur.h, level, _fp(_colmajor(T)), int(reset), _fp(H), _fp(G))
+        if f < 0:
+            raise RuntimeError(self.L.ref_last_error().decode())
+        n = self.L.ref_estimator_num_residuals(self.h)
+        r = np.zeros(n, np.float32); w = np.zeros(n, np.float32); v = np.zeros(n, np.uint16)
+        self.L.ref_estimator_vectors(self.h, _fp(r), _fp(w), v.ctypes.data_as(C.POINTER(C.c_uint16)))
+        return dict(f_norm=float(f), H=_from_colmajor(H, 6), G=G, residuals=r, weights=w, valid=v)
+
+    def run_level(self, ref, cur, level, T):
+        Tc = _colmajor(T).copy()
+        st = OrcStats()
+        if self.L.ref_run_level(self.h, ref.h, cur.h, level, _fp(Tc), C.byref(st)) != 0:
+            raise RuntimeError(self.L.ref_last_error().decode())
+        return _from_colmajor(Tc, 4), dict(numIterations=st.numIterations, finalError=st.finalError,
+                                           firstOrderOptimality=st.firstOrderOptimality, status=st.status)
+
+
+class RefVisualOdometry:
+    """the reference's own bpvo::VisualOdometry"""
+
+    def __init__(self, K, baseline, image_size, params):
+        self.L = ref_lib()
+        rows, cols = image_size
+        cp = make_params(params)
+        self.h = self.L.ref_vo_create(_fp(_colmajor(K)), float(baseline), rows, cols, C.byref(cp))
+        if not self.h:
+            raise RuntimeError(self.L.ref_last_error().decode())
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.ref_vo_destroy(self.h)
+            self.h = None
+
+    def add_frame(self, img, disp):
+        img = np.ascontiguousarray(img, dtype=np.uint8)
+        disp = _f32(disp)
+        r = OrcResult()
+        if self.L.ref_vo_add_frame(self.h, _u8(img), _fp(disp), C.byref(r)) != 0:
+            raise RuntimeError(self.L.ref_last_error().decode())
+        return dict(pose=_from_colmajor(r.pose, 4), isKeyFrame=bool(r.isKeyFrame), keyFramingReason=r.keyFramingReason,
+                    stats=[dict(numIterations=s.numIterations, finalError=s.finalError, firstOrderOptimality=s.firstOrderOptimality,
+                                status=s.status) for s in r.stats[:r.numLevels]], numPointCloud=r.numPointCloud)
+
+    def add_frame_raw(self, img_ptr, disp_ptr, result):
+        return self.L.ref_vo_add_frame(self.h, img_ptr, disp_ptr, C.byref(result))
+
+    def num_points_at_level(self, level=-1):
+        return self.L.ref_vo_num_points_at_level(self.h, level)
+
+    def trajectory(self):
+        n = self.L.ref_vo_trajectory(self.h, None, 0)
+        buf = np.zeros((max(n, 1), 16), np.float32)
+        self.L.ref_vo_trajectory(self.h, _fp(buf), n)
+        return np.stack([b.reshape(4, 4).T for b in buf[:n]]) if n else np.zeros((0, 4, 4), np.float32)
+
+    def point_cloud(self, n):
+        xyzw = np.zeros((n, 4), np.float32); w = np.zeros(n, np.float32); g = np.zeros(n, np.uint8)
+        self.L.ref_vo_point_cloud(self.h, _fp(xyzw), _fp(w), _u8(g), n)
+        return xyzw, w, g

@@ -138,3 +138,101 @@ def test_scale_estimator_state_machine(oracle, ref):
         if it == 1:
             T = T.copy(); T[0, 3] = 0.01
     ref.ref_scale_destroy(h)
+
+
+# =====================================================================================================================
+# The WHOLE hot path of the real reference (vo.cc, vo_frame.cc, vo_pose_estimator.cc, pose_estimator_{base,gn}.h,
+# template_data.cc, rigid_body_warp.cc incl. its _mm_rcp_ps Jacobians, warps.cc, photo_error.cc, the descriptors, ...)
+# compiled from /root/reference against the stand-in Eigen/OpenCV headers: the oracle must reproduce it BIT FOR BIT,
+# down to the iteration counts of every pyramid level and the key-frame decisions.
+# =====================================================================================================================
+def _frames(kind):
+    from bpvo_b200 import synth
+    if kind == "small":
+        return synth.scene_small(96, 128)
+    if kind == "odd":
+        return synth.scene_small(117, 203, seed=11)
+    return synth.scene_vga()
+
+
+@pytest.mark.parametrize("kind,desc,levels,loss", [("small", "bitplanes", 3, "tukey"), ("small", "intensity", 3, "huber"),
+                                                    ("odd", "bitplanes", 2, "huber"), ("odd", "intensity", 2, "l2"),
+                                                    ("vga", "intensity", 4, "huber")])
+def test_frame_and_linearize_bit_exact(oracle, ref, kind, desc, levels, loss):
+    sc = _frames(kind)
+    p = make_params(desc, levels, loss)
+    i0, d0 = sc.render(0); i1, d1 = sc.render(1)
+    ra, rb = oracle.RefFrame(sc.K, sc.baseline, sc.rows, sc.cols, p), oracle.RefFrame(sc.K, sc.baseline, sc.rows, sc.cols, p)
+    oa, ob = oracle.Frame(sc.K, sc.baseline, sc.rows, sc.cols, p, use_rcp=1), oracle.Frame(sc.K, sc.baseline, sc.rows, sc.cols, p, use_rcp=1)
+    for a, b in ((ra, rb), (oa, ob)):
+        a.set_data(i0, d0); a.set_template(); b.set_data(i1, d1)
+    re, oe = oracle.RefEstimator(p), oracle.Estimator(p)
+    T1 = np.array(sc.relative_pose(0, 1), dtype=np.float32)
+    for l in range(levels):
+        assert ra.num_points(l) == oa.num_points(l) > 0
+        assert np.array_equal(ra.descriptor(l), oa.descriptor(l))
+        assert np.array_equal(ra.points(l), oa.points(l))                 # makePoint
+        assert np.array_equal(ra.pixels(l), oa.pixels(l))
+        assert np.array_equal(ra.jacobians(l), oa.jacobians(l))           # SSE Jacobians with _mm_rcp_ps, Hartley normalisation
+        for it, T in enumerate([np.eye(4, dtype=np.float32), T1]):
+            r = re.linearize(ra, rb, l, T, reset=(it == 0))
+            o = oe.linearize(oa, ob, l, T, reset_scale=(it == 0))
+            for key in ("residuals", "valid", "weights", "H", "G"):
+                assert np.array_equal(r[key], o[key]), (l, it, key)
+            assert r["f_norm"] == o["f_norm"]
+
+
+@pytest.mark.parametrize("desc,levels,loss,nframes", [("bitplanes", 3, "tukey", 14), ("intensity", 3, "huber", 14), ("intensity", 2, "l2", 6)])
+def test_vo_stream_bit_exact(oracle, ref, desc, levels, loss, nframes):
+    """addFrame state machine incl. key-framing + re-estimation, trajectory and point cloud: oracle == real reference"""
+    sc = _frames("small")
+    p = make_params(desc, levels, loss)
+    vr = oracle.RefVisualOdometry(sc.K, sc.baseline, (sc.rows, sc.cols), p)
+    vo = oracle.VisualOdometry(sc.K, sc.baseline, (sc.rows, sc.cols), p, use_rcp=1)
+    n_kf = 0
+    for k in range(nframes):
+        img, d = sc.render(k)
+        a, b = vr.add_frame(img, d), vo.add_frame(img, d)
+        assert a["isKeyFrame"] == b["isKeyFrame"] and a["keyFramingReason"] == b["keyFramingReason"], k
+        assert np.array_equal(a["pose"], b["pose"]), k
+        assert [s["numIterations"] for s in a["stats"]] == [s["numIterations"] for s in b["stats"]], k
+        assert [s["status"] for s in a["stats"]] == [s["status"] for s in b["stats"]], k
+        assert np.array_equal(np.float32([s["finalError"] for s in a["stats"]]), np.float32([s["finalError"] for s in b["stats"]]))
+        assert vr.num_points_at_level() == vo.num_points_at_level()
+        assert a["numPointCloud"] == b["numPointCloud"]
+        if k > 0 and a["isKeyFrame"]:
+            n_kf += 1
+            xr, wr, gr = vr.point_cloud(a["numPointCloud"])
+            xo, wo, go = vo.point_cloud()
+            assert np.array_equal(xr, xo) and np.array_equal(wr, wo) and np.array_equal(gr, go)
+    assert np.array_equal(vr.trajectory(), vo.trajectory())
+    if nframes >= 14:
+        assert n_kf >= 1, "the stream should trigger at least one key-frame"
+
+
+def test_kitti_pair_bit_exact(oracle, ref):
+    """one full-size KITTI bit-planes pair through the reference's own estimatePose path"""
+    from bpvo_b200 import synth
+    sc = synth.scene_kitti()
+    p = make_params("bitplanes", 4, "tukey")
+    vr = oracle.RefVisualOdometry(sc.K, sc.baseline, (sc.rows, sc.cols), p)
+    vo = oracle.VisualOdometry(sc.K, sc.baseline, (sc.rows, sc.cols), p, use_rcp=1)
+    for k in range(2):
+        img, d = sc.render(k)
+        a, b = vr.add_frame(img, d), vo.add_frame(img, d)
+    assert np.array_equal(a["pose"], b["pose"])
+    assert [s["numIterations"] for s in a["stats"]] == [s["numIterations"] for s in b["stats"]]
+    assert vr.num_points_at_level(0) == vo.num_points_at_level(0)
+
+
+def test_standin_image_ops_match_cv2_golden(oracle, ref):
+    """the stand-in cv::pyrDown / cv::GaussianBlur behind oracle/_ref are the formulas pinned against cv2 4.13 (via the
+    descriptors of a frame: pyramid levels and blurred bit-planes must equal the oracle's, which is checked against cv2)"""
+    from bpvo_b200 import synth
+    sc = synth.scene_small(94, 131)
+    p = make_params("bitplanes", 3, sigmaBitPlanes=1.618)
+    img, d = sc.render(0)
+    r = oracle.RefFrame(sc.K, sc.baseline, sc.rows, sc.cols, p); o = oracle.Frame(sc.K, sc.baseline, sc.rows, sc.cols, p)
+    r.set_data(img, d); o.set_data(img, d)
+    for l in range(3):
+        assert np.array_equal(r.descriptor(l), o.descriptor(l))
