@@ -204,10 +204,15 @@ def test_vo_stream(kind, desc, levels, loss, nframes, oracle):
     sc = _scene(kind)
     vg = VisualOdometry(sc.K, sc.baseline, (sc.rows, sc.cols), p)
     vo = oracle.VisualOdometry(sc.K, sc.baseline, (sc.rows, sc.cols), p)
+    # the reference's OWN code (oracle/_ref: bpvo sources compiled against stand-in Eigen/OpenCV headers), when shipped
+    vref = oracle.RefVisualOdometry(sc.K, sc.baseline, (sc.rows, sc.cols), p) if oracle.ref_lib() is not None else None
     for k in range(nframes):
         img, d = sc.render(k)
         rg = vg.addFrame(img, d)
         ro = vo.add_frame(img, d)
+        if vref is not None:
+            rr = vref.add_frame(img, d)
+            assert np.array_equal(rr["pose"], ro["pose"]) and rr["isKeyFrame"] == ro["isKeyFrame"], "oracle != real reference code"
         assert rg.isKeyFrame == ro["isKeyFrame"], f"frame {k}: key-frame decision"
         assert rg.keyFramingReason == ro["keyFramingReason"], f"frame {k}"
         # 1e-4 relative (north_star) at the benchmark sizes; the 96x128 toy stream has ~700 points at its top level and
