@@ -705,7 +705,7 @@ struct SolveShared {
 };
 
 template <int C>
-__device__ __forceinline__ void device_linearize(const SolveArgs& a, int lvl, const M44& T, SolveShared& ss, LinShared& sh,
+__device__ __forceinline__ void device_linearize(const SolveArgs& a, int lvl, SolveShared& ss, LinShared& sh,
                                                  const TplCache& tc, const TemplateMeta& meta, unsigned* scratch, cg::grid_group& grid,
                                                  int& parity, Sel* sel) {
   const LevelTemplate& L = a.tmpl[lvl];
@@ -713,9 +713,7 @@ __device__ __forceinline__ void device_linearize(const SolveArgs& a, int lvl, co
   const int nb = gridDim.x, blk = blockIdx.x, tid = threadIdx.x;
   unsigned* hset = a.work.hist + (size_t) parity * kHistWords;
   unsigned* hother = a.work.hist + (size_t) (parity ^ 1) * kHistWords;
-  if (tid == 0) make_projection(L, T, ss.P);
-  __syncthreads();
-  const bool do_hist = (a.sp.loss != 0x12) && (ss.delta > 1e-6f);
+  const bool do_hist = (a.sp.loss != 0x12) && (ss.delta > 1e-6f);      // ss.P was set by thread 0 together with the pose
   BP_PROF(PROF_OTHER);
   Bracket br;
   br.on = do_hist && ss.br_on;
@@ -798,7 +796,10 @@ __global__ void __launch_bounds__(kLinThreads, 1) k_estimate_pose(const __grid_c
   for (int lvl = a.sp.num_levels - 1; lvl >= a.sp.max_test_level; --lvl) {
     const LevelTemplate& L = a.tmpl[lvl];
     // PoseEstimatorBase::run (pose_estimator_base.h:324-407); all control flow below is CTA-uniform AND grid-uniform
-    if (tid == 0) { ss.scale = 1.0f; ss.delta = 1e10f; ss.br_on = 0; ss.br_lo = ss.br_hi = 0.0f; ss.br_rel = 0.002f; ss.br_density = 0.0f; }   // reset() :287-293
+    if (tid == 0) {                                                            // reset() :287-293
+      ss.scale = 1.0f; ss.delta = 1e10f; ss.br_on = 0; ss.br_lo = ss.br_hi = 0.0f; ss.br_rel = 0.002f; ss.br_density = 0.0f;
+      ss.Td = ss.T; make_projection(L, ss.Td, ss.P);
+    }
     __syncthreads();
     int n_evals = 0, it = 0, status = 0x33;
     float f_prev = 0.0f, g_tol = 0.0f, dp_prev = 0.0f, f_norm, g_norm;
@@ -813,49 +814,53 @@ __global__ void __launch_bounds__(kLinThreads, 1) k_estimate_pose(const __grid_c
       continue;
     }
 
-    device_linearize<C>(a, lvl, ss.T, ss, sh, tc, meta, scratch, grid, parity, sel); ++n_evals;
-    f_norm = ss.lin.f_norm;
-    g_norm = 0.0f; for (int k = 0; k < 6; ++k) g_norm = fmaxf(g_norm, fabsf(ss.lin.G[k]));
-    g_tol = a.sp.gradient_tolerance * fmaxf(g_norm, sqrt_eps);
-    if (g_norm < g_tol) {                                                      // :346-357
-      status = 0x32; it = 1; early = true;
-    } else {
-      if (tid == 0) { bool ok = solve6_fp32_registers(ss.lin.H, ss.lin.G, ss.dp); if (!ok) ok = solve6_fallback(ss.lin.H, ss.lin.G, ss.dp); ss.lin.pad[0] = ok ? 1 : 0; }
+    // One linearize site for the whole of run(): pass "first" is the evaluation before the do-while of :373-393, every
+    // later pass is runIteration (pose_estimator_gn.h:83-100).  The pose update, and the projection matrix of the NEXT
+    // linearize, are computed by thread 0 right after the solve.
+    bool first = true, conv = false;
+    for (;;) {
+      device_linearize<C>(a, lvl, ss, sh, tc, meta, scratch, grid, parity, sel); ++n_evals;
+      f_norm = ss.lin.f_norm;
+      if (first) {
+        g_norm = 0.0f; for (int k = 0; k < 6; ++k) g_norm = fmaxf(g_norm, fabsf(ss.lin.G[k]));
+        g_tol = a.sp.gradient_tolerance * fmaxf(g_norm, sqrt_eps);
+        if (g_norm < g_tol) { status = 0x32; it = 1; early = true; break; }    // :346-357
+      }
+      BP_FINE(25);
+      if (tid == 0) {
+        bool ok = solve6_fp32_registers(ss.lin.H, ss.lin.G, ss.dp);
+        if (!ok) ok = solve6_fallback(ss.lin.H, ss.lin.G, ss.dp);
+        ss.lin.pad[0] = ok ? 1 : 0;
+        BP_FINE(26);
+        if (ok) { apply_update(ss.Td, ss.dp, meta.s, meta.c1, meta.c2, meta.c3); make_projection(L, ss.Td, ss.P); }   // :371 / :390
+      }
       __syncthreads();
-      if (!ss.lin.pad[0]) {                                                    // :359-365
-        status = 0x34; solver_error = true; early = true; it = 0; g_norm = 0.0f;
+      BP_FINE(28);
+      if (!ss.lin.pad[0]) {                                                    // :359-365 / gn.h:90-97
+        status = 0x34; solver_error = true;
+        if (first) { early = true; it = 0; g_norm = 0.0f; }
+        break;
+      }
+      if (first) { first = false; f_prev = 0.0f; dp_prev = 0.0f; }
+      else if (!(it++ < a.sp.max_iterations && n_evals < a.sp.max_fun_evals)) break;   // the do-while condition (conv is false here)
+      // top of the next do-while pass: testConvergence (:258-282) on the step just taken
+      float dpn = 0.0f; for (int k = 0; k < 6; ++k) dpn += ss.dp[k] * ss.dp[k];
+      dpn = sqrtf(dpn);
+      g_norm = 0.0f; for (int k = 0; k < 6; ++k) g_norm = fmaxf(g_norm, fabsf(ss.lin.G[k]));
+      if (dpn < a.sp.parameter_tolerance || dpn < a.sp.parameter_tolerance * (sqrt_eps + dp_prev)) { status = 0x30; conv = true; }
+      else if (f_norm < a.sp.function_tolerance || f_norm < a.sp.function_tolerance * (sqrt_eps + f_prev) ||
+               fabsf(f_norm - f_prev) < a.sp.function_tolerance) { status = 0x31; conv = true; }
+      else if (g_norm < g_tol) { status = 0x32; conv = true; }
+      dp_prev = dpn; f_prev = f_norm;
+      BP_PROF(PROF_SOLVE);
+      if (conv) {                                                              // the converged pass still applies dp once more (Q1, :390)
+        if (tid == 0) apply_update(ss.Td, ss.dp, meta.s, meta.c1, meta.c2, meta.c3);
+        __syncthreads();
+        it++;                                                                  // `while (it++ < ...)` is evaluated on the way out
+        break;
       }
     }
     if (!early) {
-      if (tid == 0) { ss.Td = ss.T; apply_update(ss.Td, ss.dp, meta.s, meta.c1, meta.c2, meta.c3); }   // :371
-      __syncthreads();
-      bool conv = false;
-      do {
-        float dpn = 0.0f; for (int k = 0; k < 6; ++k) dpn += ss.dp[k] * ss.dp[k];
-        dpn = sqrtf(dpn);
-        g_norm = 0.0f; for (int k = 0; k < 6; ++k) g_norm = fmaxf(g_norm, fabsf(ss.lin.G[k]));
-        // testConvergence (:258-282)
-        if (dpn < a.sp.parameter_tolerance || dpn < a.sp.parameter_tolerance * (sqrt_eps + dp_prev)) { status = 0x30; conv = true; }
-        else if (f_norm < a.sp.function_tolerance || f_norm < a.sp.function_tolerance * (sqrt_eps + f_prev) ||
-                 fabsf(f_norm - f_prev) < a.sp.function_tolerance) { status = 0x31; conv = true; }
-        else if (g_norm < g_tol) { status = 0x32; conv = true; }
-        dp_prev = dpn; f_prev = f_norm;
-        if (!conv) {                                                           // runIteration (pose_estimator_gn.h:83-100)
-          device_linearize<C>(a, lvl, ss.Td, ss, sh, tc, meta, scratch, grid, parity, sel); ++n_evals;
-          f_norm = ss.lin.f_norm;
-          BP_FINE(25);
-          if (tid == 0) { bool ok = solve6_fp32_registers(ss.lin.H, ss.lin.G, ss.dp); if (!ok) ok = solve6_fallback(ss.lin.H, ss.lin.G, ss.dp); ss.lin.pad[0] = ok ? 1 : 0; }
-          BP_FINE(26);
-          __syncthreads();
-          BP_FINE(27);
-          if (!ss.lin.pad[0]) { status = 0x34; solver_error = true; break; }
-        }
-        if (tid == 0) apply_update(ss.Td, ss.dp, meta.s, meta.c1, meta.c2, meta.c3);   // also when converged (Q1)
-        BP_FINE(28);
-        __syncthreads();
-        BP_FINE(29);
-        BP_PROF(PROF_SOLVE);
-      } while (it++ < a.sp.max_iterations && !conv && n_evals < a.sp.max_fun_evals);
       if (!solver_error && tid == 0) ss.T = ss.Td;                             // :395-396
       __syncthreads();
       it -= 1;                                                                 // :398
