@@ -24,22 +24,26 @@ template <int K, int Q> struct SwapRowsCols {
   }
 };
 
-template <int K> struct LdltStep {
+template <int K, bool PIVOT> struct LdltStep {
   static __device__ __forceinline__ void run(float (&a)[6][6], int (&tr)[6], float& cutoff, bool& done) {
     if (!done) {
       int idx = K; float big = fabsf(a[K][K]);
+      if (PIVOT) {
 #pragma unroll
-      for (int i = K + 1; i < 6; ++i) { const float v = fabsf(a[i][i]); if (v > big) { big = v; idx = i; } }
+        for (int i = K + 1; i < 6; ++i) { const float v = fabsf(a[i][i]); if (v > big) { big = v; idx = i; } }
+      }
       if (K == 0) cutoff = fabsf(FLT_EPSILON * big);
       if (big < cutoff) {
         done = true;                 // remaining transpositions stay identity
       } else {
         tr[K] = idx;
+        if (PIVOT) {
         if (K + 1 < 6 && idx == K + 1) SwapRowsCols<K, (K + 1 < 6 ? K + 1 : 5)>::run(a);
         if (K + 2 < 6 && idx == K + 2) SwapRowsCols<K, (K + 2 < 6 ? K + 2 : 5)>::run(a);
         if (K + 3 < 6 && idx == K + 3) SwapRowsCols<K, (K + 3 < 6 ? K + 3 : 5)>::run(a);
         if (K + 4 < 6 && idx == K + 4) SwapRowsCols<K, (K + 4 < 6 ? K + 4 : 5)>::run(a);
         if (K + 5 < 6 && idx == K + 5) SwapRowsCols<K, (K + 5 < 6 ? K + 5 : 5)>::run(a);
+        }
         float temp[6];
         if (K > 0) {
 #pragma unroll
@@ -66,8 +70,10 @@ template <int K> struct LdltStep {
   }
 };
 
-// returns true when (H*dp).isApprox(G) holds for the fp32 factorisation; otherwise the caller falls back to the
-// generic solve6() (fp32 retry is pointless: it would fail the same test; the fp64 damped path is rare)
+// returns true when (H*dp).isApprox(G) holds for the fp32 factorisation.  PIVOT = false skips Eigen's diagonal pivoting
+// (all swap code compiles away: ~4x fewer instructions on the single-thread critical path); the caller retries with
+// PIVOT = true and finally with the generic damped fp64 solve6() when the acceptance test fails.
+template <bool PIVOT>
 __device__ __forceinline__ bool solve6_fp32_registers(const float* __restrict__ H, const float* __restrict__ G, float* __restrict__ dp) {
   float a[6][6]; int tr[6]; float x[6];
 #pragma unroll
@@ -77,13 +83,15 @@ __device__ __forceinline__ bool solve6_fp32_registers(const float* __restrict__ 
     tr[i] = i; x[i] = G[i];
   }
   float cutoff = 0.0f; bool done = false;
-  LdltStep<0>::run(a, tr, cutoff, done); LdltStep<1>::run(a, tr, cutoff, done); LdltStep<2>::run(a, tr, cutoff, done);
-  LdltStep<3>::run(a, tr, cutoff, done); LdltStep<4>::run(a, tr, cutoff, done); LdltStep<5>::run(a, tr, cutoff, done);
+  LdltStep<0, PIVOT>::run(a, tr, cutoff, done); LdltStep<1, PIVOT>::run(a, tr, cutoff, done); LdltStep<2, PIVOT>::run(a, tr, cutoff, done);
+  LdltStep<3, PIVOT>::run(a, tr, cutoff, done); LdltStep<4, PIVOT>::run(a, tr, cutoff, done); LdltStep<5, PIVOT>::run(a, tr, cutoff, done);
   // solve: P b, L^-1, D^-1 (with Eigen 3.2's tolerance), L^-T, P^T
+  if (PIVOT) {
 #pragma unroll
-  for (int k = 0; k < 6; ++k) {
+    for (int k = 0; k < 6; ++k) {
 #pragma unroll
-    for (int q = k + 1; q < 6; ++q) if (tr[k] == q) { const float t = x[k]; x[k] = x[q]; x[q] = t; }
+      for (int q = k + 1; q < 6; ++q) if (tr[k] == q) { const float t = x[k]; x[k] = x[q]; x[q] = t; }
+    }
   }
 #pragma unroll
   for (int i = 0; i < 6; ++i) {
@@ -101,10 +109,12 @@ __device__ __forceinline__ bool solve6_fp32_registers(const float* __restrict__ 
 #pragma unroll
     for (int j = i + 1; j < 6; ++j) x[i] -= a[j][i] * x[j];
   }
+  if (PIVOT) {
 #pragma unroll
-  for (int k = 5; k >= 0; --k) {
+    for (int k = 5; k >= 0; --k) {
 #pragma unroll
-    for (int q = k + 1; q < 6; ++q) if (tr[k] == q) { const float t = x[k]; x[k] = x[q]; x[q] = t; }
+      for (int q = k + 1; q < 6; ++q) if (tr[k] == q) { const float t = x[k]; x[k] = x[q]; x[q] = t; }
+    }
   }
   float d = 0.0f, na = 0.0f, nb = 0.0f;
 #pragma unroll

@@ -181,7 +181,8 @@ __device__ __forceinline__ void phase_residuals(const LevelTemplate& L, const Le
                                                 unsigned* __restrict__ hist1, bool do_hist, Bracket br, const TplCache& tc,
                                                 const TemplateMeta& m, unsigned* scratch, LinShared& sh, int block, int nblocks) {
   const int tid = threadIdx.x;
-  if (do_hist) { for (int b = tid; b < kHist1Bins; b += kLinThreads) sh.hist[b] = 0; }
+  const bool do_hist1 = do_hist && !br.on;   // with a bracket the level-1 histogram is only built (phase_hist1) if the bracket misses
+  if (do_hist1) { for (int b = tid; b < kHist1Bins; b += kLinThreads) sh.hist[b] = 0; }
   if (tid < 4) sh.found[4 + tid] = 0;        // CTA-level counters: [4] valid points, [5] below bracket, [6] candidates of this CTA
   float* cta_cand = reinterpret_cast<float*>(scratch);    // CTA-local candidate list (bracket on), flushed with ONE global atomic
   __syncthreads();
@@ -224,8 +225,10 @@ __device__ __forceinline__ void phase_residuals(const LevelTemplate& L, const Le
         r.v[c] = (float) __dsub_rn(Iw, (double) i0.v[c]);
       }
       if (do_hist) {
+        if (do_hist1) {
 #pragma unroll
-        for (int c = 0; c < C; ++c) atomicAdd(&sh.hist[__float_as_uint(fabsf(r.v[c])) >> 20], 1u);
+          for (int c = 0; c < C; ++c) atomicAdd(&sh.hist[__float_as_uint(fabsf(r.v[c])) >> 20], 1u);
+        }
         my_first = min(my_first, i);
         ++cnt_valid;
         if (br.on) {
@@ -252,7 +255,7 @@ __device__ __forceinline__ void phase_residuals(const LevelTemplate& L, const Le
   if (do_hist) {
     __syncthreads();
     BP_FINE(18);
-    for (int b = tid; b < kHist1Bins; b += kLinThreads) { const unsigned v = sh.hist[b]; if (v) atomicAdd(hist1 + b, v); }
+    if (do_hist1) { for (int b = tid; b < kHist1Bins; b += kLinThreads) { const unsigned v = sh.hist[b]; if (v) atomicAdd(hist1 + b, v); } }
     for (int o = 16; o > 0; o >>= 1) {
       my_first = min(my_first, __shfl_xor_sync(0xffffffffu, my_first, o));
       cnt_valid += __shfl_xor_sync(0xffffffffu, cnt_valid, o);
@@ -279,6 +282,25 @@ __device__ __forceinline__ void phase_residuals(const LevelTemplate& L, const Le
     }
   }
   BP_FINE(19);
+}
+
+// level-1 histogram of |r| as a separate pass (on-device loop, only after a bracket miss)
+template <int C>
+__device__ __forceinline__ void phase_hist1(const Work& W, unsigned* __restrict__ hist1, const TplCache& tc, const TemplateMeta& m,
+                                            LinShared& sh, int block, int nblocks) {
+  const int tid = threadIdx.x;
+  for (int b = tid; b < kHist1Bins; b += kLinThreads) sh.hist[b] = 0;
+  __syncthreads();
+  int k = 0;
+  for (int i = first_point(block, nblocks); i < m.n; i += nblocks * kLinThreads, ++k) {
+    if (!(tc.K ? tc.valid[k * kLinThreads + tid] : W.valid[i])) continue;
+    VecC<C> r;
+    if (tc.K) tc_get<C>(tc, k, TC_R, r); else r.load_plain(W.res + (size_t) i * C);
+#pragma unroll
+    for (int c = 0; c < C; ++c) atomicAdd(&sh.hist[__float_as_uint(fabsf(r.v[c])) >> 20], 1u);
+  }
+  __syncthreads();
+  for (int b = tid; b < kHist1Bins; b += kLinThreads) { const unsigned v = sh.hist[b]; if (v) atomicAdd(hist1 + b, v); }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -732,6 +754,7 @@ __device__ __forceinline__ void device_linearize(const SolveArgs& a, int lvl, So
       sigma = scale_from_median(n, med);
       BP_PROF(PROF_SCALE);
     } else {
+      if (br.on) { phase_hist1<C>(a.work, hset, tc, meta, sh, blk, nb); grid.sync(); }      // bracket missed: build the histogram now
       phase_select<C, 2>(L, a.work, hset, sel, tc, meta, sh, blk, nb);
       BP_PROF(PROF_P2);
       grid.sync();
@@ -828,8 +851,9 @@ __global__ void __launch_bounds__(kLinThreads, 1) k_estimate_pose(const __grid_c
       }
       BP_FINE(25);
       if (tid == 0) {
-        bool ok = solve6_fp32_registers(ss.lin.H, ss.lin.G, ss.dp);
-        if (!ok) ok = solve6_fallback(ss.lin.H, ss.lin.G, ss.dp);
+        bool ok = solve6_fp32_registers<false>(ss.lin.H, ss.lin.G, ss.dp);      // unpivoted first: H is SPD and Hartley-normalised
+        if (!ok) ok = solve6_fp32_registers<true>(ss.lin.H, ss.lin.G, ss.dp);     // Eigen's pivoted LDLT
+        if (!ok) ok = solve6_fallback(ss.lin.H, ss.lin.G, ss.dp);                 // damped fp64 retry
         ss.lin.pad[0] = ok ? 1 : 0;
         BP_FINE(26);
         if (ok) { apply_update(ss.Td, ss.dp, meta.s, meta.c1, meta.c2, meta.c3); make_projection(L, ss.Td, ss.P); }   // :371 / :390
