@@ -590,11 +590,12 @@ __device__ __forceinline__ void final_sum(const Work& W, int nblocks, float sigm
     sh.red[0][tid] = t;
   }
   __syncthreads();
-  if (tid == 0) {
-    int q = 0;
-    for (int a = 0; a < 6; ++a)
-      for (int b = a; b < 6; ++b) { const float h = (float) sh.red[0][q++]; out.H[b * 6 + a] = h; out.H[a * 6 + b] = h; }
-    for (int a = 0; a < 6; ++a) out.G[a] = (float) sh.red[0][21 + a];
+  if (tid < 36) {                       // H: thread (a, b) picks its upper-triangle entry
+    const int a = tid / 6, b = tid % 6, lo = a < b ? a : b, hi = a < b ? b : a;
+    out.H[b * 6 + a] = (float) sh.red[0][lo * 6 - lo * (lo - 1) / 2 + (hi - lo)];
+  } else if (tid < 42) {
+    out.G[tid - 36] = (float) sh.red[0][21 + tid - 36];
+  } else if (tid == 42) {
     out.f_norm = sqrtf((float) sh.red[0][27]);
     out.n_good = (int) (sh.red[0][28] + 0.5);
     out.n_valid = (int) (sh.red[0][29] + 0.5);
@@ -771,7 +772,7 @@ __device__ __forceinline__ void device_linearize(const SolveArgs& a, int lvl, So
     // the median just moved; otherwise sized from the measured candidate density so that ~600 values fall inside.
     if (tid == 0) {
       const float mid_new = 0.5f * (lo + hi), mid_old = 0.5f * (ss.br_lo + ss.br_hi);
-      float rel = 0.002f;
+      float rel = 0.03f;           // first bracket of a level: wide (the median still moves by percents), the 8192-entry buffer absorbs it
       if (ss.br_on && mid_new > 0.0f) {
         const float moved = fabsf(mid_new - mid_old) / mid_new;
         if (br.on && ncand > 0) ss.br_density = (float) ncand / fmaxf(ss.br_rel, 1e-6f);       // candidates per unit of rel
@@ -820,7 +821,7 @@ __global__ void __launch_bounds__(kLinThreads, 1) k_estimate_pose(const __grid_c
     const LevelTemplate& L = a.tmpl[lvl];
     // PoseEstimatorBase::run (pose_estimator_base.h:324-407); all control flow below is CTA-uniform AND grid-uniform
     if (tid == 0) {                                                            // reset() :287-293
-      ss.scale = 1.0f; ss.delta = 1e10f; ss.br_on = 0; ss.br_lo = ss.br_hi = 0.0f; ss.br_rel = 0.002f; ss.br_density = 0.0f;
+      ss.scale = 1.0f; ss.delta = 1e10f; ss.br_on = 0; ss.br_lo = ss.br_hi = 0.0f; ss.br_rel = 0.03f; ss.br_density = 0.0f;
       ss.Td = ss.T; make_projection(L, ss.Td, ss.P);
     }
     __syncthreads();
