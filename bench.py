@@ -289,8 +289,17 @@ def run_ours(args, w, rank, world, local_rank):
         n_solves = max(1, n_solves)
         peak, how = peaks()
         achieved = alg_bytes / (ms_lin * 1e-3) / 1e9 if ms_lin > 0 else 0.0
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")      # dram__bytes_{read,write}.sum of one `ncu --set full` capture of this kernel
+        if os.path.exists(tp):
+            try:
+                tj = json.load(open(tp))
+                traffic = float(tj["dram_bytes_read"]) + float(tj["dram_bytes_write"])
+            except Exception:
+                traffic = None
         roof = {"bound": "hbm", "kernel": "k_estimate_pose<8> (persistent on-device GN solve, all levels/iterations in one launch)",
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "traffic_note": "bytes per launch from profiles/ncu_traffic.json: far BELOW the algorithmic bytes because the working set is L2-resident",
                 "peak_source": how, "ms_per_launch": ms_lin / n_solves,
                 "algorithmic_bytes_per_launch": alg_bytes / n_solves,
                 "phase_ms_per_frame": {k2: v / float(n_roof) for k2, v in phase.items()}}

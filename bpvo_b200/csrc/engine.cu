@@ -731,14 +731,18 @@ extern "C" int bpvo_b200_estimate_pose(bpvo_b200_ctx* c, const bpvo_b200_frame* 
   return BPVO_B200_OK;
 }
 
-// getWeights / residuals / valid of the last linearize, in the reference's channel-major layout
+// getWeights / residuals / valid of the last linearize, in the reference's channel-major layout.
+// *count: in = capacity of the caller's buffer in floats (ignored when the buffer is NULL), out = total C*N.
+// Only min(capacity, total) entries are computed-and-copied; the first N entries are channel 0 (what vo.cc:264 uses).
 static int export_last(bpvo_b200_ctx* c, float* w, float* r, size_t* count) {
   if (!c || !count) return bp_fail(BPVO_B200_ERR_INVALID_ARG, "null argument");
+  const size_t capacity = *count;
   if (!c->last_ref) { *count = 0; return BPVO_B200_OK; }
   int rc = wait_meta(c->last_ref); if (rc) return rc;
   const int n = c->last_ref->h_meta[c->last_level].n;
   *count = (size_t) n * c->C;
   if ((!w && !r) || n == 0) return BPVO_B200_OK;
+  const size_t ncopy = (capacity == 0 || capacity > *count) ? *count : capacity;
   CUDA_TRY(cudaSetDevice(c->p.device_id));
   // sigma of the last linearize
   CUDA_TRY(cudaMemcpyAsync(&c->h_mail->lin, c->work.out, sizeof(LinOut), cudaMemcpyDeviceToHost, c->stream));
@@ -749,10 +753,10 @@ static int export_last(bpvo_b200_ctx* c, float* w, float* r, size_t* count) {
   if (c->C == 1) k_export_weights<1><<<ceil_div(n, 256), 256, 0, c->stream>>>(c->work.res, n, sigma, c->p.lossFunction, dw, dr);
   else k_export_weights<8><<<ceil_div(n * 8, 256), 256, 0, c->stream>>>(c->work.res, n, sigma, c->p.lossFunction, dw, dr);
   LAUNCH_CHECK(c);
-  if (w) CUDA_TRY(cudaMemcpyAsync(w, dw, *count * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
-  if (r) CUDA_TRY(cudaMemcpyAsync(r, dr, *count * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  if (w) CUDA_TRY(cudaMemcpyAsync(w, dw, ncopy * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  if (r) CUDA_TRY(cudaMemcpyAsync(r, dr, ncopy * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
   CUDA_TRY(cudaStreamSynchronize(c->stream));
-  c->counters.d2h_bytes += (int64_t) (*count * sizeof(float) * ((w ? 1 : 0) + (r ? 1 : 0)));
+  c->counters.d2h_bytes += (int64_t) (ncopy * sizeof(float) * ((w ? 1 : 0) + (r ? 1 : 0)));
   return BPVO_B200_OK;
 }
 extern "C" int bpvo_b200_get_weights(bpvo_b200_ctx* c, float* w, size_t* count) { return export_last(c, w, nullptr, count); }
@@ -781,7 +785,7 @@ extern "C" int bpvo_b200_fraction_good(bpvo_b200_ctx* c, float thresh, float* fr
     *frac = (float) c->h_mail->lin.n_good / static_cast<float>(total);
     return BPVO_B200_OK;
   }
-  std::vector<float> w(total); size_t cnt = 0;
+  std::vector<float> w(total); size_t cnt = total;
   rc = export_last(c, w.data(), nullptr, &cnt); if (rc) return rc;
   size_t n = 0; for (size_t i = 0; i < cnt; ++i) n += (w[i] > thresh);
   *frac = n / static_cast<float>(cnt);

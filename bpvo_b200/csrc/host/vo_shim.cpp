@@ -171,8 +171,8 @@ class VisualOdometry::Impl {
     check(bpvo_b200_get_weights(_ctx, nullptr, &wcount));
     const size_t n = points.size();
     if (n > wcount) throw Error("size mismatch");
-    std::vector<float> weights(wcount);
-    if (wcount) check(bpvo_b200_get_weights(_ctx, weights.data(), &wcount));
+    std::vector<float> weights(n);                    // weights[i], i < n: channel 0 only (vo.cc:264, Q7) -> no bulk C*N download
+    if (n) { size_t cap = n; check(bpvo_b200_get_weights(_ctx, weights.data(), &cap)); }
     std::vector<uint8_t> image((size_t) _image_size.rows * _image_size.cols);
     check(bpvo_b200_frame_get_pyramid(_ref_frame, 0, image.data()));               // imagePointer() of the ref frame
     std::unique_ptr<PointCloud> ret(new PointCloud);

@@ -107,11 +107,12 @@ class Context:
         return _from_colmajor(T, 4), out, ev.value
 
     def _vec(self, fn, dtype=np.float32):
-        n = C.c_size_t()
+        n = C.c_size_t(0)
         _check(fn(self.h, None, C.byref(n)))
         out = np.zeros(n.value, dtype)
         if n.value:
-            _check(fn(self.h, out.ctypes.data_as(fn.argtypes[1]), C.byref(n)))
+            cap = C.c_size_t(n.value)
+            _check(fn(self.h, out.ctypes.data_as(fn.argtypes[1]), C.byref(cap)))
         return out
 
     def getWeights(self):

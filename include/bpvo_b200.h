@@ -207,8 +207,9 @@ int bpvo_b200_linearize(bpvo_b200_ctx* ctx, const bpvo_b200_frame* ref, const bp
 int bpvo_b200_estimate_pose(bpvo_b200_ctx* ctx, const bpvo_b200_frame* ref, const bpvo_b200_frame* cur,
                             const float T_init[16], float T_est[16], bpvo_b200_stats* stats, int* num_fun_evals);
 /* const WeightsVector& getWeights()  (vo_pose_estimator.cc:95-99): C*N weights of the last linearize,
- * channel-major; pass w == NULL to query *count only.  Same for residuals / valid flags
- * (PoseEstimatorBase::residuals()/getValidFlags(), pose_estimator_base.h:189-223). */
+ * channel-major.  *count: in = capacity of `w` in floats (0 = everything; ignored when w == NULL), out = C*N.
+ * min(capacity, C*N) entries are copied -- the first N are channel 0, all that vo.cc:264 reads.
+ * Same for residuals / valid flags (PoseEstimatorBase::residuals()/getValidFlags(), pose_estimator_base.h:189-223). */
 int bpvo_b200_get_weights(bpvo_b200_ctx* ctx, float* w, size_t* count);
 int bpvo_b200_get_residuals(bpvo_b200_ctx* ctx, float* r, size_t* count);
 int bpvo_b200_get_valid(bpvo_b200_ctx* ctx, uint8_t* v, size_t* count);   /* per point, N entries */

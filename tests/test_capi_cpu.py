@@ -95,3 +95,16 @@ def test_synthetic_scene_is_deterministic():
     assert 0.1 < (sc.render(0)[1] == 0).mean() < 0.3
     T = sc.relative_pose(0, 1)
     assert np.abs(T[:3, :3] @ T[:3, :3].T - np.eye(3)).max() < 1e-12
+
+
+def test_cpp_example_links_against_the_host_shim(tmp_path):
+    """examples/vo_stream.cpp uses bpvo_b200::VisualOdometry (the C++ mirror of bpvo/vo.h); it must compile
+    and link against the in-tree library with a plain g++ (no compute here: there is no GPU)."""
+    import subprocess
+    libdir = os.path.join(ROOT, "bpvo_b200")
+    exe = tmp_path / "vo_stream"
+    subprocess.run(["/usr/bin/g++", "-std=c++14", "-O2", os.path.join(ROOT, "examples", "vo_stream.cpp"),
+                    "-I" + os.path.join(libdir, "csrc", "host"), "-L" + libdir, "-lbpvo_b200", "-Wl,-rpath," + libdir,
+                    "-o", str(exe)], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 2 and "usage" in r.stderr

@@ -307,3 +307,40 @@ def test_point_sharded_two_gpus():
            "--master-port", "29517", os.path.join(ROOT, "scripts", "shard_check.py")]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     assert res.returncode == 0 and "SHARD_CHECK_OK" in res.stdout, res.stdout[-3000:] + res.stderr[-3000:]
+
+
+def test_cpp_host_shim_stream(tmp_path):
+    """examples/vo_stream.cpp (bpvo_b200::VisualOdometry, the C++ mirror of bpvo/vo.h) must walk the same
+    stream to bit-identical poses / key-frame decisions as the Python binding of the same C ABI."""
+    import os, struct, subprocess
+    from bpvo_b200 import VisualOdometry
+    from conftest import ROOT
+    sc = _scene("small")
+    p = make_params("bitplanes", 3, "tukey")
+    nframes = 6
+    frames = [sc.render(k) for k in range(nframes)]
+    binf = tmp_path / "frames.bin"
+    with open(binf, "wb") as f:
+        f.write(struct.pack("<6i", sc.rows, sc.cols, nframes, p.descriptor, p.numPyramidLevels, p.lossFunction))
+        f.write(np.asarray(sc.K, np.float32).T.tobytes())            # column-major
+        f.write(struct.pack("<f", sc.baseline))
+        for img, d in frames:
+            f.write(np.ascontiguousarray(img, np.uint8).tobytes()); f.write(np.ascontiguousarray(d, np.float32).tobytes())
+    exe = tmp_path / "vo_stream"
+    libdir = os.path.join(ROOT, "bpvo_b200")
+    subprocess.run(["/usr/bin/g++", "-std=c++14", "-O2", os.path.join(ROOT, "examples", "vo_stream.cpp"),
+                    "-I" + os.path.join(libdir, "csrc", "host"), "-L" + libdir, "-lbpvo_b200", "-Wl,-rpath," + libdir,
+                    "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe), str(binf)], check=True, capture_output=True, text=True, timeout=300).stdout.splitlines()
+    assert len(out) == nframes + 1
+    # the defaults of bpvo_b200_default_params are what make_params starts from; align the fields the file carries
+    from bpvo_b200 import AlgorithmParameters
+    q = AlgorithmParameters(); q.descriptor = p.descriptor; q.numPyramidLevels = p.numPyramidLevels; q.lossFunction = p.lossFunction
+    vg = VisualOdometry(sc.K, sc.baseline, (sc.rows, sc.cols), q)
+    for k, (img, d) in enumerate(frames):
+        r = vg.addFrame(img, d)
+        tok = out[k].split()
+        assert int(tok[0]) == int(r.isKeyFrame) and int(tok[1]) == r.keyFramingReason
+        pose = np.array([float.fromhex(t) for t in tok[3:19]], np.float32).reshape(4, 4).T
+        assert np.array_equal(pose, r.pose), f"frame {k}"
+    assert out[-1].split()[1] == str(nframes)
