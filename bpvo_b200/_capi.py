@@ -8,7 +8,8 @@ import os
 from .types import CParams
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbpvo_b200.so")
+# BPVO_B200_LIB: profiling builds of the SAME sources (e.g. libbpvo_b200_fine.so); the default is the product library
+LIB_PATH = os.environ.get("BPVO_B200_LIB") or os.path.join(_HERE, "libbpvo_b200.so")
 _LIB = None
 
 MAX_LEVELS = 16

@@ -35,10 +35,14 @@ def needs_build() -> bool:
     return not os.path.exists(LIB) or os.path.getmtime(LIB) < _newest_source_mtime()
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
-        return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES
+def build(force: bool = False, verbose: bool = False, variant: str = "") -> str:
+    """variant "fine": a second library with the fine-grained in-kernel profile marks compiled in
+    (-DBP_FINE_PROFILE -> libbpvo_b200_fine.so, loaded when BPVO_B200_LIB points at it); never the product path."""
+    lib = LIB if not variant else LIB.replace(".so", f"_{variant}.so")
+    extra = {"": [], "fine": ["-DBP_FINE_PROFILE"]}[variant]
+    if not force and os.path.exists(lib) and os.path.getmtime(lib) >= _newest_source_mtime():
+        return lib
+    cmd = [_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", lib] + SOURCES
     env = dict(os.environ)
     # the image's default CC points at a gcc wrapper without OpenMP specs; nvcc only needs a host g++
     if os.path.exists("/usr/bin/g++"):
@@ -48,9 +52,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
     if verbose:
         print(res.stderr)
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
     import sys
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, variant="fine" if "--fine" in sys.argv else ""))

@@ -12,12 +12,19 @@ constexpr int kHist1Bins = 2048;   // |r| float bits [30:20]
 constexpr int kHist2Bins = 2048;   // bits [19:9]
 constexpr int kHist3Bins = 512;    // bits [8:0]
 constexpr int kHistBins = kHist1Bins + 2 * kHist2Bins + 2 * kHist3Bins;
-constexpr int kHistWords = kHistBins + 8;   // one histogram set + bookkeeping words:
+constexpr int kSelBins = 1024, kSelList = 256;   // bracketed median: linear bins over the bracket, short list of the two wanted bins
+constexpr int kHistWords = kHistBins + 8 + kSelBins;   // one histogram set + bookkeeping words + the bracket histogram:
 //   [kHistBins+0] max(~i) over valid points i   [+1] valid points   [+2] residuals below the bracket   [+3] residuals inside it
-constexpr int kCandCap = 8192;               // capacity of the bracketed-median candidate buffer
-constexpr int kCtaCandCap = 2048;            // per-CTA staging of candidates in shared memory
-constexpr int kScratchBytes = (kCandCap + 1024 + 256) * 4;   // dynamic-smem scratch of the bracketed select
+//   [+4] length of the candidate overflow list   [+8 ...] kSelBins counts of the candidates by linear bin over the bracket
+constexpr int kCandPerCta = 12;              // bracketed median: every CTA owns a fixed region of the candidate buffer (no slot reservation) ...
+constexpr int kCtaCandCap = 1024;            // ... stages up to this many candidates in shared memory ...
+constexpr int kOvfCap = 8192;                // ... and appends what exceeds its region to a shared overflow list (wide brackets, early iterations)
+constexpr unsigned kCandPoison = 1u << 30;   // added to the candidate count when even that overflowed -> radix fallback
+constexpr int kScratchBytes = (kCtaCandCap + kSelList) * 4;   // dynamic-smem scratch of the bracketed select: CTA candidates | list
 constexpr int kPartialStride = 32; // doubles per block partial (21 H + 6 G + f + n_good + pad)
+constexpr int kHistSets = 3;       // histogram sets of the on-device loop (triple-buffered: a set is zeroed one real barrier before its next use)
+constexpr int kLLGroup = 12;       // CTAs per group of the two-level flag-in-data exchange of the normal-equation sums
+constexpr int kMaxGrid = 1024;     // upper bound of CTAs of the persistent kernel (sizes the exchange mailboxes)
 constexpr int kLinThreads = 256;   // threads per CTA of the linearize phases (1 CTA per SM; measured: 128 -> 14.7, 256 -> 12.4, 512 -> 13.5 us / GN iteration)
 
 // Per-level template ("TemplateData", bpvo/template_data.h) in the device layout:
@@ -70,12 +77,14 @@ struct LinOut {
 struct Work {
   float* res;            // [N][C] residuals of the last linearize (point-major; 0 for invalid points)
   uint8_t* valid;        // [N]
-  unsigned* hist;        // 2 sets x kHistWords (double-buffered across iterations)
+  unsigned* hist;        // kHistSets x kHistWords, followed by 8 words: [0] grid-barrier counter of the persistent kernel
+  uint4* ll;             // flag-in-data mailboxes of the persistent kernel: [2][kMaxGrid][32] CTA sums, then [2][kMaxGrid][32] group sums
   double* partials;      // [grid][kPartialStride]
   ScaleState* scale;
   LinOut* out;
   unsigned* ticket;      // last-CTA-done counter
-  float* cand;           // [kCandCap] |r| values inside the median bracket (on-device GN loop)
+  float* cand;           // [kMaxGrid][kCandPerCta] |r| values inside the median bracket, -1 = empty slot (on-device GN loop),
+                         // followed by the overflow list [kOvfCap]
 };
 
 struct SolverParams {    // PoseEstimatorParameters (pose_estimator_params.h) + loss
@@ -108,6 +117,7 @@ struct SolveArgs {
   LevelStats* stats;     // [num_levels]
   int* num_fun_evals;
   long long* prof;       // optional: per-phase cycle counters of CTA 0 (nullptr = off)
+  unsigned seq_base;     // first sequence number of this launch's exchanges (monotonic across launches of a ctx)
 };
 
 }  // namespace bp

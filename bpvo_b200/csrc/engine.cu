@@ -161,15 +161,17 @@ int bpvo_b200_create(bpvo_b200_ctx** out, const float K[9], float baseline, int 
   (void) cap0;
   CUDA_TRY(cudaMalloc(&c->work.res, capmax * c->C * sizeof(float)));
   CUDA_TRY(cudaMalloc(&c->work.valid, capmax));
-  CUDA_TRY(cudaMalloc(&c->work.hist, 2 * kHistWords * sizeof(unsigned)));
+  CUDA_TRY(cudaMalloc(&c->work.hist, (kHistSets * kHistWords + 8) * sizeof(unsigned)));
+  CUDA_TRY(cudaMalloc(&c->work.ll, (size_t) 4 * kMaxGrid * 32 * sizeof(uint4)));
+  CUDA_TRY(cudaMemsetAsync(c->work.ll, 0, (size_t) 4 * kMaxGrid * 32 * sizeof(uint4), c->stream));
   CUDA_TRY(cudaMalloc(&c->work.partials, (size_t) 1024 * kPartialStride * sizeof(double)));
   CUDA_TRY(cudaMalloc(&c->work.scale, sizeof(ScaleState)));
   CUDA_TRY(cudaMalloc(&c->work.out, sizeof(LinOut)));
   CUDA_TRY(cudaMalloc(&c->work.ticket, 4 * sizeof(unsigned)));
-  CUDA_TRY(cudaMalloc(&c->work.cand, kCandCap * sizeof(float)));
+  CUDA_TRY(cudaMalloc(&c->work.cand, ((size_t) kMaxGrid * kCandPerCta + kOvfCap) * sizeof(float)));
   CUDA_TRY(cudaMalloc(&c->sel, sizeof(Sel)));
   CUDA_TRY(cudaMalloc(&c->export_buf, capmax * c->C * 6 * sizeof(float)));
-  CUDA_TRY(cudaMemsetAsync(c->work.hist, 0, 2 * kHistWords * sizeof(unsigned), c->stream));
+  CUDA_TRY(cudaMemsetAsync(c->work.hist, 0, (kHistSets * kHistWords + 8) * sizeof(unsigned), c->stream));
   CUDA_TRY(cudaMemsetAsync(c->work.ticket, 0, 4 * sizeof(unsigned), c->stream));
   CUDA_TRY(cudaMemsetAsync(c->work.out, 0, sizeof(LinOut), c->stream));
   CUDA_TRY(cudaMemsetAsync(c->sel, 0, sizeof(Sel), c->stream));
@@ -184,8 +186,8 @@ int bpvo_b200_create(bpvo_b200_ctx** out, const float K[9], float baseline, int 
   CUDA_TRY(cudaMalloc(&c->d_T, sizeof(M44)));
   CUDA_TRY(cudaMalloc(&c->d_stats, kMaxLevels * sizeof(LevelStats)));
   CUDA_TRY(cudaMalloc(&c->d_evals, sizeof(int)));
-  CUDA_TRY(cudaMalloc(&c->d_prof, 32 * sizeof(long long)));
-  CUDA_TRY(cudaMemsetAsync(c->d_prof, 0, 32 * sizeof(long long), c->stream));
+  CUDA_TRY(cudaMalloc(&c->d_prof, 64 * sizeof(long long)));
+  CUDA_TRY(cudaMemsetAsync(c->d_prof, 0, 64 * sizeof(long long), c->stream));
   CUDA_TRY(cudaHostAlloc(&c->h_mail, sizeof(Mailbox), cudaHostAllocDefault));
   memset(c->h_mail, 0, sizeof(Mailbox));
   CUDA_TRY(cudaHostAlloc(&c->stage_img, (size_t) rows * cols, cudaHostAllocDefault));
@@ -200,7 +202,7 @@ int bpvo_b200_destroy(bpvo_b200_ctx* c) {
   cudaSetDevice(c->p.device_id);
   cudaStreamSynchronize(c->stream);
   bp_comm_destroy(c);
-  cudaFree(c->work.res); cudaFree(c->work.valid); cudaFree(c->work.hist); cudaFree(c->work.partials);
+  cudaFree(c->work.res); cudaFree(c->work.valid); cudaFree(c->work.hist); cudaFree(c->work.ll); cudaFree(c->work.partials);
   cudaFree(c->work.scale); cudaFree(c->work.out); cudaFree(c->work.ticket); cudaFree(c->work.cand); cudaFree(c->sel); cudaFree(c->export_buf);
   cudaFree(c->flags); cudaFree(c->block_counts); cudaFree(c->hpartials); cudaFree(c->hsums);
   cudaFree(c->d_T); cudaFree(c->d_stats); cudaFree(c->d_evals); cudaFree(c->d_prof);
@@ -234,12 +236,12 @@ int bpvo_b200_last_level_evals(bpvo_b200_ctx* c, int* evals) {
   for (int l = 0; l < c->L; ++l) evals[l] = c->level_evals[l];
   return BPVO_B200_OK;
 }
-int bpvo_b200_get_phase_cycles(bpvo_b200_ctx* c, long long cycles[32], int reset) {
+int bpvo_b200_get_phase_cycles(bpvo_b200_ctx* c, long long cycles[64], int reset) {
   if (!c || !cycles) return bp_fail(BPVO_B200_ERR_INVALID_ARG, "null argument");
   CUDA_TRY(cudaSetDevice(c->p.device_id));
   CUDA_TRY(cudaStreamSynchronize(c->stream));
-  CUDA_TRY(cudaMemcpy(cycles, c->d_prof, 32 * sizeof(long long), cudaMemcpyDeviceToHost));
-  if (reset) CUDA_TRY(cudaMemset(c->d_prof, 0, 32 * sizeof(long long)));
+  CUDA_TRY(cudaMemcpy(cycles, c->d_prof, 64 * sizeof(long long), cudaMemcpyDeviceToHost));
+  if (reset) CUDA_TRY(cudaMemset(c->d_prof, 0, 64 * sizeof(long long)));
   return BPVO_B200_OK;
 }
 int bpvo_b200_set_profiling(bpvo_b200_ctx* c, int enable) { if (!c) return bp_fail(BPVO_B200_ERR_INVALID_ARG, "null ctx"); c->profiling = enable != 0; return BPVO_B200_OK; }
@@ -667,10 +669,16 @@ static int launch_estimate_pose(bpvo_b200_ctx* c, const bpvo_b200_frame* ref, co
   a.sp.max_test_level = c->p.maxTestLevel; a.sp.num_levels = c->L;
   a.work = c->work; a.T_init = T_init; a.T_out = c->d_T; a.stats = c->d_stats; a.num_fun_evals = c->d_evals;
   a.prof = c->profiling ? c->d_prof : nullptr;
-  Sel* sel = c->sel; int parity = 0;
-  // both histogram sets must be zero on entry (the kernel leaves them zeroed for the next call, but the
-  // host-driven path may have dirtied set 0 in between)
-  CUDA_TRY(cudaMemsetAsync(c->work.hist, 0, 2 * kHistWords * sizeof(unsigned), c->stream));
+  Sel* sel = c->sel;
+  // the grid-barrier counter (behind the histogram sets) must be zero on entry; the kernel zeroes the sets itself
+  CUDA_TRY(cudaMemsetAsync(c->work.hist + (size_t) kHistSets * kHistWords, 0, 8 * sizeof(unsigned), c->stream));
+  // sequence numbers of the flag-in-data exchanges: unique per exchange over the life of the mailboxes
+  const unsigned seq_span = (unsigned) (c->L * (std::min(c->p.maxIterations + 2, 1200) + 2) + 2);
+  if (c->ll_seq == 0 || c->ll_seq > 0xffffffffu - seq_span) {
+    CUDA_TRY(cudaMemsetAsync(c->work.ll, 0, (size_t) 4 * kMaxGrid * 32 * sizeof(uint4), c->stream));
+    c->ll_seq = 1;
+  }
+  a.seq_base = c->ll_seq; c->ll_seq += seq_span;
   // dynamic shared memory: candidate scratch + as many template-cache slots per thread as fit (1 CTA per SM)
   const int per_slot = tpl_cache_bytes_per_slot<C>();
   int slots = (c->smem_optin - 24 * 1024 - kScratchBytes) / per_slot;
@@ -681,8 +689,8 @@ static int launch_estimate_pose(bpvo_b200_ctx* c, const bpvo_b200_frame* ref, co
     CUDA_TRY(cudaFuncSetAttribute((const void*) k_estimate_pose<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) dyn));
     configured[C == 8] = dyn;
   }
-  void* args[] = {&a, &sel, &parity, &slots};
-  int grid = c->sm_count;
+  void* args[] = {&a, &sel, &slots};
+  int grid = std::min(c->sm_count, kMaxGrid);
   CUDA_TRY(cudaLaunchCooperativeKernel((void*) k_estimate_pose<C>, dim3(grid), dim3(kLinThreads), args, dyn, c->stream));
   c->counters.launches++;
   return BPVO_B200_OK;
@@ -720,6 +728,7 @@ extern "C" int bpvo_b200_estimate_pose(bpvo_b200_ctx* c, const bpvo_b200_frame* 
     c->counters.linearize_calls += evals;
     for (int l = c->p.maxTestLevel; l < c->L; ++l) {
       if (mb->stats[l].status == -3) return bp_fail(BPVO_B200_ERR_NO_POINTS, "you should call setData before calling computeResiduals");
+      if (mb->stats[l].status == -4) return bp_fail(BPVO_B200_ERR_CUDA, "on-device GN loop: a grid barrier / exchange timed out");
       stats[l].numIterations = mb->stats[l].num_iterations; stats[l].finalError = mb->stats[l].final_error;
       stats[l].firstOrderOptimality = mb->stats[l].first_order_optimality; stats[l].status = mb->stats[l].status;
       c->level_evals[l] = mb->stats[l].num_evals;

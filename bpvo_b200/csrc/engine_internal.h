@@ -43,6 +43,7 @@ struct bpvo_b200_ctx {
   void* flush_buf = nullptr;
   const bpvo_b200_frame* last_ref = nullptr; int last_level = 0;
   bool profiling = false;
+  unsigned ll_seq = 0;           // next sequence number of the persistent kernel's exchanges
   bpvo_b200_counters counters{};
   // multi-GPU
   int shard_rank = 0, shard_size = 1;

@@ -99,12 +99,14 @@ template <int C> __device__ __forceinline__ void tc_fill(const TplCache& tc, con
 
 // fine-grained in-kernel profile (debug aid, compile with -DBP_FINE_PROFILE): CTA 0 / thread 0 accumulates the cycles
 // between consecutive marks into prof[16 + ...]
+// profile counters of CTA 0 live in shared memory while the kernel runs (a global read-modify-write per mark would
+// cost more than the phases being measured) and are added to the ctx's device buffer once, at the end of the launch:
+// [0..63] cycle / event slots, [64] last coarse mark, [65] last fine mark, [66] fine marks enabled
+__device__ __forceinline__ long long* prof_smem() { __shared__ long long s_prof[68]; return s_prof; }
 #ifdef BP_FINE_PROFILE
-__device__ long long* g_fine_prof = nullptr;
-__device__ long long g_fine_last = 0;
 #define BP_FINE(slot)                                                                                          \
-  do { if (g_fine_prof && blockIdx.x == 0 && threadIdx.x == 0) { const long long _t = clock64(); g_fine_prof[slot] += _t - g_fine_last; g_fine_last = _t; } } while (0)
-#define BP_FINE_INIT(ptr) do { if (blockIdx.x == 0) { g_fine_prof = (ptr); g_fine_last = clock64(); } } while (0)
+  do { if (blockIdx.x == 0 && threadIdx.x == 0) { long long* _s = prof_smem(); if (_s[66] == 0x5eed) { const long long _t = clock64(); _s[slot] += _t - _s[65]; _s[65] = _t; } } } while (0)
+#define BP_FINE_INIT(ptr) do { if (blockIdx.x == 0 && threadIdx.x == 0) { long long* _s = prof_smem(); _s[66] = (ptr) ? 0x5eed : 0; _s[65] = clock64(); } } while (0)
 #else
 #define BP_FINE(slot) do { } while (0)
 #define BP_FINE_INIT(ptr) do { } while (0)
@@ -119,6 +121,7 @@ struct Sel {            // radix-select bookkeeping of one linearize (global, wr
 struct LinShared {      // static shared memory of the linearize phases
   unsigned hist[2 * kHist2Bins];          // 16 KB, reused by every phase
   double red[kLinThreads / 32][kPartialStride];
+  double xch[kLinThreads / 32][kPartialStride];   // staging of exchange_sums() (separate from red: no barrier between P4's CTA sum and the exchange)
   unsigned scan[kLinThreads / 32];
   unsigned found[8];
 };
@@ -127,14 +130,14 @@ struct LinShared {      // static shared memory of the linearize phases
 // CTA-wide: locate the bins holding ranks ra and rb in a histogram of NB bins (NB multiple of blockDim).
 // Returns (bin, rank inside bin) for both, and the total count.  All threads get the results.
 // ---------------------------------------------------------------------------------------------
-template <int NB>
-__device__ __forceinline__ void block_find2(const unsigned* __restrict__ hist, unsigned ra, unsigned rb, LinShared& sh,
-                                            unsigned& bin_a, unsigned& rem_a, unsigned& bin_b, unsigned& rem_b, unsigned& total) {
-  constexpr int PER = (NB + kLinThreads - 1) / kLinThreads;
+// (counts already in registers: thread t holds bins [t * PER, t * PER + PER))
+template <int PER>
+__device__ __forceinline__ void block_find2_regs(const unsigned (&loc)[PER], unsigned ra, unsigned rb, LinShared& sh,
+                                                 unsigned& bin_a, unsigned& rem_a, unsigned& bin_b, unsigned& rem_b, unsigned& total) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  unsigned loc[PER], sum = 0;
+  unsigned sum = 0;
 #pragma unroll
-  for (int k = 0; k < PER; ++k) { const int b = tid * PER + k; loc[k] = (b < NB) ? hist[b] : 0u; sum += loc[k]; }
+  for (int k = 0; k < PER; ++k) sum += loc[k];
   unsigned incl = sum;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
@@ -156,6 +159,15 @@ __device__ __forceinline__ void block_find2(const unsigned* __restrict__ hist, u
   __syncthreads();
   bin_a = sh.found[0]; rem_a = sh.found[1]; bin_b = sh.found[2]; rem_b = sh.found[3]; total = tot;
 }
+template <int NB>
+__device__ __forceinline__ void block_find2(const unsigned* __restrict__ hist, unsigned ra, unsigned rb, LinShared& sh,
+                                            unsigned& bin_a, unsigned& rem_a, unsigned& bin_b, unsigned& rem_b, unsigned& total) {
+  constexpr int PER = (NB + kLinThreads - 1) / kLinThreads;
+  unsigned loc[PER];
+#pragma unroll
+  for (int k = 0; k < PER; ++k) { const int b = threadIdx.x * PER + k; loc[k] = (b < NB) ? hist[b] : 0u; }
+  block_find2_regs<PER>(loc, ra, rb, sh, bin_a, rem_a, bin_b, rem_b, total);
+}
 
 // projection matrix P = K * T[0:3,:] in fp32 (rigid_body_warp.h:111-114), column-major 3x4
 __host__ __device__ __forceinline__ void make_projection(const LevelTemplate& L, const M44& T, float P[12]) {
@@ -174,7 +186,9 @@ __host__ __device__ __forceinline__ void make_projection(const LevelTemplate& L,
 struct Bracket {       // median bracket carried from the previous GN iteration (on-device loop only)
   bool on;
   float lo, hi;        // candidates are the valid |r| with lo <= |r| <= hi
+  float inv_w;         // kSelBins / (hi - lo): candidates are also counted by linear bin over the bracket
 };
+__device__ __forceinline__ int sel_bin(float v, float lo, float inv_w) { return min(kSelBins - 1, (int) ((v - lo) * inv_w)); }
 
 template <int C>
 __device__ __forceinline__ void phase_residuals(const LevelTemplate& L, const LevelImage& I, const float* P, const Work& W,
@@ -184,7 +198,7 @@ __device__ __forceinline__ void phase_residuals(const LevelTemplate& L, const Le
   const bool do_hist1 = do_hist && !br.on;   // with a bracket the level-1 histogram is only built (phase_hist1) if the bracket misses
   if (do_hist1) { for (int b = tid; b < kHist1Bins; b += kLinThreads) sh.hist[b] = 0; }
   if (tid < 4) sh.found[4 + tid] = 0;        // CTA-level counters: [4] valid points, [5] below bracket, [6] candidates of this CTA
-  float* cta_cand = reinterpret_cast<float*>(scratch);    // CTA-local candidate list (bracket on), flushed with ONE global atomic
+  float* cta_cand = reinterpret_cast<float*>(scratch);    // CTA-local candidate list (bracket on)
   __syncthreads();
   BP_FINE(16);
   unsigned cnt_valid = 0, cnt_below = 0;
@@ -239,6 +253,7 @@ __device__ __forceinline__ void phase_residuals(const LevelTemplate& L, const Le
             if (a >= br.lo && a <= br.hi) {
               const unsigned slot = atomicAdd(&sh.found[6], 1u);        // shared-memory append; overflow is only counted
               if (slot < (unsigned) kCtaCandCap) cta_cand[slot] = a;
+              atomicAdd(hist1 + kHistBins + 8 + sel_bin(a, br.lo, br.inv_w), 1u);      // global bracket histogram (fire and forget)
             }
           }
         }
@@ -247,8 +262,9 @@ __device__ __forceinline__ void phase_residuals(const LevelTemplate& L, const Le
 #pragma unroll
       for (int c = 0; c < C; ++c) r.v[c] = 0.0f;
     }
-    r.store(W.res + (size_t) i * C);
-    W.valid[i] = ok ? 1 : 0;
+    // residuals / valid flags stay in shared memory while the level is cached (C = 8: written back once, after the last
+    // iteration of the finest level); C = 1 keeps the global copy for the n < 3 median rule of finish_scale()
+    if (!(tc.K && C == 8)) { r.store(W.res + (size_t) i * C); W.valid[i] = ok ? 1 : 0; }
     if (tc.K) { tc_put<C>(tc, k, TC_R, r); tc.valid[k * kLinThreads + tid] = ok ? 1 : 0; }
   }
   BP_FINE(17);
@@ -270,15 +286,26 @@ __device__ __forceinline__ void phase_residuals(const LevelTemplate& L, const Le
     if (tid == 0) {
       if (sh.found[4]) atomicAdd(hist1 + kHistBins + 1, sh.found[4]);
       if (sh.found[5]) atomicAdd(hist1 + kHistBins + 2, sh.found[5]);
-      // reserve this CTA's range in the global candidate buffer; a CTA-local overflow poisons the global count so that
-      // the select falls back to the radix path (correctness never depends on the bracket)
+      // candidate count; a CTA whose fixed region overflowed poisons it so that the select falls back to the radix path
+      // (correctness never depends on the bracket).  No return value is needed: nothing here waits for the L2.
       const unsigned nc = sh.found[6];
-      sh.found[7] = nc ? atomicAdd(hist1 + kHistBins + 3, nc > (unsigned) kCtaCandCap ? (unsigned) (2 * kCandCap) : nc) : 0u;
+      if (nc) atomicAdd(hist1 + kHistBins + 3, nc > (unsigned) kCtaCandCap ? kCandPoison : nc);
     }
     if (br.on) {
-      __syncthreads();
-      const unsigned nc = min(sh.found[6], (unsigned) kCtaCandCap), base = sh.found[7];
-      for (unsigned j = tid; j < nc; j += kLinThreads) if (base + j < (unsigned) kCandCap) W.cand[base + j] = cta_cand[j];
+      const unsigned nc = sh.found[6];
+      if (tid < kCandPerCta)                  // this CTA's region of the candidate buffer: values, then -1 = empty
+        W.cand[(size_t) block * kCandPerCta + tid] = ((unsigned) tid < nc) ? cta_cand[tid] : -1.0f;
+      if (nc > (unsigned) kCandPerCta && nc <= (unsigned) kCtaCandCap) {       // rare (wide bracket): the rest goes to the shared overflow list
+        if (tid == 0) {
+          const unsigned extra = nc - kCandPerCta, base = atomicAdd(hist1 + kHistBins + 4, extra);
+          if (base + extra > (unsigned) kOvfCap) atomicAdd(hist1 + kHistBins + 3, kCandPoison);
+          sh.found[7] = base;
+        }
+        __syncthreads();
+        const unsigned base = sh.found[7];
+        float* ovf = W.cand + (size_t) nblocks * kCandPerCta;
+        for (unsigned j = tid; j < nc - kCandPerCta; j += kLinThreads) if (base + j < (unsigned) kOvfCap) ovf[base + j] = cta_cand[kCandPerCta + j];
+      }
     }
   }
   BP_FINE(19);
@@ -392,76 +419,77 @@ __device__ __forceinline__ float finish_scale(const Work& W, const unsigned* __r
   return scale_from_median(n, med);
 }
 
-// Bracketed exact median (on-device loop): P1 counted the valid residuals below the bracket and appended the ones
-// inside it to W.cand.  If both middle ranks fall inside and the buffer did not overflow, the two order statistics
-// are found by rank counting among <= kCandCap candidates in shared memory -- no further pass over the residuals,
-// no further grid sync.  Returns false when the bracket missed (caller falls back to the 3-level radix select).
+// Bracketed exact median (on-device loop): P1 counted the valid residuals below the bracket and left the ones inside it
+// in the per-CTA regions of W.cand.  If both middle ranks fall inside and no region overflowed, the two order statistics
+// are found among the candidates (a few hundred) by linear binning + rank counting -- no further pass over the
+// residuals, no further grid barrier.  The candidates stay in REGISTERS (one L2 round trip fetches all regions and the
+// counters); only the histogram and the final short list touch shared memory.
+// Returns false when the bracket missed (caller falls back to the 3-level radix select).
+constexpr int kSelPre = 7;    // candidate slots per thread held in registers (covers 149 CTAs x kCandPerCta); more are re-read
+static_assert(kSelBins == 4 * kLinThreads, "bracket_select loads the bracket histogram as one uint4 per thread");
 template <int C>
-__device__ __forceinline__ bool bracket_select(const Work& W, const unsigned* __restrict__ hset, LinShared& sh, unsigned* scratch,
-                                               float bl, float bh, unsigned& n_out, unsigned& ncand_out, float& lo_out, float& hi_out) {
+__device__ __forceinline__ bool bracket_select(const Work& W, const unsigned* __restrict__ hset, LinShared& sh, unsigned* scratch, int nblocks,
+                                               const Bracket& br, unsigned& n_out, unsigned& ncand_out, float& lo_out, float& hi_out) {
   const int tid = threadIdx.x;
-  // one L2 round trip: the three counters and (speculatively) the first 4 candidates of every thread are requested together
-  float pre[4];
+  const unsigned total = (unsigned) nblocks * kCandPerCta;
+  // ONE L2 round trip: bracket histogram, counters and every CTA's candidate region are requested together
+  const uint4 gb = __ldcg(reinterpret_cast<const uint4*>(hset + kHistBins + 8) + tid);
+  float pre[kSelPre];
 #pragma unroll
-  for (int q = 0; q < 4; ++q) pre[q] = __ldcg(W.cand + tid + q * kLinThreads);
+  for (int q = 0; q < kSelPre; ++q) { const unsigned j = tid + q * kLinThreads; pre[q] = (j < total) ? __ldcg(W.cand + j) : -1.0f; }
   const unsigned nv = __ldcg(hset + kHistBins + 1), below = __ldcg(hset + kHistBins + 2), ncand = __ldcg(hset + kHistBins + 3);
+  const unsigned novf = __ldcg(hset + kHistBins + 4);
+  const float* ovf = W.cand + (size_t) nblocks * kCandPerCta;
   const unsigned n = nv * (unsigned) C;
   n_out = n; ncand_out = ncand;
   if (n < 3) return false;
   const unsigned t_hi = n / 2, t_lo = (n % 2 == 0) ? t_hi - 1 : t_hi;
-  if (ncand > (unsigned) kCandCap || below > t_lo || t_hi >= below + ncand) return false;
+  if (ncand >= kCandPoison || novf > (unsigned) kOvfCap || below > t_lo || t_hi >= below + ncand) return false;
   const unsigned ra = t_lo - below, rb = t_hi - below;
-  // carve-up of the dynamic-shared-memory scratch area (kScratchBytes)
-  float* cand = reinterpret_cast<float*>(scratch);                 // [kCandCap]
-  unsigned* bins = scratch + kCandCap;                             // [1024]
-  float* list = reinterpret_cast<float*>(scratch + kCandCap + 1024);   // [256]
-  constexpr int kList = 256, kBins = 1024;
-  __syncthreads();
+  BP_FINE(33);
+  float* list = reinterpret_cast<float*>(scratch + kCtaCandCap);   // [kSelList]
+  // the linear (monotone) binning over [lo, hi] puts the wanted ranks into bins holding a handful of values
+  const unsigned loc[4] = {gb.x, gb.y, gb.z, gb.w};
+  unsigned bin_a, rem_a, bin_b, rem_b, tot;
+  block_find2_regs<4>(loc, ra, rb, sh, bin_a, rem_a, bin_b, rem_b, tot);      // resets sh.found[0..7]
+  BP_FINE(36);
 #pragma unroll
-  for (int q = 0; q < 4; ++q) { const unsigned j = tid + q * kLinThreads; if (j < ncand) cand[j] = pre[q]; }
-  for (unsigned j = tid + 4 * kLinThreads; j < ncand; j += kLinThreads) cand[j] = __ldcg(W.cand + j);
-  if (tid < 4) sh.found[4 + tid] = 0;       // [4] list length, [6] lo bits, [7] hi bits
-  __syncthreads();
-  if (ncand <= 128u) {
-    if (tid < (int) ncand) {
-      const float v = cand[tid];
-      unsigned rank = 0;
-      for (unsigned j = 0; j < ncand; ++j) { const float u = cand[j]; rank += (u < v || (u == v && j < (unsigned) tid)) ? 1u : 0u; }
-      if (rank == ra) sh.found[6] = __float_as_uint(v);
-      if (rank == rb) sh.found[7] = __float_as_uint(v);
+  for (int q = 0; q < kSelPre; ++q) {
+    if (pre[q] >= 0.0f) {
+      const unsigned b = (unsigned) sel_bin(pre[q], br.lo, br.inv_w);
+      if (b == bin_a || b == bin_b) { const unsigned slot = atomicAdd(&sh.found[4], 1u); if (slot < (unsigned) kSelList) list[slot] = pre[q]; }
     }
-    __syncthreads();
-  } else {
-    // candidates live in [bl, bh]: a linear (monotone) binning puts the wanted ranks into bins holding a handful of values
-    const float inv_w = (bh > bl) ? (float) kBins / (bh - bl) : 0.0f;
-    for (int b = tid; b < kBins; b += kLinThreads) bins[b] = 0;
-    __syncthreads();
-    for (unsigned j = tid; j < ncand; j += kLinThreads) atomicAdd(&bins[min(kBins - 1, (int) ((cand[j] - bl) * inv_w))], 1u);
-    __syncthreads();
-    unsigned bin_a, rem_a, bin_b, rem_b, tot;
-    block_find2<kBins>(bins, ra, rb, sh, bin_a, rem_a, bin_b, rem_b, tot);      // resets sh.found[0..7]
-    for (unsigned j = tid; j < ncand; j += kLinThreads) {
-      const float v = cand[j];
-      const unsigned b = (unsigned) min(kBins - 1, (int) ((v - bl) * inv_w));
-      if (b == bin_a || b == bin_b) { const unsigned slot = atomicAdd(&sh.found[4], 1u); if (slot < (unsigned) kList) list[slot] = v; }
-    }
-    __syncthreads();
-    const unsigned nl = sh.found[4];
-    if (nl > (unsigned) kList) return false;       // pathological pile-up of equal values: let the radix select handle it
-    if (tid < (int) nl) {
-      const float v = list[tid];
-      const unsigned bj = (unsigned) min(kBins - 1, (int) ((v - bl) * inv_w));
-      unsigned rank = 0;
-      for (unsigned j = 0; j < nl; ++j) {
-        const float u = list[j];
-        const unsigned bu = (unsigned) min(kBins - 1, (int) ((u - bl) * inv_w));
-        rank += (bu == bj && (u < v || (u == v && j < (unsigned) tid))) ? 1u : 0u;
-      }
-      if (bj == bin_a && rank == rem_a) sh.found[6] = __float_as_uint(v);
-      if (bj == bin_b && rank == rem_b) sh.found[7] = __float_as_uint(v);
-    }
-    __syncthreads();
   }
+  for (unsigned j = tid + kSelPre * kLinThreads; j < total; j += kLinThreads) {
+    const float v = __ldcg(W.cand + j);
+    if (v >= 0.0f) {
+      const unsigned b = (unsigned) sel_bin(v, br.lo, br.inv_w);
+      if (b == bin_a || b == bin_b) { const unsigned slot = atomicAdd(&sh.found[4], 1u); if (slot < (unsigned) kSelList) list[slot] = v; }
+    }
+  }
+  for (unsigned j = tid; j < novf; j += kLinThreads) {
+    const float v = __ldcg(ovf + j);
+    const unsigned b = (unsigned) sel_bin(v, br.lo, br.inv_w);
+    if (b == bin_a || b == bin_b) { const unsigned slot = atomicAdd(&sh.found[4], 1u); if (slot < (unsigned) kSelList) list[slot] = v; }
+  }
+  __syncthreads();
+  BP_FINE(37);
+  const unsigned nl = sh.found[4];
+  if (nl > (unsigned) kSelList) return false;       // pathological pile-up of equal values: let the radix select handle it
+  if (tid < (int) nl) {
+    const float v = list[tid];
+    const unsigned bj = (unsigned) sel_bin(v, br.lo, br.inv_w);
+    unsigned rank = 0;
+    for (unsigned j = 0; j < nl; ++j) {
+      const float u = list[j];
+      const unsigned bu = (unsigned) sel_bin(u, br.lo, br.inv_w);
+      rank += (bu == bj && (u < v || (u == v && j < (unsigned) tid))) ? 1u : 0u;
+    }
+    if (bj == bin_a && rank == rem_a) sh.found[6] = __float_as_uint(v);
+    if (bj == bin_b && rank == rem_b) sh.found[7] = __float_as_uint(v);
+  }
+  __syncthreads();
+  BP_FINE(38);
   lo_out = __uint_as_float(sh.found[6]); hi_out = __uint_as_float(sh.found[7]);
   return true;
 }
@@ -485,9 +513,11 @@ __device__ __forceinline__ float robust_weight(int loss, float r, float sigma_in
 // Partial layout (kPartialStride doubles): [0..20] upper triangle of H row-major, [21..26] G, [27] sum w r^2,
 // [28] count(w > good_threshold), [29] valid points.
 // ---------------------------------------------------------------------------------------------
+// Returns, in thread k < 30, the CTA total of scalar k.  write_partials: also store it to W.partials (+ fence) for the
+// last-CTA fold of the host-driven kernels; the persistent kernel exchanges the totals itself (exchange_sums).
 template <int C>
-__device__ __forceinline__ void phase_reduce(const LevelTemplate& L, const Work& W, float sigma, int loss, float good_thr,
-                                             const TplCache& tc, const TemplateMeta& m, LinShared& sh, int block, int nblocks, bool fence = true) {
+__device__ __forceinline__ double phase_reduce(const LevelTemplate& L, const Work& W, float sigma, int loss, float good_thr,
+                                               const TplCache& tc, const TemplateMeta& m, LinShared& sh, int block, int nblocks, bool write_partials = true) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   float acc[30];
 #pragma unroll
@@ -558,13 +588,30 @@ __device__ __forceinline__ void phase_reduce(const LevelTemplate& L, const Work&
   BP_FINE(22);
   __syncthreads();
   BP_FINE(23);
+  double v = 0.0;
   if (tid < 30) {
-    double v = 0.0;
     for (int w = 0; w < n_active_warps; ++w) v += sh.red[w][tid];
-    W.partials[(size_t) block * kPartialStride + tid] = v;
-    if (fence) __threadfence();     // last-CTA pattern of the host-driven path; the persistent path relies on grid.sync()
+    if (write_partials) { W.partials[(size_t) block * kPartialStride + tid] = v; __threadfence(); }   // last-CTA pattern of the host-driven path
   }
   BP_FINE(24);
+  return v;
+}
+
+// the 30 fp64 totals in sh.red[0][0..29] -> LinOut (H symmetric column-major, G, sqrt(sum w r^2), counts)
+__device__ __forceinline__ void finish_sums(float sigma, LinShared& sh, LinOut& out /* shared or global */) {
+  const int tid = threadIdx.x;
+  if (tid < 36) {                       // H: thread (a, b) picks its upper-triangle entry
+    const int a = tid / 6, b = tid % 6, lo = a < b ? a : b, hi = a < b ? b : a;
+    out.H[b * 6 + a] = (float) sh.red[0][lo * 6 - lo * (lo - 1) / 2 + (hi - lo)];
+  } else if (tid < 42) {
+    out.G[tid - 36] = (float) sh.red[0][21 + tid - 36];
+  } else if (tid == 42) {
+    out.f_norm = sqrtf((float) sh.red[0][27]);
+    out.n_good = (int) (sh.red[0][28] + 0.5);
+    out.n_valid = (int) (sh.red[0][29] + 0.5);
+    out.sigma = sigma;
+  }
+  __syncthreads();
 }
 
 // fixed-order sum of the CTA partials -> LinOut (whole CTA participates; result valid in `out` for thread 0
@@ -590,18 +637,7 @@ __device__ __forceinline__ void final_sum(const Work& W, int nblocks, float sigm
     sh.red[0][tid] = t;
   }
   __syncthreads();
-  if (tid < 36) {                       // H: thread (a, b) picks its upper-triangle entry
-    const int a = tid / 6, b = tid % 6, lo = a < b ? a : b, hi = a < b ? b : a;
-    out.H[b * 6 + a] = (float) sh.red[0][lo * 6 - lo * (lo - 1) / 2 + (hi - lo)];
-  } else if (tid < 42) {
-    out.G[tid - 36] = (float) sh.red[0][21 + tid - 36];
-  } else if (tid == 42) {
-    out.f_norm = sqrtf((float) sh.red[0][27]);
-    out.n_good = (int) (sh.red[0][28] + 0.5);
-    out.n_valid = (int) (sh.red[0][29] + 0.5);
-    out.sigma = sigma;
-  }
-  __syncthreads();
+  finish_sums(sigma, sh, out);
 }
 
 // =============================================================================================
@@ -621,7 +657,7 @@ struct LinArgs {
 template <int C> __global__ void __launch_bounds__(kLinThreads, 1) k_residuals(LinArgs a) {
   __shared__ LinShared sh;
   const bool do_hist = (a.loss != 0x12) && (a.work.scale->delta > 1e-6f);
-  phase_residuals<C>(a.tmpl, a.img, a.P, a.work, a.hset, do_hist, Bracket{false, 0.0f, 0.0f}, TplCache{nullptr, nullptr, nullptr, 0}, *a.tmpl.meta, nullptr, sh, blockIdx.x, gridDim.x);
+  phase_residuals<C>(a.tmpl, a.img, a.P, a.work, a.hset, do_hist, Bracket{false, 0.0f, 0.0f, 0.0f}, TplCache{nullptr, nullptr, nullptr, 0}, *a.tmpl.meta, nullptr, sh, blockIdx.x, gridDim.x);
 }
 template <int C, int LEVEL> __global__ void __launch_bounds__(kLinThreads, 1) k_select(LinArgs a) {
   __shared__ LinShared sh;
@@ -703,18 +739,126 @@ __global__ void __launch_bounds__(256) k_export_weights(const float* __restrict_
 // persistent path: the whole estimatePose (all levels, all GN iterations, 6x6 solves, convergence
 // tests, pose updates) in ONE cooperative launch; the host sees only T_est and the statistics.
 // Every CTA carries the (tiny) solver state redundantly in shared memory and computes identical
-// values, so only histograms and CTA partials travel through global memory; 4 grid syncs / iteration.
+// values.  Per GN iteration the CTAs meet twice:
+//   * after P1: a grid barrier (counter + release/acquire), then every CTA finds the exact median itself;
+//   * after P4: NO barrier -- the 30 fp64 sums travel in a two-level flag-in-data exchange (each 16-byte word
+//     carries its own sequence number, so one L2 round trip delivers data and "ready" together), summed in a fixed
+//     order: bit-identical in every CTA and from run to run.
 // =============================================================================================
 // optional in-kernel phase profile (CTA 0, thread 0): cycles accumulated per phase of the GN loop
 #define BP_PROF(slot)                                                                       \
-  do { if (a.prof && blockIdx.x == 0 && threadIdx.x == 0) { const long long _t = clock64(); a.prof[slot] += _t - ss.t_last; ss.t_last = _t; } } while (0)
+  do { if (a.prof && blockIdx.x == 0 && threadIdx.x == 0) { long long* _s = prof_smem(); const long long _t = clock64(); _s[slot] += _t - _s[64]; _s[64] = _t; } } while (0)
 enum { PROF_P1 = 0, PROF_SYNC1, PROF_P2, PROF_SYNC2, PROF_P3, PROF_SYNC3, PROF_SCALE, PROF_P4, PROF_SYNC4, PROF_FINAL, PROF_SOLVE, PROF_OTHER, PROF_COUNT };
+
+constexpr unsigned kSpinLimit = 1u << 24;    // ~2 s of polling: a lost CTA ends the launch with an error status instead of hanging the GPU
+
+// Grid-wide barrier of the persistent kernel (all CTAs are co-resident: cooperative launch).  `counter` only grows;
+// `epoch` is the value it reaches when every CTA has arrived at this barrier (kept uniformly by all threads).
+__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& epoch, unsigned nblocks, int* abort_flag) {
+  epoch += nblocks;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+    unsigned v, spins = 0;
+    for (;;) {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+      if ((int) (v - epoch) >= 0) break;
+      if (++spins > kSpinLimit || *(volatile int*) abort_flag) { *abort_flag = 1; break; }
+    }
+  }
+  __syncthreads();
+}
+
+// flag-in-data words: {lo32(value), seq, hi32(value), seq}; a reader accepts a word only when both halves carry the
+// sequence number it waits for (needs only 8-byte single-copy atomicity)
+__device__ __forceinline__ void ll_post(uint4* p, double v, unsigned seq) {
+  const unsigned long long b = (unsigned long long) __double_as_longlong(v);
+  asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"((unsigned) b), "r"(seq), "r"((unsigned) (b >> 32)), "r"(seq) : "memory");
+}
+__device__ __forceinline__ bool ll_peek(const uint4* p, unsigned seq, double& v) {
+  unsigned x, f0, y, f1;
+  asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(x), "=r"(f0), "=r"(y), "=r"(f1) : "l"(p) : "memory");
+  v = __longlong_as_double((long long) (((unsigned long long) y << 32) | x));
+  return f0 == seq && f1 == seq;
+}
+
+// sum of up to NS words p[q * stride], q < cnt, all polled concurrently; fixed summation order
+template <int NS>
+__device__ __forceinline__ double ll_gather(const uint4* p, size_t stride, int cnt, unsigned seq, int* abort_flag) {
+  double v[NS]; bool ok[NS]; bool all = true;
+#pragma unroll
+  for (int q = 0; q < NS; ++q) { v[q] = 0.0; ok[q] = q >= cnt; all = all && ok[q]; }
+  unsigned spins = 0;
+  while (!all) {
+    all = true;
+#pragma unroll
+    for (int q = 0; q < NS; ++q) { if (!ok[q]) ok[q] = ll_peek(p + q * stride, seq, v[q]); all = all && ok[q]; }
+    if (!all && (++spins > kSpinLimit || *(volatile int*) abort_flag)) { *abort_flag = 1; break; }
+  }
+  double t = 0.0;
+#pragma unroll
+  for (int q = 0; q < NS; ++q) t += ok[q] && q < cnt ? v[q] : 0.0;
+  return t;
+}
+
+// All-to-all sum of the CTA totals (thread k < 30 passes `mine` = CTA total of scalar k) without a barrier:
+//   stage 1: CTA b posts its totals to slot b; the first CTA of every group of kLLGroup polls its members and posts the
+//            group totals;  stage 2: every CTA polls the <= ceil(nblocks / kLLGroup) group totals.
+// Mailboxes are double-buffered by the parity of `seq`: a CTA can be at most one exchange ahead of any other.
+// Result: sh.red[0][0..29] (valid after the trailing __syncthreads).
+__device__ __forceinline__ void exchange_sums(double mine, uint4* ll, unsigned seq, LinShared& sh, int blk, int nb, int* abort_flag) {
+  const int tid = threadIdx.x, k = tid & 31, g = tid >> 5;
+  constexpr int G = kLinThreads / 32;
+  uint4* box1 = ll + (size_t) (seq & 1u) * kMaxGrid * 32;                       // CTA totals
+  uint4* box2 = ll + (size_t) (2 + (seq & 1u)) * kMaxGrid * 32;                 // group totals
+  const int grp = blk / kLLGroup, lead = grp * kLLGroup, ngroups = (nb + kLLGroup - 1) / kLLGroup;
+  if (blk != lead) {
+    if (tid < 30) ll_post(box1 + (size_t) blk * 32 + tid, mine, seq);
+  } else {
+    BP_FINE(40);
+    const int members = min(kLLGroup, nb - lead) - 1;                          // besides the leader itself
+    constexpr int NS = (kLLGroup - 1 + G - 1) / G;
+    double v = 0.0;
+    if (k < 30) {
+      const int left = members - g;                                            // members g, g + G, ... of this thread
+      v = ll_gather<NS>(box1 + (size_t) (lead + 1 + g) * 32 + k, (size_t) G * 32, left > 0 ? (left + G - 1) / G : 0, seq, abort_flag);
+    }
+    sh.xch[g][k] = v;
+    __syncthreads();
+    if (tid < 30) {
+      double t = mine;
+#pragma unroll
+      for (int w = 0; w < G; ++w) t += sh.xch[w][tid];
+      ll_post(box2 + (size_t) grp * 32 + tid, t, seq);
+    }
+    __syncthreads();
+    BP_FINE(41);
+  }
+  double v = 0.0;
+  if (k < 30) {
+    for (int q0 = g; q0 < ngroups; q0 += 2 * G) {
+      const int left = ngroups - q0;
+      v += ll_gather<2>(box2 + (size_t) q0 * 32 + k, (size_t) G * 32, (left + G - 1) / G, seq, abort_flag);
+    }
+  }
+  BP_FINE(42);
+  sh.xch[g][k] = v;
+  __syncthreads();
+  if (tid < 30) {
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < G; ++w) t += sh.xch[w][tid];
+    sh.red[0][tid] = t;          // column tid of red[] is only ever touched by thread tid outside barriers
+  }
+  __syncthreads();
+  BP_FINE(43);
+}
 
 // the damped fp64 retry of solve6() is rare: keep it out of line so that it does not bloat the hot loop
 __device__ __noinline__ bool solve6_fallback(const float* H, const float* G, float* dp) { return solve6(H, G, dp); }
 
 struct SolveShared {
-  long long t_last;
+  int abort;           // a barrier / exchange timed out: every later wait returns immediately, the launch reports an error
   LinOut lin;
   M44 T, Td;
   float P[12];
@@ -727,79 +871,90 @@ struct SolveShared {
   float br_density;    // candidates per unit of relative half-width, from the last bracketed pass
 };
 
+// grid-uniform bookkeeping of the persistent kernel (identical in every thread of every CTA)
+struct GridSync {
+  unsigned* counter;   // grid-barrier counter (zeroed by the host before the launch)
+  unsigned epoch;      // value of *counter once every CTA has passed the last barrier
+  unsigned seq;        // sequence number of the next exchange
+  int hs;              // histogram set of the next linearize (cycles through kHistSets)
+};
+
 template <int C>
 __device__ __forceinline__ void device_linearize(const SolveArgs& a, int lvl, SolveShared& ss, LinShared& sh,
-                                                 const TplCache& tc, const TemplateMeta& meta, unsigned* scratch, cg::grid_group& grid,
-                                                 int& parity, Sel* sel) {
+                                                 const TplCache& tc, const TemplateMeta& meta, unsigned* scratch, GridSync& gs, Sel* sel) {
   const LevelTemplate& L = a.tmpl[lvl];
   const LevelImage& I = a.img[lvl];
   const int nb = gridDim.x, blk = blockIdx.x, tid = threadIdx.x;
-  unsigned* hset = a.work.hist + (size_t) parity * kHistWords;
-  unsigned* hother = a.work.hist + (size_t) (parity ^ 1) * kHistWords;
+  unsigned* hset = a.work.hist + (size_t) gs.hs * kHistWords;
+  // the set of the PREVIOUS linearize: zeroed after this iteration's barrier, next used two iterations from now, i.e.
+  // with the next iteration's barrier in between (all sets are zero at the start of a level)
+  unsigned* hprev = a.work.hist + (size_t) ((gs.hs + kHistSets - 1) % kHistSets) * kHistWords;
   const bool do_hist = (a.sp.loss != 0x12) && (ss.delta > 1e-6f);      // ss.P was set by thread 0 together with the pose
   BP_PROF(PROF_OTHER);
   Bracket br;
   br.on = do_hist && ss.br_on;
   br.lo = ss.br_lo * (1.0f - ss.br_rel); br.hi = ss.br_hi * (1.0f + ss.br_rel);
+  br.inv_w = (br.hi > br.lo) ? (float) kSelBins / (br.hi - br.lo) : 0.0f;
   phase_residuals<C>(L, I, ss.P, a.work, hset, do_hist, br, tc, meta, scratch, sh, blk, nb);
   BP_PROF(PROF_P1);
   float sigma = ss.scale;
   if (do_hist) {
-    grid.sync();
+    grid_barrier(gs.counter, gs.epoch, nb, &ss.abort);
     BP_PROF(PROF_SYNC1);
+    BP_FINE(32);
+    for (int b = blk * kLinThreads + tid; b < kHistWords; b += nb * kLinThreads) hprev[b] = 0;
     unsigned n = 0, ncand = 0; float lo = 0.0f, hi = 0.0f;
     bool hit = false;
-    if (br.on) hit = bracket_select<C>(a.work, hset, sh, scratch, br.lo, br.hi, n, ncand, lo, hi);
+    if (br.on) hit = bracket_select<C>(a.work, hset, sh, scratch, nb, br, n, ncand, lo, hi);
     if (hit) {
       const float med = (n % 2 != 0) ? hi : (float) ((double) __fadd_rn(lo, hi) / 2.0);
       sigma = scale_from_median(n, med);
       BP_PROF(PROF_SCALE);
     } else {
-      if (br.on) { phase_hist1<C>(a.work, hset, tc, meta, sh, blk, nb); grid.sync(); }      // bracket missed: build the histogram now
+      if (br.on) { phase_hist1<C>(a.work, hset, tc, meta, sh, blk, nb); grid_barrier(gs.counter, gs.epoch, nb, &ss.abort); }   // bracket missed: build the histogram now
       phase_select<C, 2>(L, a.work, hset, sel, tc, meta, sh, blk, nb);
       BP_PROF(PROF_P2);
-      grid.sync();
+      grid_barrier(gs.counter, gs.epoch, nb, &ss.abort);
       BP_PROF(PROF_SYNC2);
       phase_select<C, 3>(L, a.work, hset, sel, tc, meta, sh, blk, nb);
       BP_PROF(PROF_P3);
-      grid.sync();
+      grid_barrier(gs.counter, gs.epoch, nb, &ss.abort);
       BP_PROF(PROF_SYNC3);
       sigma = finish_scale<C>(a.work, hset, sel, sh, &lo, &hi);
       n = sel->n;
       BP_PROF(PROF_SCALE);
     }
     // Next bracket, centred on this median (every CTA computes the same).  Half-width: at least twice the distance
-    // the median just moved; otherwise sized from the measured candidate density so that ~600 values fall inside.
+    // the median just moved; otherwise sized from the measured candidate density so that ~500 values fall inside.
     if (tid == 0) {
       const float mid_new = 0.5f * (lo + hi), mid_old = 0.5f * (ss.br_lo + ss.br_hi);
       float rel = 0.03f;           // first bracket of a level: wide (the median still moves by percents), the 8192-entry buffer absorbs it
       if (ss.br_on && mid_new > 0.0f) {
         const float moved = fabsf(mid_new - mid_old) / mid_new;
         if (br.on && ncand > 0) ss.br_density = (float) ncand / fmaxf(ss.br_rel, 1e-6f);       // candidates per unit of rel
-        const float rel_density = (ss.br_density > 0.0f) ? 600.0f / ss.br_density : 0.002f;
+        const float rel_density = (ss.br_density > 0.0f) ? 500.0f / ss.br_density : 0.002f;
         rel = fmaxf(2.0f * moved, fminf(rel_density, 0.02f));
         rel = fminf(fmaxf(rel, 1e-5f), 0.05f);
       }
       ss.br_rel = rel; ss.br_lo = lo; ss.br_hi = hi; ss.br_on = (n >= 3) ? 1 : 0;
-      if (a.prof && blk == 0) { a.prof[12] += hit ? 1 : 0; a.prof[13] += 1; a.prof[14] += (br.on && !hit && ncand > (unsigned) kCandCap) ? 1 : 0; a.prof[15] += (br.on && !hit && ncand <= (unsigned) kCandCap) ? 1 : 0; }
+      if (a.prof && blk == 0) { long long* sp = prof_smem(); sp[12] += hit ? 1 : 0; sp[13] += 1; sp[14] += (br.on && !hit && ncand >= kCandPoison) ? 1 : 0; sp[15] += (br.on && !hit && ncand < kCandPoison) ? 1 : 0; }
     }
     __syncthreads();
+    BP_FINE(39);
   }   // else: P4 reads only what the SAME thread wrote in P1, no grid-wide dependency
-  phase_reduce<C>(L, a.work, sigma, a.sp.loss, a.sp.good_threshold, tc, meta, sh, blk, nb, false);
-  // zero the histogram set of the NEXT linearize (nobody touches it during this phase)
-  for (int b = blk * kLinThreads + tid; b < kHistWords; b += nb * kLinThreads) hother[b] = 0;
+  const double mine = phase_reduce<C>(L, a.work, sigma, a.sp.loss, a.sp.good_threshold, tc, meta, sh, blk, nb, false);
   BP_PROF(PROF_P4);
-  grid.sync();
+  exchange_sums(mine, a.work.ll, gs.seq, sh, blk, nb, &ss.abort);
   BP_PROF(PROF_SYNC4);
-  final_sum(a.work, nb, sigma, sh, ss.lin);
-  if (tid == 0 && do_hist) { ss.delta = fabsf(sigma - ss.scale); ss.scale = sigma; }
-  __syncthreads();
+  if (tid == 64 && do_hist) { ss.delta = fabsf(sigma - ss.scale); ss.scale = sigma; }     // read again only after finish_sums' barrier
+  finish_sums(sigma, sh, ss.lin);
   BP_PROF(PROF_FINAL);
-  parity ^= 1;
+  gs.seq += 1;
+  gs.hs = (gs.hs + 1) % kHistSets;
 }
 
 template <int C>
-__global__ void __launch_bounds__(kLinThreads, 1) k_estimate_pose(const __grid_constant__ SolveArgs a, Sel* sel, int first_parity, int cache_slots) {
+__global__ void __launch_bounds__(kLinThreads, 1) k_estimate_pose(const __grid_constant__ SolveArgs a, Sel* sel, int cache_slots) {
   __shared__ LinShared sh;
   __shared__ SolveShared ss;
   extern __shared__ __align__(16) unsigned char dyn_smem[];
@@ -810,11 +965,18 @@ __global__ void __launch_bounds__(kLinThreads, 1) k_estimate_pose(const __grid_c
   tc_full.f = reinterpret_cast<float*>(dyn_smem + kScratchBytes + (size_t) cache_slots * kLinThreads * 16);
   tc_full.valid = dyn_smem + kScratchBytes + (size_t) cache_slots * kLinThreads * (16 + 16 * C);
   tc_full.K = cache_slots;
-  cg::grid_group grid = cg::this_grid();
   const int tid = threadIdx.x;
-  int parity = first_parity;
+  GridSync gs;
+  gs.counter = a.work.hist + (size_t) kHistSets * kHistWords; gs.epoch = 0; gs.seq = a.seq_base; gs.hs = 0;
   int total_evals = 0;
-  if (tid == 0) { ss.T = a.T_init; ss.t_last = clock64(); BP_FINE_INIT(a.prof); }
+  if (a.prof && blockIdx.x == 0) {
+    long long* sp = prof_smem();
+    if (tid < 68) sp[tid] = 0;
+    __syncthreads();
+    if (tid == 0) sp[64] = clock64();
+    BP_FINE_INIT(a.prof);
+  }
+  if (tid == 0) { ss.T = a.T_init; ss.abort = 0; }
   __syncthreads();
   const float sqrt_eps = sqrtf(FLT_EPSILON);
   for (int lvl = a.sp.num_levels - 1; lvl >= a.sp.max_test_level; --lvl) {
@@ -833,6 +995,9 @@ __global__ void __launch_bounds__(kLinThreads, 1) k_estimate_pose(const __grid_c
     TplCache tc = tc_full;
     if ((meta.n + (int) gridDim.x * kLinThreads - 1) / ((int) gridDim.x * kLinThreads) > cache_slots) tc.K = 0;
     if (tc.K) tc_fill<C>(tc, L, meta.n, blockIdx.x, gridDim.x);
+    // every histogram set starts the level zeroed; the barrier orders the zeroing before the first atomics
+    for (int b = blockIdx.x * kLinThreads + tid; b < kHistSets * kHistWords; b += gridDim.x * kLinThreads) a.work.hist[b] = 0;
+    grid_barrier(gs.counter, gs.epoch, gridDim.x, &ss.abort);
     if (meta.n_total == 0) {                              // "you should call setData before calling computeResiduals" (template_data.cc:177)
       if (blockIdx.x == 0 && tid == 0) { LevelStats st; st.num_iterations = 0; st.final_error = -1.0f; st.first_order_optimality = -1.0f; st.status = -3; st.num_evals = 0; a.stats[lvl] = st; }
       continue;
@@ -843,7 +1008,7 @@ __global__ void __launch_bounds__(kLinThreads, 1) k_estimate_pose(const __grid_c
     // linearize, are computed by thread 0 right after the solve.
     bool first = true, conv = false;
     for (;;) {
-      device_linearize<C>(a, lvl, ss, sh, tc, meta, scratch, grid, parity, sel); ++n_evals;
+      device_linearize<C>(a, lvl, ss, sh, tc, meta, scratch, gs, sel); ++n_evals;
       f_norm = ss.lin.f_norm;
       if (first) {
         g_norm = 0.0f; for (int k = 0; k < 6; ++k) g_norm = fmaxf(g_norm, fabsf(ss.lin.G[k]));
@@ -852,12 +1017,27 @@ __global__ void __launch_bounds__(kLinThreads, 1) k_estimate_pose(const __grid_c
       }
       BP_FINE(25);
       if (tid == 0) {
-        bool ok = solve6_fp32_registers<false>(ss.lin.H, ss.lin.G, ss.dp);      // unpivoted first: H is SPD and Hartley-normalised
-        if (!ok) ok = solve6_fp32_registers<true>(ss.lin.H, ss.lin.G, ss.dp);     // Eigen's pivoted LDLT
-        if (!ok) ok = solve6_fallback(ss.lin.H, ss.lin.G, ss.dp);                 // damped fp64 retry
+        // unpivoted LDL^T first (H is SPD and Hartley-normalised).  The pose update and the next projection matrix are
+        // computed from dp BEFORE the isApprox verdict is needed, so that the acceptance test overlaps them.
+        float dp[6], Pn[12];
+        bool ok = solve6_fp32_registers<false>(ss.lin.H, ss.lin.G, dp);
+        M44 Tn = ss.Td;
+        apply_update(Tn, dp, meta.s, meta.c1, meta.c2, meta.c3); make_projection(L, Tn, Pn);                      // :371 / :390
+        if (!ok) {
+          ok = solve6_fp32_registers<true>(ss.lin.H, ss.lin.G, dp);               // Eigen's pivoted LDLT
+          if (!ok) ok = solve6_fallback(ss.lin.H, ss.lin.G, dp);                   // damped fp64 retry
+          Tn = ss.Td;
+          if (ok) { apply_update(Tn, dp, meta.s, meta.c1, meta.c2, meta.c3); make_projection(L, Tn, Pn); }
+        }
         ss.lin.pad[0] = ok ? 1 : 0;
         BP_FINE(26);
-        if (ok) { apply_update(ss.Td, ss.dp, meta.s, meta.c1, meta.c2, meta.c3); make_projection(L, ss.Td, ss.P); }   // :371 / :390
+#pragma unroll
+        for (int k = 0; k < 6; ++k) ss.dp[k] = dp[k];
+        if (ok) {
+          ss.Td = Tn;
+#pragma unroll
+          for (int k = 0; k < 12; ++k) ss.P[k] = Pn[k];
+        }
       }
       __syncthreads();
       BP_FINE(28);
@@ -877,6 +1057,7 @@ __global__ void __launch_bounds__(kLinThreads, 1) k_estimate_pose(const __grid_c
                fabsf(f_norm - f_prev) < a.sp.function_tolerance) { status = 0x31; conv = true; }
       else if (g_norm < g_tol) { status = 0x32; conv = true; }
       dp_prev = dpn; f_prev = f_norm;
+      BP_FINE(29);
       BP_PROF(PROF_SOLVE);
       if (conv) {                                                              // the converged pass still applies dp once more (Q1, :390)
         if (tid == 0) apply_update(ss.Td, ss.dp, meta.s, meta.c1, meta.c2, meta.c3);
@@ -891,10 +1072,24 @@ __global__ void __launch_bounds__(kLinThreads, 1) k_estimate_pose(const __grid_c
       it -= 1;                                                                 // :398
     }
     total_evals += n_evals;
+    // residuals / valid flags of the last linearize of the finest level go back to global memory for getWeights() & co.
+    if (tc.K && C == 8 && lvl == a.sp.max_test_level) {
+      int k = 0;
+      for (int i = first_point(blockIdx.x, gridDim.x); i < meta.n; i += gridDim.x * kLinThreads, ++k) {
+        VecC<C> r; tc_get<C>(tc, k, TC_R, r);
+        r.store(a.work.res + (size_t) i * C);
+        a.work.valid[i] = tc.valid[k * kLinThreads + tid];
+      }
+    }
+    if (ss.abort) status = -4;
     if (blockIdx.x == 0 && tid == 0) {
       LevelStats st; st.num_iterations = it; st.final_error = f_norm; st.first_order_optimality = g_norm; st.status = status; st.num_evals = n_evals;
       a.stats[lvl] = st;
     }
+  }
+  if (a.prof && blockIdx.x == 0) {
+    __syncthreads();
+    if (tid < 64) a.prof[tid] += prof_smem()[tid];
   }
   if (blockIdx.x == 0 && tid == 0) {
     *a.T_out = ss.T; *a.num_fun_evals = total_evals;

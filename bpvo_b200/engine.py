@@ -156,12 +156,12 @@ class Context:
               "final_sum", "solve", "other"]
 
     def phase_cycles(self, reset=True):
-        buf = (C.c_longlong * 32)()
+        buf = (C.c_longlong * 64)()
         _check(self._lib.bpvo_b200_get_phase_cycles(self.h, buf, int(reset)))
         out = dict(zip(self.PHASES, list(buf)[:len(self.PHASES)]))
         out["_bracket_hits"], out["_scale_estimates"] = buf[12], buf[13]
         out["_bracket_overflows"], out["_bracket_misses"] = buf[14], buf[15]
-        out["_fine"] = list(buf)[16:32]
+        out["_fine"] = list(buf)[16:64]
         return out
 
     def reset_counters(self):

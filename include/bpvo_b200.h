@@ -238,7 +238,7 @@ int bpvo_b200_set_profiling(bpvo_b200_ctx* ctx, int enable);   /* cudaEvent pair
 int bpvo_b200_get_counters(bpvo_b200_ctx* ctx, bpvo_b200_counters* out);
 /* SM-cycle counters of the phases of the on-device GN loop (CTA 0), accumulated while profiling is on:
  * P1, sync, P2, sync, P3, sync, scale, P4, sync, final-sum, solve, other, ... */
-int bpvo_b200_get_phase_cycles(bpvo_b200_ctx* ctx, long long cycles[32], int reset);
+int bpvo_b200_get_phase_cycles(bpvo_b200_ctx* ctx, long long cycles[64], int reset);
 int bpvo_b200_reset_counters(bpvo_b200_ctx* ctx);
 int bpvo_b200_synchronize(bpvo_b200_ctx* ctx);
 /* cudaEvent pair on the ctx stream: start records an event, stop records another, waits for it and returns
