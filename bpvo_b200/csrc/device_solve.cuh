@@ -128,6 +128,69 @@ __device__ __forceinline__ bool solve6_fp32_registers(const float* __restrict__ 
   return d <= 1e-5f * 1e-5f * fminf(na, nb);
 }
 
+// Fast path of the on-device loop: the same unpivoted LDL^T / substitutions / isApprox test as
+// solve6_fp32_registers<false>, written WITHOUT any data-dependent branch (straight-line code: the scheduler overlaps the
+// independent chains).  Rejects (returns false; the caller retries with the exact Eigen-order paths) when a pivot is not
+// safely positive or the acceptance test fails, so an accepted result is the one the branchy version produces.
+__device__ __forceinline__ bool solve6_fast(const float* __restrict__ H, const float* __restrict__ G, float* __restrict__ dp) {
+  float a[6][6], x[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+#pragma unroll
+    for (int j = 0; j <= i; ++j) a[i][j] = H[j * 6 + i];
+    x[i] = G[i];
+  }
+  const float cutoff = fabsf(FLT_EPSILON * a[0][0]);
+  bool good = true;
+#pragma unroll
+  for (int K = 0; K < 6; ++K) {
+    float temp[6];
+#pragma unroll
+    for (int j = 0; j < K; ++j) temp[j] = a[j][j] * a[K][j];
+    float s = 0.0f;
+#pragma unroll
+    for (int j = 0; j < K; ++j) s += a[K][j] * temp[j];
+    a[K][K] -= s;
+#pragma unroll
+    for (int i = K + 1; i < 6; ++i) {
+      float t = 0.0f;
+#pragma unroll
+      for (int j = 0; j < K; ++j) t += a[i][j] * temp[j];
+      a[i][K] -= t;
+    }
+    good = good && (a[K][K] > cutoff);        // also false for NaN
+    const float id = 1.0f / a[K][K];
+#pragma unroll
+    for (int i = K + 1; i < 6; ++i) a[i][K] *= id;
+  }
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+#pragma unroll
+    for (int j = 0; j < i; ++j) x[i] -= a[i][j] * x[j];
+  }
+  float dmax = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) dmax = fmaxf(dmax, a[i][i]);
+  const float tol = fmaxf(dmax * FLT_EPSILON, 1.0f / FLT_MAX);      // Eigen 3.2 zeroes the components whose pivot is below this
+#pragma unroll
+  for (int i = 0; i < 6; ++i) { good = good && (a[i][i] > tol); x[i] = x[i] / a[i][i]; }
+#pragma unroll
+  for (int i = 5; i >= 0; --i) {
+#pragma unroll
+    for (int j = i + 1; j < 6; ++j) x[i] -= a[j][i] * x[j];
+  }
+  float d = 0.0f, na = 0.0f, nb = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    float s = H[0 * 6 + i] * x[0];
+#pragma unroll
+    for (int k = 1; k < 6; ++k) s += H[k * 6 + i] * x[k];
+    d += (s - G[i]) * (s - G[i]); na += s * s; nb += G[i] * G[i];
+    dp[i] = x[i];
+  }
+  return good && d <= 1e-5f * 1e-5f * fminf(na, nb);
+}
+
 // T <- T * (Tn^-1 exp(-dp) Tn) with Tn = [sI, -s c; 0 1] in closed form:
 //   Tn^-1 [R t; 0 1] Tn = [R, c - R c + t / s; 0 1]      (rigid_body_warp.h:130-138, math_utils.h:140-168)
 // For |w| < 0.5 rad (every sane GN step) the Rodrigues coefficients are evaluated as series in theta^2:

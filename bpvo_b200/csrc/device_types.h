@@ -18,7 +18,7 @@ constexpr int kHistWords = kHistBins + 8 + kSelBins;   // one histogram set + bo
 //   [+4] length of the candidate overflow list   [+8 ...] kSelBins counts of the candidates by linear bin over the bracket
 constexpr int kCandPerCta = 12;              // bracketed median: every CTA owns a fixed region of the candidate buffer (no slot reservation) ...
 constexpr int kCtaCandCap = 1024;            // ... stages up to this many candidates in shared memory ...
-constexpr int kOvfCap = 8192;                // ... and appends what exceeds its region to a shared overflow list (wide brackets, early iterations)
+constexpr int kOvfCap = 16384;               // ... and appends what exceeds its region to a shared overflow list (wide brackets, early iterations)
 constexpr unsigned kCandPoison = 1u << 30;   // added to the candidate count when even that overflowed -> radix fallback
 constexpr int kScratchBytes = (kCtaCandCap + kSelList) * 4;   // dynamic-smem scratch of the bracketed select: CTA candidates | list
 constexpr int kPartialStride = 32; // doubles per block partial (21 H + 6 G + f + n_good + pad)

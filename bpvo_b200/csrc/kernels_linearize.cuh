@@ -272,11 +272,9 @@ __device__ __forceinline__ void phase_residuals(const LevelTemplate& L, const Le
     __syncthreads();
     BP_FINE(18);
     if (do_hist1) { for (int b = tid; b < kHist1Bins; b += kLinThreads) { const unsigned v = sh.hist[b]; if (v) atomicAdd(hist1 + b, v); } }
-    for (int o = 16; o > 0; o >>= 1) {
-      my_first = min(my_first, __shfl_xor_sync(0xffffffffu, my_first, o));
-      cnt_valid += __shfl_xor_sync(0xffffffffu, cnt_valid, o);
-      cnt_below += __shfl_xor_sync(0xffffffffu, cnt_below, o);
-    }
+    my_first = __reduce_min_sync(0xffffffffu, my_first);        // REDUX: one instruction per warp-wide integer reduction
+    cnt_valid = __reduce_add_sync(0xffffffffu, cnt_valid);
+    cnt_below = __reduce_add_sync(0xffffffffu, cnt_below);
     if ((tid & 31) == 0 && my_first != 0x7fffffff) {
       atomicMax(hist1 + kHistBins, ~(unsigned) my_first);   // word zero-initialised
       atomicAdd(&sh.found[4], cnt_valid);
@@ -453,13 +451,24 @@ __device__ __forceinline__ bool bracket_select(const Work& W, const unsigned* __
   unsigned bin_a, rem_a, bin_b, rem_b, tot;
   block_find2_regs<4>(loc, ra, rb, sh, bin_a, rem_a, bin_b, rem_b, tot);      // resets sh.found[0..7]
   BP_FINE(36);
+  BP_FINE(44);
+  unsigned match = 0;                        // branch-free membership test of the register-resident slots, then a (rare) append
 #pragma unroll
   for (int q = 0; q < kSelPre; ++q) {
-    if (pre[q] >= 0.0f) {
-      const unsigned b = (unsigned) sel_bin(pre[q], br.lo, br.inv_w);
-      if (b == bin_a || b == bin_b) { const unsigned slot = atomicAdd(&sh.found[4], 1u); if (slot < (unsigned) kSelList) list[slot] = pre[q]; }
-    }
+    const unsigned b = (unsigned) sel_bin(pre[q], br.lo, br.inv_w);
+    match |= ((pre[q] >= 0.0f && (b == bin_a || b == bin_b)) ? 1u : 0u) << q;
   }
+  BP_FINE(45);
+  while (match) {                            // usually no bit at all, rarely more than one: one short append per set bit
+    const int q = __ffs((int) match) - 1;
+    match &= match - 1;
+    float v = pre[0];
+#pragma unroll
+    for (int t = 1; t < kSelPre; ++t) v = (q == t) ? pre[t] : v;
+    const unsigned slot = atomicAdd(&sh.found[4], 1u);
+    if (slot < (unsigned) kSelList) list[slot] = v;
+  }
+  BP_FINE(46);
   for (unsigned j = tid + kSelPre * kLinThreads; j < total; j += kLinThreads) {
     const float v = __ldcg(W.cand + j);
     if (v >= 0.0f) {
@@ -467,10 +476,15 @@ __device__ __forceinline__ bool bracket_select(const Work& W, const unsigned* __
       if (b == bin_a || b == bin_b) { const unsigned slot = atomicAdd(&sh.found[4], 1u); if (slot < (unsigned) kSelList) list[slot] = v; }
     }
   }
-  for (unsigned j = tid; j < novf; j += kLinThreads) {
-    const float v = __ldcg(ovf + j);
-    const unsigned b = (unsigned) sel_bin(v, br.lo, br.inv_w);
-    if (b == bin_a || b == bin_b) { const unsigned slot = atomicAdd(&sh.found[4], 1u); if (slot < (unsigned) kSelList) list[slot] = v; }
+  for (unsigned j0 = tid; j0 < novf; j0 += 8 * kLinThreads) {      // overflow list (wide brackets): 8 independent loads in flight per thread
+    float v[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) { const unsigned j = j0 + q * kLinThreads; v[q] = (j < novf) ? __ldcg(ovf + j) : -1.0f; }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const unsigned b = (unsigned) sel_bin(v[q], br.lo, br.inv_w);
+      if (v[q] >= 0.0f && (b == bin_a || b == bin_b)) { const unsigned slot = atomicAdd(&sh.found[4], 1u); if (slot < (unsigned) kSelList) list[slot] = v[q]; }
+    }
   }
   __syncthreads();
   BP_FINE(37);
@@ -928,13 +942,13 @@ __device__ __forceinline__ void device_linearize(const SolveArgs& a, int lvl, So
     // the median just moved; otherwise sized from the measured candidate density so that ~500 values fall inside.
     if (tid == 0) {
       const float mid_new = 0.5f * (lo + hi), mid_old = 0.5f * (ss.br_lo + ss.br_hi);
-      float rel = 0.03f;           // first bracket of a level: wide (the median still moves by percents), the 8192-entry buffer absorbs it
+      float rel = 0.06f;           // first bracket of a level: wide (the median still moves by percents), the overflow list absorbs it
       if (ss.br_on && mid_new > 0.0f) {
         const float moved = fabsf(mid_new - mid_old) / mid_new;
         if (br.on && ncand > 0) ss.br_density = (float) ncand / fmaxf(ss.br_rel, 1e-6f);       // candidates per unit of rel
         const float rel_density = (ss.br_density > 0.0f) ? 500.0f / ss.br_density : 0.002f;
         rel = fmaxf(2.0f * moved, fminf(rel_density, 0.02f));
-        rel = fminf(fmaxf(rel, 1e-5f), 0.05f);
+        rel = fminf(fmaxf(rel, 1e-5f), 0.06f);
       }
       ss.br_rel = rel; ss.br_lo = lo; ss.br_hi = hi; ss.br_on = (n >= 3) ? 1 : 0;
       if (a.prof && blk == 0) { long long* sp = prof_smem(); sp[12] += hit ? 1 : 0; sp[13] += 1; sp[14] += (br.on && !hit && ncand >= kCandPoison) ? 1 : 0; sp[15] += (br.on && !hit && ncand < kCandPoison) ? 1 : 0; }
@@ -983,7 +997,7 @@ __global__ void __launch_bounds__(kLinThreads, 1) k_estimate_pose(const __grid_c
     const LevelTemplate& L = a.tmpl[lvl];
     // PoseEstimatorBase::run (pose_estimator_base.h:324-407); all control flow below is CTA-uniform AND grid-uniform
     if (tid == 0) {                                                            // reset() :287-293
-      ss.scale = 1.0f; ss.delta = 1e10f; ss.br_on = 0; ss.br_lo = ss.br_hi = 0.0f; ss.br_rel = 0.03f; ss.br_density = 0.0f;
+      ss.scale = 1.0f; ss.delta = 1e10f; ss.br_on = 0; ss.br_lo = ss.br_hi = 0.0f; ss.br_rel = 0.06f; ss.br_density = 0.0f;
       ss.Td = ss.T; make_projection(L, ss.Td, ss.P);
     }
     __syncthreads();
@@ -1020,11 +1034,12 @@ __global__ void __launch_bounds__(kLinThreads, 1) k_estimate_pose(const __grid_c
         // unpivoted LDL^T first (H is SPD and Hartley-normalised).  The pose update and the next projection matrix are
         // computed from dp BEFORE the isApprox verdict is needed, so that the acceptance test overlaps them.
         float dp[6], Pn[12];
-        bool ok = solve6_fp32_registers<false>(ss.lin.H, ss.lin.G, dp);
+        bool ok = solve6_fast(ss.lin.H, ss.lin.G, dp);
         M44 Tn = ss.Td;
         apply_update(Tn, dp, meta.s, meta.c1, meta.c2, meta.c3); make_projection(L, Tn, Pn);                      // :371 / :390
         if (!ok) {
-          ok = solve6_fp32_registers<true>(ss.lin.H, ss.lin.G, dp);               // Eigen's pivoted LDLT
+          ok = solve6_fp32_registers<false>(ss.lin.H, ss.lin.G, dp);              // same factorisation with Eigen's early-outs
+          if (!ok) ok = solve6_fp32_registers<true>(ss.lin.H, ss.lin.G, dp);      // Eigen's pivoted LDLT
           if (!ok) ok = solve6_fallback(ss.lin.H, ss.lin.G, dp);                   // damped fp64 retry
           Tn = ss.Td;
           if (ok) { apply_update(Tn, dp, meta.s, meta.c1, meta.c2, meta.c3); make_projection(L, Tn, Pn); }

@@ -68,7 +68,7 @@ def main():
     names = {0: "P1:zero+sync", 1: "P1:loop", 2: "P1:sync", 3: "P1:flush", 4: "P4:loop", 5: "P4:sync", 6: "P4:butterfly", 7: "P4:sync2",
              8: "P4:cta-sum", 9: "pre-solve", 10: "LDLT", 12: "update+sync", 13: "convergence-tests", 16: "barrier1", 17: "select:load-candidates+counters",
              19: "select:binning", 20: "select:find2", 21: "select:list", 22: "select:rank", 23: "next-bracket",
-             24: "exchange:leader-entry", 25: "exchange:leader-gather+post", 26: "exchange:stage2-gather", 27: "exchange:cta-sum"}
+             28: "list:enter", 29: "list:match", 30: "list:append", 24: "exchange:leader-entry", 25: "exchange:leader-gather+post", 26: "exchange:stage2-gather", 27: "exchange:cta-sum"}
     if sum(fine):
         out["fine_us_per_eval"] = {names.get(i, f"slot{16 + i}"): round(f / 1.965e3 / max(tot_ev, 1), 3) for i, f in enumerate(fine) if f}
     print(json.dumps(out))
