@@ -92,6 +92,7 @@ struct SolverParams {    // PoseEstimatorParameters (pose_estimator_params.h) + 
   int   max_fun_evals;   // 1200
   float parameter_tolerance, function_tolerance, gradient_tolerance;
   int   loss;            // 0x10 huber, 0x11 tukey, 0x12 L2
+  int   interp;          // InterpolationType (types.h): 0 linear, 1 cosine, 2 cubic, 3 cubic Hermite
   float good_threshold;
   int   max_test_level;
   int   num_levels;

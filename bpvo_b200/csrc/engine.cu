@@ -113,10 +113,8 @@ int bpvo_b200_create(bpvo_b200_ctx** out, const float K[9], float baseline, int 
   if (rows < 16 || cols < 24) return bp_fail(BPVO_B200_ERR_INVALID_ARG, "image too small");
   if (p->descriptor != BPVO_B200_INTENSITY && p->descriptor != BPVO_B200_BITPLANES)
     return bp_fail(BPVO_B200_ERR_UNSUPPORTED, "DescriptorType 0x%x is not on the accelerated path (Intensity, BitPlanes only)", p->descriptor);
-  if (p->interp != BPVO_B200_LINEAR)
-    return bp_fail(BPVO_B200_ERR_UNSUPPORTED, "only InterpolationType::kLinear is implemented");
-  if (p->descriptor == BPVO_B200_BITPLANES && p->sigmaPriorToCensusTransform > 0.0f)
-    return bp_fail(BPVO_B200_ERR_UNSUPPORTED, "sigmaPriorToCensusTransform > 0 (third-party u8 3x3 GaussianBlur) is not implemented");
+  if (p->interp != BPVO_B200_LINEAR && p->interp != BPVO_B200_COSINE && p->interp != BPVO_B200_CUBIC && p->interp != BPVO_B200_CUBIC_HERMITE)
+    return bp_fail(BPVO_B200_ERR_INVALID_ARG, "unknown InterpolationType");
   if (p->lossFunction != BPVO_B200_HUBER && p->lossFunction != BPVO_B200_TUKEY && p->lossFunction != BPVO_B200_L2)
     return bp_fail(BPVO_B200_ERR_INVALID_ARG, "unknown RobustFunction");
   if (p->gradientEstimation != BPVO_B200_CD3 && p->gradientEstimation != BPVO_B200_CD5)
@@ -179,6 +177,7 @@ int bpvo_b200_create(bpvo_b200_ctx** out, const float K[9], float baseline, int 
   // template-build scratch (sized for level maxTestLevel = the largest one built)
   const int r0 = c->geom[c->p.maxTestLevel].rows, c0 = c->geom[c->p.maxTestLevel].cols;
   CUDA_TRY(cudaMalloc(&c->flags, (size_t) r0 * c0));
+  if (c->C == 8 && p->sigmaPriorToCensusTransform > 0.0f) CUDA_TRY(cudaMalloc(&c->blur_tmp, (size_t) r0 * c0));   // pre-census blur output
   CUDA_TRY(cudaMalloc(&c->block_counts, (size_t) (ceil_div(r0 * c0, kSelPerBlock) + 1) * sizeof(int)));
   CUDA_TRY(cudaMalloc(&c->hpartials, 1024 * 4 * sizeof(double)));
   CUDA_TRY(cudaMalloc(&c->hsums, 4 * sizeof(double)));
@@ -204,7 +203,7 @@ int bpvo_b200_destroy(bpvo_b200_ctx* c) {
   bp_comm_destroy(c);
   cudaFree(c->work.res); cudaFree(c->work.valid); cudaFree(c->work.hist); cudaFree(c->work.ll); cudaFree(c->work.partials);
   cudaFree(c->work.scale); cudaFree(c->work.out); cudaFree(c->work.ticket); cudaFree(c->work.cand); cudaFree(c->sel); cudaFree(c->export_buf);
-  cudaFree(c->flags); cudaFree(c->block_counts); cudaFree(c->hpartials); cudaFree(c->hsums);
+  cudaFree(c->flags); cudaFree(c->blur_tmp); cudaFree(c->block_counts); cudaFree(c->hpartials); cudaFree(c->hsums);
   cudaFree(c->d_T); cudaFree(c->d_stats); cudaFree(c->d_evals); cudaFree(c->d_prof);
   cudaFreeHost(c->h_mail); cudaFreeHost(c->stage_img); cudaFreeHost(c->stage_disp);
   if (c->flush_buf) cudaFree(c->flush_buf);
@@ -262,7 +261,11 @@ int bpvo_b200_frame_create(bpvo_b200_ctx* c, bpvo_b200_frame** out) {
     CUDA_TRY(cudaMalloc(&f->pyr[l], (size_t) g.rows * g.cols));
     if (l < c->p.maxTestLevel) continue;
     const size_t npx = (size_t) g.rows * g.cols, cap = (size_t) g.capacity;
-    CUDA_TRY(cudaMalloc(&f->desc[l], (npx + 1) * c->C * sizeof(float)));
+    // one extra zero row (+ pad): the reference's cubic / Hermite footprint reaches row `rows` for yi = rows - 2
+    // (photo_error.cc:358 bounds y by rows - 1 only) and reads past its buffer there; the engine reads zeros instead
+    const size_t desc_elems = (npx + (size_t) g.cols + 4) * c->C;
+    CUDA_TRY(cudaMalloc(&f->desc[l], desc_elems * sizeof(float)));
+    CUDA_TRY(cudaMemsetAsync(f->desc[l], 0, desc_elems * sizeof(float), c->stream));
     CUDA_TRY(cudaMalloc(&f->saliency[l], npx * sizeof(float)));
     CUDA_TRY(cudaMalloc(&f->pts[l], cap * sizeof(float4)));
     CUDA_TRY(cudaMalloc(&f->gx[l], cap * c->C * sizeof(float)));
@@ -341,8 +344,16 @@ int bpvo_b200_frame_set_data(bpvo_b200_frame* f, const uint8_t* image, const flo
         // cv::getGaussianKernel(5, sigma, CV_32F): exp in double -> float taps, normalised by the double sum of the float taps
         for (int i = 0; i < 5; ++i) { const double x = i - 2.0; k[i] = (float) exp(-0.5 / (sg * sg) * x * x); sum += k[i]; }
         for (int i = 0; i < 5; ++i) k[i] = (float) (k[i] * (1.0 / sum));
+        const uint8_t* census_in = f->pyr[l];
+        if (c->p.sigmaPriorToCensusTransform > 0.0f) {      // census.cc:63-65: cv::GaussianBlur(3x3) on the u8 level image first
+          const double sc = (double) c->p.sigmaPriorToCensusTransform, e = exp(-0.5 / (sc * sc));
+          const int ka = (int) lrint(256.0 * (e / (1.0 + 2.0 * e))), kc = 256 - 2 * ka;
+          blur3_u8_kernel<<<dim3(ceil_div(g.cols, 32), ceil_div(g.rows, 8)), 256, 0, c->stream>>>(f->pyr[l], g.rows, g.cols, ka, kc, c->blur_tmp);
+          LAUNCH_CHECK(c);
+          census_in = c->blur_tmp;
+        }
         bitplanes_kernel<<<dim3(ceil_div(g.cols, kBpTW), ceil_div(g.rows, kBpTH)), 256, 0, c->stream>>>(
-            f->pyr[l], g.rows, g.cols, k[2], k[3], k[4], c->p.sigmaBitPlanes > 0.0f ? 1 : 0, f->desc[l]);
+            census_in, g.rows, g.cols, k[2], k[3], k[4], c->p.sigmaBitPlanes > 0.0f ? 1 : 0, f->desc[l]);
       }
       LAUNCH_CHECK(c);
     }
@@ -548,7 +559,7 @@ static int launch_linearize(bpvo_b200_ctx* c, const bpvo_b200_frame* ref, const 
   LinArgs a;
   a.tmpl = make_level_template(ref, level);
   a.img.desc = cur->desc[level]; a.img.rows = c->geom[level].rows; a.img.cols = c->geom[level].cols;
-  a.work = c->work; a.loss = c->p.lossFunction; a.good_thr = c->p.goodPointThreshold;
+  a.work = c->work; a.loss = c->p.lossFunction; a.interp = c->p.interp; a.good_thr = c->p.goodPointThreshold;
   a.hset = c->work.hist; a.sel = c->sel;
   make_projection(a.tmpl, T, a.P);
   const int grid = lin_grid(c, level);
@@ -665,7 +676,7 @@ static int launch_estimate_pose(bpvo_b200_ctx* c, const bpvo_b200_frame* ref, co
   }
   a.sp.max_iterations = c->p.maxIterations; a.sp.max_fun_evals = 1200;
   a.sp.parameter_tolerance = c->p.parameterTolerance; a.sp.function_tolerance = c->p.functionTolerance; a.sp.gradient_tolerance = c->p.gradientTolerance;
-  a.sp.loss = c->p.lossFunction; a.sp.good_threshold = c->p.goodPointThreshold;
+  a.sp.loss = c->p.lossFunction; a.sp.interp = c->p.interp; a.sp.good_threshold = c->p.goodPointThreshold;
   a.sp.max_test_level = c->p.maxTestLevel; a.sp.num_levels = c->L;
   a.work = c->work; a.T_init = T_init; a.T_out = c->d_T; a.stats = c->d_stats; a.num_fun_evals = c->d_evals;
   a.prof = c->profiling ? c->d_prof : nullptr;

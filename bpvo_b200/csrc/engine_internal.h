@@ -36,7 +36,7 @@ struct bpvo_b200_ctx {
   bp::Work work{};
   bp::Sel* sel = nullptr;
   float* export_buf = nullptr;
-  uint8_t* flags = nullptr; int* block_counts = nullptr; double* hpartials = nullptr;
+  uint8_t* flags = nullptr; uint8_t* blur_tmp = nullptr; int* block_counts = nullptr; double* hpartials = nullptr;
   bp::M44* d_T = nullptr; bp::LevelStats* d_stats = nullptr; int* d_evals = nullptr; long long* d_prof = nullptr;
   Mailbox* h_mail = nullptr;
   uint8_t* stage_img = nullptr; float* stage_disp = nullptr;

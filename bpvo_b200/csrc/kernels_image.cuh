@@ -56,6 +56,29 @@ __global__ void __launch_bounds__(256) intensity_kernel(const uint8_t* __restric
 }
 
 // ---------------------------------------------------------------------------------------------
+// cv::GaussianBlur(3x3) on CV_8U ahead of the census (census.cc:63-65, sigmaPriorToCensusTransform > 0).
+// Third-party fixed-point arithmetic (OpenCV 4.x, pinned bit-exact to cv2 4.13 by the oracle's golden vectors):
+// 8-bit taps [a, 256 - 2a, a], row pass in 8.8, column pass in 16.16, ONE rounding (v + 2^15) >> 16, reflect-101.
+// Thread per pixel; the 3x3 u8 neighbourhood comes from L1/L2 (2 B of traffic per pixel against the 33 B of the
+// descriptor that follows).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) blur3_u8_kernel(const uint8_t* __restrict__ src, int rows, int cols, int ka, int kc,
+                                                       uint8_t* __restrict__ dst) {
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (x >= cols || y >= rows) return;
+  const int xm = reflect101(x - 1, cols), xp = reflect101(x + 1, cols);
+  int h[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const uint8_t* s = src + (size_t) reflect101(y - 1 + k, rows) * cols;
+    h[k] = kc * (int) __ldg(s + x) + ka * ((int) __ldg(s + xm) + (int) __ldg(s + xp));
+  }
+  const int v = (kc * h[1] + ka * (h[0] + h[2]) + (1 << 15)) >> 16;
+  dst[(size_t) y * cols + x] = (uint8_t) min(v, 255);
+}
+
+// ---------------------------------------------------------------------------------------------
 // bit-planes descriptor, fused: census (3x3, neighbour >= centre, border rows/cols = 0) ->
 // 8 bit channels -> separable 5x5 Gaussian (f32, reflect-101 on the census image) -> interleaved
 // [rows][cols][8] f32 store (32 B per pixel, two 16-B stores per thread, fully coalesced).

@@ -183,6 +183,74 @@ __host__ __device__ __forceinline__ void make_projection(const LevelTemplate& L,
 // ---------------------------------------------------------------------------------------------
 // P1: residuals (+ level-1 histogram when the scale is to be re-estimated)
 // ---------------------------------------------------------------------------------------------
+// ---------------------------------------------------------------------------------------------
+// The other InterpolationTypes of PhotoError::Impl::run (photo_error.cc:391-444): cosine, cubic (A = -0.5) and cubic
+// Hermite.  Unlike the linear case the reference evaluates them in FLOAT (coefficients from float(xf), float dot
+// products), with a few double sub-expressions (cos(x * M_PI) / 2.0, the Hermite tangents' / 2.0); every operation
+// is spelled with its own rounding (no FMA contraction), sums in the unvectorised left-to-right order of a fixed-size
+// Eigen dot product.  Quirks kept: the cubic / Hermite footprint starts AT xi (not xi - 1) in x and at yi - 1 in y
+// (:413-416, :430-433).  Cold path (kLinear is the default and the benchmarked one): kept out of line.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void coeffs_cubic(float x, float c[4]) {          // interpolateCubic<float>, photo_error.cc:267-279
+  const float A = -0.5f;
+  const float x1 = __fadd_rn(x, 1.0f);
+  c[0] = __fsub_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fsub_rn(__fmul_rn(A, x1), 5.0f * A), x1), 8.0f * A), x1), 4.0f * A);
+  c[1] = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(__fmul_rn(A + 2.0f, x), A + 3.0f), x), x), 1.0f);
+  const float y = __fsub_rn(1.0f, x);
+  c[2] = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(__fmul_rn(A + 2.0f, y), A + 3.0f), y), y), 1.0f);
+  c[3] = __fsub_rn(__fsub_rn(__fsub_rn(1.0f, c[0]), c[1]), c[2]);
+}
+__device__ __forceinline__ void coeffs_cosine(float x, float c[2]) {         // interpolateCosine<float>, :281-290 (double inside)
+  const double m = __ddiv_rn(__dsub_rn(1.0, cos(__dmul_rn((double) x, 3.14159265358979323846))), 2.0);
+  c[0] = (float) __dsub_rn(1.0, m); c[1] = (float) m;
+}
+__device__ __forceinline__ float hermite1(float y0, float y1, float y2, float y3, float mu) {   // interpolateCubicHermite(y, mu), :311-334
+  const float mu2 = __fmul_rn(mu, mu), mu3 = __fmul_rn(mu, mu2);
+  const float m0 = (float) __dadd_rn(__ddiv_rn((double) __fsub_rn(y1, y0), 2.0), __ddiv_rn((double) __fsub_rn(y2, y1), 2.0));
+  const float m1 = (float) __dadd_rn(__ddiv_rn((double) __fsub_rn(y2, y1), 2.0), __ddiv_rn((double) __fsub_rn(y3, y2), 2.0));
+  const float a0 = __fadd_rn(__fsub_rn(__fmul_rn(2.0f, mu3), __fmul_rn(3.0f, mu2)), 1.0f);
+  const float a1 = __fadd_rn(__fsub_rn(mu3, __fmul_rn(2.0f, mu2)), mu);
+  const float a2 = __fsub_rn(mu3, mu2);
+  const float a3 = __fadd_rn(__fmul_rn(-2.0f, mu3), __fmul_rn(3.0f, mu2));
+  return __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(a0, y1), __fmul_rn(a1, m0)), __fmul_rn(a2, m1)), __fmul_rn(a3, y2));
+}
+template <int C>
+__device__ __noinline__ void sample_nonlinear(int interp, const float* __restrict__ desc, int cols, int xi, int yi, float xf, float yf,
+                                              const float* __restrict__ i0, float* __restrict__ r) {
+  if (interp == 1) {                                     // kCosine: 2 x 2 footprint at (xi, yi)
+    float Cx[2], Cy[2];
+    coeffs_cosine(xf, Cx); coeffs_cosine(yf, Cy);
+    const float* p1 = desc + ((size_t) yi * cols + xi) * C;
+    const float* p2 = p1 + (size_t) cols * C;
+    for (int c = 0; c < C; ++c) {
+      const float d1 = __fadd_rn(__fmul_rn(__ldg(p1 + c), Cx[0]), __fmul_rn(__ldg(p1 + C + c), Cx[1]));
+      const float d2 = __fadd_rn(__fmul_rn(__ldg(p2 + c), Cx[0]), __fmul_rn(__ldg(p2 + C + c), Cx[1]));
+      r[c] = __fsub_rn(__fadd_rn(__fmul_rn(Cy[0], d1), __fmul_rn(Cy[1], d2)), i0[c]);
+    }
+  } else if (interp == 2) {                              // kCubic: rows yi-1 .. yi+2, columns xi .. xi+3
+    float Cx[4], Cy[4];
+    coeffs_cubic(xf, Cx); coeffs_cubic(yf, Cy);
+    for (int c = 0; c < C; ++c) {
+      float Iw = 0.0f;
+      for (int k = 0; k < 4; ++k) {
+        const float* p = desc + ((size_t) (yi - 1 + k) * cols + xi) * C + c;
+        const float d = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(__ldg(p), Cx[0]), __fmul_rn(__ldg(p + C), Cx[1])), __fmul_rn(__ldg(p + 2 * C), Cx[2])), __fmul_rn(__ldg(p + 3 * C), Cx[3]));
+        Iw = (k == 0) ? __fmul_rn(Cy[0], d) : __fadd_rn(Iw, __fmul_rn(Cy[k], d));
+      }
+      r[c] = __fsub_rn(Iw, i0[c]);
+    }
+  } else {                                               // kCubicHermite: same footprint
+    for (int c = 0; c < C; ++c) {
+      float V[4];
+      for (int k = 0; k < 4; ++k) {
+        const float* p = desc + ((size_t) (yi - 1 + k) * cols + xi) * C + c;
+        V[k] = hermite1(__ldg(p), __ldg(p + C), __ldg(p + 2 * C), __ldg(p + 3 * C), xf);
+      }
+      r[c] = __fsub_rn(hermite1(V[0], V[1], V[2], V[3], yf), i0[c]);
+    }
+  }
+}
+
 struct Bracket {       // median bracket carried from the previous GN iteration (on-device loop only)
   bool on;
   float lo, hi;        // candidates are the valid |r| with lo <= |r| <= hi
@@ -193,7 +261,7 @@ __device__ __forceinline__ int sel_bin(float v, float lo, float inv_w) { return 
 template <int C>
 __device__ __forceinline__ void phase_residuals(const LevelTemplate& L, const LevelImage& I, const float* P, const Work& W,
                                                 unsigned* __restrict__ hist1, bool do_hist, Bracket br, const TplCache& tc,
-                                                const TemplateMeta& m, unsigned* scratch, LinShared& sh, int block, int nblocks) {
+                                                const TemplateMeta& m, unsigned* scratch, LinShared& sh, int block, int nblocks, int interp = 0) {
   const int tid = threadIdx.x;
   const bool do_hist1 = do_hist && !br.on;   // with a bracket the level-1 histogram is only built (phase_hist1) if the bracket misses
   if (do_hist1) { for (int b = tid; b < kHist1Bins; b += kLinThreads) sh.hist[b] = 0; }
@@ -205,6 +273,7 @@ __device__ __forceinline__ void phase_residuals(const LevelTemplate& L, const Le
   const double P00 = P[0], P10 = P[1], P20 = P[2], P01 = P[3], P11 = P[4], P21 = P[5],
                P02 = P[6], P12 = P[7], P22 = P[8], P03 = P[9], P13 = P[10], P23 = P[11];
   const int cols = I.cols, rows = I.rows;
+  const int border_lo = (interp == 0 || interp == 1) ? 0 : 1, border_hi = (interp == 0 || interp == 1) ? 1 : 3;
   const int n_pts = m.n;
   int my_first = 0x7fffffff;
   int k = 0;
@@ -221,22 +290,32 @@ __device__ __forceinline__ void phase_residuals(const LevelTemplate& L, const Le
     if (ok) {
       xi = (int) u; xi -= (xi > u);      // Floor(double), photo_error.cc:261-265
       yi = (int) v; yi -= (yi > v);
-      ok = xi >= 0 && xi < cols - 1 && yi >= 0 && yi < rows - 1;
+      ok = xi >= border_lo && xi < cols - border_hi && yi >= border_lo && yi < rows - 1;     // photo_error.cc:346-358 (y bound is always rows - 1)
     }
     VecC<C> r;
     if (ok) {
       const double xf = __dsub_rn(u, (double) xi), yf = __dsub_rn(v, (double) yi);
       const double wx = __dsub_rn(1.0, xf), wy = __dsub_rn(1.0, yf);
-      const float* tap = I.desc + ((size_t) yi * cols + xi) * C;
-      VecC<C> t00, t01, t10, t11, i0;
-      t00.load(tap); t01.load(tap + C); t10.load(tap + (size_t) cols * C); t11.load(tap + (size_t) cols * C + C);
+      VecC<C> i0;
       if (tc.K) tc_get<C>(tc, k, TC_I0, i0); else i0.load(L.i0 + (size_t) i * C);
+      if (interp == 0) {
+        const float* tap = I.desc + ((size_t) yi * cols + xi) * C;
+        VecC<C> t00, t01, t10, t11;
+        t00.load(tap); t01.load(tap + C); t10.load(tap + (size_t) cols * C); t11.load(tap + (size_t) cols * C + C);
 #pragma unroll
-      for (int c = 0; c < C; ++c) {
-        const double top = __dadd_rn(__dmul_rn((double) t00.v[c], wx), __dmul_rn((double) t01.v[c], xf));
-        const double bot = __dadd_rn(__dmul_rn((double) t10.v[c], wx), __dmul_rn((double) t11.v[c], xf));
-        const double Iw = __dadd_rn(__dmul_rn(wy, top), __dmul_rn(yf, bot));
-        r.v[c] = (float) __dsub_rn(Iw, (double) i0.v[c]);
+        for (int c = 0; c < C; ++c) {
+          const double top = __dadd_rn(__dmul_rn((double) t00.v[c], wx), __dmul_rn((double) t01.v[c], xf));
+          const double bot = __dadd_rn(__dmul_rn((double) t10.v[c], wx), __dmul_rn((double) t11.v[c], xf));
+          const double Iw = __dadd_rn(__dmul_rn(wy, top), __dmul_rn(yf, bot));
+          r.v[c] = (float) __dsub_rn(Iw, (double) i0.v[c]);
+        }
+      } else {
+        float i0l[C], rl[C];                 // only these copies live in local memory (the out-of-line call takes addresses)
+#pragma unroll
+        for (int c = 0; c < C; ++c) i0l[c] = i0.v[c];
+        sample_nonlinear<C>(interp, I.desc, cols, xi, yi, (float) xf, (float) yf, i0l, rl);
+#pragma unroll
+        for (int c = 0; c < C; ++c) r.v[c] = rl[c];
       }
       if (do_hist) {
         if (do_hist1) {
@@ -663,6 +742,7 @@ struct LinArgs {
   Work work;
   float P[12];
   int loss;
+  int interp;
   float good_thr;
   unsigned* hset;     // histogram set (zeroed by the host before K1)
   Sel* sel;
@@ -671,7 +751,7 @@ struct LinArgs {
 template <int C> __global__ void __launch_bounds__(kLinThreads, 1) k_residuals(LinArgs a) {
   __shared__ LinShared sh;
   const bool do_hist = (a.loss != 0x12) && (a.work.scale->delta > 1e-6f);
-  phase_residuals<C>(a.tmpl, a.img, a.P, a.work, a.hset, do_hist, Bracket{false, 0.0f, 0.0f, 0.0f}, TplCache{nullptr, nullptr, nullptr, 0}, *a.tmpl.meta, nullptr, sh, blockIdx.x, gridDim.x);
+  phase_residuals<C>(a.tmpl, a.img, a.P, a.work, a.hset, do_hist, Bracket{false, 0.0f, 0.0f, 0.0f}, TplCache{nullptr, nullptr, nullptr, 0}, *a.tmpl.meta, nullptr, sh, blockIdx.x, gridDim.x, a.interp);
 }
 template <int C, int LEVEL> __global__ void __launch_bounds__(kLinThreads, 1) k_select(LinArgs a) {
   __shared__ LinShared sh;
@@ -909,7 +989,7 @@ __device__ __forceinline__ void device_linearize(const SolveArgs& a, int lvl, So
   br.on = do_hist && ss.br_on;
   br.lo = ss.br_lo * (1.0f - ss.br_rel); br.hi = ss.br_hi * (1.0f + ss.br_rel);
   br.inv_w = (br.hi > br.lo) ? (float) kSelBins / (br.hi - br.lo) : 0.0f;
-  phase_residuals<C>(L, I, ss.P, a.work, hset, do_hist, br, tc, meta, scratch, sh, blk, nb);
+  phase_residuals<C>(L, I, ss.P, a.work, hset, do_hist, br, tc, meta, scratch, sh, blk, nb, a.sp.interp);
   BP_PROF(PROF_P1);
   float sigma = ss.scale;
   if (do_hist) {

@@ -48,7 +48,7 @@ typedef enum {
 enum { BPVO_B200_HUBER = 0x10, BPVO_B200_TUKEY = 0x11, BPVO_B200_L2 = 0x12 };
 enum { BPVO_B200_INTENSITY = 0x30, BPVO_B200_BITPLANES = 0x37 };
 enum { BPVO_B200_CD3 = 0, BPVO_B200_CD5 = 1 };
-enum { BPVO_B200_LINEAR = 0 };
+enum { BPVO_B200_LINEAR = 0, BPVO_B200_COSINE = 1, BPVO_B200_CUBIC = 2, BPVO_B200_CUBIC_HERMITE = 3 };   /* InterpolationType, types.h:163-169 */
 enum { BPVO_B200_PARAM_TOL = 0x30, BPVO_B200_FUNC_TOL = 0x31, BPVO_B200_GRAD_TOL = 0x32,
        BPVO_B200_MAX_ITERS = 0x33, BPVO_B200_SOLVER_ERROR = 0x34 };
 enum { BPVO_B200_KF_LARGE_TRANSLATION = 0x40, BPVO_B200_KF_LARGE_ROTATION = 0x41,
@@ -63,7 +63,7 @@ enum { BPVO_B200_KF_LARGE_TRANSLATION = 0x40, BPVO_B200_KF_LARGE_ROTATION = 0x41
 typedef struct {
   int32_t numPyramidLevels;               /* <=0: auto (vo.cc:101-104) */
   int32_t minImageDimensionForPyramid;
-  float   sigmaPriorToCensusTransform;    /* > 0 is UNSUPPORTED (third-party u8 blur) */
+  float   sigmaPriorToCensusTransform;    /* > 0: cv::GaussianBlur(3x3) on u8 before the census (census.cc:63-65), OpenCV-4 fixed point */
   float   sigmaBitPlanes;
   int32_t maxIterations;
   float   parameterTolerance;

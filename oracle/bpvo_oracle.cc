@@ -303,7 +303,7 @@ static void gaussian_blur5(const float* src, int rows, int cols, float sigma, fl
 
 // census (bpvo/census.cc:42-91, v128.h:87-120): bit k set iff neighbour_k >= centre (unsigned),
 // k: 0=NW 1=N 2=NE 3=W 4=E 5=SW 6=S 7=SE; first/last row and column are 0.  sigma>0 pre-blur
-// (census.cc:64-65, a third-party u8 3x3 GaussianBlur) is NOT restated: unsupported here.
+// (census.cc:64-65, a third-party u8 3x3 GaussianBlur) is gaussian_blur3_u8() below, applied by compute_descriptor().
 static void census(const uint8_t* src, int rows, int cols, uint8_t* dst) {
   memset(dst, 0, (size_t) rows * cols);
   for (int y = 1; y < rows - 1; ++y) {
@@ -507,6 +507,31 @@ struct Descriptor {
   const float* channel(int c) const { return planes.data() + (size_t) c * rows * cols; }
 };
 
+// cv::GaussianBlur(src, dst, Size(3,3), s, s) on CV_8U (census.cc:64-65) -- THIRD-PARTY arithmetic, restated from
+// OpenCV 4.x's fixed-point path and pinned bit-exact against cv2 4.13.0 golden vectors (tests/golden/cv2_golden.npz):
+// taps k = getGaussianKernel(3, s) = [a, 1 - 2a', a] with a = e / (1 + 2e), e = exp(-1 / (2 s^2)), quantised to 8
+// fractional bits (a8 = round(256 a), centre = 256 - 2 a8 so that the taps sum to exactly 1); separable, row pass kept
+// in 8.8 fixed point, column pass in 16.16, one rounding at the end: (v + 2^15) >> 16; BORDER_REFLECT_101.
+// (OpenCV 2.4.11, the version the reference's README names, filters u8 through a different fixed-point path; the
+// difference, if any, is a rounding unit in some pixels -- "parity unpinned by the reference" for sigma_ct > 0.)
+static void gaussian_blur3_u8(const uint8_t* src, int rows, int cols, double sigma, uint8_t* dst) {
+  const double e = std::exp(-0.5 / (sigma * sigma));
+  const int a8 = (int) std::lrint(256.0 * (e / (1.0 + 2.0 * e))), c8 = 256 - 2 * a8;
+  auto refl = [](int i, int n) { if (n == 1) return 0; while (i < 0 || i >= n) { if (i < 0) i = -i; else i = 2 * (n - 1) - i; } return i; };
+  std::vector<int> h((size_t) rows * cols);
+  for (int y = 0; y < rows; ++y)
+    for (int x = 0; x < cols; ++x) {
+      const uint8_t* s = src + (size_t) y * cols;
+      h[(size_t) y * cols + x] = c8 * (int) s[x] + a8 * ((int) s[refl(x - 1, cols)] + (int) s[refl(x + 1, cols)]);
+    }
+  for (int y = 0; y < rows; ++y)
+    for (int x = 0; x < cols; ++x) {
+      const int v = c8 * h[(size_t) y * cols + x] + a8 * (h[(size_t) refl(y - 1, rows) * cols + x] + h[(size_t) refl(y + 1, rows) * cols + x]);
+      const int q = (v + (1 << 15)) >> 16;
+      dst[(size_t) y * cols + x] = (uint8_t) (q > 255 ? 255 : q);
+    }
+}
+
 static void compute_descriptor(const orc_params& p, const uint8_t* img, int rows, int cols, Descriptor& d) {
   d.rows = rows; d.cols = cols;
   const size_t n = (size_t) rows * cols;
@@ -514,10 +539,12 @@ static void compute_descriptor(const orc_params& p, const uint8_t* img, int rows
     d.channels = 1; d.planes.resize(n);
     for (size_t i = 0; i < n; ++i) d.planes[i] = (float) img[i];
   } else if (p.descriptor == ORC_BITPLANES) {       // bitplanes_descriptor.cc:84-91
-    if (p.sigmaPriorToCensusTransform > 0.0f)
-      throw std::logic_error("oracle: sigmaPriorToCensusTransform > 0 (u8 3x3 GaussianBlur) is not restated");
     d.channels = 8; d.planes.resize(8 * n);
-    std::vector<uint8_t> C(n); census(img, rows, cols, C.data());
+    std::vector<uint8_t> C(n), blurred;
+    if (p.sigmaPriorToCensusTransform > 0.0f) {       // census.cc:63-65
+      blurred.resize(n); gaussian_blur3_u8(img, rows, cols, (double) p.sigmaPriorToCensusTransform, blurred.data()); img = blurred.data();
+    }
+    census(img, rows, cols, C.data());
     const int nt = std::max(1, p.num_threads);
     (void) nt;
 #if defined(_OPENMP)
@@ -1047,6 +1074,7 @@ void orc_default_params(orc_params* p) {        // bpvo/types.cc:31-66
 void orc_pyr_down(const uint8_t* src, int rows, int cols, uint8_t* dst) { pyr_down(src, rows, cols, dst); }
 void orc_gaussian_blur5(const float* src, int rows, int cols, float sigma, float* dst) { gaussian_blur5(src, rows, cols, sigma, dst); }
 void orc_census(const uint8_t* src, int rows, int cols, uint8_t* dst) { census(src, rows, cols, dst); }
+void orc_gaussian_blur3_u8(const uint8_t* src, int rows, int cols, float sigma, uint8_t* dst) { gaussian_blur3_u8(src, rows, cols, (double) sigma, dst); }
 int orc_descriptor(const orc_params* p, const uint8_t* img, int rows, int cols, float* planes) {
   ORC_TRY
   Descriptor d; compute_descriptor(*p, img, rows, cols, d);

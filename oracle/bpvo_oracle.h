@@ -94,6 +94,7 @@ void orc_pyr_down(const uint8_t* src, int rows, int cols, uint8_t* dst);
 void orc_gaussian_blur5(const float* src, int rows, int cols, float sigma, float* dst);
 /* bpvo/census.cc:59-91 with sigma<=0 */
 void orc_census(const uint8_t* src, int rows, int cols, uint8_t* dst);
+void orc_gaussian_blur3_u8(const uint8_t* src, int rows, int cols, float sigma, uint8_t* dst);   /* cv::GaussianBlur 3x3 on CV_8U, cv2-4.13 fixed point */
 /* descriptor of one level: planar C x rows x cols f32 (bitplanes_descriptor.cc:84-91 / intensity_descriptor.cc:31-43) */
 int  orc_descriptor(const orc_params* p, const uint8_t* img, int rows, int cols, float* planes);
 /* DenseDescriptor::computeSaliencyMap incl. its live indexing bugs (dense_descriptor.cc:92-100, imgproc.cc:45-142) */

@@ -63,6 +63,7 @@ def lib():
         "orc_pyr_down": (None, [u8p, C.c_int, C.c_int, u8p]),
         "orc_gaussian_blur5": (None, [fp, C.c_int, C.c_int, C.c_float, fp]),
         "orc_census": (None, [u8p, C.c_int, C.c_int, u8p]),
+        "orc_gaussian_blur3_u8": (None, [u8p, C.c_int, C.c_int, C.c_float, u8p]),
         "orc_descriptor": (C.c_int, [C.POINTER(OrcParams), u8p, C.c_int, C.c_int, fp]),
         "orc_saliency": (None, [fp, C.c_int, C.c_int, C.c_int, fp]),
         "orc_median": (C.c_float, [fp, C.c_size_t]),
@@ -158,6 +159,13 @@ def gaussian_blur5(img, sigma):
     img = _f32(img)
     out = np.empty_like(img)
     lib().orc_gaussian_blur5(_fp(img), img.shape[0], img.shape[1], float(sigma), _fp(out))
+    return out
+
+
+def gaussian_blur3_u8(img, sigma):
+    img = np.ascontiguousarray(img, np.uint8)
+    out = np.zeros_like(img)
+    lib().orc_gaussian_blur3_u8(_u8(img), img.shape[0], img.shape[1], float(sigma), _u8(out))
     return out
 
 
@@ -420,6 +428,7 @@ def ref_lib():
     fp, u8p, u16p = C.POINTER(C.c_float), C.POINTER(C.c_uint8), C.POINTER(C.c_uint16)
     sig = {
         "ref_census": (None, [u8p, C.c_int, C.c_int, u8p]),
+        "ref_census_sigma": (None, [u8p, C.c_int, C.c_int, C.c_float, u8p]),
         "ref_saliency": (None, [fp, C.c_int, C.c_int, C.c_int, fp]),
         "ref_local_max": (None, [fp, C.c_int, C.c_int, C.c_int, C.c_int, u8p]),
         "ref_median": (C.c_float, [fp, C.c_size_t]),

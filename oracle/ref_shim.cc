@@ -24,6 +24,13 @@ void ref_census(const uint8_t* src, int rows, int cols, uint8_t* dst) {
   memcpy(dst, C.ptr<uint8_t>(), (size_t) rows * cols);
 }
 
+// bpvo::census with the pre-census blur (census.cc:63-65): sigma > 0 runs cv::GaussianBlur(3x3) of the stand-in OpenCV
+void ref_census_sigma(const uint8_t* src, int rows, int cols, float sigma, uint8_t* dst) {
+  cv::Mat I(rows, cols, CV_8UC1, (void*) src);
+  cv::Mat C = census(I, sigma);
+  memcpy(dst, C.ptr<uint8_t>(), (size_t) rows * cols);
+}
+
 // DenseDescriptor::computeSaliencyMap (dense_descriptor.cc:92-100) driving the real
 // gradientAbsoluteMagnitude / gradientAbsoluteMagnitudeAcc (imgproc.cc:45-142)
 void ref_saliency(const float* planes, int channels, int rows, int cols, float* dst) {

@@ -1,6 +1,7 @@
 // Implementations behind oracle/refstub/opencv2: the three OpenCV calls the hot path makes.
 //   cv::pyrDown (CV_8U)            5x5 [1 4 6 4 1]^2, BORDER_REFLECT_101, (sum + 128) >> 8     (bit-exact vs cv2 4.13 golden vectors)
 //   cv::GaussianBlur (5x5, CV_32F) separable, symmetric-tap order, no FMA                        (<= 1 ulp vs cv2 4.13 golden vectors)
+//   cv::GaussianBlur (3x3, CV_8U)  fixed point 8.8 / 16.16, one rounding                          (bit-exact vs cv2 4.13 golden vectors)
 //   cv::Mat::convertTo(CV_32F)     exact
 // Test infrastructure only.
 #include <opencv2/imgproc/imgproc.hpp>
@@ -47,9 +48,32 @@ void pyrDown(const Mat& srcm, Mat& dstm) {
   dstm = out;
 }
 
+// 3x3 on CV_8U (census.cc:65): OpenCV 4.x fixed-point path -- 8-bit taps summing to 256, row pass 8.8, column pass 16.16,
+// one rounding (bit-exact vs cv2 4.13 golden vectors)
+static void blur3_u8(const Mat& srcm, Mat& dstm, double sigma) {
+  const int rows = srcm.rows, cols = srcm.cols;
+  const double e = std::exp(-0.5 / (sigma * sigma));
+  const int ka = (int) std::lrint(256.0 * (e / (1.0 + 2.0 * e))), kc = 256 - 2 * ka;
+  const uint8_t* src = srcm.ptr<uint8_t>();
+  std::vector<int> tmp((size_t) rows * cols);
+  for (int y = 0; y < rows; ++y) {
+    const uint8_t* s = src + (size_t) y * cols;
+    for (int x = 0; x < cols; ++x) tmp[(size_t) y * cols + x] = kc * s[x] + ka * (s[reflect101(x - 1, cols)] + s[reflect101(x + 1, cols)]);
+  }
+  Mat out; out.create(rows, cols, CV_8UC1);
+  uint8_t* dst = out.ptr<uint8_t>();
+  for (int y = 0; y < rows; ++y) {
+    const int* r0 = tmp.data() + (size_t) y * cols;
+    const int* rm = tmp.data() + (size_t) reflect101(y - 1, rows) * cols; const int* rp = tmp.data() + (size_t) reflect101(y + 1, rows) * cols;
+    for (int x = 0; x < cols; ++x) dst[(size_t) y * cols + x] = (uint8_t) std::min(255, (kc * r0[x] + ka * (rm[x] + rp[x]) + 32768) >> 16);
+  }
+  dstm = out;
+}
+
 void GaussianBlur(const Mat& srcm, Mat& dstm, Size ksize, double sigmaX, double) {
+  if ((srcm.type() & 7) == CV_8U && ksize.width == 3 && ksize.height == 3 && sigmaX > 0) { blur3_u8(srcm, dstm, sigmaX); return; }
   if ((srcm.type() & 7) != CV_32F || ksize.width != 5 || ksize.height != 5)
-    throw std::logic_error("refstub: GaussianBlur only supports 5x5 on CV_32F (the u8 3x3 pre-census blur is not restated)");
+    throw std::logic_error("refstub: GaussianBlur only supports 5x5 on CV_32F and 3x3 on CV_8U");
   const int rows = srcm.rows, cols = srcm.cols;
   float k[5];
   { const double s = sigmaX > 0 ? sigmaX : ((5 - 1) * 0.5 - 1) * 0.3 + 0.8; const double sc = -0.5 / (s * s); double sum = 0;

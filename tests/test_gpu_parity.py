@@ -148,6 +148,55 @@ def test_linearize(kind, desc, levels, loss, oracle):
         _cmp_linearize(ctx, gref, gcur, oref, ocur, oest, l, T2, False, 1e-4)
 
 
+@pytest.mark.parametrize("interp", ["kCosine", "kCubic", "kCubicHermite"])
+@pytest.mark.parametrize("kind,desc,loss", [("small", "intensity", "huber"), ("odd", "bitplanes", "tukey")])
+def test_linearize_other_interpolants(kind, desc, loss, interp, oracle):
+    """InterpolationType kCosine / kCubic / kCubicHermite (photo_error.cc:391-444): float arithmetic in the reference,
+    so residuals / weights are compared at 1e-5 (north_star), valid flags (border 1 / 3 for the cubic footprints) exactly.
+    Points whose 4-row footprint reaches row `rows` (yi = rows - 2) are excluded: the reference reads past its image there."""
+    from bpvo_b200.types import InterpolationType
+    levels = 2
+    p = make_params(desc, levels, loss, interp=getattr(InterpolationType, interp))
+    sc, ctx, gref, gcur, oref, ocur = _pair(kind, p, oracle, use_rcp=0)
+    oest = oracle.Estimator(ctx.params)
+    T = np.array(sc.relative_pose(0, 1), dtype=np.float32)
+    for l in range(levels - 1, -1, -1):
+        g = ctx.linearize(gref, gcur, l, T, True)
+        o = oest.linearize(oref, ocur, l, T, True)
+        N, C = gref.numPoints(l), ctx.channels
+        v_g, v_o = ctx.getValidFlags().astype(np.uint16), o["valid"][:N]
+        assert np.array_equal(v_g, v_o)
+        assert 0 < int(v_o.sum()) <= N
+        r_g, r_o = ctx.getResiduals().reshape(C, N), o["residuals"].reshape(C, N)
+        keep = np.ones(N, bool)
+        if interp != "kCosine":
+            rows, cols = gref.level_size(l)
+            K = np.array(sc.K, np.float64) / (1 << l); K[2, 2] = 1.0
+            X = gref.points(l).astype(np.float64)
+            h = (K.astype(np.float32).astype(np.float64) @ T[:3, :].astype(np.float64)) @ X.T
+            keep = np.floor(h[1] / h[2]) < rows - 2.5
+            assert keep.sum() > 0.9 * N
+        err = np.abs(r_g - r_o)[:, keep].max()
+        assert err <= 1e-5 * max(1.0, np.abs(r_o).max()), (interp, l, err)
+        if keep.all():
+            assert abs(g["sigma"] - o["sigma"]) <= 1e-5 * max(1.0, abs(o["sigma"]))
+            assert np.abs(ctx.getWeights() - o["weights"]).max() <= 1e-4
+            assert rel_err(g["H"], o["H"]) < 1e-3
+
+
+@pytest.mark.parametrize("kind,levels,sigma_ct", [("small", 3, 0.75), ("odd", 2, 0.5), ("kitti", 4, 0.75)])
+def test_pre_census_blur(kind, levels, sigma_ct, oracle):
+    """sigmaPriorToCensusTransform > 0 (census.cc:63-65, conf/perf_bitplanes.cfg uses 0.75): pyramid, descriptor and the
+    template selection stay bit-exact; one linearize within the usual bounds"""
+    p = make_params("bitplanes", levels, "tukey", sigmaPriorToCensusTransform=sigma_ct)
+    sc, ctx, gref, gcur, oref, ocur = _pair(kind, p, oracle, use_rcp=0)
+    for l in range(levels):
+        assert np.abs(gref.descriptor(l) - oref.descriptor(l)).max() <= 1e-6, l
+        assert np.array_equal(gref.point_inds(l), oref.point_inds(l)), l
+    oest = oracle.Estimator(ctx.params)
+    _cmp_linearize(ctx, gref, gcur, oref, ocur, oest, 0, np.eye(4, dtype=np.float32), True, 1e-4)
+
+
 def test_linearize_vs_rcp_oracle(oracle):
     """reference-faithful oracle (12-bit reciprocal Jacobians): H, G agree to the rcp error bound"""
     p = make_params("bitplanes", 3, "tukey")

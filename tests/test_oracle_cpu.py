@@ -43,6 +43,17 @@ def _census_numpy(img):
     return out
 
 
+def test_gaussian_blur3_u8_matches_cv2_golden(oracle):
+    """cv::GaussianBlur(3x3) on CV_8U before the census (census.cc:65): bit-exact against cv2 4.13"""
+    g = np.load(os.path.join(GOLD, "cv2_golden.npz"))
+    n = 0
+    while f"cblur_in_{n}" in g.files:
+        out = oracle.gaussian_blur3_u8(g[f"cblur_in_{n}"], float(g[f"cblur_sigma_{n}"]))
+        assert np.array_equal(out, g[f"cblur_out_{n}"]), n
+        n += 1
+    assert n >= 5
+
+
 def test_census_against_numpy(oracle):
     rng = np.random.RandomState(1)
     for shape in [(20, 33), (37, 64), (19, 18)]:

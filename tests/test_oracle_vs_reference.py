@@ -41,6 +41,17 @@ def test_census_bit_exact(oracle, ref, shape):
     assert np.array_equal(oracle.census(img), out)
 
 
+@pytest.mark.parametrize("shape,sigma", [((20, 33), 0.75), ((37, 64), 0.5), ((94, 311), 0.75), ((40, 18), 1.3)])
+def test_census_with_pre_blur_bit_exact(oracle, ref, shape, sigma):
+    """sigmaPriorToCensusTransform > 0 (census.cc:63-65): the reference's census() over the stand-in cv::GaussianBlur(3x3, u8)
+    == the oracle's fixed-point blur (pinned against cv2 golden vectors in test_oracle_cpu.py) followed by its census"""
+    rng = np.random.RandomState(shape[0])
+    img = rng.randint(0, 256, size=shape).astype(np.uint8)
+    out = np.zeros_like(img)
+    ref.ref_census_sigma(_u8(img), shape[0], shape[1], sigma, _u8(out))
+    assert np.array_equal(oracle.census(oracle.gaussian_blur3_u8(img, sigma)), out)
+
+
 @pytest.mark.parametrize("shape", [(12, 16), (11, 19), (9, 22), (47, 156), (94, 311), (60, 80)])
 @pytest.mark.parametrize("channels", [1, 8])
 def test_saliency_bit_exact_including_the_bugs(oracle, ref, shape, channels):
