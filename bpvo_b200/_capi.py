@@ -80,6 +80,9 @@ def _signatures():
         "bpvo_b200_comm_unique_id": (C.c_int, [u8p]),
         "bpvo_b200_comm_init": (C.c_int, [vp, C.c_int, C.c_int, u8p]),
         "bpvo_b200_comm_destroy": (C.c_int, [vp]),
+        "bpvo_b200_peer_export": (C.c_int, [vp, u8p]),
+        "bpvo_b200_peer_init": (C.c_int, [vp, u8p]),
+        "bpvo_b200_peer_set_min_points": (C.c_int, [vp, C.c_int]),
         "bpvo_b200_set_profiling": (C.c_int, [vp, C.c_int]),
         "bpvo_b200_get_counters": (C.c_int, [vp, C.POINTER(CCounters)]),
         "bpvo_b200_reset_counters": (C.c_int, [vp]),

@@ -49,7 +49,18 @@ int nccl_fail(const char* what, ncclResult_t r) {
 
 }  // namespace
 
+static void peer_release(bpvo_b200_ctx* c) {
+  for (int r = 0; r < bp::kXRanks; ++r) {
+    if (c->xpeer[r] && c->xpeer[r] != c->xbox) cudaIpcCloseMemHandle(c->xpeer[r]);
+    c->xpeer[r] = nullptr;
+  }
+  if (c->xbox) { cudaFree(c->xbox); c->xbox = nullptr; }
+  if (c->lbox) { cudaFree(c->lbox); c->lbox = nullptr; }
+  c->peer_mode = false; c->x_seq = 0;
+}
+
 int bp_comm_destroy(bpvo_b200_ctx* c) {
+  peer_release(c);
   if (c->comm) { nccl().CommDestroy((ncclComm_t) c->comm); c->comm = nullptr; }
   if (c->comm_buf) { cudaFree(c->comm_buf); c->comm_buf = nullptr; }
   c->shard_rank = 0; c->shard_size = 1;
@@ -95,6 +106,51 @@ int bpvo_b200_comm_init(bpvo_b200_ctx* c, int rank, int nranks, const uint8_t id
   if (r != 0) return nccl_fail("ncclCommInitRank", r);
   c->comm = comm; c->shard_rank = rank; c->shard_size = nranks;
   if (cudaMalloc(&c->comm_buf, 64 * sizeof(double)) != cudaSuccess) return bp_fail(BPVO_B200_ERR_CUDA, "cudaMalloc(comm_buf) failed");
+  return BPVO_B200_OK;
+}
+
+// ---- peer-memory mode (on-device GN loop across GPUs) -----------------------------------------------------------------
+static const size_t kXBoxBytes = (size_t) 2 * bp::kXRanks * bp::kXWords * sizeof(uint2);
+
+int bpvo_b200_peer_export(bpvo_b200_ctx* c, uint8_t handle[64]) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  if (!c || !handle) return bp_fail(BPVO_B200_ERR_INVALID_ARG, "null argument");
+  if (cudaSetDevice(c->p.device_id) != cudaSuccess) return bp_fail(BPVO_B200_ERR_CUDA, "cudaSetDevice failed");
+  if (!c->xbox) {
+    if (cudaMalloc(&c->xbox, kXBoxBytes) != cudaSuccess) return bp_fail(BPVO_B200_ERR_CUDA, "cudaMalloc(mailbox) failed");
+    if (cudaMalloc(&c->lbox, 2 * 64 * sizeof(uint4)) != cudaSuccess) return bp_fail(BPVO_B200_ERR_CUDA, "cudaMalloc(lbox) failed");
+    cudaMemset(c->xbox, 0, kXBoxBytes); cudaMemset(c->lbox, 0, 2 * 64 * sizeof(uint4));
+    cudaDeviceSynchronize();
+  }
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, c->xbox);
+  if (e != cudaSuccess) return bp_fail(BPVO_B200_ERR_COMM, "cudaIpcGetMemHandle failed: %s", cudaGetErrorString(e));
+  memcpy(handle, &h, 64);
+  return BPVO_B200_OK;
+}
+
+int bpvo_b200_peer_init(bpvo_b200_ctx* c, const uint8_t* handles) {
+  if (!c || !handles) return bp_fail(BPVO_B200_ERR_INVALID_ARG, "null argument");
+  if (c->shard_size <= 1) return bp_fail(BPVO_B200_ERR_INVALID_ARG, "peer_init needs comm_init with nranks > 1 first");
+  if (c->shard_size > bp::kXRanks) return bp_fail(BPVO_B200_ERR_UNSUPPORTED, "peer-memory mode supports up to %d ranks", bp::kXRanks);
+  if (!c->xbox) return bp_fail(BPVO_B200_ERR_INVALID_ARG, "call peer_export first");
+  if (!c->coop) return bp_fail(BPVO_B200_ERR_UNSUPPORTED, "device without cooperative launch");
+  if (cudaSetDevice(c->p.device_id) != cudaSuccess) return bp_fail(BPVO_B200_ERR_CUDA, "cudaSetDevice failed");
+  for (int r = 0; r < c->shard_size; ++r) {
+    if (r == c->shard_rank) { c->xpeer[r] = c->xbox; continue; }
+    cudaIpcMemHandle_t h; memcpy(&h, handles + (size_t) r * 64, 64);
+    void* p = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) { cudaGetLastError(); return bp_fail(BPVO_B200_ERR_COMM, "cudaIpcOpenMemHandle(rank %d) failed: %s", r, cudaGetErrorString(e)); }
+    c->xpeer[r] = (uint2*) p;
+  }
+  c->peer_mode = true; c->x_seq = 1;
+  return BPVO_B200_OK;
+}
+
+int bpvo_b200_peer_set_min_points(bpvo_b200_ctx* c, int min_points) {
+  if (!c || min_points < 0) return bp_fail(BPVO_B200_ERR_INVALID_ARG, "bad argument");
+  c->shard_min_points = min_points;
   return BPVO_B200_OK;
 }
 

@@ -40,6 +40,8 @@ struct TemplateMeta {     // device-resident header of a level's template (writt
   int n_total;            // points kept globally (== n when unsharded)
   int first;              // global scan-order index of this rank's first point
   float s, c1, c2, c3;    // Hartley normalisation: Tn = [sI, -s c; 0 1]  (warps.cc:27-48)
+  int replicated;         // multi-GPU: this level is too small to shard -- every rank keeps ALL its points (n == n_total) and
+  int pad[3];             // runs it like a single GPU, bit-identically, with no exchange
 };
 
 struct LevelTemplate {
@@ -87,6 +89,17 @@ struct Work {
                          // followed by the overflow list [kOvfCap]
 };
 
+// point-sharded multi-GPU mode with the GN loop on the device: every rank owns a mailbox in ITS memory that the peers
+// write over NVLink (CUDA IPC mappings); 8-byte flag-in-data words {value, sequence number}
+constexpr int kXRanks = 8;
+constexpr int kXWords = 4096 + 64;   // 32-bit values per (parity, source rank) slot: the largest message is the level-2 histogram pair
+struct PeerArgs {
+  int rank, nranks;            // nranks <= 1: single GPU (everything below unused)
+  unsigned xseq_base;          // first sequence number of this launch's cross-rank exchanges (identical on every rank)
+  uint2* box[kXRanks];         // box[r] = rank r's mailbox [2][kXRanks][kXWords] (box[rank] is local memory)
+  uint4* lbox;                 // local broadcast words [2][64]: what rank-wide results CTA 0 hands to the other CTAs
+};
+
 struct SolverParams {    // PoseEstimatorParameters (pose_estimator_params.h) + loss
   int   max_iterations;
   int   max_fun_evals;   // 1200
@@ -119,6 +132,7 @@ struct SolveArgs {
   int* num_fun_evals;
   long long* prof;       // optional: per-phase cycle counters of CTA 0 (nullptr = off)
   unsigned seq_base;     // first sequence number of this launch's exchanges (monotonic across launches of a ctx)
+  PeerArgs peer;
 };
 
 }  // namespace bp

@@ -391,7 +391,8 @@ int bpvo_b200_frame_set_template(bpvo_b200_frame* f) {
     const int nb = ceil_div(npx, kSelPerBlock);
     select_flags_kernel<<<nb, kSelThreads, 0, c->stream>>>(sa, c->flags, c->block_counts);
     LAUNCH_CHECK(c);
-    select_scan_kernel<<<1, 1024, 0, c->stream>>>(c->block_counts, nb, f->d_meta + l, c->shard_rank, c->shard_size);
+    select_scan_kernel<<<1, 1024, 0, c->stream>>>(c->block_counts, nb, f->d_meta + l, c->shard_rank, c->shard_size,
+                                                   c->peer_mode ? c->shard_min_points : 0);
     LAUNCH_CHECK(c);
     PointArgs pa; pa.rows = g.rows; pa.cols = g.cols; pa.Dcols = c->cols; pa.level = l;
     pa.fx = g.fx; pa.fy = g.fy; pa.cx = g.cx; pa.cy = g.cy; pa.Bf = g.Bf;
@@ -535,7 +536,7 @@ int bpvo_b200_frame_get_normalization(const bpvo_b200_frame* f, int level, float
 int bp_hartley(bpvo_b200_ctx* c, bpvo_b200_frame* f, int l) {
   const int nb = std::max(1, std::min(ceil_div(c->geom[l].capacity, 256 * 8), c->sm_count * 2));
   for (int phase = 0; phase < 2; ++phase) {
-    hartley_sum_kernel<<<nb, 256, 0, c->stream>>>(f->pts[l], f->d_meta + l, c->hpartials, c->work.ticket + 1, c->hsums, phase);
+    hartley_sum_kernel<<<nb, 256, 0, c->stream>>>(f->pts[l], f->d_meta + l, c->hpartials, c->work.ticket + 1, c->hsums, phase, c->shard_rank);
     LAUNCH_CHECK(c);
     int rc = bp_comm_allreduce_f64(c, c->hsums, 3);
     if (rc) return rc;
@@ -690,6 +691,21 @@ static int launch_estimate_pose(bpvo_b200_ctx* c, const bpvo_b200_frame* ref, co
     c->ll_seq = 1;
   }
   a.seq_base = c->ll_seq; c->ll_seq += seq_span;
+  if (c->peer_mode) {
+    // cross-rank exchanges: at most 6 per linearize (histogram + list + sums, or 3 radix histograms + sums); every rank
+    // advances identically (lock-step launches).  Wrap-around would need a collective reset of the mailboxes: refuse instead.
+    const unsigned xspan = seq_span * 8u;
+    if (c->x_seq > 0x7fffffffu) {
+      // collective reset (all ranks reach this at the same launch): barrier, clear the own mailbox, barrier, restart at 1
+      int rc = bp_comm_allreduce_f64(c, c->comm_buf, 1); if (rc) return rc;
+      CUDA_TRY(cudaMemsetAsync(c->xbox, 0, (size_t) 2 * kXRanks * kXWords * sizeof(uint2), c->stream));
+      rc = bp_comm_allreduce_f64(c, c->comm_buf, 1); if (rc) return rc;
+      c->x_seq = 1;
+    }
+    a.peer.rank = c->shard_rank; a.peer.nranks = c->shard_size; a.peer.xseq_base = c->x_seq; a.peer.lbox = c->lbox;
+    for (int r = 0; r < c->shard_size; ++r) a.peer.box[r] = c->xpeer[r];
+    c->x_seq += xspan;
+  }
   // dynamic shared memory: candidate scratch + as many template-cache slots per thread as fit (1 CTA per SM)
   const int per_slot = tpl_cache_bytes_per_slot<C>();
   int slots = (c->smem_optin - 24 * 1024 - kScratchBytes) / per_slot;
@@ -716,7 +732,7 @@ extern "C" int bpvo_b200_estimate_pose(bpvo_b200_ctx* c, const bpvo_b200_frame* 
   M44 T; memcpy(T.m, T_init, sizeof(T.m));
   int evals = 0;
   c->counters.solve_calls++;
-  const bool host_loop = (c->p.flags & BPVO_B200_FLAG_HOST_SOLVE) || !c->coop || c->shard_size > 1;
+  const bool host_loop = (c->p.flags & BPVO_B200_FLAG_HOST_SOLVE) || !c->coop || (c->shard_size > 1 && !c->peer_mode);
   if (host_loop) {
     for (int l = c->L - 1; l >= c->p.maxTestLevel; --l) {              // vo_pose_estimator.cc:76-84
       rc = host_run_level(c, ref, cur, l, T, stats[l], evals);

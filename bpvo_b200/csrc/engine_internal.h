@@ -50,6 +50,13 @@ struct bpvo_b200_ctx {
   void* comm = nullptr;          // ncclComm_t
   double* comm_buf = nullptr;    // device staging for the exchanges (sharded mode)
   double* hsums = nullptr;       // [4] Hartley phase totals
+  // peer-memory mode: the on-device GN loop exchanges over NVLink through IPC-mapped mailboxes (comm.cu)
+  bool peer_mode = false;
+  int shard_min_points = 131072; // peer mode: levels with fewer points are replicated on every rank instead of sharded
+  uint2* xbox = nullptr;         // this rank's mailbox
+  uint2* xpeer[bp::kXRanks] = {};
+  uint4* lbox = nullptr;
+  unsigned x_seq = 0;
 };
 
 struct bpvo_b200_frame {

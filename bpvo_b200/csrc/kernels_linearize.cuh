@@ -948,6 +948,193 @@ __device__ __forceinline__ void exchange_sums(double mine, uint4* ll, unsigned s
   BP_FINE(43);
 }
 
+// =============================================================================================
+// Cross-rank exchanges of the point-sharded mode, INSIDE the persistent kernel (peer-memory mode, comm.cu):
+// every rank's mailbox lives in its own memory and is written by the peers with plain stores over NVLink (CUDA IPC
+// mappings); 8-byte words {value, sequence number} validate themselves, so a message needs no fence and no separate
+// flag: the receiver polls its LOCAL memory.  Slots are double-buffered by sequence parity (a rank can be at most one
+// exchange ahead of any other: it needs everybody's previous message to get there).  Only CTA 0 of a rank talks to
+// the peers; it hands rank-wide results to the other CTAs through a local grid barrier or local flag-in-data words.
+// All ranks take identical decisions from identical data, so the exchange sequence is the same everywhere.
+// =============================================================================================
+__device__ __forceinline__ void x_put(uint2* p, unsigned v, unsigned seq) {
+  asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(v), "r"(seq) : "memory");
+}
+__device__ __forceinline__ bool x_peek(const uint2* p, unsigned seq, unsigned& v) {
+  unsigned f;
+  asm volatile("ld.relaxed.sys.global.v2.u32 {%0, %1}, [%2];" : "=r"(v), "=r"(f) : "l"(p) : "memory");
+  return f == seq;
+}
+__device__ __forceinline__ uint2* x_slot(const PeerArgs& pa, int owner, unsigned seq, int src) {
+  return pa.box[owner] + ((size_t) (seq & 1u) * kXRanks + src) * kXWords;
+}
+__device__ __forceinline__ unsigned x_wait(const uint2* p, unsigned seq, int* abort_flag) {
+  unsigned v, spins = 0;
+  while (!x_peek(p, seq, v)) { if (++spins > kSpinLimit || *(volatile int*) abort_flag) { *abort_flag = 1; v = 0; break; } }
+  return v;
+}
+// CTA 0: send buf[0..n) (shared memory) to every peer
+__device__ __forceinline__ void x_send(const PeerArgs& pa, unsigned seq, const unsigned* buf, int n) {
+  for (int p = 0; p < pa.nranks; ++p) {
+    if (p == pa.rank) continue;
+    uint2* dst = x_slot(pa, p, seq, pa.rank);
+    for (int i = threadIdx.x; i < n; i += kLinThreads) x_put(dst + i, buf[i], seq);
+  }
+}
+// CTA 0: sum (u32) of buf[0..n) over all ranks, in place (shared memory); thread t owns words t, t + 256, ...
+__device__ __forceinline__ void x_allreduce_u32(const PeerArgs& pa, unsigned& xseq, unsigned* buf, int n, int* abort_flag) {
+  const unsigned seq = xseq++;
+  x_send(pa, seq, buf, n);
+  for (int r = 0; r < pa.nranks; ++r) {
+    if (r == pa.rank) continue;
+    const uint2* src = x_slot(pa, pa.rank, seq, r);
+    for (int i0 = threadIdx.x; i0 < n; i0 += 8 * kLinThreads) {       // 8 words in flight per thread
+      unsigned v[8]; bool ok[8]; bool all = true;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) { ok[q] = i0 + q * kLinThreads >= n; v[q] = 0; all = all && ok[q]; }
+      unsigned spins = 0;
+      while (!all) {
+        all = true;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { if (!ok[q]) ok[q] = x_peek(src + i0 + q * kLinThreads, seq, v[q]); all = all && ok[q]; }
+        if (!all && (++spins > kSpinLimit || *(volatile int*) abort_flag)) { *abort_flag = 1; break; }
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) if (i0 + q * kLinThreads < n && ok[q]) buf[i0 + q * kLinThreads] += v[q];
+    }
+  }
+  __syncthreads();
+}
+// CTA 0, thread k < 30: sum of `mine` over all ranks in RANK ORDER (bit-identical on every rank)
+__device__ __forceinline__ double x_allreduce_f64_ordered(const PeerArgs& pa, unsigned& xseq, double mine, int* abort_flag) {
+  const unsigned seq = xseq++;
+  const int k = threadIdx.x;
+  double t = 0.0;
+  if (k < 30) {
+    const unsigned long long b = (unsigned long long) __double_as_longlong(mine);
+    for (int p = 0; p < pa.nranks; ++p) {
+      if (p == pa.rank) continue;
+      uint2* dst = x_slot(pa, p, seq, pa.rank);
+      x_put(dst + 2 * k, (unsigned) b, seq); x_put(dst + 2 * k + 1, (unsigned) (b >> 32), seq);
+    }
+    unsigned lo[kXRanks], hi[kXRanks]; bool ok[kXRanks]; bool all = true;
+#pragma unroll
+    for (int r = 0; r < kXRanks; ++r) { ok[r] = (r >= pa.nranks) || (r == pa.rank); lo[r] = hi[r] = 0; all = all && ok[r]; }
+    unsigned spins = 0;
+    while (!all) {
+      all = true;
+#pragma unroll
+      for (int r = 0; r < kXRanks; ++r) {
+        if (!ok[r]) { const uint2* src = x_slot(pa, pa.rank, seq, r); unsigned a, c; const bool g0 = x_peek(src + 2 * k, seq, a), g1 = x_peek(src + 2 * k + 1, seq, c); if (g0 && g1) { lo[r] = a; hi[r] = c; ok[r] = true; } }
+        all = all && ok[r];
+      }
+      if (!all && (++spins > kSpinLimit || *(volatile int*) abort_flag)) { *abort_flag = 1; break; }
+    }
+#pragma unroll
+    for (int r = 0; r < kXRanks; ++r)
+      if (r < pa.nranks) t += (r == pa.rank) ? mine : __longlong_as_double((long long) (((unsigned long long) hi[r] << 32) | lo[r]));
+  }
+  return t;
+}
+
+// CTA 0 of every rank: the bracketed exact median over ALL ranks' residuals.  Same algorithm as bracket_select(), with
+// two exchanges: the bracket histogram + counters are all-reduced, then the (few) candidates of the two wanted bins are
+// all-gathered.  Every rank computes the same verdict and the same pair of order statistics.
+constexpr unsigned kXPoison = 1u << 26;      // per-rank stand-in for kCandPoison that cannot overflow a u32 sum over 8 ranks
+template <int C>
+__device__ __forceinline__ bool bracket_select_xrank(const PeerArgs& pa, unsigned& xseq, const Work& W, const unsigned* __restrict__ hset, LinShared& sh,
+                                                     unsigned* scratch, int nblocks, const Bracket& br, int* abort_flag,
+                                                     unsigned& n_out, unsigned& ncand_out, float& lo_out, float& hi_out) {
+  const int tid = threadIdx.x;
+  const unsigned total = (unsigned) nblocks * kCandPerCta;
+  const uint4 gb = __ldcg(reinterpret_cast<const uint4*>(hset + kHistBins + 8) + tid);
+  float pre[kSelPre];
+#pragma unroll
+  for (int q = 0; q < kSelPre; ++q) { const unsigned j = tid + q * kLinThreads; pre[q] = (j < total) ? __ldcg(W.cand + j) : -1.0f; }
+  const unsigned nv_l = __ldcg(hset + kHistBins + 1), below_l = __ldcg(hset + kHistBins + 2), ncand_l = __ldcg(hset + kHistBins + 3);
+  const unsigned novf = __ldcg(hset + kHistBins + 4);
+  const float* ovf = W.cand + (size_t) nblocks * kCandPerCta;
+  unsigned* buf = sh.hist;
+  buf[4 * tid + 0] = gb.x; buf[4 * tid + 1] = gb.y; buf[4 * tid + 2] = gb.z; buf[4 * tid + 3] = gb.w;
+  if (tid == 0) { buf[kSelBins] = nv_l; buf[kSelBins + 1] = below_l; buf[kSelBins + 2] = (ncand_l >= kCandPoison || novf > (unsigned) kOvfCap) ? kXPoison : ncand_l; }
+  __syncthreads();
+  x_allreduce_u32(pa, xseq, buf, kSelBins + 3, abort_flag);
+  const unsigned n = buf[kSelBins] * (unsigned) C, below = buf[kSelBins + 1], ncand = buf[kSelBins + 2];
+  n_out = n; ncand_out = ncand;
+  if (n < 3 || ncand >= kXPoison) return false;
+  const unsigned t_hi = n / 2, t_lo = (n % 2 == 0) ? t_hi - 1 : t_hi;
+  if (below > t_lo || t_hi >= below + ncand) return false;
+  const unsigned ra = t_lo - below, rb = t_hi - below;
+  float* list = reinterpret_cast<float*>(scratch + kCtaCandCap);   // [kSelList]
+  const unsigned loc[4] = {buf[4 * tid + 0], buf[4 * tid + 1], buf[4 * tid + 2], buf[4 * tid + 3]};
+  unsigned bin_a, rem_a, bin_b, rem_b, tot;
+  block_find2_regs<4>(loc, ra, rb, sh, bin_a, rem_a, bin_b, rem_b, tot);      // resets sh.found[0..7]
+  // this rank's candidates in the two wanted bins -> list[0 .. nl)
+#pragma unroll
+  for (int q = 0; q < kSelPre; ++q) {
+    const unsigned b = (unsigned) sel_bin(pre[q], br.lo, br.inv_w);
+    if (pre[q] >= 0.0f && (b == bin_a || b == bin_b)) { const unsigned slot = atomicAdd(&sh.found[4], 1u); if (slot < (unsigned) kSelList) list[slot] = pre[q]; }
+  }
+  for (unsigned j = tid + kSelPre * kLinThreads; j < total; j += kLinThreads) {
+    const float v = __ldcg(W.cand + j);
+    const unsigned b = (unsigned) sel_bin(v, br.lo, br.inv_w);
+    if (v >= 0.0f && (b == bin_a || b == bin_b)) { const unsigned slot = atomicAdd(&sh.found[4], 1u); if (slot < (unsigned) kSelList) list[slot] = v; }
+  }
+  for (unsigned j = tid; j < novf; j += kLinThreads) {
+    const float v = __ldcg(ovf + j);
+    const unsigned b = (unsigned) sel_bin(v, br.lo, br.inv_w);
+    if (b == bin_a || b == bin_b) { const unsigned slot = atomicAdd(&sh.found[4], 1u); if (slot < (unsigned) kSelList) list[slot] = v; }
+  }
+  __syncthreads();
+  // all-gather of the short lists: word 0 = count (0xffffffff: too many here -> everybody falls back), then the values
+  const unsigned nl_own = sh.found[4];
+  const bool own_bad = nl_own > 63u;
+  const unsigned seq = xseq++;
+  if (tid == 0) buf[0] = own_bad ? 0xffffffffu : nl_own;
+  if (!own_bad && tid < (int) nl_own) buf[1 + tid] = __float_as_uint(list[tid]);
+  __syncthreads();
+  x_send(pa, seq, buf, own_bad ? 1 : 1 + (int) nl_own);
+  unsigned base = own_bad ? 0u : nl_own;
+  bool bad = own_bad;
+  for (int r = 0; r < pa.nranks; ++r) {
+    if (r == pa.rank) continue;
+    const uint2* src = x_slot(pa, pa.rank, seq, r);
+    const unsigned nr = x_wait(src, seq, abort_flag);
+    if (nr == 0xffffffffu) { bad = true; continue; }
+    if (tid < (int) nr && base + tid < (unsigned) kSelList) list[base + tid] = __uint_as_float(x_wait(src + 1 + tid, seq, abort_flag));
+    base += nr;
+  }
+  __syncthreads();
+  if (bad || base > (unsigned) kSelList || *(volatile int*) abort_flag) return false;
+  if (tid < (int) base) {
+    const float v = list[tid];
+    const unsigned bj = (unsigned) sel_bin(v, br.lo, br.inv_w);
+    unsigned rank = 0;
+    for (unsigned j = 0; j < base; ++j) {
+      const float u = list[j];
+      const unsigned bu = (unsigned) sel_bin(u, br.lo, br.inv_w);
+      rank += (bu == bj && (u < v || (u == v && j < (unsigned) tid))) ? 1u : 0u;
+    }
+    if (bj == bin_a && rank == rem_a) sh.found[6] = __float_as_uint(v);
+    if (bj == bin_b && rank == rem_b) sh.found[7] = __float_as_uint(v);
+  }
+  __syncthreads();
+  lo_out = __uint_as_float(sh.found[6]); hi_out = __uint_as_float(sh.found[7]);
+  return true;
+}
+
+// all CTAs: a histogram range of this rank's set -> its sum over all ranks, in place; ends with a grid barrier
+__device__ __forceinline__ void xrank_hist_allreduce(const PeerArgs& pa, unsigned& xseq, unsigned* hist, int n, LinShared& sh,
+                                                     unsigned* counter, unsigned& epoch, int nblocks, int* abort_flag) {
+  if (blockIdx.x == 0) {
+    for (int i = threadIdx.x; i < n; i += kLinThreads) sh.hist[i] = __ldcg(hist + i);
+    __syncthreads();
+    x_allreduce_u32(pa, xseq, sh.hist, n, abort_flag);
+    for (int i = threadIdx.x; i < n; i += kLinThreads) hist[i] = sh.hist[i];
+  }                                  // (only CTA 0 ever uses xseq)
+  grid_barrier(counter, epoch, nblocks, abort_flag);
+}
+
 // the damped fp64 retry of solve6() is rare: keep it out of line so that it does not bloat the hot loop
 __device__ __noinline__ bool solve6_fallback(const float* H, const float* G, float* dp) { return solve6(H, G, dp); }
 
@@ -970,6 +1157,7 @@ struct GridSync {
   unsigned* counter;   // grid-barrier counter (zeroed by the host before the launch)
   unsigned epoch;      // value of *counter once every CTA has passed the last barrier
   unsigned seq;        // sequence number of the next exchange
+  unsigned xseq;       // sequence number of the next cross-rank exchange (peer-memory mode)
   int hs;              // histogram set of the next linearize (cycles through kHistSets)
 };
 
@@ -999,20 +1187,43 @@ __device__ __forceinline__ void device_linearize(const SolveArgs& a, int lvl, So
     for (int b = blk * kLinThreads + tid; b < kHistWords; b += nb * kLinThreads) hprev[b] = 0;
     unsigned n = 0, ncand = 0; float lo = 0.0f, hi = 0.0f;
     bool hit = false;
-    if (br.on) hit = bracket_select<C>(a.work, hset, sh, scratch, nb, br, n, ncand, lo, hi);
+    const bool multi = a.peer.nranks > 1 && !meta.replicated;
+    if (br.on && !multi) hit = bracket_select<C>(a.work, hset, sh, scratch, nb, br, n, ncand, lo, hi);
+    if (br.on && multi) {
+      // CTA 0 talks to the peers (two exchanges) and hands the verdict to the other CTAs through three local words
+      uint4* lb = a.peer.lbox + (size_t) (gs.seq & 1u) * 64;
+      if (blk == 0) {
+        hit = bracket_select_xrank<C>(a.peer, gs.xseq, a.work, hset, sh, scratch, nb, br, &ss.abort, n, ncand, lo, hi);
+        if (tid == 0) {
+          ll_post(lb + 0, __longlong_as_double((long long) (((unsigned long long) n << 32) | (hit ? 1u : 0u))), gs.seq);
+          ll_post(lb + 1, __longlong_as_double((long long) (((unsigned long long) __float_as_uint(hi) << 32) | __float_as_uint(lo))), gs.seq);
+          ll_post(lb + 2, __longlong_as_double((long long) (unsigned long long) ncand), gs.seq);
+        }
+      } else {
+        if (tid < 3) sh.xch[0][tid] = ll_gather<1>(lb + tid, 0, 1, gs.seq, &ss.abort);
+        __syncthreads();
+        const unsigned long long w0 = (unsigned long long) __double_as_longlong(sh.xch[0][0]), w1 = (unsigned long long) __double_as_longlong(sh.xch[0][1]),
+                                 w2 = (unsigned long long) __double_as_longlong(sh.xch[0][2]);
+        hit = (w0 & 1u) != 0; n = (unsigned) (w0 >> 32); lo = __uint_as_float((unsigned) w1); hi = __uint_as_float((unsigned) (w1 >> 32)); ncand = (unsigned) w2;
+        __syncthreads();
+      }
+    }
     if (hit) {
       const float med = (n % 2 != 0) ? hi : (float) ((double) __fadd_rn(lo, hi) / 2.0);
       sigma = scale_from_median(n, med);
       BP_PROF(PROF_SCALE);
     } else {
       if (br.on) { phase_hist1<C>(a.work, hset, tc, meta, sh, blk, nb); grid_barrier(gs.counter, gs.epoch, nb, &ss.abort); }   // bracket missed: build the histogram now
+      if (multi) xrank_hist_allreduce(a.peer, gs.xseq, hset, kHist1Bins, sh, gs.counter, gs.epoch, nb, &ss.abort);
       phase_select<C, 2>(L, a.work, hset, sel, tc, meta, sh, blk, nb);
       BP_PROF(PROF_P2);
       grid_barrier(gs.counter, gs.epoch, nb, &ss.abort);
+      if (multi) xrank_hist_allreduce(a.peer, gs.xseq, hset + kHist1Bins, 2 * kHist2Bins, sh, gs.counter, gs.epoch, nb, &ss.abort);
       BP_PROF(PROF_SYNC2);
       phase_select<C, 3>(L, a.work, hset, sel, tc, meta, sh, blk, nb);
       BP_PROF(PROF_P3);
       grid_barrier(gs.counter, gs.epoch, nb, &ss.abort);
+      if (multi) xrank_hist_allreduce(a.peer, gs.xseq, hset + kHist1Bins + 2 * kHist2Bins, 2 * kHist3Bins, sh, gs.counter, gs.epoch, nb, &ss.abort);
       BP_PROF(PROF_SYNC3);
       sigma = finish_scale<C>(a.work, hset, sel, sh, &lo, &hi);
       n = sel->n;
@@ -1039,6 +1250,16 @@ __device__ __forceinline__ void device_linearize(const SolveArgs& a, int lvl, So
   const double mine = phase_reduce<C>(L, a.work, sigma, a.sp.loss, a.sp.good_threshold, tc, meta, sh, blk, nb, false);
   BP_PROF(PROF_P4);
   exchange_sums(mine, a.work.ll, gs.seq, sh, blk, nb, &ss.abort);
+  if (a.peer.nranks > 1 && !meta.replicated) {        // rank totals -> totals over all ranks (summed in rank order by CTA 0, then handed to the other CTAs)
+    uint4* lb = a.peer.lbox + (size_t) (gs.seq & 1u) * 64 + 32;
+    if (blk == 0) {
+      const double t = x_allreduce_f64_ordered(a.peer, gs.xseq, tid < 30 ? sh.red[0][tid] : 0.0, &ss.abort);
+      if (tid < 30) { ll_post(lb + tid, t, gs.seq); sh.red[0][tid] = t; }
+    } else {
+      if (tid < 30) sh.red[0][tid] = ll_gather<1>(lb + tid, 0, 1, gs.seq, &ss.abort);
+    }
+    __syncthreads();
+  }
   BP_PROF(PROF_SYNC4);
   if (tid == 64 && do_hist) { ss.delta = fabsf(sigma - ss.scale); ss.scale = sigma; }     // read again only after finish_sums' barrier
   finish_sums(sigma, sh, ss.lin);
@@ -1061,7 +1282,7 @@ __global__ void __launch_bounds__(kLinThreads, 1) k_estimate_pose(const __grid_c
   tc_full.K = cache_slots;
   const int tid = threadIdx.x;
   GridSync gs;
-  gs.counter = a.work.hist + (size_t) kHistSets * kHistWords; gs.epoch = 0; gs.seq = a.seq_base; gs.hs = 0;
+  gs.counter = a.work.hist + (size_t) kHistSets * kHistWords; gs.epoch = 0; gs.seq = a.seq_base; gs.xseq = a.peer.xseq_base; gs.hs = 0;
   int total_evals = 0;
   if (a.prof && blockIdx.x == 0) {
     long long* sp = prof_smem();

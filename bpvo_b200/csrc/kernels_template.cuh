@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(kSelThreads) select_flags_kernel(SelectArgs a,
 
 // pass 2: exclusive scan of the block counts (single CTA), trim to a multiple of 16, shard split
 __global__ void __launch_bounds__(1024) select_scan_kernel(int* __restrict__ block_counts, int nb, TemplateMeta* __restrict__ meta,
-                                                            int shard_rank, int shard_size) {
+                                                            int shard_rank, int shard_size, int shard_min_points) {
   __shared__ int s_warp[32];
   __shared__ int s_carry;
   if (threadIdx.x == 0) s_carry = 0;
@@ -162,9 +162,11 @@ __global__ void __launch_bounds__(1024) select_scan_kernel(int* __restrict__ blo
     const int n_raw = s_carry;
     const int n_total = n_raw - (n_raw % 16);                 // template_data.cc:85-89
     // contiguous scan-order blocks, multiples of 16
+    // ... unless the level is too small for sharding to pay (peer-memory mode): then every rank keeps everything
     const int groups = n_total / 16;
-    const int g0 = (int) ((long long) groups * shard_rank / shard_size), g1 = (int) ((long long) groups * (shard_rank + 1) / shard_size);
-    meta->n_raw = n_raw; meta->n_total = n_total; meta->first = g0 * 16; meta->n = (g1 - g0) * 16;
+    const bool rep = shard_size > 1 && n_total < shard_min_points;
+    const int g0 = rep ? 0 : (int) ((long long) groups * shard_rank / shard_size), g1 = rep ? groups : (int) ((long long) groups * (shard_rank + 1) / shard_size);
+    meta->n_raw = n_raw; meta->n_total = n_total; meta->first = g0 * 16; meta->n = (g1 - g0) * 16; meta->replicated = rep ? 1 : 0;
   }
 }
 
@@ -216,10 +218,11 @@ __global__ void __launch_bounds__(kSelThreads) select_scatter_kernel(PointArgs a
 // kernel then finishes the phase.  In the point-sharded multi-GPU mode `sums` is all-reduced in between.
 __global__ void __launch_bounds__(256) hartley_sum_kernel(const float4* __restrict__ pts, const TemplateMeta* __restrict__ meta,
                                                           double* __restrict__ partials, unsigned* __restrict__ ticket,
-                                                          double* __restrict__ sums, int phase) {
+                                                          double* __restrict__ sums, int phase, int shard_rank) {
   __shared__ double s_red[8][4];
   __shared__ bool s_last;
-  const int n = meta->n;
+  // a replicated level (multi-GPU) is summed by rank 0 only: the all-reduce then returns exactly the single-GPU sums
+  const int n = (meta->replicated && shard_rank != 0) ? 0 : meta->n;
   double a0 = 0, a1 = 0, a2 = 0;
   const float c1 = meta->c1, c2 = meta->c2, c3 = meta->c3;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -244,12 +247,22 @@ __global__ void __launch_bounds__(256) hartley_sum_kernel(const float4* __restri
     s_last = (t == gridDim.x - 1);
   }
   __syncthreads();
-  if (s_last && threadIdx.x == 0) {
+  if (s_last) {                            // fixed-order fold of the CTA partials by the whole last CTA
     __threadfence();
     double t0 = 0, t1 = 0, t2 = 0;
-    for (unsigned b = 0; b < gridDim.x; ++b) { t0 += partials[b * 4]; t1 += partials[b * 4 + 1]; t2 += partials[b * 4 + 2]; }
-    sums[0] = t0; sums[1] = t1; sums[2] = t2;
-    *ticket = 0;
+    for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x) { t0 += __ldcg(partials + b * 4); t1 += __ldcg(partials + b * 4 + 1); t2 += __ldcg(partials + b * 4 + 2); }
+    for (int o = 16; o > 0; o >>= 1) {
+      t0 += __shfl_xor_sync(0xffffffffu, t0, o); t1 += __shfl_xor_sync(0xffffffffu, t1, o); t2 += __shfl_xor_sync(0xffffffffu, t2, o);
+    }
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) { s_red[threadIdx.x >> 5][0] = t0; s_red[threadIdx.x >> 5][1] = t1; s_red[threadIdx.x >> 5][2] = t2; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double u0 = 0, u1 = 0, u2 = 0;
+      for (int w = 0; w < 8; ++w) { u0 += s_red[w][0]; u1 += s_red[w][1]; u2 += s_red[w][2]; }
+      sums[0] = u0; sums[1] = u1; sums[2] = u2;
+      *ticket = 0;
+    }
   }
 }
 

@@ -143,6 +143,28 @@ class Context:
     def comm_destroy(self):
         _check(self._lib.bpvo_b200_comm_destroy(self.h))
 
+    def peer_export(self) -> bytes:
+        """this rank's mailbox as a cudaIpcMemHandle_t (64 bytes) for the peer-memory mode"""
+        buf = (C.c_uint8 * 64)()
+        _check(self._lib.bpvo_b200_peer_export(self.h, buf))
+        return bytes(buf)
+
+    def peer_init(self, handles):
+        """handles: the peer_export() results of ALL ranks in rank order (after comm_init)"""
+        blob = b"".join(handles)
+        buf = (C.c_uint8 * len(blob)).from_buffer_copy(blob)
+        _check(self._lib.bpvo_b200_peer_init(self.h, buf))
+
+    def peer_set_min_points(self, n: int):
+        _check(self._lib.bpvo_b200_peer_set_min_points(self.h, int(n)))
+
+    def peer_init_distributed(self, dist):
+        """convenience: exchange the handles with torch.distributed.all_gather_object and map the peers"""
+        mine = self.peer_export()
+        allh = [None] * dist.get_world_size()
+        dist.all_gather_object(allh, mine)
+        self.peer_init(allh)
+
     # -- measurement --------------------------------------------------------------------------------
     def set_profiling(self, on: bool):
         _check(self._lib.bpvo_b200_set_profiling(self.h, int(on)))

@@ -230,6 +230,18 @@ int bpvo_b200_comm_unique_id(uint8_t id[128]);
  * frame_num_points / get_points / get_weights / get_residuals then refer to the local shard. */
 int bpvo_b200_comm_init(bpvo_b200_ctx* ctx, int rank, int nranks, const uint8_t id[128]);
 int bpvo_b200_comm_destroy(bpvo_b200_ctx* ctx);
+/* Peer-memory mode (optional, after comm_init; one process per GPU on one NVLink/NVSwitch node, <= 8 ranks): the
+ * point-sharded estimate_pose runs the SAME persistent on-device GN loop as a single GPU, and the ranks exchange the
+ * bracket histogram + the handful of median candidates + the 30 fp64 sums INSIDE the kernel through flag-in-data
+ * mailboxes in each other's memory (CUDA IPC mappings, stores over NVLink) -- no NCCL launch and no host round trip
+ * per iteration.  peer_export allocates this rank's mailbox and returns its cudaIpcMemHandle_t (64 bytes, distribute
+ * to all ranks e.g. with torch.distributed.all_gather); peer_init maps the peers' mailboxes (handles in rank order). */
+int bpvo_b200_peer_export(bpvo_b200_ctx* ctx, uint8_t handle[64]);
+int bpvo_b200_peer_init(bpvo_b200_ctx* ctx, const uint8_t* handles /* nranks x 64 bytes */);
+/* pyramid levels whose template has fewer points than this are REPLICATED (every rank keeps all points and runs the
+ * level like a single GPU, bit-identically, no exchange) instead of sharded: "when the point count justifies it".
+ * Default 131072; 0 shards every level.  Applies to templates built afterwards. */
+int bpvo_b200_peer_set_min_points(bpvo_b200_ctx* ctx, int min_points);
 
 /* ---------------------------------------------------------------------------------------------
  * measurement helpers

@@ -358,6 +358,23 @@ def test_point_sharded_two_gpus():
     assert res.returncode == 0 and "SHARD_CHECK_OK" in res.stdout, res.stdout[-3000:] + res.stderr[-3000:]
 
 
+def test_peer_memory_mode_two_gpus():
+    """peer-memory mode: the point-sharded estimate_pose as ONE persistent kernel per GPU, bracket histogram / median
+    candidates / normal-equation sums exchanged inside the kernel over NVLink (scripts/peer_check.py under torchrun);
+    skipped when the box has a single GPU"""
+    import os
+    import subprocess
+    import sys
+    from bpvo_b200 import _capi
+    from conftest import ROOT
+    if _capi.lib().bpvo_b200_device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29523", os.path.join(ROOT, "scripts", "peer_check.py")]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0 and "PEER_CHECK_OK" in res.stdout, res.stdout[-3000:] + res.stderr[-3000:]
+
+
 def test_cpp_host_shim_stream(tmp_path):
     """examples/vo_stream.cpp (bpvo_b200::VisualOdometry, the C++ mirror of bpvo/vo.h) must walk the same
     stream to bit-identical poses / key-frame decisions as the Python binding of the same C ABI."""
