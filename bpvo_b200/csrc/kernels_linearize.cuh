@@ -982,26 +982,36 @@ __device__ __forceinline__ void x_send(const PeerArgs& pa, unsigned seq, const u
   }
 }
 // CTA 0: sum (u32) of buf[0..n) over all ranks, in place (shared memory); thread t owns words t, t + 256, ...
+// All peers are polled concurrently (up to kXRanks x 4 words in flight per thread): one round trip, whatever the rank count.
 __device__ __forceinline__ void x_allreduce_u32(const PeerArgs& pa, unsigned& xseq, unsigned* buf, int n, int* abort_flag) {
   const unsigned seq = xseq++;
   x_send(pa, seq, buf, n);
-  for (int r = 0; r < pa.nranks; ++r) {
-    if (r == pa.rank) continue;
-    const uint2* src = x_slot(pa, pa.rank, seq, r);
-    for (int i0 = threadIdx.x; i0 < n; i0 += 8 * kLinThreads) {       // 8 words in flight per thread
-      unsigned v[8]; bool ok[8]; bool all = true;
+  const uint2* base = x_slot(pa, pa.rank, seq, 0);
+  constexpr int Q = 5;                                      // words per thread and chunk: the 1027-word bracket message is ONE chunk
+  for (int i0 = threadIdx.x; i0 < n; i0 += Q * kLinThreads) {
+    unsigned acc[Q];
+    unsigned long long pending = 0;                         // bit r * 8 + q: word q of rank r still missing
 #pragma unroll
-      for (int q = 0; q < 8; ++q) { ok[q] = i0 + q * kLinThreads >= n; v[q] = 0; all = all && ok[q]; }
-      unsigned spins = 0;
-      while (!all) {
-        all = true;
+    for (int q = 0; q < Q; ++q) acc[q] = 0u;
+    for (int r = 0; r < pa.nranks; ++r)
 #pragma unroll
-        for (int q = 0; q < 8; ++q) { if (!ok[q]) ok[q] = x_peek(src + i0 + q * kLinThreads, seq, v[q]); all = all && ok[q]; }
-        if (!all && (++spins > kSpinLimit || *(volatile int*) abort_flag)) { *abort_flag = 1; break; }
+      for (int q = 0; q < Q; ++q)
+        if (r != pa.rank && i0 + q * kLinThreads < n) pending |= 1ull << (r * 8 + q);
+    unsigned spins = 0;
+    while (pending) {
+      for (int r = 0; r < pa.nranks; ++r) {
+        if (!((pending >> (r * 8)) & 0xffull)) continue;
+#pragma unroll
+        for (int q = 0; q < Q; ++q)
+          if (pending & (1ull << (r * 8 + q))) {
+            unsigned v;
+            if (x_peek(base + (size_t) r * kXWords + i0 + q * kLinThreads, seq, v)) { acc[q] += v; pending &= ~(1ull << (r * 8 + q)); }
+          }
       }
-#pragma unroll
-      for (int q = 0; q < 8; ++q) if (i0 + q * kLinThreads < n && ok[q]) buf[i0 + q * kLinThreads] += v[q];
+      if (pending && (++spins > kSpinLimit || *(volatile int*) abort_flag)) { *abort_flag = 1; break; }
     }
+#pragma unroll
+    for (int q = 0; q < Q; ++q) if (i0 + q * kLinThreads < n) buf[i0 + q * kLinThreads] += acc[q];
   }
   __syncthreads();
 }
@@ -1086,23 +1096,32 @@ __device__ __forceinline__ bool bracket_select_xrank(const PeerArgs& pa, unsigne
     if (b == bin_a || b == bin_b) { const unsigned slot = atomicAdd(&sh.found[4], 1u); if (slot < (unsigned) kSelList) list[slot] = v; }
   }
   __syncthreads();
-  // all-gather of the short lists: word 0 = count (0xffffffff: too many here -> everybody falls back), then the values
+  // all-gather of the short lists: word 0 = count (0xffffffff: too many here -> everybody falls back), then the values.
+  // Thread (r = tid / 32, j = tid % 32) fetches value j of rank r: all peers are polled concurrently.
   const unsigned nl_own = sh.found[4];
-  const bool own_bad = nl_own > 63u;
+  const bool own_bad = nl_own > 31u;
   const unsigned seq = xseq++;
   if (tid == 0) buf[0] = own_bad ? 0xffffffffu : nl_own;
   if (!own_bad && tid < (int) nl_own) buf[1 + tid] = __float_as_uint(list[tid]);
   __syncthreads();
   x_send(pa, seq, buf, own_bad ? 1 : 1 + (int) nl_own);
-  unsigned base = own_bad ? 0u : nl_own;
-  bool bad = own_bad;
-  for (int r = 0; r < pa.nranks; ++r) {
-    if (r == pa.rank) continue;
-    const uint2* src = x_slot(pa, pa.rank, seq, r);
-    const unsigned nr = x_wait(src, seq, abort_flag);
-    if (nr == 0xffffffffu) { bad = true; continue; }
-    if (tid < (int) nr && base + tid < (unsigned) kSelList) list[base + tid] = __uint_as_float(x_wait(src + 1 + tid, seq, abort_flag));
-    base += nr;
+  static_assert(kLinThreads / 32 == kXRanks, "one warp per source rank in the list gather");
+  unsigned* cnt = sh.scan;                                   // [kXRanks]: per-rank counts
+  float* mine = reinterpret_cast<float*>(buf + 64);         // own values, saved before the merged list overwrites list[]
+  if (!own_bad && tid < (int) nl_own) mine[tid] = list[tid];
+  if (tid < kXRanks) cnt[tid] = (tid >= pa.nranks) ? 0u : (tid == pa.rank) ? (own_bad ? 0xffffffffu : nl_own) : x_wait(x_slot(pa, pa.rank, seq, tid), seq, abort_flag);
+  __syncthreads();
+  bool bad = false; unsigned base = 0, my_off = 0;
+  {
+    const int r_of_t = tid >> 5;
+#pragma unroll
+    for (int r = 0; r < kXRanks; ++r) { const unsigned c = cnt[r]; if (c == 0xffffffffu) bad = true; else { if (r < r_of_t) my_off += c; base += c; } }
+  }
+  __syncthreads();
+  if (!bad && base <= (unsigned) kSelList) {
+    const int r = tid >> 5, j = tid & 31;
+    if (r < pa.nranks && j < (int) cnt[r])
+      list[my_off + j] = (r == pa.rank) ? mine[j] : __uint_as_float(x_wait(x_slot(pa, pa.rank, seq, r) + 1 + j, seq, abort_flag));
   }
   __syncthreads();
   if (bad || base > (unsigned) kSelList || *(volatile int*) abort_flag) return false;

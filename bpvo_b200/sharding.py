@@ -5,6 +5,10 @@
   `allreduce` callable (torch.distributed on CPU/gloo in the tests, NCCL on the device): three histogram exchanges over
   the float bit patterns of |r| (bits [30:20], [19:9], [8:0]) for the two middle ranks n/2-1 and n/2.
 * `normal_equations_exchange` -- the 30 fp64 scalars (21 H + 6 G + sum w r^2 + good count + valid count).
+* `bracket_select_exchange` -- the usual path of the peer-memory mode (the GN loop on the device, kernels_linearize.cuh
+  `bracket_select_xrank`): ONE all-reduce of a 1024-bin linear histogram over a bracket around the previous median (+ the
+  counts of valid residuals and of residuals below the bracket), then ONE all-gather of the handful of values in the two
+  wanted bins.  Returns None when the bracket misses (the radix exchange above is the fallback).
 """
 from __future__ import annotations
 
@@ -70,3 +74,43 @@ def normal_equations_exchange(J: np.ndarray, r: np.ndarray, w: np.ndarray, valid
     vec[27] = float(np.sum(wv * r.astype(np.float64) ** 2))
     vec[29] = float(valid.sum())
     return allreduce(vec)
+
+
+SEL_BINS = 1024
+
+
+def _sel_bin(v: np.ndarray, lo: np.float32, inv_w: np.float32) -> np.ndarray:
+    """kernels_linearize.cuh sel_bin(): min(kSelBins - 1, (int) ((v - lo) * inv_w)) in fp32"""
+    t = (np.asarray(v, np.float32) - np.float32(lo)) * np.float32(inv_w)
+    return np.minimum(SEL_BINS - 1, t.astype(np.int64))
+
+
+def bracket_select_exchange(local_abs_residuals: np.ndarray, br_lo, br_hi, allreduce, allgather):
+    """-> (n, lo, hi) like radix_select_exchange, or None on a bracket miss.  `allgather(np.ndarray[float32]) -> list`
+    returns every rank's (variable-length) array."""
+    a = np.ascontiguousarray(local_abs_residuals, dtype=np.float32)
+    br_lo, br_hi = np.float32(br_lo), np.float32(br_hi)
+    inv_w = np.float32(SEL_BINS) / (br_hi - br_lo) if br_hi > br_lo else np.float32(0.0)
+    cand = a[(a >= br_lo) & (a <= br_hi)]
+    msg = np.zeros(SEL_BINS + 3, np.int64)
+    msg[:SEL_BINS] = np.bincount(_sel_bin(cand, br_lo, inv_w), minlength=SEL_BINS)
+    msg[SEL_BINS:] = (a.size, int((a < br_lo).sum()), cand.size)
+    g = allreduce(msg)
+    n, below, ncand = int(g[SEL_BINS]), int(g[SEL_BINS + 1]), int(g[SEL_BINS + 2])
+    if n < 3:
+        return None
+    t_hi = n // 2
+    t_lo = t_hi - 1 if n % 2 == 0 else t_hi
+    if below > t_lo or t_hi >= below + ncand:
+        return None
+    c = np.cumsum(g[:SEL_BINS])
+    want = []
+    for t in (t_lo - below, t_hi - below):
+        b = int(np.searchsorted(c, t, side="right"))
+        want.append((b, t - (int(c[b - 1]) if b else 0)))
+    bins = _sel_bin(cand, br_lo, inv_w)
+    mine = cand[(bins == want[0][0]) | (bins == want[1][0])]
+    merged = np.concatenate([np.asarray(x, np.float32) for x in allgather(mine)])
+    mb = _sel_bin(merged, br_lo, inv_w)
+    out = [np.sort(merged[mb == b])[rem] for b, rem in want]
+    return n, out[0], out[1]

@@ -49,6 +49,16 @@ def _worker(rank, world, port, q):
         assert lo == all_abs[n_valid // 2 - 1 if n_valid % 2 == 0 else n_valid // 2] and hi == all_abs[n_valid // 2]
         sigma = np.float32(np.float32(1.4826) * (np.float32(1.0) + np.float32(5.0) / np.float32(n_valid - 6))) * np.float32(sharding.median_from_pair(n_valid, lo, hi))
         assert sigma == np.float32(full["sigma"])
+        # 1b. the peer-memory mode's usual path: bracket histogram all-reduce + short-list all-gather (exact when it hits)
+        def allgather(x):
+            out = [None] * world
+            dist.all_gather_object(out, np.asarray(x, np.float32))
+            return out
+        med = np.float32(0.5) * (np.float32(lo) + np.float32(hi))
+        hit = sharding.bracket_select_exchange(absr, med * np.float32(0.97), med * np.float32(1.03), allreduce, allgather)
+        assert hit is not None and hit[0] == n_valid and hit[1] == lo and hit[2] == hi, hit
+        miss = sharding.bracket_select_exchange(absr, med * np.float32(1.5), med * np.float32(1.6), allreduce, allgather)
+        assert miss is None
         # 2. the 30 normal-equation scalars
         vec = sharding.normal_equations_exchange(J.reshape(-1, 6), r.ravel(), w.ravel(), v.ravel(), allreduce)
         H = np.zeros((6, 6)); H[np.triu_indices(6)] = vec[:21]; H = H + np.triu(H, 1).T
