@@ -2,7 +2,7 @@
 """bench.py -- frames/sec and GN-iterations/sec of the per-frame Gauss-Newton dense-alignment path
 (bpvo's VisualOdometry::addFrame) on synthetic KITTI-sized bit-planes streams.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload kitti|vga|kitti_dense|1080p]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload kitti|vga|kitti_dense|1080p|1080p_dense]
 
 A "step" is one addFrame() = image+disparity in -> pose out (pyramid, bit-planes descriptors, the whole
 coarse-to-fine GN solve, key-frame work when it triggers).  Prints ONE JSON line (rank 0).
@@ -40,6 +40,9 @@ WORKLOADS = {
                 name="vga_640x480_intensity_4levels_huber"),
     "1080p": dict(scene="1080p", descriptor="bitplanes", levels=5, loss="tukey", nms=1,
                   name="1080p_bitplanes_8ch_5levels_tukey"),
+    # BASELINE.json configs[3]: 1920x1080 bit-planes, 5 levels, Tukey, template points sharded across the GPUs (dense selection)
+    "1080p_dense": dict(scene="1080p", descriptor="bitplanes", levels=5, loss="tukey", nms=-1,
+                        name="1080p_bitplanes_8ch_5levels_tukey_dense"),
 }
 
 
@@ -324,6 +327,10 @@ def run_ours(args, w, rank, world, local_rank):
     if rank == 0 and world == 1 and args.workload == "kitti" and not args.no_dense:
         dense = dense_variant_roofline(local_rank)
 
+    sharded = None
+    if world > 1 and args.workload == "kitti" and not args.no_dense:
+        sharded = sharded_variant(rank, world, local_rank, dist, torch)
+
     if rank == 0:
         line = {
             "metric": "frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -340,12 +347,51 @@ def run_ours(args, w, rank, world, local_rank):
             "roofline": roof,
             "cpu_baseline": cpu,
             "roofline_dense_variant": dense,
+            "sharded_1080p_dense_variant": sharded,
         }
         print(json.dumps(line), flush=True)
     pin_img.free(); pin_dsp.free()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def sharded_variant(rank, world, local_rank, dist, torch):
+    """BASELINE.json configs[3] beside the replica numbers (N > 1 only): ONE 1080p dense bit-planes stream whose template
+    points are sharded over all N GPUs, the GN loop on the device, exchanges inside the kernel over NVLink (peer-memory
+    mode; levels under 131072 points stay replicated).  Reports us per GN iteration against the same solve on one GPU."""
+    from bpvo_b200.engine import Context
+    w = WORKLOADS["1080p_dense"]
+    sc = make_scene(w, 0xB200)
+    p = make_params(w)
+    i0, d0 = sc.render(0); i1, d1 = sc.render(1)
+    T0 = np.eye(4, dtype=np.float32)
+    out = {"workload": w["name"], "n_gpus": world}
+    for mode in ("single_gpu", "sharded"):
+        ctx = Context(sc.K, sc.baseline, (sc.rows, sc.cols), p, device_id=local_rank)
+        if mode == "sharded":
+            uid = [Context.comm_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(uid, src=0)
+            ctx.comm_init(rank, world, uid[0])
+            ctx.peer_init_distributed(dist)
+        a, b = ctx.frame(), ctx.frame()
+        a.setData(i0, d0); a.setTemplate(); b.setData(i1, d1)
+        ctx.estimatePose(a, b, T0)
+        ctx.set_profiling(True); ctx.reset_counters()
+        dist.barrier()
+        evals = 0
+        for _ in range(3):
+            T, _, n = ctx.estimatePose(a, b, T0)
+            evals += n
+        t = torch.tensor([ctx.counters()["ms_linearize"]], dtype=torch.float64, device=f"cuda:{local_rank}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        out[mode] = {"us_per_gn_iter": 1e3 * float(t[0]) / max(evals, 1), "gn_iters": evals,
+                     "points_per_level_local": [a.numPoints(l) for l in range(p.numPyramidLevels)]}
+        if mode == "sharded":
+            ctx.comm_destroy()
+        a.close(); b.close(); ctx.close()
+    out["speedup_vs_one_gpu"] = out["single_gpu"]["us_per_gn_iter"] / out["sharded"]["us_per_gn_iter"]
+    return out
 
 
 def dense_variant_roofline(local_rank):
