@@ -177,7 +177,7 @@ def run_reference(args, w, rank, world):
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -349,7 +349,7 @@ def run_ours(args, w, rank, world, local_rank):
             "roofline_dense_variant": dense,
             "sharded_1080p_dense_variant": sharded,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     pin_img.free(); pin_dsp.free()
     if dist is not None:
         dist.barrier()
@@ -448,7 +448,24 @@ def cpu_baseline(w, args):
             "sample": f"first {n} addFrame calls of the same synthetic stream ({t_used:.1f} s of CPU work), single thread = reference default build"}
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    """the ONE JSON line goes to the process's original stdout; everything else any library prints (NCCL's version banner,
+    torchrun notices) was redirected to stderr at start-up"""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=64)
