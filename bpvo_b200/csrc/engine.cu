@@ -828,6 +828,32 @@ extern "C" int bpvo_b200_fraction_good(bpvo_b200_ctx* c, float thresh, float* fr
   return BPVO_B200_OK;
 }
 
+// getPointCloudFromRefFrame (vo.cc:249-281) assembled on the device, one D2H
+extern "C" int bpvo_b200_point_cloud(bpvo_b200_ctx* c, const bpvo_b200_frame* ref, bpvo_b200_point_info* records, int* n) {
+  static_assert(sizeof(bpvo_b200_point_info) == 24 && sizeof(PointInfo) == 24, "24-byte point records");
+  if (!c || !ref || !n) return bp_fail(BPVO_B200_ERR_INVALID_ARG, "null argument");
+  if (ref->ctx != c) return bp_fail(BPVO_B200_ERR_INVALID_ARG, "frame belongs to another ctx");
+  if (!ref->has_template) return bp_fail(BPVO_B200_ERR_NO_DATA, "frame has no template");
+  if (c->last_ref != ref || c->last_level != c->p.maxTestLevel) return bp_fail(BPVO_B200_ERR_INVALID_ARG, "size mismatch: the last linearize did not run against this frame");
+  int rc = wait_meta(ref); if (rc) return rc;
+  const int level = c->p.maxTestLevel, np = ref->h_meta[level].n, cap = *n;
+  *n = np;
+  if (!records || np == 0) return BPVO_B200_OK;
+  if (cap < np) return bp_fail(BPVO_B200_ERR_INVALID_ARG, "point cloud buffer too small (%d < %d)", cap, np);
+  CUDA_TRY(cudaSetDevice(c->p.device_id));
+  // sigma of the last linearize (already on the host after estimate_pose / linearize)
+  const float sigma = c->h_mail->lin.sigma;
+  const LevelGeom& g = c->geom[level];
+  PointInfo* d = reinterpret_cast<PointInfo*>(c->export_buf);          // capacity: capmax * C * 6 floats >= 6 floats per point
+  if (c->C == 1) k_point_cloud<1><<<ceil_div(np, 256), 256, 0, c->stream>>>(ref->pts[level], np, ref->pyr[0], c->rows, c->cols, g.fx, g.fy, g.cx, g.cy, c->work.res, sigma, c->p.lossFunction, d);
+  else k_point_cloud<8><<<ceil_div(np, 256), 256, 0, c->stream>>>(ref->pts[level], np, ref->pyr[0], c->rows, c->cols, g.fx, g.fy, g.cx, g.cy, c->work.res, sigma, c->p.lossFunction, d);
+  LAUNCH_CHECK(c);
+  CUDA_TRY(cudaMemcpyAsync(records, d, (size_t) np * sizeof(PointInfo), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  c->counters.d2h_bytes += (int64_t) np * sizeof(PointInfo);
+  return BPVO_B200_OK;
+}
+
 // device-time of back-to-back linearize launches (no host round trip), for the roofline figure
 extern "C" int bpvo_b200_time_linearize(bpvo_b200_ctx* c, const bpvo_b200_frame* ref, const bpvo_b200_frame* cur, int level,
                                          const float T[16], int iters, int flush_l2, float* ms_per_iter) {

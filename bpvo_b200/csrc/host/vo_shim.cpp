@@ -166,31 +166,14 @@ class VisualOdometry::Impl {
 
   // getPointCloudFromRefFrame (vo.cc:249-281): weights[i], i < N, are channel 0 of the last linearize (Q7)
   std::unique_ptr<PointCloud> getPointCloudFromRefFrame() const {
-    const PointVector& points = pointsAtLevel(_params.maxTestLevel);
-    size_t wcount = 0;
-    check(bpvo_b200_get_weights(_ctx, nullptr, &wcount));
-    const size_t n = points.size();
-    if (n > wcount) throw Error("size mismatch");
-    std::vector<float> weights(n);                    // weights[i], i < n: channel 0 only (vo.cc:264, Q7) -> no bulk C*N download
-    if (n) { size_t cap = n; check(bpvo_b200_get_weights(_ctx, weights.data(), &cap)); }
-    std::vector<uint8_t> image((size_t) _image_size.rows * _image_size.cols);
-    check(bpvo_b200_frame_get_pyramid(_ref_frame, 0, image.data()));               // imagePointer() of the ref frame
+    // assembled on the device (xyzw, grey level at K_l X in the full-resolution ref image, channel-0 weight): one download
+    static_assert(sizeof(PointWithInfo) == sizeof(bpvo_b200_point_info), "PointWithInfo is the 24-byte device record");
     std::unique_ptr<PointCloud> ret(new PointCloud);
-    ret->points.resize(n); ret->pose = Matrix44::Identity();
-    const int L = _params.maxTestLevel;
-    float fx = _K(0, 0), fy = _K(1, 1), cx = _K(0, 2), cy = _K(1, 2);
-    for (int l = 0; l < L; ++l) { fx *= 0.5f; fy *= 0.5f; cx *= 0.5f; cy *= 0.5f; }
-    for (size_t i = 0; i < n; ++i) {
-      const Point& X = points[i];
-      // warp.getImagePoint: x = K * X.head<3>() (rigid_body_warp.h:123-128)
-      float x0 = fx * X.x; x0 += 0.0f * X.y; x0 += cx * X.z;
-      float x1 = 0.0f * X.x; x1 += fy * X.y; x1 += cy * X.z;
-      float x2 = 0.0f * X.x; x2 += 0.0f * X.y; x2 += 1.0f * X.z;
-      const float z_i = 1.0f / x2, u = z_i * x0, v = z_i * x1;
-      const uint8_t c = (v >= 0 && v < _image_size.rows && u >= 0 && u < _image_size.cols) ? image[(size_t) ((int) v) * _image_size.cols + (int) u] : 0;
-      PointWithInfo& pi = ret->points[i];
-      pi.xyzw = X; pi.rgba[0] = pi.rgba[1] = pi.rgba[2] = c; pi.rgba[3] = 255; pi.weight = weights[i];
-    }
+    ret->pose = Matrix44::Identity();
+    int n = 0;
+    check(bpvo_b200_point_cloud(_ctx, _ref_frame, nullptr, &n));
+    ret->points.resize((size_t) n);
+    if (n) { int cap = n; check(bpvo_b200_point_cloud(_ctx, _ref_frame, reinterpret_cast<bpvo_b200_point_info*>(ret->points.data()), &cap)); }
     return ret;
   }
 

@@ -829,6 +829,28 @@ __global__ void __launch_bounds__(256) k_export_weights(const float* __restrict_
   if (r_out) r_out[(size_t) c * n + i] = r;
 }
 
+// getPointCloudFromRefFrame (vo.cc:249-281) on the device: xyzw, grey level of the ref image at K_l X, channel-0 weight
+struct PointInfo { float x, y, z, w; unsigned rgba; float weight; };
+template <int C>
+__global__ void __launch_bounds__(256) k_point_cloud(const float4* __restrict__ pts, int n, const uint8_t* __restrict__ image, int rows, int cols,
+                                                     float fx, float fy, float cx, float cy, const float* __restrict__ res, float sigma, int loss,
+                                                     PointInfo* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 X = __ldg(pts + i);
+  // warp.getImagePoint: x = K * X.head<3>() (rigid_body_warp.h:123-128), dense 3x3 product with the zero terms kept
+  float x0 = __fmul_rn(fx, X.x); x0 = __fadd_rn(x0, __fmul_rn(0.0f, X.y)); x0 = __fadd_rn(x0, __fmul_rn(cx, X.z));
+  float x1 = __fmul_rn(0.0f, X.x); x1 = __fadd_rn(x1, __fmul_rn(fy, X.y)); x1 = __fadd_rn(x1, __fmul_rn(cy, X.z));
+  float x2 = __fmul_rn(0.0f, X.x); x2 = __fadd_rn(x2, __fmul_rn(0.0f, X.y)); x2 = __fadd_rn(x2, __fmul_rn(1.0f, X.z));
+  const float z_i = __fdiv_rn(1.0f, x2), u = __fmul_rn(z_i, x0), v = __fmul_rn(z_i, x1);
+  const unsigned c = (v >= 0 && v < rows && u >= 0 && u < cols) ? (unsigned) __ldg(image + (size_t) ((int) v) * cols + (int) u) : 0u;
+  PointInfo o;
+  o.x = X.x; o.y = X.y; o.z = X.z; o.w = X.w;
+  o.rgba = c | (c << 8) | (c << 16) | (255u << 24);
+  o.weight = robust_weight(loss, res[(size_t) i * C], __fdiv_rn(1.0f, sigma));
+  out[i] = o;
+}
+
 // =============================================================================================
 // persistent path: the whole estimatePose (all levels, all GN iterations, 6x6 solves, convergence
 // tests, pose updates) in ONE cooperative launch; the host sees only T_est and the statistics.

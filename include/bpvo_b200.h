@@ -215,6 +215,13 @@ int bpvo_b200_get_residuals(bpvo_b200_ctx* ctx, float* r, size_t* count);
 int bpvo_b200_get_valid(bpvo_b200_ctx* ctx, uint8_t* v, size_t* count);   /* per point, N entries */
 /* float getFractionOfGoodPoints(float thresh)  (vo_pose_estimator.cc:101-107), counted on the device */
 int bpvo_b200_fraction_good(bpvo_b200_ctx* ctx, float thresh, float* frac);
+/* getPointCloudFromRefFrame (vo.cc:249-281) assembled on the device: per template point of `ref` at maxTestLevel one
+ * 24-byte record {x, y, z, w (float), r, g, b, a (uint8), weight (float)} = bpvo::PointWithInfo without its alignment
+ * padding: colour = the ref frame's full-resolution image at the projection K_l * X (bounds and truncation as
+ * vo.cc:269-272), weight = channel 0 of the last linearize's weights (Q7; invalid points carry 1, Q6).  One D2H of
+ * 24 N bytes instead of points + weights + the whole image.  *n: in = capacity in records, out = N. */
+typedef struct { float x, y, z, w; uint8_t rgba[4]; float weight; } bpvo_b200_point_info;
+int bpvo_b200_point_cloud(bpvo_b200_ctx* ctx, const bpvo_b200_frame* ref, bpvo_b200_point_info* records, int* n);
 
 /* ---------------------------------------------------------------------------------------------
  * multi-GPU: template points sharded across ranks, 28-scalar exchange per GN iteration
