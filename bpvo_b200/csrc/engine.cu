@@ -706,17 +706,16 @@ static int launch_estimate_pose(bpvo_b200_ctx* c, const bpvo_b200_frame* ref, co
     for (int r = 0; r < c->shard_size; ++r) a.peer.box[r] = c->xpeer[r];
     c->x_seq += xspan;
   }
-  // dynamic shared memory: candidate scratch + as many template-cache slots per thread as fit (1 CTA per SM)
-  const int per_slot = tpl_cache_bytes_per_slot<C>();
-  int slots = (c->smem_optin - 24 * 1024 - kScratchBytes) / per_slot;
-  slots = std::max(0, std::min(slots, 8));
-  const size_t dyn = (size_t) kScratchBytes + (size_t) slots * per_slot;
-  static thread_local size_t configured[2] = {0, 0};
-  if (configured[C == 8] != dyn) {
+  // dynamic shared memory: candidate scratch + everything else the SM has for the template cache (1 CTA per SM; the
+  // kernel plans per level which fields fit)
+  int cache_bytes = ((c->smem_optin - 24 * 1024 - kScratchBytes) / 1024) * 1024;
+  cache_bytes = std::max(0, cache_bytes);
+  const size_t dyn = (size_t) kScratchBytes + (size_t) cache_bytes;
+  if (c->dyn_configured != dyn) {        // per ctx: the attribute is per device, and a process may drive several
     CUDA_TRY(cudaFuncSetAttribute((const void*) k_estimate_pose<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) dyn));
-    configured[C == 8] = dyn;
+    c->dyn_configured = dyn;
   }
-  void* args[] = {&a, &sel, &slots};
+  void* args[] = {&a, &sel, &cache_bytes};
   int grid = std::min(c->sm_count, kMaxGrid);
   CUDA_TRY(cudaLaunchCooperativeKernel((void*) k_estimate_pose<C>, dim3(grid), dim3(kLinThreads), args, dyn, c->stream));
   c->counters.launches++;

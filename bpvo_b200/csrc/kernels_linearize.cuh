@@ -64,36 +64,66 @@ template <> struct VecC<1> {
 // loop visits the same points ~50 times per level: staging (X,Y,Z), I0, gx, gy once per level and keeping r between the
 // phases removes every per-iteration global load except the four bilinear taps.  Slot k of thread t holds point
 // first_point + k * gridsize.  Layout (all conflict-free): float4 pts[K][512] | float f[K][4 fields][C][512] | u8 valid[K][512].
+// Fields are addressed by 32-bit byte offsets into the kernel's dynamic shared memory (kTcNone = not cached: read from
+// global memory): six registers instead of six 64-bit pointers in a kernel that sits at the register limit.
+constexpr unsigned kTcNone = 0xffffffffu;
 struct TplCache {
-  float4* pts;
-  float* f;
-  uint8_t* valid;
-  int K;                 // slots per thread resident (0 = cache off: host-driven kernels, or the level does not fit)
+  unsigned pts;          // float4 [K][256]
+  unsigned f[4];         // TC_I0, TC_GX, TC_GY, TC_R: float [K][C][256] each
+  unsigned valid;        // u8 [K][256], cached together with TC_R
+  int K;                 // slots per thread the level needs (0 = cache off: host-driven kernels)
 };
 enum { TC_I0 = 0, TC_GX = 1, TC_GY = 2, TC_R = 3 };
-
-template <int C> __host__ __device__ constexpr int tpl_cache_bytes_per_slot() { return kLinThreads * (16 + 16 * C + 1); }
+__device__ __forceinline__ TplCache tpl_cache_off() { TplCache t; t.pts = t.f[0] = t.f[1] = t.f[2] = t.f[3] = t.valid = kTcNone; t.K = 0; return t; }
+__device__ __forceinline__ unsigned char* tc_base() { extern __shared__ __align__(16) unsigned char dyn_smem[]; return dyn_smem; }
+__device__ __forceinline__ float4& tc_point(const TplCache& tc, int k) { return reinterpret_cast<float4*>(tc_base() + tc.pts)[k * kLinThreads + threadIdx.x]; }
+__device__ __forceinline__ uint8_t& tc_valid(const TplCache& tc, int k) { return (tc_base() + tc.valid)[k * kLinThreads + threadIdx.x]; }
 
 template <int C> __device__ __forceinline__ void tc_get(const TplCache& tc, int k, int field, VecC<C>& v) {
-  const float* p = tc.f + ((size_t) (k * 4 + field) * C) * kLinThreads + threadIdx.x;
+  const float* p = reinterpret_cast<const float*>(tc_base() + tc.f[field]) + ((size_t) k * C) * kLinThreads + threadIdx.x;
 #pragma unroll
   for (int c = 0; c < C; ++c) v.v[c] = p[c * kLinThreads];
 }
 template <int C> __device__ __forceinline__ void tc_put(const TplCache& tc, int k, int field, const VecC<C>& v) {
-  float* p = tc.f + ((size_t) (k * 4 + field) * C) * kLinThreads + threadIdx.x;
+  float* p = reinterpret_cast<float*>(tc_base() + tc.f[field]) + ((size_t) k * C) * kLinThreads + threadIdx.x;
 #pragma unroll
   for (int c = 0; c < C; ++c) p[c * kLinThreads] = v.v[c];
+}
+
+// Which fields of a level live in shared memory: all-or-nothing per field, in the order of the global traffic they save
+// per GN iteration -- residuals + valid flags (written by P1, read by the select passes and P4), points (P1 + P4),
+// gx, gy (P4), I0 (P1).  KITTI semi-dense: everything (1 slot); KITTI dense level 0
+// (11 slots): residuals + points; a 1080p level sharded over 8 GPUs (6 slots): everything but I0.  `first` = offset of the cache area, `bytes` its size.
+template <int C>
+__device__ __forceinline__ TplCache tpl_cache_plan(unsigned first, int bytes, int need) {
+  TplCache t = tpl_cache_off();
+  if (need <= 0) return t;
+  t.K = need;
+  const int sz_f = need * kLinThreads * 4 * C, sz_pts = need * kLinThreads * 16, sz_valid = need * kLinThreads;
+  const bool has_r = sz_f + sz_valid <= bytes;   if (has_r) bytes -= sz_f + sz_valid;
+  const bool has_p = sz_pts <= bytes;            if (has_p) bytes -= sz_pts;
+  const bool has_gx = sz_f <= bytes;             if (has_gx) bytes -= sz_f;
+  const bool has_gy = sz_f <= bytes;             if (has_gy) bytes -= sz_f;
+  const bool has_i0 = sz_f <= bytes;
+  unsigned p = first;                            // layout: pts (16-B aligned) | R | I0 | GX | GY | valid
+  if (has_p) { t.pts = p; p += sz_pts; }
+  if (has_r) { t.f[TC_R] = p; p += sz_f; }
+  if (has_i0) { t.f[TC_I0] = p; p += sz_f; }
+  if (has_gx) { t.f[TC_GX] = p; p += sz_f; }
+  if (has_gy) { t.f[TC_GY] = p; p += sz_f; }
+  if (has_r) t.valid = p;
+  return t;
 }
 
 // stage this CTA's points of level L into the cache (thread-private slots: no barrier needed afterwards)
 template <int C> __device__ __forceinline__ void tc_fill(const TplCache& tc, const LevelTemplate& L, int n, int block, int nblocks) {
   int k = 0;
   for (int i = first_point(block, nblocks); i < n && k < tc.K; i += nblocks * kLinThreads, ++k) {
-    tc.pts[k * kLinThreads + threadIdx.x] = __ldg(L.pts + i);
+    if (tc.pts != kTcNone) tc_point(tc, k) = __ldg(L.pts + i);
     VecC<C> v;
-    v.load(L.i0 + (size_t) i * C); tc_put<C>(tc, k, TC_I0, v);
-    v.load(L.gx + (size_t) i * C); tc_put<C>(tc, k, TC_GX, v);
-    v.load(L.gy + (size_t) i * C); tc_put<C>(tc, k, TC_GY, v);
+    if (tc.f[TC_I0] != kTcNone) { v.load(L.i0 + (size_t) i * C); tc_put<C>(tc, k, TC_I0, v); }
+    if (tc.f[TC_GX] != kTcNone) { v.load(L.gx + (size_t) i * C); tc_put<C>(tc, k, TC_GX, v); }
+    if (tc.f[TC_GY] != kTcNone) { v.load(L.gy + (size_t) i * C); tc_put<C>(tc, k, TC_GY, v); }
   }
 }
 
@@ -278,7 +308,7 @@ __device__ __forceinline__ void phase_residuals(const LevelTemplate& L, const Le
   int my_first = 0x7fffffff;
   int k = 0;
   for (int i = first_point(block, nblocks); i < n_pts; i += nblocks * kLinThreads, ++k) {
-    const float4 X = tc.K ? tc.pts[k * kLinThreads + tid] : __ldg(L.pts + i);
+    const float4 X = (tc.pts != kTcNone) ? tc_point(tc, k) : __ldg(L.pts + i);
     const double X0 = X.x, X1 = X.y, X2 = X.z, X3 = X.w;
     const double h0 = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(P00, X0), __dmul_rn(P01, X1)), __dmul_rn(P02, X2)), __dmul_rn(P03, X3));
     const double h1 = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(P10, X0), __dmul_rn(P11, X1)), __dmul_rn(P12, X2)), __dmul_rn(P13, X3));
@@ -297,7 +327,7 @@ __device__ __forceinline__ void phase_residuals(const LevelTemplate& L, const Le
       const double xf = __dsub_rn(u, (double) xi), yf = __dsub_rn(v, (double) yi);
       const double wx = __dsub_rn(1.0, xf), wy = __dsub_rn(1.0, yf);
       VecC<C> i0;
-      if (tc.K) tc_get<C>(tc, k, TC_I0, i0); else i0.load(L.i0 + (size_t) i * C);
+      if (tc.f[TC_I0] != kTcNone) tc_get<C>(tc, k, TC_I0, i0); else i0.load(L.i0 + (size_t) i * C);
       if (interp == 0) {
         const float* tap = I.desc + ((size_t) yi * cols + xi) * C;
         VecC<C> t00, t01, t10, t11;
@@ -343,8 +373,8 @@ __device__ __forceinline__ void phase_residuals(const LevelTemplate& L, const Le
     }
     // residuals / valid flags stay in shared memory while the level is cached (C = 8: written back once, after the last
     // iteration of the finest level); C = 1 keeps the global copy for the n < 3 median rule of finish_scale()
-    if (!(tc.K && C == 8)) { r.store(W.res + (size_t) i * C); W.valid[i] = ok ? 1 : 0; }
-    if (tc.K) { tc_put<C>(tc, k, TC_R, r); tc.valid[k * kLinThreads + tid] = ok ? 1 : 0; }
+    if (!(tc.f[TC_R] != kTcNone && C == 8)) { r.store(W.res + (size_t) i * C); W.valid[i] = ok ? 1 : 0; }
+    if (tc.f[TC_R] != kTcNone) { tc_put<C>(tc, k, TC_R, r); tc_valid(tc, k) = ok ? 1 : 0; }
   }
   BP_FINE(17);
   if (do_hist) {
@@ -397,9 +427,9 @@ __device__ __forceinline__ void phase_hist1(const Work& W, unsigned* __restrict_
   __syncthreads();
   int k = 0;
   for (int i = first_point(block, nblocks); i < m.n; i += nblocks * kLinThreads, ++k) {
-    if (!(tc.K ? tc.valid[k * kLinThreads + tid] : W.valid[i])) continue;
+    if (!((tc.f[TC_R] != kTcNone) ? tc_valid(tc, k) : W.valid[i])) continue;
     VecC<C> r;
-    if (tc.K) tc_get<C>(tc, k, TC_R, r); else r.load_plain(W.res + (size_t) i * C);
+    if (tc.f[TC_R] != kTcNone) tc_get<C>(tc, k, TC_R, r); else r.load_plain(W.res + (size_t) i * C);
 #pragma unroll
     for (int c = 0; c < C; ++c) atomicAdd(&sh.hist[__float_as_uint(fabsf(r.v[c])) >> 20], 1u);
   }
@@ -446,9 +476,9 @@ __device__ __forceinline__ void phase_select(const LevelTemplate& L, const Work&
   const int n_pts = m.n;
   int k = 0;
   for (int i = first_point(block, nblocks); i < n_pts; i += nblocks * kLinThreads, ++k) {
-    if (!(tc.K ? tc.valid[k * kLinThreads + tid] : W.valid[i])) continue;
+    if (!((tc.f[TC_R] != kTcNone) ? tc_valid(tc, k) : W.valid[i])) continue;
     VecC<C> r;
-    if (tc.K) tc_get<C>(tc, k, TC_R, r); else r.load_plain(W.res + (size_t) i * C);
+    if (tc.f[TC_R] != kTcNone) tc_get<C>(tc, k, TC_R, r); else r.load_plain(W.res + (size_t) i * C);
 #pragma unroll
     for (int c = 0; c < C; ++c) {
       const unsigned bits = __float_as_uint(fabsf(r.v[c]));
@@ -620,11 +650,14 @@ __device__ __forceinline__ double phase_reduce(const LevelTemplate& L, const Wor
   const float w_invalid_good = (1.0f > good_thr) ? (float) C : 0.0f;   // invalid entries carry weight 1 in getWeights() (Q6)
   int ks = 0;
   for (int i = first_point(block, nblocks); i < m.n; i += nblocks * kLinThreads, ++ks) {
-    if (!(tc.K ? tc.valid[ks * kLinThreads + tid] : W.valid[i])) { acc[28] += w_invalid_good; continue; }
-    const float4 X = tc.K ? tc.pts[ks * kLinThreads + tid] : __ldg(L.pts + i);
+    if (!((tc.f[TC_R] != kTcNone) ? tc_valid(tc, ks) : W.valid[i])) { acc[28] += w_invalid_good; continue; }
+    const float4 X = (tc.pts != kTcNone) ? tc_point(tc, ks) : __ldg(L.pts + i);
     VecC<C> r, gx, gy;
-    if (tc.K) { tc_get<C>(tc, ks, TC_R, r); tc_get<C>(tc, ks, TC_GX, gx); tc_get<C>(tc, ks, TC_GY, gy); }
-    else { r.load_plain(W.res + (size_t) i * C); gx.load(L.gx + (size_t) i * C); gy.load(L.gy + (size_t) i * C); }
+    // (this order -- gx, gy, then r -- and per-field tests measured fastest in same-box A/B runs; a separate straight-line
+    //  path for the all-cached case, or r first, cost 1-3 %: the kernel sits at the register limit and ptxas is touchy)
+    if (tc.f[TC_GX] != kTcNone) tc_get<C>(tc, ks, TC_GX, gx); else gx.load(L.gx + (size_t) i * C);
+    if (tc.f[TC_GY] != kTcNone) tc_get<C>(tc, ks, TC_GY, gy); else gy.load(L.gy + (size_t) i * C);
+    if (tc.f[TC_R] != kTcNone) tc_get<C>(tc, ks, TC_R, r); else r.load_plain(W.res + (size_t) i * C);
     float sxx = 0, sxy = 0, syy = 0, bx = 0, by = 0, e = 0, good = 0;
 #pragma unroll
     for (int c = 0; c < C; ++c) {
@@ -751,13 +784,13 @@ struct LinArgs {
 template <int C> __global__ void __launch_bounds__(kLinThreads, 1) k_residuals(LinArgs a) {
   __shared__ LinShared sh;
   const bool do_hist = (a.loss != 0x12) && (a.work.scale->delta > 1e-6f);
-  phase_residuals<C>(a.tmpl, a.img, a.P, a.work, a.hset, do_hist, Bracket{false, 0.0f, 0.0f, 0.0f}, TplCache{nullptr, nullptr, nullptr, 0}, *a.tmpl.meta, nullptr, sh, blockIdx.x, gridDim.x, a.interp);
+  phase_residuals<C>(a.tmpl, a.img, a.P, a.work, a.hset, do_hist, Bracket{false, 0.0f, 0.0f, 0.0f}, tpl_cache_off(), *a.tmpl.meta, nullptr, sh, blockIdx.x, gridDim.x, a.interp);
 }
 template <int C, int LEVEL> __global__ void __launch_bounds__(kLinThreads, 1) k_select(LinArgs a) {
   __shared__ LinShared sh;
   const bool do_hist = (a.loss != 0x12) && (a.work.scale->delta > 1e-6f);
   if (!do_hist) return;
-  phase_select<C, LEVEL>(a.tmpl, a.work, a.hset, a.sel, TplCache{nullptr, nullptr, nullptr, 0}, *a.tmpl.meta, sh, blockIdx.x, gridDim.x);
+  phase_select<C, LEVEL>(a.tmpl, a.work, a.hset, a.sel, tpl_cache_off(), *a.tmpl.meta, sh, blockIdx.x, gridDim.x);
 }
 // point-sharded mode: the last CTA leaves this rank's 30 fp64 sums in a.sums (all-reduced by the host over NCCL),
 // k_finalize_sums then builds the LinOut every rank sees identically.
@@ -767,7 +800,7 @@ template <int C> __global__ void __launch_bounds__(kLinThreads, 1) k_reduce_shar
   const bool do_hist = (a.loss != 0x12) && (a.work.scale->delta > 1e-6f);
   float sigma = a.work.scale->scale;
   if (do_hist) sigma = finish_scale<C>(a.work, a.hset, a.sel, sh);
-  phase_reduce<C>(a.tmpl, a.work, sigma, a.loss, a.good_thr, TplCache{nullptr, nullptr, nullptr, 0}, *a.tmpl.meta, sh, blockIdx.x, gridDim.x);
+  phase_reduce<C>(a.tmpl, a.work, sigma, a.loss, a.good_thr, tpl_cache_off(), *a.tmpl.meta, sh, blockIdx.x, gridDim.x);
   __syncthreads();
   if (threadIdx.x == 0) s_last = (atomicAdd(a.work.ticket, 1u) == gridDim.x - 1);
   __syncthreads();
@@ -801,7 +834,7 @@ template <int C> __global__ void __launch_bounds__(kLinThreads, 1) k_reduce(LinA
   const bool do_hist = (a.loss != 0x12) && (a.work.scale->delta > 1e-6f);
   float sigma = a.work.scale->scale;
   if (do_hist) sigma = finish_scale<C>(a.work, a.hset, a.sel, sh);
-  phase_reduce<C>(a.tmpl, a.work, sigma, a.loss, a.good_thr, TplCache{nullptr, nullptr, nullptr, 0}, *a.tmpl.meta, sh, blockIdx.x, gridDim.x);
+  phase_reduce<C>(a.tmpl, a.work, sigma, a.loss, a.good_thr, tpl_cache_off(), *a.tmpl.meta, sh, blockIdx.x, gridDim.x);
   __syncthreads();
   if (threadIdx.x == 0) s_last = (atomicAdd(a.work.ticket, 1u) == gridDim.x - 1);
   __syncthreads();
@@ -1310,17 +1343,12 @@ __device__ __forceinline__ void device_linearize(const SolveArgs& a, int lvl, So
 }
 
 template <int C>
-__global__ void __launch_bounds__(kLinThreads, 1) k_estimate_pose(const __grid_constant__ SolveArgs a, Sel* sel, int cache_slots) {
+__global__ void __launch_bounds__(kLinThreads, 1) k_estimate_pose(const __grid_constant__ SolveArgs a, Sel* sel, int cache_bytes) {
   __shared__ LinShared sh;
   __shared__ SolveShared ss;
   extern __shared__ __align__(16) unsigned char dyn_smem[];
-  // dynamic shared memory: [candidate scratch kScratchBytes][template cache cache_slots * bytes_per_slot]
+  // dynamic shared memory: [candidate scratch kScratchBytes][template cache: cache_bytes, planned per level]
   unsigned* scratch = reinterpret_cast<unsigned*>(dyn_smem);
-  TplCache tc_full;
-  tc_full.pts = reinterpret_cast<float4*>(dyn_smem + kScratchBytes);
-  tc_full.f = reinterpret_cast<float*>(dyn_smem + kScratchBytes + (size_t) cache_slots * kLinThreads * 16);
-  tc_full.valid = dyn_smem + kScratchBytes + (size_t) cache_slots * kLinThreads * (16 + 16 * C);
-  tc_full.K = cache_slots;
   const int tid = threadIdx.x;
   GridSync gs;
   gs.counter = a.work.hist + (size_t) kHistSets * kHistWords; gs.epoch = 0; gs.seq = a.seq_base; gs.xseq = a.peer.xseq_base; gs.hs = 0;
@@ -1347,10 +1375,9 @@ __global__ void __launch_bounds__(kLinThreads, 1) k_estimate_pose(const __grid_c
     float f_prev = 0.0f, g_tol = 0.0f, dp_prev = 0.0f, f_norm, g_norm;
     bool solver_error = false, early = false;
     const TemplateMeta meta = *L.meta;
-    // template cache for this level: on when every thread's points fit into the resident slots
-    TplCache tc = tc_full;
-    if ((meta.n + (int) gridDim.x * kLinThreads - 1) / ((int) gridDim.x * kLinThreads) > cache_slots) tc.K = 0;
-    if (tc.K) tc_fill<C>(tc, L, meta.n, blockIdx.x, gridDim.x);
+    // template cache for this level: as many whole fields as fit (tpl_cache_plan)
+    const TplCache tc = tpl_cache_plan<C>((unsigned) kScratchBytes, cache_bytes, (meta.n + (int) gridDim.x * kLinThreads - 1) / ((int) gridDim.x * kLinThreads));
+    tc_fill<C>(tc, L, meta.n, blockIdx.x, gridDim.x);
     // every histogram set starts the level zeroed; the barrier orders the zeroing before the first atomics
     for (int b = blockIdx.x * kLinThreads + tid; b < kHistSets * kHistWords; b += gridDim.x * kLinThreads) a.work.hist[b] = 0;
     grid_barrier(gs.counter, gs.epoch, gridDim.x, &ss.abort);
@@ -1430,12 +1457,12 @@ __global__ void __launch_bounds__(kLinThreads, 1) k_estimate_pose(const __grid_c
     }
     total_evals += n_evals;
     // residuals / valid flags of the last linearize of the finest level go back to global memory for getWeights() & co.
-    if (tc.K && C == 8 && lvl == a.sp.max_test_level) {
+    if (tc.f[TC_R] != kTcNone && C == 8 && lvl == a.sp.max_test_level) {
       int k = 0;
       for (int i = first_point(blockIdx.x, gridDim.x); i < meta.n; i += gridDim.x * kLinThreads, ++k) {
         VecC<C> r; tc_get<C>(tc, k, TC_R, r);
         r.store(a.work.res + (size_t) i * C);
-        a.work.valid[i] = tc.valid[k * kLinThreads + tid];
+        a.work.valid[i] = tc_valid(tc, k);
       }
     }
     if (ss.abort) status = -4;
