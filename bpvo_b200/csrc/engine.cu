@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -131,7 +132,9 @@ int bpvo_b200_create(bpvo_b200_ctx** out, const float K[9], float baseline, int 
   CUDA_TRY(cudaSetDevice(p->device_id));
 
   bpvo_b200_ctx* c = new bpvo_b200_ctx();
-  c->p = *p; c->rows = rows; c->cols = cols; c->L = p->numPyramidLevels; c->baseline = baseline;
+  c->p = *p; c->rows = rows; c->cols = cols;
+  c->L = p->numPyramidLevels; c->baseline = baseline;
+  if (getenv("BPVO_B200_NO_GRAPHS")) c->p.flags |= BPVO_B200_FLAG_NO_GRAPHS;      // A/B switch for measurements
   c->C = (p->descriptor == BPVO_B200_BITPLANES) ? 8 : 1;
   memcpy(c->K, K, sizeof(c->K));
   cudaDeviceProp prop;
@@ -293,6 +296,7 @@ int bpvo_b200_frame_destroy(bpvo_b200_frame* f) {
     cudaFree(f->gx[l]); cudaFree(f->gy[l]); cudaFree(f->i0[l]); cudaFree(f->inds[l]);
   }
   cudaFree(f->d_meta); cudaFreeHost(f->h_meta); cudaEventDestroy(f->meta_ready);
+  for (int k = 0; k < 2; ++k) if (f->graph_exec[k]) cudaGraphExecDestroy(f->graph_exec[k]);
   if (c->last_ref == f) c->last_ref = nullptr;
   delete f;
   return BPVO_B200_OK;
@@ -305,26 +309,10 @@ static bool is_dma_able(const void* p) {
   return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
 }
 
-// setData (vo_frame.cc:48-55) -> DenseDescriptorPyramid::init (dense_descriptor_pyramid.cc:67-78)
-int bpvo_b200_frame_set_data(bpvo_b200_frame* f, const uint8_t* image, const float* disparity) {
-  if (!f) return bp_fail(BPVO_B200_ERR_INVALID_ARG, "null frame");
-  if (!image || !disparity) return bp_fail(BPVO_B200_ERR_INVALID_ARG, "nullptr image/disparity");     // vo.cc:68
-  bpvo_b200_ctx* c = f->ctx;
-  CUDA_TRY(cudaSetDevice(c->p.device_id));
-  const size_t npx = (size_t) c->rows * c->cols;
-  {
-    PhaseTimer t(c, &c->counters.ms_upload);
-    const uint8_t* src_i = image; const float* src_d = disparity;
-    if (!(is_dma_able(image) && is_dma_able(disparity))) {
-      CUDA_TRY(cudaEventSynchronize(c->stage_free));
-      memcpy(c->stage_img, image, npx); memcpy(c->stage_disp, disparity, npx * sizeof(float));
-      src_i = c->stage_img; src_d = c->stage_disp;
-    }
-    CUDA_TRY(cudaMemcpyAsync(f->pyr[0], src_i, npx, cudaMemcpyDefault, c->stream));
-    CUDA_TRY(cudaMemcpyAsync(f->disp, src_d, npx * sizeof(float), cudaMemcpyDefault, c->stream));
-    CUDA_TRY(cudaEventRecord(c->stage_free, c->stream));
-    c->counters.h2d_bytes += (int64_t) (npx * 5);
-  }
+static int run_as_graph(bpvo_b200_ctx* c, bpvo_b200_frame* f, int which, int (*enqueue)(bpvo_b200_ctx*, bpvo_b200_frame*));
+
+// the kernel sequence of setData: DenseDescriptorPyramid::init (dense_descriptor_pyramid.cc:67-78)
+static int enqueue_descriptors(bpvo_b200_ctx* c, bpvo_b200_frame* f) {
   {
     PhaseTimer t(c, &c->counters.ms_pyramid);
     for (int l = 1; l < c->L; ++l) {
@@ -358,6 +346,31 @@ int bpvo_b200_frame_set_data(bpvo_b200_frame* f, const uint8_t* image, const flo
       LAUNCH_CHECK(c);
     }
   }
+  return BPVO_B200_OK;
+}
+
+// setData (vo_frame.cc:48-55) -> DenseDescriptorPyramid::init (dense_descriptor_pyramid.cc:67-78)
+int bpvo_b200_frame_set_data(bpvo_b200_frame* f, const uint8_t* image, const float* disparity) {
+  if (!f) return bp_fail(BPVO_B200_ERR_INVALID_ARG, "null frame");
+  if (!image || !disparity) return bp_fail(BPVO_B200_ERR_INVALID_ARG, "nullptr image/disparity");     // vo.cc:68
+  bpvo_b200_ctx* c = f->ctx;
+  CUDA_TRY(cudaSetDevice(c->p.device_id));
+  const size_t npx = (size_t) c->rows * c->cols;
+  {
+    PhaseTimer t(c, &c->counters.ms_upload);
+    const uint8_t* src_i = image; const float* src_d = disparity;
+    if (!(is_dma_able(image) && is_dma_able(disparity))) {
+      CUDA_TRY(cudaEventSynchronize(c->stage_free));
+      memcpy(c->stage_img, image, npx); memcpy(c->stage_disp, disparity, npx * sizeof(float));
+      src_i = c->stage_img; src_d = c->stage_disp;
+    }
+    CUDA_TRY(cudaMemcpyAsync(f->pyr[0], src_i, npx, cudaMemcpyDefault, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(f->disp, src_d, npx * sizeof(float), cudaMemcpyDefault, c->stream));
+    CUDA_TRY(cudaEventRecord(c->stage_free, c->stream));
+    c->counters.h2d_bytes += (int64_t) (npx * 5);
+  }
+  int rc = run_as_graph(c, f, 0, enqueue_descriptors);
+  if (rc) return rc;
   f->has_data = true;
   return BPVO_B200_OK;
 }
@@ -370,13 +383,8 @@ static LevelTemplate make_level_template(const bpvo_b200_frame* f, int l) {
   return t;
 }
 
-// setTemplate (vo_frame.cc:61-93) -> TemplateData::setData per level (template_data.cc:37-142); fully asynchronous
-int bpvo_b200_frame_set_template(bpvo_b200_frame* f) {
-  if (!f) return bp_fail(BPVO_B200_ERR_INVALID_ARG, "null frame");
-  if (!f->has_data) return bp_fail(BPVO_B200_ERR_NO_DATA, "no data in frame");                       // vo_frame.cc:63
-  bpvo_b200_ctx* c = f->ctx;
-  CUDA_TRY(cudaSetDevice(c->p.device_id));
-  PhaseTimer t(c, &c->counters.ms_template);
+// the launch sequence of setTemplate: TemplateData::setData per level (template_data.cc:37-142) + the header read-back
+static int enqueue_template(bpvo_b200_ctx* c, bpvo_b200_frame* f) {
   for (int l = c->L - 1; l >= c->p.maxTestLevel; --l) {
     const LevelGeom& g = c->geom[l];
     const int npx = g.rows * g.cols;
@@ -412,6 +420,48 @@ int bpvo_b200_frame_set_template(bpvo_b200_frame* f) {
     LAUNCH_CHECK(c);
   }
   CUDA_TRY(cudaMemcpyAsync(f->h_meta, f->d_meta, kMaxLevels * sizeof(TemplateMeta), cudaMemcpyDeviceToHost, c->stream));
+  return BPVO_B200_OK;
+}
+
+// Replays a frame's fixed launch sequence as ONE CUDA graph launch (the ~36 small dependent kernels of a template build
+// are launch-bound).  Captured per frame object on first use -- a frame's buffers never move, handles only swap roles.
+// Not used while profiling (cudaEvent pairs per phase) or in the sharded mode (NCCL calls in the sequence).
+static int run_as_graph(bpvo_b200_ctx* c, bpvo_b200_frame* f, int which, int (*enqueue)(bpvo_b200_ctx*, bpvo_b200_frame*)) {
+  const bool graphable = c->shard_size <= 1 && !c->profiling && !(c->p.flags & BPVO_B200_FLAG_NO_GRAPHS) && !f->graph_failed[which];
+  if (!graphable) return enqueue(c, f);
+  if (!f->graph_exec[which]) {
+    const int64_t before = c->counters.launches;
+    cudaGraph_t g = nullptr;
+    bool ok = cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+    int rc = BPVO_B200_OK;
+    if (ok) {
+      rc = enqueue(c, f);
+      ok = cudaStreamEndCapture(c->stream, &g) == cudaSuccess && rc == BPVO_B200_OK && g != nullptr;
+    }
+    if (ok) ok = cudaGraphInstantiate(&f->graph_exec[which], g, 0) == cudaSuccess;
+    if (g) cudaGraphDestroy(g);
+    f->graph_launches[which] = (int) (c->counters.launches - before);
+    c->counters.launches = before;
+    if (!ok) {                         // capture not possible here: fall back to plain launches for this frame
+      cudaGetLastError();
+      f->graph_exec[which] = nullptr; f->graph_failed[which] = true;
+      return enqueue(c, f);
+    }
+  }
+  CUDA_TRY(cudaGraphLaunch(f->graph_exec[which], c->stream));
+  c->counters.launches += f->graph_launches[which];
+  return BPVO_B200_OK;
+}
+
+// setTemplate (vo_frame.cc:61-93); fully asynchronous
+int bpvo_b200_frame_set_template(bpvo_b200_frame* f) {
+  if (!f) return bp_fail(BPVO_B200_ERR_INVALID_ARG, "null frame");
+  if (!f->has_data) return bp_fail(BPVO_B200_ERR_NO_DATA, "no data in frame");                       // vo_frame.cc:63
+  bpvo_b200_ctx* c = f->ctx;
+  CUDA_TRY(cudaSetDevice(c->p.device_id));
+  PhaseTimer t(c, &c->counters.ms_template);
+  int rc = run_as_graph(c, f, 1, enqueue_template);
+  if (rc) return rc;
   CUDA_TRY(cudaEventRecord(f->meta_ready, c->stream));
   c->counters.d2h_bytes += kMaxLevels * sizeof(TemplateMeta);
   f->has_template = true;

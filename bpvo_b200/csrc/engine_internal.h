@@ -75,6 +75,10 @@ struct bpvo_b200_frame {
   bp::TemplateMeta* d_meta = nullptr;
   bp::TemplateMeta* h_meta = nullptr;   // pinned mirror, valid after meta_ready
   cudaEvent_t meta_ready = nullptr;
+  // CUDA graphs of this frame's fixed launch sequences: [0] pyramid + descriptors (setData), [1] template build
+  cudaGraphExec_t graph_exec[2] = {nullptr, nullptr};
+  int graph_launches[2] = {0, 0};
+  bool graph_failed[2] = {false, false};
 };
 
 int bp_fail(int code, const char* fmt, ...);

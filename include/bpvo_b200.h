@@ -55,6 +55,7 @@ enum { BPVO_B200_KF_LARGE_TRANSLATION = 0x40, BPVO_B200_KF_LARGE_ROTATION = 0x41
        BPVO_B200_KF_SMALL_FRAC_GOOD = 0x42, BPVO_B200_KF_NONE = 0x43, BPVO_B200_KF_FIRST_FRAME = 0x44 };
 
 /* flags */
+#define BPVO_B200_FLAG_NO_GRAPHS    2  /* launch the per-frame kernel sequences one by one instead of as CUDA graphs */
 #define BPVO_B200_FLAG_HOST_SOLVE   1  /* estimate_pose drives the GN loop from the host (one sync per iteration)
                                           instead of the on-device loop; same results, used for parity tests */
 
