@@ -599,10 +599,15 @@ int bp_hartley(bpvo_b200_ctx* c, bpvo_b200_frame* f, int l) {
 // -------------------------------------------------------------------------------------------------
 // linearize (fine seam) and estimate_pose (coarse seam)
 // -------------------------------------------------------------------------------------------------
-static int lin_grid(const bpvo_b200_ctx* c, int level) {
-  // one CTA of 512 threads per SM at most; fewer when the level cannot hold that many points
-  const int need = ceil_div(c->geom[level].capacity, kLinThreads);
-  return std::max(1, std::min(c->sm_count, need));
+static int lin_grid(const bpvo_b200_ctx* c, const bpvo_b200_frame* ref, int level, int ctas_per_sm) {
+  // host-driven kernels: as many 256-thread CTAs as their register use lets an SM hold (k_residuals / k_reduce: 2,
+  // k_select: 4) when the level has the points to fill them (the template's size once its header has arrived on the
+  // host, its upper bound before that); one CTA per SM otherwise
+  int n = c->geom[level].capacity;
+  if (ref && ref->has_template && cudaEventQuery(ref->meta_ready) == cudaSuccess) n = ref->h_meta[level].n;
+  const int need = ceil_div(n, kLinThreads);
+  const int per_sm = (need >= 4 * c->sm_count * ctas_per_sm) ? ctas_per_sm : 1;
+  return std::max(1, std::min(std::min(c->sm_count * per_sm, 1024), need));
 }
 
 template <int C>
@@ -613,7 +618,7 @@ static int launch_linearize(bpvo_b200_ctx* c, const bpvo_b200_frame* ref, const 
   a.work = c->work; a.loss = c->p.lossFunction; a.interp = c->p.interp; a.good_thr = c->p.goodPointThreshold;
   a.hset = c->work.hist; a.sel = c->sel;
   make_projection(a.tmpl, T, a.P);
-  const int grid = lin_grid(c, level);
+  const int grid = lin_grid(c, ref, level, 2), grid_sel = lin_grid(c, ref, level, 4);
   const bool robust = c->p.lossFunction != BPVO_B200_L2;
   if (robust) CUDA_TRY(cudaMemsetAsync(c->work.hist, 0, kHistWords * sizeof(unsigned), c->stream));
   k_residuals<C><<<grid, kLinThreads, 0, c->stream>>>(a); LAUNCH_CHECK(c);
@@ -621,9 +626,9 @@ static int launch_linearize(bpvo_b200_ctx* c, const bpvo_b200_frame* ref, const 
   int rc;
   if (robust) {
     if (sharded && (rc = bp_comm_allreduce_u32(c, a.hset, kHist1Bins))) return rc;                       // global level-1 histogram
-    k_select<C, 2><<<grid, kLinThreads, 0, c->stream>>>(a); LAUNCH_CHECK(c);
+    k_select<C, 2><<<grid_sel, kLinThreads, 0, c->stream>>>(a); LAUNCH_CHECK(c);
     if (sharded && (rc = bp_comm_allreduce_u32(c, a.hset + kHist1Bins, 2 * kHist2Bins))) return rc;
-    k_select<C, 3><<<grid, kLinThreads, 0, c->stream>>>(a); LAUNCH_CHECK(c);
+    k_select<C, 3><<<grid_sel, kLinThreads, 0, c->stream>>>(a); LAUNCH_CHECK(c);
     if (sharded && (rc = bp_comm_allreduce_u32(c, a.hset + kHist1Bins + 2 * kHist2Bins, 2 * kHist3Bins))) return rc;
   }
   if (!sharded) {

@@ -12,6 +12,7 @@ timeout 600 python bench.py --impl reference --steps 16 --warmup 1 > gpurun_out/
 timeout 300 python scripts/profile_kernels.py --workload kitti > gpurun_out/${TAG}_kernels_semidense.json 2> gpurun_out/${TAG}_kernels_semidense.err
 BPVO_B200_LIB=$PWD/bpvo_b200/libbpvo_b200_fine.so timeout 300 python scripts/profile_kernels.py --workload kitti > gpurun_out/${TAG}_kernels_semidense_fine.json 2> gpurun_out/${TAG}_kernels_semidense_fine.err
 timeout 300 python scripts/profile_kernels.py --workload kitti_dense > gpurun_out/${TAG}_kernels_dense.json 2> gpurun_out/${TAG}_kernels_dense.err
+timeout 300 python scripts/profile_kernels.py --workload 1080p_dense > gpurun_out/${TAG}_kernels_1080p_dense.json 2> gpurun_out/${TAG}_kernels_1080p_dense.err
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file gpurun_out/${TAG}_launches.csv \
     python bench.py --steps 6 --warmup 3 --no-cpu-baseline --no-dense > gpurun_out/${TAG}_ncu_bench.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_estimate_pose -s 3 -c 1 -o gpurun_out/${TAG}_k_estimate_pose \
