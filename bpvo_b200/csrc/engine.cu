@@ -604,9 +604,12 @@ static int lin_grid(const bpvo_b200_ctx* c, const bpvo_b200_frame* ref, int leve
   // k_select: 4) when the level has the points to fill them (the template's size once its header has arrived on the
   // host, its upper bound before that); one CTA per SM otherwise
   int n = c->geom[level].capacity;
-  if (ref && ref->has_template && cudaEventQuery(ref->meta_ready) == cudaSuccess) n = ref->h_meta[level].n;
+  if (ref && ref->has_template) {
+    if (cudaEventQuery(ref->meta_ready) == cudaSuccess) n = ref->h_meta[level].n;
+    else cudaGetLastError();           // cudaErrorNotReady must not be mistaken for a launch failure later
+  }
   const int need = ceil_div(n, kLinThreads);
-  const int per_sm = (need >= 4 * c->sm_count * ctas_per_sm) ? ctas_per_sm : 1;
+  const int per_sm = (need >= 2 * c->sm_count * ctas_per_sm) ? ctas_per_sm : 1;
   return std::max(1, std::min(std::min(c->sm_count * per_sm, 1024), need));
 }
 
