@@ -324,8 +324,10 @@ def run_ours(args, w, rank, world, local_rank):
     dense = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline(w, args)
+    hbm_bound = None
     if rank == 0 and world == 1 and args.workload == "kitti" and not args.no_dense:
         dense = dense_variant_roofline(local_rank)
+        hbm_bound = hbm_bound_variant(local_rank)
 
     sharded = None
     if world > 1 and args.workload == "kitti" and not args.no_dense:
@@ -347,6 +349,7 @@ def run_ours(args, w, rank, world, local_rank):
             "roofline": roof,
             "cpu_baseline": cpu,
             "roofline_dense_variant": dense,
+            "roofline_hbm_bound_variant": hbm_bound,
             "sharded_1080p_dense_variant": sharded,
         }
         emit(line)
@@ -392,6 +395,33 @@ def sharded_variant(rank, world, local_rank, dist, torch):
         a.close(); b.close(); ctx.close()
     out["speedup_vs_one_gpu"] = out["single_gpu"]["us_per_gn_iter"] / out["sharded"]["us_per_gn_iter"]
     return out
+
+
+def hbm_bound_variant(local_rank):
+    """where the path IS bandwidth bound: one host-driven linearize (4 kernels) at level 0 of the dense 1080p workload
+    (BASELINE.json configs[3] on one GPU: 1.83 M points, 622 MB algorithmic per GN iteration, working set beyond the L2),
+    cudaEvent time per linearize with an L2 flush (256 MB memset) before every repetition, against the measured HBM peak"""
+    from bpvo_b200.engine import Context
+    w = WORKLOADS["1080p_dense"]
+    sc = make_scene(w, 0xB200)
+    p = make_params(w)
+    ctx = Context(sc.K, sc.baseline, (sc.rows, sc.cols), p, device_id=local_rank)
+    a, b = ctx.frame(), ctx.frame()
+    i0, d0 = sc.render(0); i1, d1 = sc.render(1)
+    a.setData(i0, d0); a.setTemplate(); b.setData(i1, d1)
+    T = np.eye(4, dtype=np.float32)
+    N = a.numPoints(0)
+    r, c = a.level_size(0)
+    B = algorithmic_bytes_per_iter(N, 8, r, c)
+    ctx.time_linearize(a, b, 0, T, iters=3, flush_l2=False)
+    ms_cold = ctx.time_linearize(a, b, 0, T, iters=10, flush_l2=True)
+    ms_warm = ctx.time_linearize(a, b, 0, T, iters=10, flush_l2=False)
+    a.close(); b.close(); ctx.close()
+    peak, how = peaks()
+    return {"workload": w["name"] + " level 0, host-driven linearize (k_residuals + k_select<2,3> + k_reduce)", "bound": "hbm", "points": N,
+            "algorithmic_bytes_per_iter": B, "us_per_iter_l2_flushed": 1e3 * ms_cold, "us_per_iter_warm": 1e3 * ms_warm,
+            "achieved": B / ms_cold / 1e6, "peak": peak, "unit": "GB/s", "frac": B / ms_cold / 1e6 / peak, "frac_warm": B / ms_warm / 1e6 / peak,
+            "peak_source": how}
 
 
 def dense_variant_roofline(local_rank):
