@@ -39,7 +39,11 @@ def build(force: bool = False, verbose: bool = False, variant: str = "") -> str:
     """variant "fine": a second library with the fine-grained in-kernel profile marks compiled in
     (-DBP_FINE_PROFILE -> libbpvo_b200_fine.so, loaded when BPVO_B200_LIB points at it); never the product path."""
     lib = LIB if not variant else LIB.replace(".so", f"_{variant}.so")
-    extra = {"": [], "fine": ["-DBP_FINE_PROFILE"]}[variant]
+    extra = {"": [], "fine": ["-DBP_FINE_PROFILE"]}.get(variant)
+    if extra is None:                      # ad-hoc A/B variants: "name:-DFOO=1,-DBAR=2"
+        variant, _, flags = variant.partition(":")
+        extra = [x for x in flags.split(",") if x]
+        lib = LIB.replace(".so", f"_{variant}.so")
     if not force and os.path.exists(lib) and os.path.getmtime(lib) >= _newest_source_mtime():
         return lib
     cmd = [_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", lib] + SOURCES
@@ -57,4 +61,4 @@ def build(force: bool = False, verbose: bool = False, variant: str = "") -> str:
 
 if __name__ == "__main__":
     import sys
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, variant="fine" if "--fine" in sys.argv else ""))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, variant="fine" if "--fine" in sys.argv else next((a.split("=", 1)[1] for a in sys.argv if a.startswith("--variant=")), "")))

@@ -16,14 +16,20 @@ constexpr int kSelBins = 1024, kSelList = 256;   // bracketed median: linear bin
 constexpr int kHistWords = kHistBins + 8 + kSelBins;   // one histogram set + bookkeeping words + the bracket histogram:
 //   [kHistBins+0] max(~i) over valid points i   [+1] valid points   [+2] residuals below the bracket   [+3] residuals inside it
 //   [+4] length of the candidate overflow list   [+8 ...] kSelBins counts of the candidates by linear bin over the bracket
-constexpr int kCandPerCta = 12;              // bracketed median: every CTA owns a fixed region of the candidate buffer (no slot reservation) ...
+#ifndef BP_CAND_PER_CTA
+#define BP_CAND_PER_CTA 12
+#endif
+constexpr int kCandPerCta = BP_CAND_PER_CTA;             // bracketed median: every CTA owns a fixed region of the candidate buffer (no slot reservation) ...
 constexpr int kCtaCandCap = 1024;            // ... stages up to this many candidates in shared memory ...
 constexpr int kOvfCap = 16384;               // ... and appends what exceeds its region to a shared overflow list (wide brackets, early iterations)
 constexpr unsigned kCandPoison = 1u << 30;   // added to the candidate count when even that overflowed -> radix fallback
 constexpr int kScratchBytes = (kCtaCandCap + kSelList) * 4;   // dynamic-smem scratch of the bracketed select: CTA candidates | list
 constexpr int kPartialStride = 32; // doubles per block partial (21 H + 6 G + f + n_good + pad)
 constexpr int kHistSets = 3;       // histogram sets of the on-device loop (triple-buffered: a set is zeroed one real barrier before its next use)
-constexpr int kLLGroup = 12;       // CTAs per group of the two-level flag-in-data exchange of the normal-equation sums
+#ifndef BP_LL_GROUP
+#define BP_LL_GROUP 24        /* same-box A/B over 8 / 12 / 16 / 24 / 37 / 74 / 148: 24 is the fastest (by 0.4 % over 12) */
+#endif
+constexpr int kLLGroup = BP_LL_GROUP;      // CTAs per group of the two-level flag-in-data exchange of the normal-equation sums
 constexpr int kMaxGrid = 1024;     // upper bound of CTAs of the persistent kernel (sizes the exchange mailboxes)
 constexpr int kLinThreads = 256;   // threads per CTA of the linearize phases (1 CTA per SM; measured: 128 -> 14.7, 256 -> 12.4, 512 -> 13.5 us / GN iteration)
 

@@ -532,7 +532,7 @@ __device__ __forceinline__ float finish_scale(const Work& W, const unsigned* __r
 // residuals, no further grid barrier.  The candidates stay in REGISTERS (one L2 round trip fetches all regions and the
 // counters); only the histogram and the final short list touch shared memory.
 // Returns false when the bracket missed (caller falls back to the 3-level radix select).
-constexpr int kSelPre = 7;    // candidate slots per thread held in registers (covers 149 CTAs x kCandPerCta); more are re-read
+constexpr int kSelPre = (148 * kCandPerCta + kLinThreads - 1) / kLinThreads + ((149 * kCandPerCta > ((148 * kCandPerCta + kLinThreads - 1) / kLinThreads) * kLinThreads) ? 1 : 0);    // candidate slots per thread held in registers (covers 149 CTAs x kCandPerCta); more are re-read
 static_assert(kSelBins == 4 * kLinThreads, "bracket_select loads the bracket histogram as one uint4 per thread");
 template <int C>
 __device__ __forceinline__ bool bracket_select(const Work& W, const unsigned* __restrict__ hset, LinShared& sh, unsigned* scratch, int nblocks,
@@ -899,6 +899,9 @@ __global__ void __launch_bounds__(256) k_point_cloud(const float4* __restrict__ 
   do { if (a.prof && blockIdx.x == 0 && threadIdx.x == 0) { long long* _s = prof_smem(); const long long _t = clock64(); _s[slot] += _t - _s[64]; _s[64] = _t; } } while (0)
 enum { PROF_P1 = 0, PROF_SYNC1, PROF_P2, PROF_SYNC2, PROF_P3, PROF_SYNC3, PROF_SCALE, PROF_P4, PROF_SYNC4, PROF_FINAL, PROF_SOLVE, PROF_OTHER, PROF_COUNT };
 
+#ifndef BP_BRACKET_TARGET
+#define BP_BRACKET_TARGET 500     /* candidates the bracket is sized for once the median has settled */
+#endif
 constexpr unsigned kSpinLimit = 1u << 24;    // ~2 s of polling: a lost CTA ends the launch with an error status instead of hanging the GPU
 
 // Grid-wide barrier of the persistent kernel (all CTAs are co-resident: cooperative launch).  `counter` only grows;
@@ -1311,7 +1314,7 @@ __device__ __forceinline__ void device_linearize(const SolveArgs& a, int lvl, So
       if (ss.br_on && mid_new > 0.0f) {
         const float moved = fabsf(mid_new - mid_old) / mid_new;
         if (br.on && ncand > 0) ss.br_density = (float) ncand / fmaxf(ss.br_rel, 1e-6f);       // candidates per unit of rel
-        const float rel_density = (ss.br_density > 0.0f) ? 500.0f / ss.br_density : 0.002f;
+        const float rel_density = (ss.br_density > 0.0f) ? (float) BP_BRACKET_TARGET / ss.br_density : 0.002f;
         rel = fmaxf(2.0f * moved, fminf(rel_density, 0.02f));
         rel = fminf(fmaxf(rel, 1e-5f), 0.06f);
       }
