@@ -144,7 +144,7 @@ int bpvo_b200_peer_init(bpvo_b200_ctx* c, const uint8_t* handles) {
     if (e != cudaSuccess) { cudaGetLastError(); return bp_fail(BPVO_B200_ERR_COMM, "cudaIpcOpenMemHandle(rank %d) failed: %s", r, cudaGetErrorString(e)); }
     c->xpeer[r] = (uint2*) p;
   }
-  c->peer_mode = true; c->x_seq = 1;
+  c->peer_mode = true; c->x_seq = c->x_seq_init ? c->x_seq_init : 1;
   return BPVO_B200_OK;
 }
 

@@ -135,6 +135,8 @@ int bpvo_b200_create(bpvo_b200_ctx** out, const float K[9], float baseline, int 
   c->p = *p; c->rows = rows; c->cols = cols;
   c->L = p->numPyramidLevels; c->baseline = baseline;
   if (getenv("BPVO_B200_NO_GRAPHS")) c->p.flags |= BPVO_B200_FLAG_NO_GRAPHS;      // A/B switch for measurements
+  // test hook: start the exchange sequence numbers close to their wrap-around so that the reset paths get exercised
+  if (const char* e = getenv("BPVO_B200_SEQ_INIT")) { c->ll_seq = (unsigned) strtoul(e, nullptr, 0); c->x_seq_init = c->ll_seq; }
   c->C = (p->descriptor == BPVO_B200_BITPLANES) ? 8 : 1;
   memcpy(c->K, K, sizeof(c->K));
   cudaDeviceProp prop;

@@ -57,7 +57,7 @@ struct bpvo_b200_ctx {
   uint2* xbox = nullptr;         // this rank's mailbox
   uint2* xpeer[bp::kXRanks] = {};
   uint4* lbox = nullptr;
-  unsigned x_seq = 0;
+  unsigned x_seq = 0, x_seq_init = 0;
 };
 
 struct bpvo_b200_frame {

@@ -87,6 +87,20 @@ def main():
     report["vo_stream"] = {"frames": 8, "worst_pose_rel_err_vs_single_gpu": worst}
     vo.ctx.comm_destroy()
 
+    # ---- sequence-number wrap-around of the cross-rank mailboxes: collective reset (test hook BPVO_B200_SEQ_INIT) ----------
+    os.environ["BPVO_B200_SEQ_INIT"] = "0xfffff800"
+    vo2 = VisualOdometry(sc.K, sc.baseline, (sc.rows, sc.cols), p, device_id=local)
+    del os.environ["BPVO_B200_SEQ_INIT"]
+    vo2.ctx.comm_init(rank, world, uid()); vo2.ctx.peer_init_distributed(dist); vo2.ctx.peer_set_min_points(0)
+    vo3 = VisualOdometry(sc.K, sc.baseline, (sc.rows, sc.cols), p, device_id=local)
+    vo3.ctx.comm_init(rank, world, uid()); vo3.ctx.peer_init_distributed(dist); vo3.ctx.peer_set_min_points(0)
+    for k in range(4):
+        img, d = sc.render(k)
+        ra, rb = vo2.addFrame(img, d), vo3.addFrame(img, d)
+        assert np.array_equal(ra.pose, rb.pose), f"frame {k}: the mailbox reset changed the result"
+    report["sequence_reset"] = "ok"
+    vo2.ctx.comm_destroy(); vo3.ctx.comm_destroy()
+
     # ---- timing: dense 1080p (configs[3]), one GN iteration ------------------------------------------------------------
     sc = synth.scene_1080p()
     p = make_params("bitplanes", 5, "tukey", nonMaxSuppRadius=-1)

@@ -342,6 +342,29 @@ def test_full_size_properties():
     assert np.abs(T02[:3, 3] - gt[:3, 3]).max() < 0.02 and np.abs(T02[:3, :3] - gt[:3, :3]).max() < 2e-3
 
 
+def test_exchange_sequence_wraparound(monkeypatch):
+    """the flag-in-data exchanges of the persistent kernel are validated by 32-bit sequence numbers; a ctx whose counter
+    starts just below the wrap-around (test hook BPVO_B200_SEQ_INIT) must reset its mailboxes and keep producing the
+    bit-identical solve"""
+    from bpvo_b200.engine import Context
+    sc = _scene("small")
+    p = make_params("bitplanes", 3, "tukey")
+    i0, d0 = sc.render(0); i1, d1 = sc.render(1)
+    T0 = np.eye(4, dtype=np.float32)
+
+    def solve(n):
+        ctx = Context(sc.K, sc.baseline, (sc.rows, sc.cols), p)
+        a, b = ctx.frame(), ctx.frame()
+        a.setData(i0, d0); a.setTemplate(); b.setData(i1, d1)
+        out = [ctx.estimatePose(a, b, T0) for _ in range(n)]
+        a.close(); b.close(); ctx.close()
+        return out
+    ref_T, ref_stats, ref_n = solve(1)[0]
+    monkeypatch.setenv("BPVO_B200_SEQ_INIT", "0xfffff800")          # 2048 below the wrap: ~12 solves of this size
+    for T, stats, n in solve(40):
+        assert np.array_equal(T, ref_T) and n == ref_n
+
+
 def test_point_sharded_two_gpus():
     """point-sharded mode (NCCL exchange of the median histograms and the 30 normal-equation sums) on 2 GPUs of one box:
     scripts/shard_check.py under torchrun; skipped when the box has a single GPU"""
