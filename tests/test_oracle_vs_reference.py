@@ -193,6 +193,53 @@ def test_frame_and_linearize_bit_exact(oracle, ref, kind, desc, levels, loss):
             assert r["f_norm"] == o["f_norm"]
 
 
+@pytest.mark.parametrize("desc,opts", [("intensity", dict(interp=1)), ("bitplanes", dict(interp=1)),          # kCosine
+                                       ("intensity", dict(interp=2)), ("bitplanes", dict(interp=2)),          # kCubic
+                                       ("intensity", dict(interp=3)), ("bitplanes", dict(interp=3)),          # kCubicHermite
+                                       ("bitplanes", dict(gradientEstimation=1)),                             # kCentralDifference_5
+                                       ("bitplanes", dict(sigmaPriorToCensusTransform=0.75, sigmaBitPlanes=1.618)),
+                                       ("intensity", dict(nonMaxSuppRadius=2)), ("bitplanes", dict(withNormalization=0))])
+def test_option_variants_bit_exact(oracle, ref, desc, opts):
+    """the options beside the defaults -- the other InterpolationTypes (photo_error.cc:391-444), the 5-point gradient
+    (template_data.cc:125-129), the pre-census blur (census.cc:63-65), NMS radius 2, no Hartley normalisation -- through
+    the reference's own sources vs the oracle: descriptors, template, residuals, weights, H, G bit for bit.
+    (Cubic / Hermite: points whose footprint reaches the row past the image are excluded -- the reference reads whatever
+    follows its buffer there, photo_error.cc:358.)"""
+    sc = _frames("small")
+    levels = 2
+    p = make_params(desc, levels, "tukey", **opts)
+    i0, d0 = sc.render(0); i1, d1 = sc.render(1)
+    ra, rb = oracle.RefFrame(sc.K, sc.baseline, sc.rows, sc.cols, p), oracle.RefFrame(sc.K, sc.baseline, sc.rows, sc.cols, p)
+    oa, ob = oracle.Frame(sc.K, sc.baseline, sc.rows, sc.cols, p, use_rcp=1), oracle.Frame(sc.K, sc.baseline, sc.rows, sc.cols, p, use_rcp=1)
+    for a, b in ((ra, rb), (oa, ob)):
+        a.set_data(i0, d0); a.set_template(); b.set_data(i1, d1)
+    re, oe = oracle.RefEstimator(p), oracle.Estimator(p)
+    T1 = np.array(sc.relative_pose(0, 1), dtype=np.float32)
+    footprint4 = opts.get("interp", 0) in (2, 3)
+    for l in range(levels):
+        N = ra.num_points(l)
+        assert N == oa.num_points(l) > 0
+        assert np.array_equal(ra.descriptor(l), oa.descriptor(l))
+        assert np.array_equal(ra.points(l), oa.points(l))
+        assert np.array_equal(ra.pixels(l), oa.pixels(l))
+        assert np.array_equal(ra.jacobians(l), oa.jacobians(l))
+        r = re.linearize(ra, rb, l, T1, reset=True)
+        o = oe.linearize(oa, ob, l, T1, reset_scale=True)
+        assert np.array_equal(r["valid"], o["valid"])
+        if not footprint4:
+            for key in ("residuals", "weights", "H", "G"):
+                assert np.array_equal(r[key], o[key]), (l, key)
+        else:
+            rows = sc.rows >> l if sc.rows % (1 << l) == 0 else (sc.rows + (1 << l) - 1) >> l
+            K = np.array(sc.K, np.float64) / (1 << l); K[2, 2] = 1.0
+            X = ra.points(l).astype(np.float64).reshape(-1, 4)
+            h = (K.astype(np.float32).astype(np.float64) @ T1[:3, :].astype(np.float64)) @ X.T
+            keep = np.floor(h[1] / h[2]) < rows - 2.5
+            C = r["residuals"].size // N
+            assert keep.sum() > 0.9 * N
+            assert np.array_equal(r["residuals"].reshape(C, N)[:, keep], o["residuals"].reshape(C, N)[:, keep]), l
+
+
 @pytest.mark.parametrize("desc,levels,loss,nframes", [("bitplanes", 3, "tukey", 14), ("intensity", 3, "huber", 14), ("intensity", 2, "l2", 6)])
 def test_vo_stream_bit_exact(oracle, ref, desc, levels, loss, nframes):
     """addFrame state machine incl. key-framing + re-estimation, trajectory and point cloud: oracle == real reference"""
