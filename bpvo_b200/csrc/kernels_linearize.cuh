@@ -10,23 +10,25 @@
 //   PoseEstimatorBase::run + solve + testConvergence (device loop)              pose_estimator_base.h:90-148, 258-282, 324-407
 //   VisualOdometryPoseEstimator::estimatePose (level loop)                      vo_pose_estimator.cc:63-93
 //
-// Structure of one linearize (4 phases; kernel boundaries in the host-driven path, grid syncs in
-// the persistent path):
+// Structure of one linearize (kernel boundaries in the host-driven path, one barrier + one exchange in the persistent one):
 //   P1 residuals : thread per point: fp64 project -> floor -> valid -> 4 bilinear taps x C channels
-//                  (one 32-B sector per tap for C = 8) -> r = f32(Iw - I0) ; level-1 radix histogram of |r|
-//   P2 select-2  : every CTA scans the 2048-bin histogram, then histograms bits [19:9] of the two median bins
-//   P3 select-3  : same for bits [8:0]  -> the two middle order statistics, exactly
+//                  (one 32-B sector per tap for C = 8) -> r = f32(Iw - I0); bookkeeping for the robust scale
+//   median       : exact order statistics n/2-1, n/2 of |r|.  Persistent kernel: bracket around the previous median ->
+//                  bracket histogram + the few candidates in the two wanted bins (bracket_select); fallback and
+//                  host-driven path: 3-level radix select over the float bit patterns (P2 select-2, P3 select-3)
 //   P4 reduce    : sigma -> weight -> rank-2 per-point update of the 21+6+1 normal-equation scalars
-//                  (J = gx*A + gy*B) -> fp64 warp shuffle -> CTA partial -> fixed-order final sum
-// HBM/L2-bound gather-and-reduce: no tensor cores (no dense contraction on this path).
+//                  (J = gx*A + gy*B) -> transposing warp butterfly -> fp64 CTA totals -> fixed-order sum over CTAs
+//                  (persistent: two-level flag-in-data exchange; host-driven: last-CTA fold)
+//   solve        : (persistent) 6x6 LDL^T, acceptance test, pose update, convergence tests in every CTA
+//   multi-GPU    : (peer-memory mode) the bracket histogram, the candidates and the 30 sums also cross the ranks, inside
+//                  the kernel, through peer-mapped mailboxes
+// Latency / L2 bound at semi-dense sizes, HBM bound for dense megapixel levels: no tensor cores (no dense contraction).
 #pragma once
 
-#include <cooperative_groups.h>
 #include "device_types.h"
 #include "device_solve.cuh"
 
 namespace bp {
-namespace cg = cooperative_groups;
 
 // Point -> thread mapping of every linearize phase: warp g = warp_in_cta * nblocks + cta owns points
 // [32 g, 32 g + 32) (+ multiples of the grid size).  Small levels therefore spread one or two warps onto EVERY
