@@ -1017,6 +1017,7 @@ __device__ __forceinline__ void exchange_sums(double mine, uint4* ll, unsigned s
 // the peers; it hands rank-wide results to the other CTAs through a local grid barrier or local flag-in-data words.
 // All ranks take identical decisions from identical data, so the exchange sequence is the same everywhere.
 // =============================================================================================
+constexpr unsigned kXSpinLimit = 1u << 27;   // cross-rank waits tolerate host-side skew between the processes (tens of seconds) before giving up
 __device__ __forceinline__ void x_put(uint2* p, unsigned v, unsigned seq) {
   asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(v), "r"(seq) : "memory");
 }
@@ -1030,7 +1031,7 @@ __device__ __forceinline__ uint2* x_slot(const PeerArgs& pa, int owner, unsigned
 }
 __device__ __forceinline__ unsigned x_wait(const uint2* p, unsigned seq, int* abort_flag) {
   unsigned v, spins = 0;
-  while (!x_peek(p, seq, v)) { if (++spins > kSpinLimit || *(volatile int*) abort_flag) { *abort_flag = 1; v = 0; break; } }
+  while (!x_peek(p, seq, v)) { if (++spins > kXSpinLimit || *(volatile int*) abort_flag) { *abort_flag = 1; v = 0; break; } }
   return v;
 }
 // CTA 0: send buf[0..n) (shared memory) to every peer
@@ -1068,7 +1069,7 @@ __device__ __forceinline__ void x_allreduce_u32(const PeerArgs& pa, unsigned& xs
             if (x_peek(base + (size_t) r * kXWords + i0 + q * kLinThreads, seq, v)) { acc[q] += v; pending &= ~(1ull << (r * 8 + q)); }
           }
       }
-      if (pending && (++spins > kSpinLimit || *(volatile int*) abort_flag)) { *abort_flag = 1; break; }
+      if (pending && (++spins > kXSpinLimit || *(volatile int*) abort_flag)) { *abort_flag = 1; break; }
     }
 #pragma unroll
     for (int q = 0; q < Q; ++q) if (i0 + q * kLinThreads < n) buf[i0 + q * kLinThreads] += acc[q];
@@ -1098,7 +1099,7 @@ __device__ __forceinline__ double x_allreduce_f64_ordered(const PeerArgs& pa, un
         if (!ok[r]) { const uint2* src = x_slot(pa, pa.rank, seq, r); unsigned a, c; const bool g0 = x_peek(src + 2 * k, seq, a), g1 = x_peek(src + 2 * k + 1, seq, c); if (g0 && g1) { lo[r] = a; hi[r] = c; ok[r] = true; } }
         all = all && ok[r];
       }
-      if (!all && (++spins > kSpinLimit || *(volatile int*) abort_flag)) { *abort_flag = 1; break; }
+      if (!all && (++spins > kXSpinLimit || *(volatile int*) abort_flag)) { *abort_flag = 1; break; }
     }
 #pragma unroll
     for (int r = 0; r < kXRanks; ++r)
