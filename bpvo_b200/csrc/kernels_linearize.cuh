@@ -904,7 +904,8 @@ enum { PROF_P1 = 0, PROF_SYNC1, PROF_P2, PROF_SYNC2, PROF_P3, PROF_SYNC3, PROF_S
 #ifndef BP_BRACKET_TARGET
 #define BP_BRACKET_TARGET 500     /* candidates the bracket is sized for once the median has settled */
 #endif
-constexpr unsigned kSpinLimit = 1u << 24;    // ~2 s of polling: a lost CTA ends the launch with an error status instead of hanging the GPU
+constexpr unsigned kSpinLimit = 1u << 27;    // tens of seconds of polling (the other CTAs of a rank must outwait CTA 0, which may be waiting for a
+                                             // peer process that is seconds behind): a lost CTA / rank ends the launch with an error status instead of hanging the GPU
 
 // Grid-wide barrier of the persistent kernel (all CTAs are co-resident: cooperative launch).  `counter` only grows;
 // `epoch` is the value it reaches when every CTA has arrived at this barrier (kept uniformly by all threads).
@@ -1017,7 +1018,7 @@ __device__ __forceinline__ void exchange_sums(double mine, uint4* ll, unsigned s
 // the peers; it hands rank-wide results to the other CTAs through a local grid barrier or local flag-in-data words.
 // All ranks take identical decisions from identical data, so the exchange sequence is the same everywhere.
 // =============================================================================================
-constexpr unsigned kXSpinLimit = 1u << 27;   // cross-rank waits tolerate host-side skew between the processes (tens of seconds) before giving up
+constexpr unsigned kXSpinLimit = kSpinLimit;  // cross-rank waits: the same patience
 __device__ __forceinline__ void x_put(uint2* p, unsigned v, unsigned seq) {
   asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(v), "r"(seq) : "memory");
 }
