@@ -4,7 +4,7 @@
  *
  * The reference has no FFI of its own; its seam is the pair of internal C++ classes that bpvo/vo.cc
  * drives (VisualOdometryFrame, VisualOdometryPoseEstimator) plus the public VisualOdometry class that
- * apps/*.cc and matlab/vo_mex.cc:204-208 bind.  Every entry point below names the reference
+ * the programs under apps/ and matlab/vo_mex.cc:204-208 bind.  Every entry point below names the reference
  * interface it replaces (file:line relative to the reference root).  INTEGRATION.md shows the
  * reference-side shim a maintainer would add.
  *
