@@ -76,6 +76,7 @@ def _signatures():
         "bpvo_b200_get_weights": (C.c_int, [vp, fp, szp]),
         "bpvo_b200_get_residuals": (C.c_int, [vp, fp, szp]),
         "bpvo_b200_get_valid": (C.c_int, [vp, u8p, szp]),
+        "bpvo_b200_debug_cache_plan": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint32)]),
         "bpvo_b200_point_cloud": (C.c_int, [vp, vp, C.c_void_p, ip]),
         "bpvo_b200_fraction_good": (C.c_int, [vp, C.c_float, fp]),
         "bpvo_b200_comm_unique_id": (C.c_int, [u8p]),

@@ -913,6 +913,16 @@ extern "C" int bpvo_b200_point_cloud(bpvo_b200_ctx* c, const bpvo_b200_frame* re
   return BPVO_B200_OK;
 }
 
+// host evaluation of the persistent kernel's per-level shared-memory plan (tests / documentation)
+extern "C" int bpvo_b200_debug_cache_plan(int channels, int cache_bytes, int slots_needed, unsigned out[8]) {
+  if (!out || (channels != 1 && channels != 8)) return bp_fail(BPVO_B200_ERR_INVALID_ARG, "bad argument");
+  const TplCache t = (channels == 8) ? tpl_cache_plan<8>((unsigned) kScratchBytes, cache_bytes, slots_needed)
+                                     : tpl_cache_plan<1>((unsigned) kScratchBytes, cache_bytes, slots_needed);
+  out[0] = t.pts; out[1] = t.f[TC_I0]; out[2] = t.f[TC_GX]; out[3] = t.f[TC_GY]; out[4] = t.f[TC_R]; out[5] = t.valid;
+  out[6] = (unsigned) t.K; out[7] = (unsigned) kScratchBytes;
+  return BPVO_B200_OK;
+}
+
 // device-time of back-to-back linearize launches (no host round trip), for the roofline figure
 extern "C" int bpvo_b200_time_linearize(bpvo_b200_ctx* c, const bpvo_b200_frame* ref, const bpvo_b200_frame* cur, int level,
                                          const float T[16], int iters, int flush_l2, float* ms_per_iter) {

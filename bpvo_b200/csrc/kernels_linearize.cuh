@@ -76,7 +76,7 @@ struct TplCache {
   int K;                 // slots per thread the level needs (0 = cache off: host-driven kernels)
 };
 enum { TC_I0 = 0, TC_GX = 1, TC_GY = 2, TC_R = 3 };
-__device__ __forceinline__ TplCache tpl_cache_off() { TplCache t; t.pts = t.f[0] = t.f[1] = t.f[2] = t.f[3] = t.valid = kTcNone; t.K = 0; return t; }
+__host__ __device__ __forceinline__ TplCache tpl_cache_off() { TplCache t; t.pts = t.f[0] = t.f[1] = t.f[2] = t.f[3] = t.valid = kTcNone; t.K = 0; return t; }
 __device__ __forceinline__ unsigned char* tc_base() { extern __shared__ __align__(16) unsigned char dyn_smem[]; return dyn_smem; }
 __device__ __forceinline__ float4& tc_point(const TplCache& tc, int k) { return reinterpret_cast<float4*>(tc_base() + tc.pts)[k * kLinThreads + threadIdx.x]; }
 __device__ __forceinline__ uint8_t& tc_valid(const TplCache& tc, int k) { return (tc_base() + tc.valid)[k * kLinThreads + threadIdx.x]; }
@@ -97,7 +97,7 @@ template <int C> __device__ __forceinline__ void tc_put(const TplCache& tc, int 
 // gx, gy (P4), I0 (P1).  KITTI semi-dense: everything (1 slot); KITTI dense level 0
 // (11 slots): residuals + points; a 1080p level sharded over 8 GPUs (6 slots): everything but I0.  `first` = offset of the cache area, `bytes` its size.
 template <int C>
-__device__ __forceinline__ TplCache tpl_cache_plan(unsigned first, int bytes, int need) {
+__host__ __device__ __forceinline__ TplCache tpl_cache_plan(unsigned first, int bytes, int need) {
   TplCache t = tpl_cache_off();
   if (need <= 0) return t;
   t.K = need;

@@ -267,6 +267,11 @@ int bpvo_b200_timer_start(bpvo_b200_ctx* ctx);
 int bpvo_b200_timer_stop(bpvo_b200_ctx* ctx, float* ms);
 /* linearize() evaluations per pyramid level of the last estimate_pose (numLevels ints) */
 int bpvo_b200_last_level_evals(bpvo_b200_ctx* ctx, int* evals);
+/* the on-device GN loop's shared-memory plan for a level whose threads own `slots_needed` points each, given
+ * `cache_bytes` of dynamic shared memory: byte offsets of {points, I0, gx, gy, residuals, valid flags}
+ * (0xffffffff = that field stays in global memory), slots, offset of the cache area.  Host-side evaluation of the
+ * kernel's own planning function, for tests and documentation. */
+int bpvo_b200_debug_cache_plan(int channels, int cache_bytes, int slots_needed, unsigned out[8]);
 /* pinned host allocation for zero-staging uploads (cudaHostAlloc / cudaFreeHost) */
 void* bpvo_b200_host_alloc(size_t bytes);
 void  bpvo_b200_host_free(void* p);

@@ -108,3 +108,52 @@ def test_cpp_example_links_against_the_host_shim(tmp_path):
                     "-o", str(exe)], check=True)
     r = subprocess.run([str(exe)], capture_output=True, text=True)
     assert r.returncode == 2 and "usage" in r.stderr
+
+
+def test_shared_memory_plan_of_the_device_loop():
+    """tpl_cache_plan (kernels_linearize.cuh) evaluated on the host: whole fields in the order residuals + valid, points,
+    gx, gy, I0; no overlap, inside the budget, 16-byte aligned points; the three regimes DESIGN.md names"""
+    import ctypes as C
+    from bpvo_b200 import _capi
+    lib = _capi.lib()
+    NONE = 0xffffffff
+    budget = (227 * 1024 - 24 * 1024 - 5120) // 1024 * 1024          # what engine.cu requests on a B200
+
+    def plan(ch, bytes_, need):
+        out = (C.c_uint32 * 8)()
+        assert lib.bpvo_b200_debug_cache_plan(ch, bytes_, need, out) == 0
+        return dict(pts=out[0], i0=out[1], gx=out[2], gy=out[3], r=out[4], valid=out[5], K=out[6], first=out[7])
+
+    def check(ch, bytes_, need):
+        p = plan(ch, bytes_, need)
+        size = dict(pts=need * 256 * 16, i0=need * 256 * 4 * ch, gx=need * 256 * 4 * ch, gy=need * 256 * 4 * ch, r=need * 256 * 4 * ch, valid=need * 256)
+        spans = sorted((p[k], p[k] + size[k]) for k in size if p[k] != NONE)
+        for (a0, a1), (b0, b1) in zip(spans, spans[1:]):
+            assert a1 <= b0, (p, "overlap")
+        if spans:
+            assert spans[0][0] >= p["first"] and spans[-1][1] <= p["first"] + bytes_, (p, "outside the cache area")
+        assert (p["r"] == NONE) == (p["valid"] == NONE)
+        if p["pts"] != NONE:
+            assert p["pts"] % 16 == 0
+        # priority: a field is only cached when everything before it in the order is
+        order = ["r", "pts", "gx", "gy", "i0"]
+        cached = [p[k] != NONE for k in order]
+        # (all-or-nothing per field, greedy: a later, smaller field may still fit when an earlier one did not -- only r -> pts differ in size)
+        assert cached[2] >= cached[3] >= cached[4]
+        return p
+
+    semi = check(8, budget, 1)                        # KITTI semi-dense: everything on chip
+    assert all(semi[k] != NONE for k in ("pts", "i0", "gx", "gy", "r", "valid"))
+    dense = check(8, budget, 11)                      # KITTI dense level 0: residuals + points
+    assert dense["r"] != NONE and dense["pts"] != NONE and dense["gx"] == NONE and dense["i0"] == NONE
+    shard = check(8, budget, 6)                       # a 1080p level over 8 GPUs with 6 points per thread: all but I0
+    assert shard["gy"] != NONE and shard["i0"] == NONE
+    shard7 = check(8, budget, 7)                      # ... and with 7 (228 576 points on 148 x 256 threads): still all but I0
+    assert shard7["gy"] != NONE and shard7["i0"] == NONE
+    huge = check(8, budget, 48)                       # dense 1080p level 0 on one GPU: only the 3-D points fit
+    assert huge["pts"] != NONE and all(huge[k] == NONE for k in ("i0", "gx", "gy", "r"))
+    assert all(check(8, budget, 60)[k] == NONE for k in ("pts", "i0", "gx", "gy", "r"))
+    for ch in (1, 8):
+        for need in range(0, 60):
+            for b in (0, 4096, 50000, budget):
+                check(ch, b, need)
