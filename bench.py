@@ -36,6 +36,13 @@ WORKLOADS = {
                   name="kitti_1241x376_bitplanes_8ch_4levels_tukey"),
     "kitti_dense": dict(scene="kitti", descriptor="bitplanes", levels=4, loss="tukey", nms=-1,
                         name="kitti_1241x376_bitplanes_8ch_4levels_tukey_dense"),
+    # the same stream at the tolerances / loss the reference SHIPS for KITTI (conf/kitti_bitplanes.cfg: 5 levels, Huber, pTol 1e-6,
+    # fTol 1e-4, maxIterations 100, key-frame thresholds 1.0 m / 2.5 / 0.6); minSaliency stays at the ctor default 0.1: the
+    # file's 2.5 selects no point at all with the reference's bit-planes saliency (channel 0 only, max 2)
+    "kitti_cfg": dict(scene="kitti", descriptor="bitplanes", levels=5, loss="huber", nms=1,
+                      extra=dict(parameterTolerance=1e-6, functionTolerance=1e-4, maxIterations=100, minTranslationMagToKeyFrame=1.0,
+                                 minRotationMagToKeyFrame=2.5, maxFractionOfGoodPointsToKeyFrame=0.6),
+                      name="kitti_1241x376_bitplanes_8ch_5levels_huber_shipped_tolerances"),
     "vga": dict(scene="vga", descriptor="intensity", levels=4, loss="huber", nms=1,
                 name="vga_640x480_intensity_4levels_huber"),
     "1080p": dict(scene="1080p", descriptor="bitplanes", levels=5, loss="tukey", nms=1,
@@ -57,7 +64,7 @@ def make_params(w):
         descriptor={"intensity": DescriptorType.kIntensity, "bitplanes": DescriptorType.kBitPlanes}[w["descriptor"]],
         numPyramidLevels=w["levels"],
         lossFunction={"tukey": LossFunctionType.kTukey, "huber": LossFunctionType.kHuber, "l2": LossFunctionType.kL2}[w["loss"]],
-        nonMaxSuppRadius=w["nms"], verbosity=VerbosityType.kSilent)
+        nonMaxSuppRadius=w["nms"], verbosity=VerbosityType.kSilent, **w.get("extra", {}))
 
 
 def peaks():

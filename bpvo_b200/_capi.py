@@ -26,6 +26,11 @@ class CResult(C.Structure):
                 ("numFunEvals", C.c_int32), ("numPointCloud", C.c_int32)]
 
 
+class CLinOut(C.Structure):
+    _fields_ = [("H", C.c_float * 36), ("G", C.c_float * 6), ("f_norm", C.c_float), ("sigma", C.c_float),
+                ("n_valid", C.c_int32), ("n_good", C.c_int32), ("solve_ok", C.c_int32), ("scale_path", C.c_int32)]
+
+
 class CCounters(C.Structure):
     _fields_ = [("ms_upload", C.c_double), ("ms_pyramid", C.c_double), ("ms_descriptor", C.c_double),
                 ("ms_template", C.c_double), ("ms_linearize", C.c_double), ("ms_total", C.c_double),
@@ -77,6 +82,9 @@ def _signatures():
         "bpvo_b200_get_residuals": (C.c_int, [vp, fp, szp]),
         "bpvo_b200_get_valid": (C.c_int, [vp, u8p, szp]),
         "bpvo_b200_debug_cache_plan": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint32)]),
+        "bpvo_b200_debug_device_linearize": (C.c_int, [vp, vp, vp, C.c_int, fp, C.c_int, C.POINTER(CLinOut), C.c_int, C.c_int]),
+        "bpvo_b200_debug_set_trace": (C.c_int, [vp, C.c_int]),
+        "bpvo_b200_debug_get_trace": (C.c_int, [vp, fp, C.c_int, ip, C.c_int]),
         "bpvo_b200_point_cloud": (C.c_int, [vp, vp, C.c_void_p, ip]),
         "bpvo_b200_fraction_good": (C.c_int, [vp, C.c_float, fp]),
         "bpvo_b200_comm_unique_id": (C.c_int, [u8p]),

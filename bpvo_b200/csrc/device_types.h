@@ -125,6 +125,22 @@ struct LevelStats {      // OptimizerStatistics (types.h:444-482)
   int   num_evals;       // linearize() calls at this level
 };
 
+// Parity / diagnosis hooks of the persistent kernel (all off in production launches: n == 0, trace == nullptr).
+//   poses / out / n / level : instead of the GN loop, evaluate linearize() `n` times at `level` at the caller's poses
+//                             (no solve, no pose update; scale state reset before the first) and store every LinOut --
+//                             the SAME device_linearize() the GN loop runs (template cache, bracketed median from the
+//                             second evaluation on, flag-in-data exchange), comparable entry by entry with the fine seam
+//   trace                   : one row of kTraceCols floats per linearize of the GN loop
+constexpr int kTraceCols = 8;      // level, eval, f_norm, |dp|, max|G|, sigma, scale re-estimated (0/1) + 2 * bracket hit, status so far
+struct DebugArgs {
+  const M44* poses;
+  LinOut* out;
+  int n, level;
+  float* trace;
+  int trace_cap;         // rows
+  int* trace_rows;       // rows written (device word)
+};
+
 // everything the on-device GN loop needs for one estimatePose
 struct SolveArgs {
   LevelTemplate tmpl[kMaxLevels];
@@ -139,6 +155,7 @@ struct SolveArgs {
   long long* prof;       // optional: per-phase cycle counters of CTA 0 (nullptr = off)
   unsigned seq_base;     // first sequence number of this launch's exchanges (monotonic across launches of a ctx)
   PeerArgs peer;
+  DebugArgs dbg;
 };
 
 }  // namespace bp

@@ -209,7 +209,7 @@ int bpvo_b200_destroy(bpvo_b200_ctx* c) {
   cudaFree(c->work.res); cudaFree(c->work.valid); cudaFree(c->work.hist); cudaFree(c->work.ll); cudaFree(c->work.partials);
   cudaFree(c->work.scale); cudaFree(c->work.out); cudaFree(c->work.ticket); cudaFree(c->work.cand); cudaFree(c->sel); cudaFree(c->export_buf);
   cudaFree(c->flags); cudaFree(c->blur_tmp); cudaFree(c->block_counts); cudaFree(c->hpartials); cudaFree(c->hsums);
-  cudaFree(c->d_T); cudaFree(c->d_stats); cudaFree(c->d_evals); cudaFree(c->d_prof);
+  cudaFree(c->d_T); cudaFree(c->d_stats); cudaFree(c->d_evals); cudaFree(c->d_prof); cudaFree(c->d_trace); cudaFree(c->d_trace_rows);
   cudaFreeHost(c->h_mail); cudaFreeHost(c->stage_img); cudaFreeHost(c->stage_disp);
   if (c->flush_buf) cudaFree(c->flush_buf);
   cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->tm0); cudaEventDestroy(c->tm1); cudaEventDestroy(c->stage_free);
@@ -727,10 +727,19 @@ static int host_run_level(bpvo_b200_ctx* c, const bpvo_b200_frame* ref, const bp
   return BPVO_B200_OK;
 }
 
+// optional overrides of a persistent-kernel launch (parity hooks, bpvo_b200_debug_device_linearize)
+struct SolveOverride {
+  DebugArgs dbg{};
+  int grid = 0;            // 0 = one CTA per SM
+  int cache_bytes = -1;    // -1 = everything the SM has
+};
+
 template <int C>
-static int launch_estimate_pose(bpvo_b200_ctx* c, const bpvo_b200_frame* ref, const bpvo_b200_frame* cur, const M44& T_init) {
+static int launch_estimate_pose(bpvo_b200_ctx* c, const bpvo_b200_frame* ref, const bpvo_b200_frame* cur, const M44& T_init, const SolveOverride* ov = nullptr) {
   SolveArgs a;
   memset(&a, 0, sizeof(a));
+  if (ov) a.dbg = ov->dbg;
+  if (c->d_trace && !(ov && ov->dbg.n > 0)) { a.dbg.trace = c->d_trace; a.dbg.trace_cap = kTraceRows; a.dbg.trace_rows = c->d_trace_rows; }
   for (int l = c->p.maxTestLevel; l < c->L; ++l) {
     a.tmpl[l] = make_level_template(ref, l);
     a.img[l].desc = cur->desc[l]; a.img[l].rows = c->geom[l].rows; a.img[l].cols = c->geom[l].cols;
@@ -745,7 +754,7 @@ static int launch_estimate_pose(bpvo_b200_ctx* c, const bpvo_b200_frame* ref, co
   // the grid-barrier counter (behind the histogram sets) must be zero on entry; the kernel zeroes the sets itself
   CUDA_TRY(cudaMemsetAsync(c->work.hist + (size_t) kHistSets * kHistWords, 0, 8 * sizeof(unsigned), c->stream));
   // sequence numbers of the flag-in-data exchanges: unique per exchange over the life of the mailboxes
-  const unsigned seq_span = (unsigned) (c->L * (std::min(c->p.maxIterations + 2, 1200) + 2) + 2);
+  const unsigned seq_span = (unsigned) (c->L * (std::min(c->p.maxIterations + 2, 1200) + 2) + 2) + (unsigned) (ov ? ov->dbg.n : 0);
   if (c->ll_seq == 0 || c->ll_seq > 0xffffffffu - seq_span) {
     CUDA_TRY(cudaMemsetAsync(c->work.ll, 0, (size_t) 4 * kMaxGrid * 32 * sizeof(uint4), c->stream));
     c->ll_seq = 1;
@@ -770,6 +779,7 @@ static int launch_estimate_pose(bpvo_b200_ctx* c, const bpvo_b200_frame* ref, co
   // kernel plans per level which fields fit)
   int cache_bytes = ((c->smem_optin - 24 * 1024 - kScratchBytes) / 1024) * 1024;
   cache_bytes = std::max(0, cache_bytes);
+  if (ov && ov->cache_bytes >= 0) cache_bytes = std::min(cache_bytes, ov->cache_bytes);
   const size_t dyn = (size_t) kScratchBytes + (size_t) cache_bytes;
   if (c->dyn_configured != dyn) {        // per ctx: the attribute is per device, and a process may drive several
     CUDA_TRY(cudaFuncSetAttribute((const void*) k_estimate_pose<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) dyn));
@@ -777,6 +787,7 @@ static int launch_estimate_pose(bpvo_b200_ctx* c, const bpvo_b200_frame* ref, co
   }
   void* args[] = {&a, &sel, &cache_bytes};
   int grid = std::min(c->sm_count, kMaxGrid);
+  if (ov && ov->grid > 0) grid = std::min(grid, ov->grid);
   CUDA_TRY(cudaLaunchCooperativeKernel((void*) k_estimate_pose<C>, dim3(grid), dim3(kLinThreads), args, dyn, c->stream));
   c->counters.launches++;
   return BPVO_B200_OK;
@@ -910,6 +921,70 @@ extern "C" int bpvo_b200_point_cloud(bpvo_b200_ctx* c, const bpvo_b200_frame* re
   CUDA_TRY(cudaMemcpyAsync(records, d, (size_t) np * sizeof(PointInfo), cudaMemcpyDeviceToHost, c->stream));
   CUDA_TRY(cudaStreamSynchronize(c->stream));
   c->counters.d2h_bytes += (int64_t) np * sizeof(PointInfo);
+  return BPVO_B200_OK;
+}
+
+// Parity hook: `n` consecutive linearize() evaluations of one level THROUGH THE PERSISTENT KERNEL at the caller's poses
+// (see DebugArgs in device_types.h).  Residuals / valid flags / weights of the last one are then served by get_residuals & co.
+extern "C" int bpvo_b200_debug_device_linearize(bpvo_b200_ctx* c, const bpvo_b200_frame* ref, const bpvo_b200_frame* cur, int level,
+                                                 const float* T, int n, bpvo_b200_lin_out* out, int grid_ctas, int cache_bytes) {
+  static_assert(sizeof(bpvo_b200_lin_out) == sizeof(LinOut), "bpvo_b200_lin_out mirrors LinOut");
+  int rc = check_pair(c, ref, cur); if (rc) return rc;
+  if (level < c->p.maxTestLevel || level >= c->L || !T || !out || n <= 0 || n > 1024) return bp_fail(BPVO_B200_ERR_INVALID_ARG, "bad level / poses / count");
+  if (!c->coop) return bp_fail(BPVO_B200_ERR_UNSUPPORTED, "device without cooperative launch");
+  CUDA_TRY(cudaSetDevice(c->p.device_id));
+  M44* d_poses = nullptr; LinOut* d_out = nullptr;
+  CUDA_TRY(cudaMalloc(&d_poses, (size_t) n * sizeof(M44)));
+  cudaError_t e = cudaMalloc(&d_out, (size_t) n * sizeof(LinOut));
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_poses, T, (size_t) n * sizeof(M44), cudaMemcpyHostToDevice, c->stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(d_out, 0, (size_t) n * sizeof(LinOut), c->stream);
+  if (e == cudaSuccess) {
+    SolveOverride ov;
+    ov.dbg.poses = d_poses; ov.dbg.out = d_out; ov.dbg.n = n; ov.dbg.level = level;
+    ov.grid = grid_ctas; ov.cache_bytes = cache_bytes;
+    M44 T0; memcpy(T0.m, T, sizeof(T0.m));
+    rc = (c->C == 1) ? launch_estimate_pose<1>(c, ref, cur, T0, &ov) : launch_estimate_pose<8>(c, ref, cur, T0, &ov);
+    if (rc == BPVO_B200_OK) {
+      e = cudaMemcpyAsync(out, d_out, (size_t) n * sizeof(LinOut), cudaMemcpyDeviceToHost, c->stream);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(&c->h_mail->lin, c->work.out, sizeof(LinOut), cudaMemcpyDeviceToHost, c->stream);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(c->h_mail->stats, c->d_stats, kMaxLevels * sizeof(LevelStats), cudaMemcpyDeviceToHost, c->stream);
+    }
+  }
+  cudaError_t e2 = cudaStreamSynchronize(c->stream);
+  cudaFree(d_poses); cudaFree(d_out);
+  if (rc) return rc;
+  if (e != cudaSuccess || e2 != cudaSuccess) return bp_fail(BPVO_B200_ERR_CUDA, "debug_device_linearize failed: %s", cudaGetErrorString(e != cudaSuccess ? e : e2));
+  if (c->h_mail->stats[level].status == -4) return bp_fail(BPVO_B200_ERR_CUDA, "on-device GN loop: a grid barrier / exchange timed out");
+  if (c->h_mail->stats[level].status == -3) return bp_fail(BPVO_B200_ERR_NO_POINTS, "you should call setData before calling computeResiduals");
+  c->last_ref = ref; c->last_level = level;
+  return BPVO_B200_OK;
+}
+
+// Diagnosis hook: per-linearize trace of the on-device GN loop (level, eval, f_norm, |dp|, max|G|, sigma, scale path, status)
+extern "C" int bpvo_b200_debug_set_trace(bpvo_b200_ctx* c, int enable) {
+  if (!c) return bp_fail(BPVO_B200_ERR_INVALID_ARG, "null ctx");
+  CUDA_TRY(cudaSetDevice(c->p.device_id));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  if (enable && !c->d_trace) {
+    CUDA_TRY(cudaMalloc(&c->d_trace, (size_t) kTraceRows * kTraceCols * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&c->d_trace_rows, sizeof(int)));
+  }
+  if (!enable && c->d_trace) { cudaFree(c->d_trace); cudaFree(c->d_trace_rows); c->d_trace = nullptr; c->d_trace_rows = nullptr; }
+  if (c->d_trace) CUDA_TRY(cudaMemset(c->d_trace_rows, 0, sizeof(int)));
+  return BPVO_B200_OK;
+}
+extern "C" int bpvo_b200_debug_get_trace(bpvo_b200_ctx* c, float* rows, int max_rows, int* n_rows, int reset) {
+  if (!c || !n_rows) return bp_fail(BPVO_B200_ERR_INVALID_ARG, "null argument");
+  *n_rows = 0;
+  if (!c->d_trace) return BPVO_B200_OK;
+  CUDA_TRY(cudaSetDevice(c->p.device_id));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  int n = 0;
+  CUDA_TRY(cudaMemcpy(&n, c->d_trace_rows, sizeof(int), cudaMemcpyDeviceToHost));
+  n = std::min(n, kTraceRows);
+  *n_rows = n;
+  if (rows && max_rows > 0) CUDA_TRY(cudaMemcpy(rows, c->d_trace, (size_t) std::min(n, max_rows) * kTraceCols * sizeof(float), cudaMemcpyDeviceToHost));
+  if (reset) CUDA_TRY(cudaMemset(c->d_trace_rows, 0, sizeof(int)));
   return BPVO_B200_OK;
 }
 

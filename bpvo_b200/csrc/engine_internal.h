@@ -22,6 +22,8 @@ struct Mailbox {          // pinned host memory the device results land in
   int evals;
 };
 
+constexpr int kTraceRows = 8192;   // rows of the GN-loop trace buffer (bpvo_b200_debug_set_trace)
+
 struct bpvo_b200_frame;
 
 struct bpvo_b200_ctx {
@@ -38,6 +40,7 @@ struct bpvo_b200_ctx {
   float* export_buf = nullptr;
   uint8_t* flags = nullptr; uint8_t* blur_tmp = nullptr; int* block_counts = nullptr; double* hpartials = nullptr;
   bp::M44* d_T = nullptr; bp::LevelStats* d_stats = nullptr; int* d_evals = nullptr; long long* d_prof = nullptr;
+  float* d_trace = nullptr; int* d_trace_rows = nullptr;   // bpvo_b200_debug_set_trace
   Mailbox* h_mail = nullptr;
   uint8_t* stage_img = nullptr; float* stage_disp = nullptr;
   void* flush_buf = nullptr;

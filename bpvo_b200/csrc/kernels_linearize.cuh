@@ -1253,6 +1253,7 @@ __device__ __forceinline__ void device_linearize(const SolveArgs& a, int lvl, So
   // with the next iteration's barrier in between (all sets are zero at the start of a level)
   unsigned* hprev = a.work.hist + (size_t) ((gs.hs + kHistSets - 1) % kHistSets) * kHistWords;
   const bool do_hist = (a.sp.loss != 0x12) && (ss.delta > 1e-6f);      // ss.P was set by thread 0 together with the pose
+  if (tid == 0) ss.lin.pad[1] = do_hist ? 1 : 0;                       // diagnosis: 0 = scale kept, 1 = radix select, 3 = bracketed select
   BP_PROF(PROF_OTHER);
   Bracket br;
   br.on = do_hist && ss.br_on;
@@ -1323,6 +1324,7 @@ __device__ __forceinline__ void device_linearize(const SolveArgs& a, int lvl, So
         rel = fminf(fmaxf(rel, 1e-5f), 0.06f);
       }
       ss.br_rel = rel; ss.br_lo = lo; ss.br_hi = hi; ss.br_on = (n >= 3) ? 1 : 0;
+      if (hit) ss.lin.pad[1] = 3;
       if (a.prof && blk == 0) { long long* sp = prof_smem(); sp[12] += hit ? 1 : 0; sp[13] += 1; sp[14] += (br.on && !hit && ncand >= kCandPoison) ? 1 : 0; sp[15] += (br.on && !hit && ncand < kCandPoison) ? 1 : 0; }
     }
     __syncthreads();
@@ -1371,6 +1373,7 @@ __global__ void __launch_bounds__(kLinThreads, 1) k_estimate_pose(const __grid_c
   __syncthreads();
   const float sqrt_eps = sqrtf(FLT_EPSILON);
   for (int lvl = a.sp.num_levels - 1; lvl >= a.sp.max_test_level; --lvl) {
+    if (a.dbg.n > 0 && lvl != a.dbg.level) continue;                           // parity hook: one level only
     const LevelTemplate& L = a.tmpl[lvl];
     // PoseEstimatorBase::run (pose_estimator_base.h:324-407); all control flow below is CTA-uniform AND grid-uniform
     if (tid == 0) {                                                            // reset() :287-293
@@ -1398,8 +1401,19 @@ __global__ void __launch_bounds__(kLinThreads, 1) k_estimate_pose(const __grid_c
     // linearize, are computed by thread 0 right after the solve.
     bool first = true, conv = false;
     for (;;) {
+      if (a.dbg.n > 0) {                                                       // parity hook: the caller's pose, no solve
+        if (tid == 0) { ss.Td = a.dbg.poses[n_evals]; make_projection(L, ss.Td, ss.P); }
+        __syncthreads();
+      }
       device_linearize<C>(a, lvl, ss, sh, tc, meta, scratch, gs, sel); ++n_evals;
       f_norm = ss.lin.f_norm;
+      if (a.dbg.n > 0) {
+        if (blockIdx.x == 0 && tid == 0) a.dbg.out[n_evals - 1] = ss.lin;
+        g_norm = 0.0f; status = 0x33; it = n_evals;
+        __syncthreads();
+        if (n_evals < a.dbg.n) continue;
+        early = true; break;
+      }
       if (first) {
         g_norm = 0.0f; for (int k = 0; k < 6; ++k) g_norm = fmaxf(g_norm, fabsf(ss.lin.G[k]));
         g_tol = a.sp.gradient_tolerance * fmaxf(g_norm, sqrt_eps);
@@ -1447,6 +1461,13 @@ __global__ void __launch_bounds__(kLinThreads, 1) k_estimate_pose(const __grid_c
       else if (f_norm < a.sp.function_tolerance || f_norm < a.sp.function_tolerance * (sqrt_eps + f_prev) ||
                fabsf(f_norm - f_prev) < a.sp.function_tolerance) { status = 0x31; conv = true; }
       else if (g_norm < g_tol) { status = 0x32; conv = true; }
+      if (a.dbg.trace && blockIdx.x == 0 && tid == 0) {
+        const int row = atomicAdd(a.dbg.trace_rows, 1);
+        if (row < a.dbg.trace_cap) {
+          float* t = a.dbg.trace + (size_t) row * kTraceCols;
+          t[0] = (float) lvl; t[1] = (float) n_evals; t[2] = f_norm; t[3] = dpn; t[4] = g_norm; t[5] = ss.lin.sigma; t[6] = (float) ss.lin.pad[1]; t[7] = (float) status;
+        }
+      }
       dp_prev = dpn; f_prev = f_norm;
       BP_FINE(29);
       BP_PROF(PROF_SOLVE);
@@ -1464,7 +1485,7 @@ __global__ void __launch_bounds__(kLinThreads, 1) k_estimate_pose(const __grid_c
     }
     total_evals += n_evals;
     // residuals / valid flags of the last linearize of the finest level go back to global memory for getWeights() & co.
-    if (tc.f[TC_R] != kTcNone && C == 8 && lvl == a.sp.max_test_level) {
+    if (tc.f[TC_R] != kTcNone && C == 8 && (lvl == a.sp.max_test_level || a.dbg.n > 0)) {
       int k = 0;
       for (int i = first_point(blockIdx.x, gridDim.x); i < meta.n; i += gridDim.x * kLinThreads, ++k) {
         VecC<C> r; tc_get<C>(tc, k, TC_R, r);

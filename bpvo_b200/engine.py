@@ -106,6 +106,27 @@ class Context:
         out = [OptimizerStatistics(s.numIterations, s.finalError, s.firstOrderOptimality, s.status) for s in stats[:L]]
         return _from_colmajor(T, 4), out, ev.value
 
+    def debug_device_linearize(self, ref: "Frame", cur: "Frame", level: int, poses, grid_ctas: int = 0, cache_bytes: int = -1):
+        """parity hook: len(poses) consecutive linearize() evaluations of `level` INSIDE the persistent kernel
+        (bpvo_b200_debug_device_linearize); -> one dict per evaluation, same keys as linearize() + scale_path"""
+        n = len(poses)
+        buf = np.concatenate([_colmajor(T) for T in poses]).astype(np.float32)
+        out = (_capi.CLinOut * n)()
+        _check(self._lib.bpvo_b200_debug_device_linearize(self.h, ref.h, cur.h, level, _fp(buf), n, out, int(grid_ctas), int(cache_bytes)))
+        return [dict(f_norm=o.f_norm, H=_from_colmajor(o.H, 6), G=np.array(o.G, np.float32), sigma=o.sigma, n_valid=o.n_valid,
+                     n_good=o.n_good, scale_path=o.scale_path) for o in out]
+
+    def set_trace(self, on: bool):
+        _check(self._lib.bpvo_b200_debug_set_trace(self.h, int(on)))
+
+    def get_trace(self, reset: bool = True):
+        """rows {level, eval, f_norm, |dp|, max|G|, sigma, scale_path, status} of the GN loop since the last reset"""
+        n = C.c_int32()
+        _check(self._lib.bpvo_b200_debug_get_trace(self.h, None, 0, C.byref(n), 0))
+        rows = np.zeros((max(n.value, 1), 8), np.float32)
+        _check(self._lib.bpvo_b200_debug_get_trace(self.h, _fp(rows), n.value, C.byref(n), int(reset)))
+        return rows[:n.value]
+
     def _vec(self, fn, dtype=np.float32):
         n = C.c_size_t(0)
         _check(fn(self.h, None, C.byref(n)))

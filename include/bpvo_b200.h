@@ -267,6 +267,22 @@ int bpvo_b200_timer_start(bpvo_b200_ctx* ctx);
 int bpvo_b200_timer_stop(bpvo_b200_ctx* ctx, float* ms);
 /* linearize() evaluations per pyramid level of the last estimate_pose (numLevels ints) */
 int bpvo_b200_last_level_evals(bpvo_b200_ctx* ctx, int* evals);
+/* Parity hooks of the on-device GN loop (the kernel bpvo_b200_estimate_pose launches; no reference counterpart).
+ * debug_device_linearize: `n` consecutive PoseEstimatorGN::linearize evaluations (pose_estimator_gn.h:70-81) of `level`
+ * executed INSIDE that persistent kernel at the caller's poses T[0..n) (16 floats each, column-major) -- its shared-memory
+ * template cache, its bracketed exact median (from the 2nd evaluation on), its flag-in-data exchange of the sums -- with no
+ * solve and no pose update; the scale-estimator state is reset before the first.  out[e] must equal what e + 1 calls of
+ * bpvo_b200_linearize (first_call_of_level on the first) return; get_residuals / get_valid / get_weights then serve the
+ * last evaluation.  grid_ctas (0 = one CTA per SM) and cache_bytes (-1 = all shared memory) force the multi-slot and
+ * partially-cached code paths at small sizes.  scale_path: 0 = scale kept, 1 = radix select, 3 = bracketed select. */
+typedef struct { float H[36]; float G[6]; float f_norm; float sigma; int32_t n_valid; int32_t n_good; int32_t solve_ok; int32_t scale_path; } bpvo_b200_lin_out;
+int bpvo_b200_debug_device_linearize(bpvo_b200_ctx* ctx, const bpvo_b200_frame* ref, const bpvo_b200_frame* cur, int level,
+                                     const float* T, int n, bpvo_b200_lin_out* out, int grid_ctas, int cache_bytes);
+/* per-linearize trace of the GN loop inside bpvo_b200_estimate_pose: rows of 8 floats {level, evaluation, f_norm, |dp|,
+ * max|G|, sigma, scale_path, status so far}, what PoseEstimatorBase::run prints at verbosity kIteration
+ * (pose_estimator_base.h:231-247).  set_trace(1) allocates and clears the buffer (8192 rows), set_trace(0) frees it. */
+int bpvo_b200_debug_set_trace(bpvo_b200_ctx* ctx, int enable);
+int bpvo_b200_debug_get_trace(bpvo_b200_ctx* ctx, float* rows, int max_rows, int* n_rows, int reset);
 /* the on-device GN loop's shared-memory plan for a level whose threads own `slots_needed` points each, given
  * `cache_bytes` of dynamic shared memory: byte offsets of {points, I0, gx, gy, residuals, valid flags}
  * (0xffffffff = that field stays in global memory), slots, offset of the cache area.  Host-side evaluation of the

@@ -920,6 +920,8 @@ struct orc_estimator {
   std::vector<double> xy;
   float f_norm_prev = 0.0f, g_tol = 0.0f; int num_fun_evals = 0; int total_fun_evals = 0;
   float last_sigma = 1.0f;
+  std::vector<float> trace; bool trace_on = false;    // rows {level, eval, f_norm, |dp|, max|G|, sigma, converged, status}: what
+                                                       // run() prints at verbosity kIteration (pose_estimator_base.h:231-247)
   explicit orc_estimator(const orc_params& p) : params(p) {}
 
   void reset() { scale.reset(); f_norm_prev = 0.0f; g_tol = 0.0f; num_fun_evals = 0; }   // pose_estimator_base.h:287-293
@@ -967,6 +969,7 @@ struct orc_estimator {
       float dp_norm = 0; for (int i = 0; i < 6; ++i) dp_norm += dp[i]*dp[i]; dp_norm = std::sqrt(dp_norm);
       g_norm = gnorm();
       has_converged = test_convergence(dp_norm, dp_norm_prev, g_norm, f_norm, ret.status);
+      if (trace_on) { const float row[8] = {(float) td.level, (float) num_fun_evals, f_norm, dp_norm, g_norm, last_sigma, has_converged ? 1.0f : 0.0f, (float) ret.status}; trace.insert(trace.end(), row, row + 8); }
       dp_norm_prev = dp_norm; f_norm_prev = f_norm;
       if (!has_converged) {                            // runIteration (pose_estimator_gn.h:83-100)
         f_norm = linearize(td, desc, dT, H, G);
@@ -1114,6 +1117,12 @@ void orc_frame_normalization(const orc_frame* f, int l, float Tn[16]) { memcpy(T
 
 orc_estimator* orc_estimator_create(const orc_params* p) { return new orc_estimator(*p); }
 void orc_estimator_destroy(orc_estimator* e) { delete e; }
+void orc_estimator_set_trace(orc_estimator* e, int on) { e->trace_on = on != 0; e->trace.clear(); }
+int orc_estimator_get_trace(orc_estimator* e, float* rows, int max_rows) {
+  const int n = (int) (e->trace.size() / 8);
+  if (rows) memcpy(rows, e->trace.data(), sizeof(float) * 8 * (size_t) std::min(n, max_rows));
+  return n;
+}
 float orc_linearize(orc_estimator* e, const orc_frame* ref, const orc_frame* cur, int level, const float T[16],
                     int reset_scale, float H[36], float G[6], float* sigma) {
   ORC_TRY

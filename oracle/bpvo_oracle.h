@@ -139,6 +139,10 @@ const uint16_t* orc_estimator_valid(const orc_estimator*);          /* replicate
 int  orc_estimate_pose(orc_estimator*, const orc_frame* ref, const orc_frame* cur,
                        const float T_init[16], float T_est[16], orc_stats* stats /*numLevels*/);
 float orc_fraction_good(const orc_estimator*, float thresh);        /* vo_pose_estimator.cc:101-107 */
+/* per-iteration trace of run(): rows of 8 floats {level, eval, f_norm, |dp|, max|G|, sigma, converged, status} = the table
+ * PoseEstimatorBase::run prints at verbosity kIteration (pose_estimator_base.h:231-247, 295-299) */
+void orc_estimator_set_trace(orc_estimator*, int on);
+int  orc_estimator_get_trace(orc_estimator*, float* rows, int max_rows);
 
 /* ---- VisualOdometry level (bpvo/vo.cc:94-281) ---- */
 typedef struct orc_vo orc_vo;

@@ -93,6 +93,8 @@ def lib():
         "orc_estimator_valid": (C.POINTER(C.c_uint16), [vp]),
         "orc_estimate_pose": (C.c_int, [vp, vp, vp, fp, fp, C.POINTER(OrcStats)]),
         "orc_fraction_good": (C.c_float, [vp, C.c_float]),
+        "orc_estimator_set_trace": (None, [vp, C.c_int]),
+        "orc_estimator_get_trace": (C.c_int, [vp, fp, C.c_int]),
         "orc_vo_create": (vp, [fp, C.c_float, C.c_int, C.c_int, C.POINTER(OrcParams)]),
         "orc_vo_destroy": (None, [vp]),
         "orc_vo_add_frame": (C.c_int, [vp, u8p, fp, C.POINTER(OrcResult)]),
@@ -341,6 +343,16 @@ class Estimator:
 
     def fraction_good(self, thresh):
         return float(lib().orc_fraction_good(self.h, float(thresh)))
+
+    def set_trace(self, on=True):
+        lib().orc_estimator_set_trace(self.h, int(on))
+
+    def get_trace(self):
+        """rows {level, eval, f_norm, |dp|, max|G|, sigma, converged, status} of run() since set_trace(True)"""
+        n = lib().orc_estimator_get_trace(self.h, None, 0)
+        rows = np.zeros((max(n, 1), 8), np.float32)
+        lib().orc_estimator_get_trace(self.h, _fp(rows), n)
+        return rows[:n]
 
 
 class VisualOdometry:

@@ -22,6 +22,8 @@ def _scene(kind):
         return synth.scene_vga()
     if kind == "kitti":
         return synth.scene_kitti()
+    if kind == "1080p":
+        return synth.scene_1080p()
     raise ValueError(kind)
 
 
