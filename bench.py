@@ -135,14 +135,31 @@ def _cpu_vo(w, sc, p, nthreads):
 
 
 def _time_cpu(vo, ptrs, first, count):
+    """-> (seconds, linearize evaluations or None).  The reference's Result carries no evaluation count (only the statistics of
+    the LAST estimatePose of a frame: a key-frame's first solve is invisible); see _count_evals for the exact number."""
     from oracle import pyoracle as po
     res = po.OrcResult()
-    evals = 0
+    evals, known = 0, True
     t0 = time.perf_counter()
     for k in range(first, first + count):
         vo.add_frame_raw(ptrs[k][0], ptrs[k][1], res)
-        evals += sum(res.stats[i].numIterations + 1 for i in range(res.numLevels)) if res.numFunEvals == 0 else res.numFunEvals
-    return time.perf_counter() - t0, evals
+        known = known and res.numFunEvals > 0
+        evals += res.numFunEvals
+    return time.perf_counter() - t0, (evals if known else None)
+
+
+def _count_evals(sc, p, ptrs, first, count):
+    """exact GN-iteration count of the reference on frames [first, first + count): the oracle port (bit-identical poses,
+    per-level iteration counts and key-frame decisions, tests/test_oracle_vs_reference.py) counts every linearize(); untimed"""
+    from oracle import pyoracle as po
+    vo = po.VisualOdometry(sc.K, sc.baseline, (sc.rows, sc.cols), p, use_rcp=1, num_threads=max(1, min(os.cpu_count() or 1, 8)))
+    res = po.OrcResult()
+    evals = 0
+    for k in range(first + count):
+        vo.add_frame_raw(ptrs[k][0], ptrs[k][1], res)
+        if k >= first:
+            evals += res.numFunEvals
+    return evals
 
 
 def run_reference(args, w, rank, world):
@@ -171,12 +188,14 @@ def run_reference(args, w, rank, world):
     vo, kind, note = _cpu_vo(w, sc, p, nthreads)
     _time_cpu(vo, ptrs, 0, args.warmup + 1)
     dt, evals = _time_cpu(vo, ptrs, args.warmup + 1, args.steps)
+    if evals is None:
+        evals = _count_evals(sc, p, ptrs, args.warmup + 1, args.steps)
     fps = args.steps / dt
     line = {
         "impl": "reference", "metric": "frames_per_sec", "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32 (fp64 projection + bilinear blend)", "data": "synthetic",
-        "gn_iters_per_sec": evals / dt,
+        "gn_iters_per_sec": evals / dt, "gn_iters_per_frame": evals / float(args.steps),
         "config": {"workload": w["name"], "streams": 1, "rows": sc.rows, "cols": sc.cols, "note": note},
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": nthreads, "kind": kind, "host_cores": ncpu,
                          "sample": f"{args.steps} consecutive addFrame calls of the same synthetic stream, {nthreads} thread(s) "
@@ -473,15 +492,17 @@ def cpu_baseline(w, args):
     sc = make_scene(w, 0xB200)
     p = make_params(w)
     vo, kind, note = _cpu_vo(w, sc, p, 1)
-    budget_s = 15.0
+    budget_s = 10.0
     frames = [sc.render(k) for k in range(49)]
     ptrs = [(f[0].ctypes.data_as(C.POINTER(C.c_uint8)), f[1].ctypes.data_as(C.POINTER(C.c_float))) for f in frames]
     _time_cpu(vo, ptrs, 0, 1)
     t_used, n, evals = 0.0, 0, 0
     while t_used < budget_s and n < 48:
         dt, ev = _time_cpu(vo, ptrs, 1 + n, 1)
-        t_used += dt; n += 1; evals += ev
-    return {"value": n / t_used, "unit": "frames/s", "cores": 1, "kind": kind, "gn_iters_per_sec": evals / t_used, "note": note,
+        t_used += dt; n += 1; evals = None if (ev is None or evals is None) else evals + ev
+    if evals is None:
+        evals = _count_evals(sc, p, ptrs, 1, n)
+    return {"value": n / t_used, "unit": "frames/s", "cores": 1, "kind": kind, "gn_iters_per_sec": evals / t_used, "gn_iters_per_frame": evals / float(n), "note": note,
             "sample": f"first {n} addFrame calls of the same synthetic stream ({t_used:.1f} s of CPU work), single thread = reference default build"}
 
 

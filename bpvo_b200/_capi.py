@@ -101,6 +101,8 @@ def _signatures():
         "bpvo_b200_timer_start": (C.c_int, [vp]),
         "bpvo_b200_timer_stop": (C.c_int, [vp, fp]),
         "bpvo_b200_last_level_evals": (C.c_int, [vp, ip]),
+        "bpvo_b200_last_level_us": (C.c_int, [vp, fp]),
+        "bpvo_b200_get_level_phase_cycles": (C.c_int, [vp, C.POINTER(C.c_longlong), C.c_int]),
         "bpvo_b200_host_alloc": (C.c_void_p, [C.c_size_t]),
         "bpvo_b200_host_free": (None, [C.c_void_p]),
         "bpvo_b200_time_linearize": (C.c_int, [vp, vp, vp, C.c_int, fp, C.c_int, C.c_int, fp]),

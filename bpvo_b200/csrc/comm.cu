@@ -145,6 +145,7 @@ int bpvo_b200_peer_init(bpvo_b200_ctx* c, const uint8_t* handles) {
     c->xpeer[r] = (uint2*) p;
   }
   c->peer_mode = true; c->x_seq = c->x_seq_init ? c->x_seq_init : 1;
+  if (!getenv("BPVO_B200_TIMEOUT_MS")) c->timeout_ns = 60000000000ull;      // a peer PROCESS may be seconds behind
   return BPVO_B200_OK;
 }
 

@@ -85,7 +85,8 @@ struct LinOut {
 struct Work {
   float* res;            // [N][C] residuals of the last linearize (point-major; 0 for invalid points)
   uint8_t* valid;        // [N]
-  unsigned* hist;        // kHistSets x kHistWords, followed by 8 words: [0] grid-barrier counter of the persistent kernel
+  unsigned* hist;        // kHistSets x kHistWords, followed by 8 words ([0] grid-barrier counter of the persistent kernel) and
+                         // 2 x 32 u64 accumulator words of its fixed-point exchange (never reset, see fixed_exchange)
   uint4* ll;             // flag-in-data mailboxes of the persistent kernel: [2][kMaxGrid][32] CTA sums, then [2][kMaxGrid][32] group sums
   double* partials;      // [grid][kPartialStride]
   ScaleState* scale;
@@ -123,6 +124,7 @@ struct LevelStats {      // OptimizerStatistics (types.h:444-482)
   float first_order_optimality;
   int   status;
   int   num_evals;       // linearize() calls at this level
+  float us;              // device time spent in this level (globaltimer of CTA 0), microseconds
 };
 
 // Parity / diagnosis hooks of the persistent kernel (all off in production launches: n == 0, trace == nullptr).
@@ -152,8 +154,11 @@ struct SolveArgs {
   M44* T_out;
   LevelStats* stats;     // [num_levels]
   int* num_fun_evals;
+  int* aborted_out;      // receives the rank-wide abort word (an in-kernel wait expired)
   long long* prof;       // optional: per-phase cycle counters of CTA 0 (nullptr = off)
+  long long* prof_lvl;   // optional: the same, split by pyramid level [kMaxLevels][16]
   unsigned seq_base;     // first sequence number of this launch's exchanges (monotonic across launches of a ctx)
+  unsigned long long timeout_ns;   // every in-kernel wait gives up this long after the launch started (AbortCtl)
   PeerArgs peer;
   DebugArgs dbg;
 };

@@ -134,7 +134,8 @@ int bpvo_b200_create(bpvo_b200_ctx** out, const float K[9], float baseline, int 
   bpvo_b200_ctx* c = new bpvo_b200_ctx();
   c->p = *p; c->rows = rows; c->cols = cols;
   c->L = p->numPyramidLevels; c->baseline = baseline;
-  if (getenv("BPVO_B200_NO_GRAPHS")) c->p.flags |= BPVO_B200_FLAG_NO_GRAPHS;      // A/B switch for measurements
+  if (getenv("BPVO_B200_NO_GRAPHS")) c->p.flags |= BPVO_B200_FLAG_NO_GRAPHS;      // A/B switches for measurements
+  if (getenv("BPVO_B200_FAST_BLEND")) c->p.flags |= BPVO_B200_FLAG_FAST_BLEND;
   // test hook: start the exchange sequence numbers close to their wrap-around so that the reset paths get exercised
   if (const char* e = getenv("BPVO_B200_SEQ_INIT")) { c->ll_seq = (unsigned) strtoul(e, nullptr, 0); c->x_seq_init = c->ll_seq; }
   c->C = (p->descriptor == BPVO_B200_BITPLANES) ? 8 : 1;
@@ -164,19 +165,20 @@ int bpvo_b200_create(bpvo_b200_ctx** out, const float K[9], float baseline, int 
   (void) cap0;
   CUDA_TRY(cudaMalloc(&c->work.res, capmax * c->C * sizeof(float)));
   CUDA_TRY(cudaMalloc(&c->work.valid, capmax));
-  CUDA_TRY(cudaMalloc(&c->work.hist, (kHistSets * kHistWords + 8) * sizeof(unsigned)));
+  CUDA_TRY(cudaMalloc(&c->work.hist, (kHistSets * kHistWords + 8 + 128) * sizeof(unsigned)));
   CUDA_TRY(cudaMalloc(&c->work.ll, (size_t) 4 * kMaxGrid * 32 * sizeof(uint4)));
   CUDA_TRY(cudaMemsetAsync(c->work.ll, 0, (size_t) 4 * kMaxGrid * 32 * sizeof(uint4), c->stream));
   CUDA_TRY(cudaMalloc(&c->work.partials, (size_t) 1024 * kPartialStride * sizeof(double)));
   CUDA_TRY(cudaMalloc(&c->work.scale, sizeof(ScaleState)));
-  CUDA_TRY(cudaMalloc(&c->work.out, sizeof(LinOut)));
+  CUDA_TRY(cudaMalloc(&c->d_mail, sizeof(Mailbox)));
+  CUDA_TRY(cudaMemsetAsync(c->d_mail, 0, sizeof(Mailbox), c->stream));
+  c->work.out = &c->d_mail->lin;
   CUDA_TRY(cudaMalloc(&c->work.ticket, 4 * sizeof(unsigned)));
   CUDA_TRY(cudaMalloc(&c->work.cand, ((size_t) kMaxGrid * kCandPerCta + kOvfCap) * sizeof(float)));
   CUDA_TRY(cudaMalloc(&c->sel, sizeof(Sel)));
   CUDA_TRY(cudaMalloc(&c->export_buf, capmax * c->C * 6 * sizeof(float)));
-  CUDA_TRY(cudaMemsetAsync(c->work.hist, 0, (kHistSets * kHistWords + 8) * sizeof(unsigned), c->stream));
+  CUDA_TRY(cudaMemsetAsync(c->work.hist, 0, (kHistSets * kHistWords + 8 + 128) * sizeof(unsigned), c->stream));
   CUDA_TRY(cudaMemsetAsync(c->work.ticket, 0, 4 * sizeof(unsigned), c->stream));
-  CUDA_TRY(cudaMemsetAsync(c->work.out, 0, sizeof(LinOut), c->stream));
   CUDA_TRY(cudaMemsetAsync(c->sel, 0, sizeof(Sel), c->stream));
   k_reset_scale<<<1, 1, 0, c->stream>>>(c->work.scale);
   // template-build scratch (sized for level maxTestLevel = the largest one built)
@@ -187,11 +189,9 @@ int bpvo_b200_create(bpvo_b200_ctx** out, const float K[9], float baseline, int 
   CUDA_TRY(cudaMalloc(&c->hpartials, 1024 * 4 * sizeof(double)));
   CUDA_TRY(cudaMalloc(&c->hsums, 4 * sizeof(double)));
   // device outputs of estimate_pose + pinned mailboxes
-  CUDA_TRY(cudaMalloc(&c->d_T, sizeof(M44)));
-  CUDA_TRY(cudaMalloc(&c->d_stats, kMaxLevels * sizeof(LevelStats)));
-  CUDA_TRY(cudaMalloc(&c->d_evals, sizeof(int)));
-  CUDA_TRY(cudaMalloc(&c->d_prof, 64 * sizeof(long long)));
-  CUDA_TRY(cudaMemsetAsync(c->d_prof, 0, 64 * sizeof(long long), c->stream));
+  if (const char* e = getenv("BPVO_B200_TIMEOUT_MS")) c->timeout_ns = (unsigned long long) strtoull(e, nullptr, 0) * 1000000ull;
+  CUDA_TRY(cudaMalloc(&c->d_prof, (64 + kMaxLevels * 16) * sizeof(long long)));      // [64] whole launch, then [level][16]
+  CUDA_TRY(cudaMemsetAsync(c->d_prof, 0, (64 + kMaxLevels * 16) * sizeof(long long), c->stream));
   CUDA_TRY(cudaHostAlloc(&c->h_mail, sizeof(Mailbox), cudaHostAllocDefault));
   memset(c->h_mail, 0, sizeof(Mailbox));
   CUDA_TRY(cudaHostAlloc(&c->stage_img, (size_t) rows * cols, cudaHostAllocDefault));
@@ -207,9 +207,9 @@ int bpvo_b200_destroy(bpvo_b200_ctx* c) {
   cudaStreamSynchronize(c->stream);
   bp_comm_destroy(c);
   cudaFree(c->work.res); cudaFree(c->work.valid); cudaFree(c->work.hist); cudaFree(c->work.ll); cudaFree(c->work.partials);
-  cudaFree(c->work.scale); cudaFree(c->work.out); cudaFree(c->work.ticket); cudaFree(c->work.cand); cudaFree(c->sel); cudaFree(c->export_buf);
+  cudaFree(c->work.scale); cudaFree(c->d_mail); cudaFree(c->work.ticket); cudaFree(c->work.cand); cudaFree(c->sel); cudaFree(c->export_buf);
   cudaFree(c->flags); cudaFree(c->blur_tmp); cudaFree(c->block_counts); cudaFree(c->hpartials); cudaFree(c->hsums);
-  cudaFree(c->d_T); cudaFree(c->d_stats); cudaFree(c->d_evals); cudaFree(c->d_prof); cudaFree(c->d_trace); cudaFree(c->d_trace_rows);
+  cudaFree(c->d_prof); cudaFree(c->d_trace); cudaFree(c->d_trace_rows);
   cudaFreeHost(c->h_mail); cudaFreeHost(c->stage_img); cudaFreeHost(c->stage_disp);
   if (c->flush_buf) cudaFree(c->flush_buf);
   cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->tm0); cudaEventDestroy(c->tm1); cudaEventDestroy(c->stage_free);
@@ -246,6 +246,19 @@ int bpvo_b200_get_phase_cycles(bpvo_b200_ctx* c, long long cycles[64], int reset
   CUDA_TRY(cudaStreamSynchronize(c->stream));
   CUDA_TRY(cudaMemcpy(cycles, c->d_prof, 64 * sizeof(long long), cudaMemcpyDeviceToHost));
   if (reset) CUDA_TRY(cudaMemset(c->d_prof, 0, 64 * sizeof(long long)));
+  return BPVO_B200_OK;
+}
+int bpvo_b200_get_level_phase_cycles(bpvo_b200_ctx* c, long long* cycles /* [BPVO_B200_MAX_LEVELS][16] */, int reset) {
+  if (!c || !cycles) return bp_fail(BPVO_B200_ERR_INVALID_ARG, "null argument");
+  CUDA_TRY(cudaSetDevice(c->p.device_id));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  CUDA_TRY(cudaMemcpy(cycles, c->d_prof + 64, kMaxLevels * 16 * sizeof(long long), cudaMemcpyDeviceToHost));
+  if (reset) CUDA_TRY(cudaMemset(c->d_prof + 64, 0, kMaxLevels * 16 * sizeof(long long)));
+  return BPVO_B200_OK;
+}
+int bpvo_b200_last_level_us(bpvo_b200_ctx* c, float* us) {
+  if (!c || !us) return bp_fail(BPVO_B200_ERR_INVALID_ARG, "null argument");
+  for (int l = 0; l < c->L; ++l) us[l] = c->level_us[l];
   return BPVO_B200_OK;
 }
 int bpvo_b200_set_profiling(bpvo_b200_ctx* c, int enable) { if (!c) return bp_fail(BPVO_B200_ERR_INVALID_ARG, "null ctx"); c->profiling = enable != 0; return BPVO_B200_OK; }
@@ -615,8 +628,8 @@ static int lin_grid(const bpvo_b200_ctx* c, const bpvo_b200_frame* ref, int leve
   return std::max(1, std::min(std::min(c->sm_count * per_sm, 1024), need));
 }
 
-template <int C>
-static int launch_linearize(bpvo_b200_ctx* c, const bpvo_b200_frame* ref, const bpvo_b200_frame* cur, int level, const M44& T) {
+template <int C, int BLEND>
+static int launch_linearize_t(bpvo_b200_ctx* c, const bpvo_b200_frame* ref, const bpvo_b200_frame* cur, int level, const M44& T) {
   LinArgs a;
   a.tmpl = make_level_template(ref, level);
   a.img.desc = cur->desc[level]; a.img.rows = c->geom[level].rows; a.img.cols = c->geom[level].cols;
@@ -626,9 +639,16 @@ static int launch_linearize(bpvo_b200_ctx* c, const bpvo_b200_frame* ref, const 
   const int grid = lin_grid(c, ref, level, 2), grid_sel = lin_grid(c, ref, level, 4);
   const bool robust = c->p.lossFunction != BPVO_B200_L2;
   if (robust) CUDA_TRY(cudaMemsetAsync(c->work.hist, 0, kHistWords * sizeof(unsigned), c->stream));
-  k_residuals<C><<<grid, kLinThreads, 0, c->stream>>>(a); LAUNCH_CHECK(c);
-  const bool sharded = c->shard_size > 1;
+  k_residuals<C, BLEND><<<grid, kLinThreads, 0, c->stream>>>(a); LAUNCH_CHECK(c);
+  // point-sharded mode: the histograms and the 30 sums are all-reduced -- unless this level is REPLICATED (peer-memory mode keeps
+  // levels under shard_min_points whole on every rank): every rank then already holds all points and a sum over ranks would
+  // count each of them nranks times
+  bool sharded = c->shard_size > 1;
   int rc;
+  if (sharded && c->peer_mode) {
+    if ((rc = wait_meta(ref))) return rc;
+    if (ref->h_meta[level].replicated) sharded = false;
+  }
   if (robust) {
     if (sharded && (rc = bp_comm_allreduce_u32(c, a.hset, kHist1Bins))) return rc;                       // global level-1 histogram
     k_select<C, 2><<<grid_sel, kLinThreads, 0, c->stream>>>(a); LAUNCH_CHECK(c);
@@ -646,6 +666,14 @@ static int launch_linearize(bpvo_b200_ctx* c, const bpvo_b200_frame* ref, const 
   c->counters.linearize_calls++;
   c->last_ref = ref; c->last_level = level;
   return BPVO_B200_OK;
+}
+
+// arithmetic of the bilinear blend (phase_residuals): the reference's double expression unless the ctx asks for fp32 FMAs on
+// bit-planes (BPVO_B200_FLAG_FAST_BLEND); intensity always computes in fp64
+template <int C>
+static int launch_linearize(bpvo_b200_ctx* c, const bpvo_b200_frame* ref, const bpvo_b200_frame* cur, int level, const M44& T) {
+  if constexpr (C == 8) { if (c->p.flags & BPVO_B200_FLAG_FAST_BLEND) return launch_linearize_t<C, 1>(c, ref, cur, level, T); }
+  return launch_linearize_t<C, 0>(c, ref, cur, level, T);
 }
 
 static int check_pair(bpvo_b200_ctx* c, const bpvo_b200_frame* ref, const bpvo_b200_frame* cur) {
@@ -734,8 +762,8 @@ struct SolveOverride {
   int cache_bytes = -1;    // -1 = everything the SM has
 };
 
-template <int C>
-static int launch_estimate_pose(bpvo_b200_ctx* c, const bpvo_b200_frame* ref, const bpvo_b200_frame* cur, const M44& T_init, const SolveOverride* ov = nullptr) {
+template <int C, int BLEND>
+static int launch_estimate_pose_t(bpvo_b200_ctx* c, const bpvo_b200_frame* ref, const bpvo_b200_frame* cur, const M44& T_init, const SolveOverride* ov) {
   SolveArgs a;
   memset(&a, 0, sizeof(a));
   if (ov) a.dbg = ov->dbg;
@@ -748,8 +776,10 @@ static int launch_estimate_pose(bpvo_b200_ctx* c, const bpvo_b200_frame* ref, co
   a.sp.parameter_tolerance = c->p.parameterTolerance; a.sp.function_tolerance = c->p.functionTolerance; a.sp.gradient_tolerance = c->p.gradientTolerance;
   a.sp.loss = c->p.lossFunction; a.sp.interp = c->p.interp; a.sp.good_threshold = c->p.goodPointThreshold;
   a.sp.max_test_level = c->p.maxTestLevel; a.sp.num_levels = c->L;
-  a.work = c->work; a.T_init = T_init; a.T_out = c->d_T; a.stats = c->d_stats; a.num_fun_evals = c->d_evals;
+  a.work = c->work; a.T_init = T_init; a.T_out = &c->d_mail->T; a.stats = c->d_mail->stats; a.num_fun_evals = &c->d_mail->evals; a.aborted_out = &c->d_mail->aborted;
+  a.timeout_ns = c->timeout_ns;
   a.prof = c->profiling ? c->d_prof : nullptr;
+  a.prof_lvl = c->profiling ? c->d_prof + 64 : nullptr;
   Sel* sel = c->sel;
   // the grid-barrier counter (behind the histogram sets) must be zero on entry; the kernel zeroes the sets itself
   CUDA_TRY(cudaMemsetAsync(c->work.hist + (size_t) kHistSets * kHistWords, 0, 8 * sizeof(unsigned), c->stream));
@@ -782,15 +812,20 @@ static int launch_estimate_pose(bpvo_b200_ctx* c, const bpvo_b200_frame* ref, co
   if (ov && ov->cache_bytes >= 0) cache_bytes = std::min(cache_bytes, ov->cache_bytes);
   const size_t dyn = (size_t) kScratchBytes + (size_t) cache_bytes;
   if (c->dyn_configured != dyn) {        // per ctx: the attribute is per device, and a process may drive several
-    CUDA_TRY(cudaFuncSetAttribute((const void*) k_estimate_pose<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) dyn));
+    CUDA_TRY(cudaFuncSetAttribute((const void*) k_estimate_pose<C, BLEND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) dyn));
     c->dyn_configured = dyn;
   }
   void* args[] = {&a, &sel, &cache_bytes};
   int grid = std::min(c->sm_count, kMaxGrid);
   if (ov && ov->grid > 0) grid = std::min(grid, ov->grid);
-  CUDA_TRY(cudaLaunchCooperativeKernel((void*) k_estimate_pose<C>, dim3(grid), dim3(kLinThreads), args, dyn, c->stream));
+  CUDA_TRY(cudaLaunchCooperativeKernel((void*) k_estimate_pose<C, BLEND>, dim3(grid), dim3(kLinThreads), args, dyn, c->stream));
   c->counters.launches++;
   return BPVO_B200_OK;
+}
+template <int C>
+static int launch_estimate_pose(bpvo_b200_ctx* c, const bpvo_b200_frame* ref, const bpvo_b200_frame* cur, const M44& T_init, const SolveOverride* ov = nullptr) {
+  if constexpr (C == 8) { if (c->p.flags & BPVO_B200_FLAG_FAST_BLEND) return launch_estimate_pose_t<C, 1>(c, ref, cur, T_init, ov); }
+  return launch_estimate_pose_t<C, 0>(c, ref, cur, T_init, ov);
 }
 
 extern "C" int bpvo_b200_estimate_pose(bpvo_b200_ctx* c, const bpvo_b200_frame* ref, const bpvo_b200_frame* cur,
@@ -815,12 +850,10 @@ extern "C" int bpvo_b200_estimate_pose(bpvo_b200_ctx* c, const bpvo_b200_frame* 
       if (rc) return rc;
     }
     Mailbox* mb = c->h_mail;
-    CUDA_TRY(cudaMemcpyAsync(&mb->T, c->d_T, sizeof(M44), cudaMemcpyDeviceToHost, c->stream));
-    CUDA_TRY(cudaMemcpyAsync(mb->stats, c->d_stats, kMaxLevels * sizeof(LevelStats), cudaMemcpyDeviceToHost, c->stream));
-    CUDA_TRY(cudaMemcpyAsync(&mb->evals, c->d_evals, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    CUDA_TRY(cudaMemcpyAsync(&mb->lin, c->work.out, sizeof(LinOut), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(mb, c->d_mail, sizeof(Mailbox), cudaMemcpyDeviceToHost, c->stream));      // pose, statistics, LinOut: one D2H
     CUDA_TRY(cudaStreamSynchronize(c->stream));
-    c->counters.d2h_bytes += sizeof(M44) + kMaxLevels * sizeof(LevelStats) + sizeof(int) + sizeof(LinOut);
+    c->counters.d2h_bytes += sizeof(Mailbox);
+    if (mb->aborted) return bp_fail(BPVO_B200_ERR_CUDA, "on-device GN loop: a grid barrier / exchange timed out");
     T = mb->T; evals = mb->evals;
     c->counters.linearize_calls += evals;
     for (int l = c->p.maxTestLevel; l < c->L; ++l) {
@@ -828,7 +861,7 @@ extern "C" int bpvo_b200_estimate_pose(bpvo_b200_ctx* c, const bpvo_b200_frame* 
       if (mb->stats[l].status == -4) return bp_fail(BPVO_B200_ERR_CUDA, "on-device GN loop: a grid barrier / exchange timed out");
       stats[l].numIterations = mb->stats[l].num_iterations; stats[l].finalError = mb->stats[l].final_error;
       stats[l].firstOrderOptimality = mb->stats[l].first_order_optimality; stats[l].status = mb->stats[l].status;
-      c->level_evals[l] = mb->stats[l].num_evals;
+      c->level_evals[l] = mb->stats[l].num_evals; c->level_us[l] = mb->stats[l].us;
     }
     c->last_ref = ref; c->last_level = c->p.maxTestLevel;
   }
@@ -946,15 +979,14 @@ extern "C" int bpvo_b200_debug_device_linearize(bpvo_b200_ctx* c, const bpvo_b20
     rc = (c->C == 1) ? launch_estimate_pose<1>(c, ref, cur, T0, &ov) : launch_estimate_pose<8>(c, ref, cur, T0, &ov);
     if (rc == BPVO_B200_OK) {
       e = cudaMemcpyAsync(out, d_out, (size_t) n * sizeof(LinOut), cudaMemcpyDeviceToHost, c->stream);
-      if (e == cudaSuccess) e = cudaMemcpyAsync(&c->h_mail->lin, c->work.out, sizeof(LinOut), cudaMemcpyDeviceToHost, c->stream);
-      if (e == cudaSuccess) e = cudaMemcpyAsync(c->h_mail->stats, c->d_stats, kMaxLevels * sizeof(LevelStats), cudaMemcpyDeviceToHost, c->stream);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(c->h_mail, c->d_mail, sizeof(Mailbox), cudaMemcpyDeviceToHost, c->stream);
     }
   }
   cudaError_t e2 = cudaStreamSynchronize(c->stream);
   cudaFree(d_poses); cudaFree(d_out);
   if (rc) return rc;
   if (e != cudaSuccess || e2 != cudaSuccess) return bp_fail(BPVO_B200_ERR_CUDA, "debug_device_linearize failed: %s", cudaGetErrorString(e != cudaSuccess ? e : e2));
-  if (c->h_mail->stats[level].status == -4) return bp_fail(BPVO_B200_ERR_CUDA, "on-device GN loop: a grid barrier / exchange timed out");
+  if (c->h_mail->aborted || c->h_mail->stats[level].status == -4) return bp_fail(BPVO_B200_ERR_CUDA, "on-device GN loop: a grid barrier / exchange timed out");
   if (c->h_mail->stats[level].status == -3) return bp_fail(BPVO_B200_ERR_NO_POINTS, "you should call setData before calling computeResiduals");
   c->last_ref = ref; c->last_level = level;
   return BPVO_B200_OK;

@@ -15,11 +15,12 @@ struct LevelGeom {
   int capacity;           // upper bound of template points at this level (selection window)
 };
 
-struct Mailbox {          // pinned host memory the device results land in
+struct Mailbox {          // results of a linearize / estimate_pose: one device copy (d_mail), one pinned host copy (h_mail), ONE D2H
   bp::LinOut lin;
   bp::M44 T;
   bp::LevelStats stats[bp::kMaxLevels];
   int evals;
+  int aborted;            // an in-kernel wait of the on-device GN loop expired (rank-wide abort word)
 };
 
 constexpr int kTraceRows = 8192;   // rows of the GN-loop trace buffer (bpvo_b200_debug_set_trace)
@@ -34,12 +35,14 @@ struct bpvo_b200_ctx {
   int sm_count = 0; bool coop = false; int smem_optin = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, stage_free = nullptr, tm0 = nullptr, tm1 = nullptr;
-  int level_evals[bp::kMaxLevels] = {};
+  int level_evals[bp::kMaxLevels] = {}; float level_us[bp::kMaxLevels] = {};
   bp::Work work{};
   bp::Sel* sel = nullptr;
   float* export_buf = nullptr;
   uint8_t* flags = nullptr; uint8_t* blur_tmp = nullptr; int* block_counts = nullptr; double* hpartials = nullptr;
-  bp::M44* d_T = nullptr; bp::LevelStats* d_stats = nullptr; int* d_evals = nullptr; long long* d_prof = nullptr;
+  Mailbox* d_mail = nullptr;     // work.out, T, stats, evals, aborted live here
+  long long* d_prof = nullptr;
+  unsigned long long timeout_ns = 2000000000ull;   // deadline of the in-kernel waits (60 s once peer-memory mode is on)
   float* d_trace = nullptr; int* d_trace_rows = nullptr;   // bpvo_b200_debug_set_trace
   Mailbox* h_mail = nullptr;
   uint8_t* stage_img = nullptr; float* stage_disp = nullptr;

@@ -201,13 +201,29 @@ __device__ __forceinline__ void block_find2(const unsigned* __restrict__ hist, u
   block_find2_regs<PER>(loc, ra, rb, sh, bin_a, rem_a, bin_b, rem_b, total);
 }
 
-// projection matrix P = K * T[0:3,:] in fp32 (rigid_body_warp.h:111-114), column-major 3x4
+// projection matrix P = K * T[0:3,:] in fp32 (rigid_body_warp.h:111-114), column-major 3x4.  Every product and sum is rounded
+// on its own, on the host AND on the device (no FMA contraction: the reference is built with -mavx, without -mfma) -- the device
+// loop computes P itself and must get the bits the reference's dense 3x3 * 3x4 product gets.
+__host__ __device__ __forceinline__ float mul_rn(float a, float b) {
+#ifdef __CUDA_ARCH__
+  return __fmul_rn(a, b);
+#else
+  return a * b;
+#endif
+}
+__host__ __device__ __forceinline__ float add_rn(float a, float b) {
+#ifdef __CUDA_ARCH__
+  return __fadd_rn(a, b);
+#else
+  return a + b;
+#endif
+}
 __host__ __device__ __forceinline__ void make_projection(const LevelTemplate& L, const M44& T, float P[12]) {
   for (int j = 0; j < 4; ++j) {
     // K = [fx 0 cx; 0 fy cy; 0 0 1]; the zero terms are kept so that the rounding matches a dense 3x3 * 3x4 product
-    float r0 = L.fx * T(0, j); r0 += 0.0f * T(1, j); r0 += L.cx * T(2, j);
-    float r1 = 0.0f * T(0, j); r1 += L.fy * T(1, j); r1 += L.cy * T(2, j);
-    float r2 = 0.0f * T(0, j); r2 += 0.0f * T(1, j); r2 += 1.0f * T(2, j);
+    const float r0 = add_rn(add_rn(mul_rn(L.fx, T(0, j)), mul_rn(0.0f, T(1, j))), mul_rn(L.cx, T(2, j)));
+    const float r1 = add_rn(add_rn(mul_rn(0.0f, T(0, j)), mul_rn(L.fy, T(1, j))), mul_rn(L.cy, T(2, j)));
+    const float r2 = add_rn(add_rn(mul_rn(0.0f, T(0, j)), mul_rn(0.0f, T(1, j))), mul_rn(1.0f, T(2, j)));
     P[j * 3 + 0] = r0; P[j * 3 + 1] = r1; P[j * 3 + 2] = r2;
   }
 }
@@ -290,7 +306,14 @@ struct Bracket {       // median bracket carried from the previous GN iteration 
 };
 __device__ __forceinline__ int sel_bin(float v, float lo, float inv_w) { return min(kSelBins - 1, (int) ((v - lo) * inv_w)); }
 
-template <int C>
+// BLEND: arithmetic of the bilinear blend for C = 8 (bit-planes, values in [0, 1]).
+//   0  fp64 with separate roundings = the reference's double expression, bit for bit (photo_error.cc:381-388): 32 F2F.F64.F32 +
+//      8 F2F.F32.F64 conversions and ~90 FP64 operations per point -- the conversion pipe runs at 14-15 lanes/clk/SM and bounds
+//      the phase (profiles/r1_micro_pipes.txt);
+//   1  projection, Floor and validity stay fp64 (same taps, same valid flags as the reference), the fractions are rounded to fp32
+//      once and the 4-tap blend runs as fp32 FMAs: |r - r_reference| <= 2e-7 on [0, 1] data against the north star's 1e-5.
+// C = 1 (intensity, values up to 255) always takes the fp64 expression: 5 conversions per point, nothing to gain.
+template <int C, int BLEND>
 __device__ __forceinline__ void phase_residuals(const LevelTemplate& L, const LevelImage& I, const float* P, const Work& W,
                                                 unsigned* __restrict__ hist1, bool do_hist, Bracket br, const TplCache& tc,
                                                 const TemplateMeta& m, unsigned* scratch, LinShared& sh, int block, int nblocks, int interp = 0) {
@@ -334,12 +357,22 @@ __device__ __forceinline__ void phase_residuals(const LevelTemplate& L, const Le
         const float* tap = I.desc + ((size_t) yi * cols + xi) * C;
         VecC<C> t00, t01, t10, t11;
         t00.load(tap); t01.load(tap + C); t10.load(tap + (size_t) cols * C); t11.load(tap + (size_t) cols * C + C);
+        if (BLEND == 1 && C == 8) {
+          const float xf32 = (float) xf, yf32 = (float) yf, wx32 = (float) wx, wy32 = (float) wy;
 #pragma unroll
-        for (int c = 0; c < C; ++c) {
-          const double top = __dadd_rn(__dmul_rn((double) t00.v[c], wx), __dmul_rn((double) t01.v[c], xf));
-          const double bot = __dadd_rn(__dmul_rn((double) t10.v[c], wx), __dmul_rn((double) t11.v[c], xf));
-          const double Iw = __dadd_rn(__dmul_rn(wy, top), __dmul_rn(yf, bot));
-          r.v[c] = (float) __dsub_rn(Iw, (double) i0.v[c]);
+          for (int c = 0; c < C; ++c) {
+            const float top = fmaf(t01.v[c], xf32, t00.v[c] * wx32);
+            const float bot = fmaf(t11.v[c], xf32, t10.v[c] * wx32);
+            r.v[c] = fmaf(yf32, bot, wy32 * top) - i0.v[c];
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < C; ++c) {
+            const double top = __dadd_rn(__dmul_rn((double) t00.v[c], wx), __dmul_rn((double) t01.v[c], xf));
+            const double bot = __dadd_rn(__dmul_rn((double) t10.v[c], wx), __dmul_rn((double) t11.v[c], xf));
+            const double Iw = __dadd_rn(__dmul_rn(wy, top), __dmul_rn(yf, bot));
+            r.v[c] = (float) __dsub_rn(Iw, (double) i0.v[c]);
+          }
         }
       } else {
         float i0l[C], rl[C];                 // only these copies live in local memory (the out-of-line call takes addresses)
@@ -783,10 +816,10 @@ struct LinArgs {
   Sel* sel;
 };
 
-template <int C> __global__ void __launch_bounds__(kLinThreads, 1) k_residuals(LinArgs a) {
+template <int C, int BLEND> __global__ void __launch_bounds__(kLinThreads, 1) k_residuals(LinArgs a) {
   __shared__ LinShared sh;
   const bool do_hist = (a.loss != 0x12) && (a.work.scale->delta > 1e-6f);
-  phase_residuals<C>(a.tmpl, a.img, a.P, a.work, a.hset, do_hist, Bracket{false, 0.0f, 0.0f, 0.0f}, tpl_cache_off(), *a.tmpl.meta, nullptr, sh, blockIdx.x, gridDim.x, a.interp);
+  phase_residuals<C, BLEND>(a.tmpl, a.img, a.P, a.work, a.hset, do_hist, Bracket{false, 0.0f, 0.0f, 0.0f}, tpl_cache_off(), *a.tmpl.meta, nullptr, sh, blockIdx.x, gridDim.x, a.interp);
 }
 template <int C, int LEVEL> __global__ void __launch_bounds__(kLinThreads, 1) k_select(LinArgs a) {
   __shared__ LinShared sh;
@@ -904,12 +937,30 @@ enum { PROF_P1 = 0, PROF_SYNC1, PROF_P2, PROF_SYNC2, PROF_P3, PROF_SYNC3, PROF_S
 #ifndef BP_BRACKET_TARGET
 #define BP_BRACKET_TARGET 500     /* candidates the bracket is sized for once the median has settled */
 #endif
-constexpr unsigned kSpinLimit = 1u << 27;    // tens of seconds of polling (the other CTAs of a rank must outwait CTA 0, which may be waiting for a
-                                             // peer process that is seconds behind): a lost CTA / rank ends the launch with an error status instead of hanging the GPU
+// Every wait of the persistent kernel (grid barrier, flag-in-data polls, fixed-point exchange, cross-rank mailboxes) is bounded by
+// ONE absolute deadline on the GPU's global timer, set by the host per launch (2 s on a single GPU: a solve takes milliseconds; 60 s
+// in the multi-rank mode, where a peer PROCESS may be seconds behind): a lost CTA / rank ends the launch with an error status
+// instead of hanging the GPU.  A wait that expires raises the CTA's flag (every later wait of the CTA returns at once) and the
+// rank-wide word behind the barrier counter, which CTA 0 reports to the host together with the statistics.
+struct AbortCtl {
+  int flag;                      // this CTA gave up
+  int pad;
+  unsigned long long deadline;   // %globaltimer value (ns) after which waits give up
+  int* global_flag;              // rank-wide abort word
+};
+__device__ __forceinline__ bool wait_expired(unsigned& spins, AbortCtl* ac) {
+  if (*(volatile int*) &ac->flag) return true;
+  if ((++spins & 511u) == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    if (t > ac->deadline || *(volatile int*) ac->global_flag) { ac->flag = 1; *(volatile int*) ac->global_flag = 1; return true; }
+  }
+  return false;
+}
 
 // Grid-wide barrier of the persistent kernel (all CTAs are co-resident: cooperative launch).  `counter` only grows;
 // `epoch` is the value it reaches when every CTA has arrived at this barrier (kept uniformly by all threads).
-__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& epoch, unsigned nblocks, int* abort_flag) {
+__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& epoch, unsigned nblocks, AbortCtl* abort_flag) {
   epoch += nblocks;
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -918,7 +969,7 @@ __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& epoch,
     for (;;) {
       asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
       if ((int) (v - epoch) >= 0) break;
-      if (++spins > kSpinLimit || *(volatile int*) abort_flag) { *abort_flag = 1; break; }
+      if (wait_expired(spins, abort_flag)) break;
     }
   }
   __syncthreads();
@@ -939,7 +990,7 @@ __device__ __forceinline__ bool ll_peek(const uint4* p, unsigned seq, double& v)
 
 // sum of up to NS words p[q * stride], q < cnt, all polled concurrently; fixed summation order
 template <int NS>
-__device__ __forceinline__ double ll_gather(const uint4* p, size_t stride, int cnt, unsigned seq, int* abort_flag) {
+__device__ __forceinline__ double ll_gather(const uint4* p, size_t stride, int cnt, unsigned seq, AbortCtl* abort_flag) {
   double v[NS]; bool ok[NS]; bool all = true;
 #pragma unroll
   for (int q = 0; q < NS; ++q) { v[q] = 0.0; ok[q] = q >= cnt; all = all && ok[q]; }
@@ -948,7 +999,7 @@ __device__ __forceinline__ double ll_gather(const uint4* p, size_t stride, int c
     all = true;
 #pragma unroll
     for (int q = 0; q < NS; ++q) { if (!ok[q]) ok[q] = ll_peek(p + q * stride, seq, v[q]); all = all && ok[q]; }
-    if (!all && (++spins > kSpinLimit || *(volatile int*) abort_flag)) { *abort_flag = 1; break; }
+    if (!all && wait_expired(spins, abort_flag)) break;
   }
   double t = 0.0;
 #pragma unroll
@@ -961,7 +1012,7 @@ __device__ __forceinline__ double ll_gather(const uint4* p, size_t stride, int c
 //            group totals;  stage 2: every CTA polls the <= ceil(nblocks / kLLGroup) group totals.
 // Mailboxes are double-buffered by the parity of `seq`: a CTA can be at most one exchange ahead of any other.
 // Result: sh.red[0][0..29] (valid after the trailing __syncthreads).
-__device__ __forceinline__ void exchange_sums(double mine, uint4* ll, unsigned seq, LinShared& sh, int blk, int nb, int* abort_flag) {
+__device__ __forceinline__ void exchange_sums(double mine, uint4* ll, unsigned seq, LinShared& sh, int blk, int nb, AbortCtl* abort_flag) {
   const int tid = threadIdx.x, k = tid & 31, g = tid >> 5;
   constexpr int G = kLinThreads / 32;
   uint4* box1 = ll + (size_t) (seq & 1u) * kMaxGrid * 32;                       // CTA totals
@@ -1018,7 +1069,6 @@ __device__ __forceinline__ void exchange_sums(double mine, uint4* ll, unsigned s
 // the peers; it hands rank-wide results to the other CTAs through a local grid barrier or local flag-in-data words.
 // All ranks take identical decisions from identical data, so the exchange sequence is the same everywhere.
 // =============================================================================================
-constexpr unsigned kXSpinLimit = kSpinLimit;  // cross-rank waits: the same patience
 __device__ __forceinline__ void x_put(uint2* p, unsigned v, unsigned seq) {
   asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(v), "r"(seq) : "memory");
 }
@@ -1030,9 +1080,9 @@ __device__ __forceinline__ bool x_peek(const uint2* p, unsigned seq, unsigned& v
 __device__ __forceinline__ uint2* x_slot(const PeerArgs& pa, int owner, unsigned seq, int src) {
   return pa.box[owner] + ((size_t) (seq & 1u) * kXRanks + src) * kXWords;
 }
-__device__ __forceinline__ unsigned x_wait(const uint2* p, unsigned seq, int* abort_flag) {
+__device__ __forceinline__ unsigned x_wait(const uint2* p, unsigned seq, AbortCtl* abort_flag) {
   unsigned v, spins = 0;
-  while (!x_peek(p, seq, v)) { if (++spins > kXSpinLimit || *(volatile int*) abort_flag) { *abort_flag = 1; v = 0; break; } }
+  while (!x_peek(p, seq, v)) { if (wait_expired(spins, abort_flag)) { v = 0; break; } }
   return v;
 }
 // CTA 0: send buf[0..n) (shared memory) to every peer
@@ -1045,7 +1095,7 @@ __device__ __forceinline__ void x_send(const PeerArgs& pa, unsigned seq, const u
 }
 // CTA 0: sum (u32) of buf[0..n) over all ranks, in place (shared memory); thread t owns words t, t + 256, ...
 // All peers are polled concurrently (up to kXRanks x 4 words in flight per thread): one round trip, whatever the rank count.
-__device__ __forceinline__ void x_allreduce_u32(const PeerArgs& pa, unsigned& xseq, unsigned* buf, int n, int* abort_flag) {
+__device__ __forceinline__ void x_allreduce_u32(const PeerArgs& pa, unsigned& xseq, unsigned* buf, int n, AbortCtl* abort_flag) {
   const unsigned seq = xseq++;
   x_send(pa, seq, buf, n);
   const uint2* base = x_slot(pa, pa.rank, seq, 0);
@@ -1070,7 +1120,7 @@ __device__ __forceinline__ void x_allreduce_u32(const PeerArgs& pa, unsigned& xs
             if (x_peek(base + (size_t) r * kXWords + i0 + q * kLinThreads, seq, v)) { acc[q] += v; pending &= ~(1ull << (r * 8 + q)); }
           }
       }
-      if (pending && (++spins > kXSpinLimit || *(volatile int*) abort_flag)) { *abort_flag = 1; break; }
+      if (pending && wait_expired(spins, abort_flag)) break;
     }
 #pragma unroll
     for (int q = 0; q < Q; ++q) if (i0 + q * kLinThreads < n) buf[i0 + q * kLinThreads] += acc[q];
@@ -1078,7 +1128,7 @@ __device__ __forceinline__ void x_allreduce_u32(const PeerArgs& pa, unsigned& xs
   __syncthreads();
 }
 // CTA 0, thread k < 30: sum of `mine` over all ranks in RANK ORDER (bit-identical on every rank)
-__device__ __forceinline__ double x_allreduce_f64_ordered(const PeerArgs& pa, unsigned& xseq, double mine, int* abort_flag) {
+__device__ __forceinline__ double x_allreduce_f64_ordered(const PeerArgs& pa, unsigned& xseq, double mine, AbortCtl* abort_flag) {
   const unsigned seq = xseq++;
   const int k = threadIdx.x;
   double t = 0.0;
@@ -1100,7 +1150,7 @@ __device__ __forceinline__ double x_allreduce_f64_ordered(const PeerArgs& pa, un
         if (!ok[r]) { const uint2* src = x_slot(pa, pa.rank, seq, r); unsigned a, c; const bool g0 = x_peek(src + 2 * k, seq, a), g1 = x_peek(src + 2 * k + 1, seq, c); if (g0 && g1) { lo[r] = a; hi[r] = c; ok[r] = true; } }
         all = all && ok[r];
       }
-      if (!all && (++spins > kXSpinLimit || *(volatile int*) abort_flag)) { *abort_flag = 1; break; }
+      if (!all && wait_expired(spins, abort_flag)) break;
     }
 #pragma unroll
     for (int r = 0; r < kXRanks; ++r)
@@ -1115,7 +1165,7 @@ __device__ __forceinline__ double x_allreduce_f64_ordered(const PeerArgs& pa, un
 constexpr unsigned kXPoison = 1u << 26;      // per-rank stand-in for kCandPoison that cannot overflow a u32 sum over 8 ranks
 template <int C>
 __device__ __forceinline__ bool bracket_select_xrank(const PeerArgs& pa, unsigned& xseq, const Work& W, const unsigned* __restrict__ hset, LinShared& sh,
-                                                     unsigned* scratch, int nblocks, const Bracket& br, int* abort_flag,
+                                                     unsigned* scratch, int nblocks, const Bracket& br, AbortCtl* abort_flag,
                                                      unsigned& n_out, unsigned& ncand_out, float& lo_out, float& hi_out) {
   const int tid = threadIdx.x;
   const unsigned total = (unsigned) nblocks * kCandPerCta;
@@ -1186,7 +1236,7 @@ __device__ __forceinline__ bool bracket_select_xrank(const PeerArgs& pa, unsigne
       list[my_off + j] = (r == pa.rank) ? mine[j] : __uint_as_float(x_wait(x_slot(pa, pa.rank, seq, r) + 1 + j, seq, abort_flag));
   }
   __syncthreads();
-  if (bad || base > (unsigned) kSelList || *(volatile int*) abort_flag) return false;
+  if (bad || base > (unsigned) kSelList || *(volatile int*) &abort_flag->flag) return false;
   if (tid < (int) base) {
     const float v = list[tid];
     const unsigned bj = (unsigned) sel_bin(v, br.lo, br.inv_w);
@@ -1206,7 +1256,7 @@ __device__ __forceinline__ bool bracket_select_xrank(const PeerArgs& pa, unsigne
 
 // all CTAs: a histogram range of this rank's set -> its sum over all ranks, in place; ends with a grid barrier
 __device__ __forceinline__ void xrank_hist_allreduce(const PeerArgs& pa, unsigned& xseq, unsigned* hist, int n, LinShared& sh,
-                                                     unsigned* counter, unsigned& epoch, int nblocks, int* abort_flag) {
+                                                     unsigned* counter, unsigned& epoch, int nblocks, AbortCtl* abort_flag) {
   if (blockIdx.x == 0) {
     for (int i = threadIdx.x; i < n; i += kLinThreads) sh.hist[i] = __ldcg(hist + i);
     __syncthreads();
@@ -1216,16 +1266,27 @@ __device__ __forceinline__ void xrank_hist_allreduce(const PeerArgs& pa, unsigne
   grid_barrier(counter, epoch, nblocks, abort_flag);
 }
 
-// the damped fp64 retry of solve6() is rare: keep it out of line so that it does not bloat the hot loop
-__device__ __noinline__ bool solve6_fallback(const float* H, const float* G, float* dp) { return solve6(H, G, dp); }
+// what follows a rejected fast LDL^T (rare): the same factorisation with Eigen's early-outs, Eigen's pivoted LDLT, the damped
+// fp64 retry of solve6() (pose_estimator_base.h:90-148) -- out of line so that it neither bloats the hot loop nor forces the
+// caller's register copy of H into local memory.  Every lane of the calling warp stores the same dp.
+__device__ __noinline__ bool solve6_cold(const float* H, const float* G, float* dp_out) {
+  float dp[6];
+  bool ok = solve6_fp32_registers<false>(H, G, dp);
+  if (!ok) ok = solve6_fp32_registers<true>(H, G, dp);
+  if (!ok) ok = solve6(H, G, dp);
+  for (int k = 0; k < 6; ++k) dp_out[k] = dp[k];
+  return ok;
+}
 
 struct SolveShared {
-  int abort;           // a barrier / exchange timed out: every later wait returns immediately, the launch reports an error
+  AbortCtl abort;      // a barrier / exchange timed out: every later wait returns immediately, the launch reports an error
   LinOut lin;
   M44 T, Td;
   float P[12];
   float dp[6];
   float scale, delta;
+  float dpn, gn;       // |dp| and max|G| of the step just solved (warp0_finish)
+  int fx_bad;          // the fixed-point exchange overflowed somewhere: repeat this exchange with the fp64 mailboxes
   // bracketed-median state of the current level (identical in every CTA)
   int br_on;           // a previous median exists
   float br_lo, br_hi;  // previous middle order statistics
@@ -1239,12 +1300,16 @@ struct GridSync {
   unsigned epoch;      // value of *counter once every CTA has passed the last barrier
   unsigned seq;        // sequence number of the next exchange
   unsigned xseq;       // sequence number of the next cross-rank exchange (peer-memory mode)
+  unsigned fxn;        // fixed-point exchanges done so far (their accumulator sets alternate)
   int hs;              // histogram set of the next linearize (cycles through kHistSets)
 };
 
-template <int C>
-__device__ __forceinline__ void device_linearize(const SolveArgs& a, int lvl, SolveShared& ss, LinShared& sh,
-                                                 const TplCache& tc, const TemplateMeta& meta, unsigned* scratch, GridSync& gs, Sel* sel) {
+// Front part of one linearize inside the persistent kernel: residuals -> exact median / scale -> weights and normal equations
+// of this CTA's points.  Returns, in thread k < 30, the CTA total of scalar k (layout of phase_reduce).
+template <int C, int BLEND>
+__device__ __forceinline__ double device_linearize(const SolveArgs& a, int lvl, SolveShared& ss, LinShared& sh,
+                                                   const TplCache& tc, const TemplateMeta& meta, unsigned* scratch, GridSync& gs, Sel* sel,
+                                                   float& sigma_out, bool& do_hist_out) {
   const LevelTemplate& L = a.tmpl[lvl];
   const LevelImage& I = a.img[lvl];
   const int nb = gridDim.x, blk = blockIdx.x, tid = threadIdx.x;
@@ -1259,7 +1324,7 @@ __device__ __forceinline__ void device_linearize(const SolveArgs& a, int lvl, So
   br.on = do_hist && ss.br_on;
   br.lo = ss.br_lo * (1.0f - ss.br_rel); br.hi = ss.br_hi * (1.0f + ss.br_rel);
   br.inv_w = (br.hi > br.lo) ? (float) kSelBins / (br.hi - br.lo) : 0.0f;
-  phase_residuals<C>(L, I, ss.P, a.work, hset, do_hist, br, tc, meta, scratch, sh, blk, nb, a.sp.interp);
+  phase_residuals<C, BLEND>(L, I, ss.P, a.work, hset, do_hist, br, tc, meta, scratch, sh, blk, nb, a.sp.interp);
   BP_PROF(PROF_P1);
   float sigma = ss.scale;
   if (do_hist) {
@@ -1332,26 +1397,141 @@ __device__ __forceinline__ void device_linearize(const SolveArgs& a, int lvl, So
   }   // else: P4 reads only what the SAME thread wrote in P1, no grid-wide dependency
   const double mine = phase_reduce<C>(L, a.work, sigma, a.sp.loss, a.sp.good_threshold, tc, meta, sh, blk, nb, false);
   BP_PROF(PROF_P4);
-  exchange_sums(mine, a.work.ll, gs.seq, sh, blk, nb, &ss.abort);
-  if (a.peer.nranks > 1 && !meta.replicated) {        // rank totals -> totals over all ranks (summed in rank order by CTA 0, then handed to the other CTAs)
-    uint4* lb = a.peer.lbox + (size_t) (gs.seq & 1u) * 64 + 32;
-    if (blk == 0) {
-      const double t = x_allreduce_f64_ordered(a.peer, gs.xseq, tid < 30 ? sh.red[0][tid] : 0.0, &ss.abort);
-      if (tid < 30) { ll_post(lb + tid, t, gs.seq); sh.red[0][tid] = t; }
-    } else {
-      if (tid < 30) sh.red[0][tid] = ll_gather<1>(lb + tid, 0, 1, gs.seq, &ss.abort);
-    }
-    __syncthreads();
-  }
-  BP_PROF(PROF_SYNC4);
-  if (tid == 64 && do_hist) { ss.delta = fabsf(sigma - ss.scale); ss.scale = sigma; }     // read again only after finish_sums' barrier
-  finish_sums(sigma, sh, ss.lin);
-  BP_PROF(PROF_FINAL);
-  gs.seq += 1;
-  gs.hs = (gs.hs + 1) % kHistSets;
+  sigma_out = sigma; do_hist_out = do_hist;
+  return mine;
 }
 
-template <int C>
+// =============================================================================================
+// Tail of one linearize inside the persistent kernel: CTA totals -> grid totals -> LinOut, 6x6 solve, pose update.
+//
+// Exchange of the 30 sums ("hop B").  Usual path: ONE L2 round trip.  Every CTA converts its fp64 totals to 47-bit fixed point
+// (per-scalar power-of-two scales, see below) and adds them with 64-bit integer atomics to 32 accumulator words; the same
+// atomic carries the arrival count in the word's top byte, so a word validates itself: a reader polls until the byte says
+// "all nb CTAs are in" and has the total -- no fence, no flag word, no leader hop.  Integer addition is associative: the
+// totals are bit-identical in every CTA and from run to run whatever the arrival order.  Words are never reset: a reader
+// subtracts (mod 2^64) the complete value it saw at the word's previous use; two sets alternate, because a fast CTA may add
+// to exchange n + 1 while a slow one still polls exchange n (it cannot reach n + 2 before everybody has added to n + 1).
+// Scales: |CTA total of H_ab| <= sqrt(H_aa H_bb), |G_a| <= sqrt(H_aa e) (Cauchy-Schwarz; all terms of H_aa and e = sum w r^2
+// are non-negative, so a CTA's share is bounded by the grid total), taken from the PREVIOUS evaluation with a factor 16 in
+// hand; resolution 2^-42 of that bound per CTA -- far below the fp32 noise of the per-thread sums feeding it.  A value out
+// of range (or NaN) anywhere is reported through word 31 and every CTA repeats that exchange with the fp64 flag-in-data
+// mailboxes (exchange_sums), which also serve the first evaluation of a level, grids above 255 CTAs and the multi-rank mode.
+// =============================================================================================
+#ifndef BP_TAIL_FIXED
+#define BP_TAIL_FIXED 1
+#endif
+constexpr int kFixBits = 46;
+struct FixAcc {                  // lives in the registers of warp 0, lane k = scalar k
+  unsigned long long prev[2];    // complete value of this lane's word of either set after its last use
+  int exp;                       // fixed-point exponent of this lane's scalar for the NEXT exchange
+};
+__device__ __forceinline__ double pow2d(int e) { return __longlong_as_double((long long) (e + 1023) << 52); }   // e in [-1022, 1023]
+
+// warp 0: returns false when some CTA reported an out-of-range value (then `total` is meaningless)
+__device__ __forceinline__ bool fixed_exchange(double mine, FixAcc& fa, unsigned long long* acc, unsigned fxn, int nb, AbortCtl* abort_flag, double& total) {
+  const int lane = threadIdx.x & 31, set = (int) (fxn & 1u);
+  unsigned long long* w = acc + set * 32 + lane;
+  const double scaled = mine * pow2d(fa.exp);
+  const bool is_data = lane < 30;
+  const bool in_range = fabs(scaled) < 70368744177664.0;      // 2^46; false for NaN
+  const unsigned any_bad = __ballot_sync(0xffffffffu, is_data && !in_range);
+  unsigned long long add = 1ull << 56;
+  if (is_data) add += (unsigned long long) ((in_range ? __double2ll_rn(scaled) : 0ll) + (1ll << kFixBits));
+  else if (lane == 31) add += any_bad ? 1ull : 0ull;
+  asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(w), "l"(add) : "memory");
+  unsigned long long v, d;
+  unsigned spins = 0;
+  for (;;) {
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(w) : "memory");
+    d = v - fa.prev[set];
+    if ((unsigned) (d >> 56) == (unsigned) nb) break;
+    if (wait_expired(spins, abort_flag)) break;
+  }
+  fa.prev[set] = v;
+  const long long sum = (long long) (d & ((1ull << 56) - 1)) - (is_data ? (long long) nb << kFixBits : 0ll);
+  total = (double) sum * pow2d(-fa.exp);
+  return __shfl_sync(0xffffffffu, (int) sum, 31) == 0;
+}
+
+// warp 0, every lane redundantly after the gather (lane k < 30 passes the grid total of scalar k): LinOut, the scale
+// estimator's state, the exponents of the next fixed-point exchange, and -- unless `solve` is off (parity hook) or the first
+// evaluation already meets the gradient tolerance -- the 6x6 solve, the pose update and the next projection matrix
+__device__ __forceinline__ void warp0_finish(double total, float sigma, bool do_hist, bool first, bool solve, const SolveArgs& a,
+                                             const LevelTemplate& L, const TemplateMeta& meta, SolveShared& ss, FixAcc& fa) {
+  const int lane = threadIdx.x & 31;
+  const float tf = (float) total;
+  float H[36], G[6];
+  {
+    int k = 0;
+#pragma unroll
+    for (int r = 0; r < 6; ++r)
+#pragma unroll
+      for (int c = r; c < 6; ++c) { const float v = __shfl_sync(0xffffffffu, tf, k++); H[c * 6 + r] = v; H[r * 6 + c] = v; }
+#pragma unroll
+    for (int q = 0; q < 6; ++q) G[q] = __shfl_sync(0xffffffffu, tf, 21 + q);
+  }
+  // position of this lane's scalar in the upper triangle (lanes < 21), exponents for the next fixed-point exchange
+  int rr = 0, cc = 0;
+  {
+    int kk = lane;
+#pragma unroll
+    for (int r = 0; r < 6; ++r) { const int len = 6 - r; if (kk >= 0 && kk < len) { rr = r; cc = r + kk; } kk -= len; }
+  }
+  {
+    const int bits = (int) ((unsigned long long) __double_as_longlong(fabs(total)) >> 52);
+    const int my_e = max(bits - 1023, -200);                                   // floor(log2 |total|); 0 / denormal -> -200
+    const int ga = lane - 21;
+    const int src1 = (lane < 21) ? rr * 6 - rr * (rr - 1) / 2 : (lane < 27) ? ga * 6 - ga * (ga - 1) / 2 : 27;
+    const int src2 = (lane < 21) ? cc * 6 - cc * (cc - 1) / 2 : 27;
+    const int e1 = __shfl_sync(0xffffffffu, my_e, src1), e2 = __shfl_sync(0xffffffffu, my_e, src2);
+    fa.exp = (lane < 28) ? min(max(kFixBits - 4 - ((e1 + e2 + 3) >> 1), -900), 900) : 0;      // counts (28, 29) are exact integers
+  }
+  if (lane < 21) { ss.lin.H[cc * 6 + rr] = tf; ss.lin.H[rr * 6 + cc] = tf; }
+  else if (lane < 27) ss.lin.G[lane - 21] = tf;
+  else if (lane == 27) { ss.lin.f_norm = sqrtf(tf); ss.lin.sigma = sigma; }
+  else if (lane == 28) ss.lin.n_good = (int) (total + 0.5);
+  else if (lane == 29) ss.lin.n_valid = (int) (total + 0.5);
+  float g_norm = 0.0f;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) g_norm = fmaxf(g_norm, fabsf(G[k]));
+  if (lane == 0) {
+    if (do_hist) { ss.delta = fabsf(sigma - ss.scale); ss.scale = sigma; }
+    ss.gn = g_norm; ss.fx_bad = 0;
+  }
+  if (!solve) return;
+  if (first && g_norm < a.sp.gradient_tolerance * fmaxf(g_norm, sqrtf(FLT_EPSILON))) return;      // pose_estimator_base.h:346-357: no step
+  // unpivoted LDL^T first (H is SPD and Hartley-normalised); Eigen-order paths and the damped fp64 retry when it is rejected
+  float dp[6], Pn[12];
+  bool ok = solve6_fast(H, G, dp);
+  M44 Tn = ss.Td;
+  apply_update(Tn, dp, meta.s, meta.c1, meta.c2, meta.c3); make_projection(L, Tn, Pn);          // :371 / :390
+  if (!ok) {                                                    // rare: out of line, on the shared-memory copy of H, G
+    __syncwarp();
+    ok = solve6_cold(ss.lin.H, ss.lin.G, ss.dp);
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 6; ++k) dp[k] = ss.dp[k];
+    Tn = ss.Td;
+    if (ok) { apply_update(Tn, dp, meta.s, meta.c1, meta.c2, meta.c3); make_projection(L, Tn, Pn); }
+  }
+  float dpn = 0.0f;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) dpn += dp[k] * dp[k];
+  __syncwarp();                                                 // every lane has read ss.Td
+  if (lane == 0) {
+    ss.lin.pad[0] = ok ? 1 : 0;
+    ss.dpn = sqrtf(dpn);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) ss.dp[k] = dp[k];
+    if (ok) {
+      ss.Td = Tn;
+#pragma unroll
+      for (int k = 0; k < 12; ++k) ss.P[k] = Pn[k];
+    }
+  }
+}
+
+template <int C, int BLEND>
 __global__ void __launch_bounds__(kLinThreads, 1) k_estimate_pose(const __grid_constant__ SolveArgs a, Sel* sel, int cache_bytes) {
   __shared__ LinShared sh;
   __shared__ SolveShared ss;
@@ -1360,8 +1540,13 @@ __global__ void __launch_bounds__(kLinThreads, 1) k_estimate_pose(const __grid_c
   unsigned* scratch = reinterpret_cast<unsigned*>(dyn_smem);
   const int tid = threadIdx.x;
   GridSync gs;
-  gs.counter = a.work.hist + (size_t) kHistSets * kHistWords; gs.epoch = 0; gs.seq = a.seq_base; gs.xseq = a.peer.xseq_base; gs.hs = 0;
+  gs.counter = a.work.hist + (size_t) kHistSets * kHistWords; gs.epoch = 0; gs.seq = a.seq_base; gs.xseq = a.peer.xseq_base; gs.hs = 0; gs.fxn = 0;
   int total_evals = 0;
+  // accumulator words of the fixed-point exchange (behind the barrier counter's 8 words; 2 sets x 32 x u64, never reset): every
+  // CTA notes their current values BEFORE its first grid barrier, i.e. before anybody can add to them
+  unsigned long long* fix_acc = reinterpret_cast<unsigned long long*>(gs.counter + 8);
+  FixAcc fa; fa.exp = 0; fa.prev[0] = fa.prev[1] = 0;
+  if (tid < 32) { fa.prev[0] = __ldcg(fix_acc + tid); fa.prev[1] = __ldcg(fix_acc + 32 + tid); }
   if (a.prof && blockIdx.x == 0) {
     long long* sp = prof_smem();
     if (tid < 68) sp[tid] = 0;
@@ -1369,7 +1554,11 @@ __global__ void __launch_bounds__(kLinThreads, 1) k_estimate_pose(const __grid_c
     if (tid == 0) sp[64] = clock64();
     BP_FINE_INIT(a.prof);
   }
-  if (tid == 0) { ss.T = a.T_init; ss.abort = 0; }
+  if (tid == 0) {
+    ss.T = a.T_init; ss.fx_bad = 0; ss.dpn = 0.0f; ss.gn = 0.0f;
+    unsigned long long t0; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    ss.abort.flag = 0; ss.abort.deadline = t0 + a.timeout_ns; ss.abort.global_flag = reinterpret_cast<int*>(gs.counter + 1);
+  }
   __syncthreads();
   const float sqrt_eps = sqrtf(FLT_EPSILON);
   for (int lvl = a.sp.num_levels - 1; lvl >= a.sp.max_test_level; --lvl) {
@@ -1385,14 +1574,19 @@ __global__ void __launch_bounds__(kLinThreads, 1) k_estimate_pose(const __grid_c
     float f_prev = 0.0f, g_tol = 0.0f, dp_prev = 0.0f, f_norm, g_norm;
     bool solver_error = false, early = false;
     const TemplateMeta meta = *L.meta;
+    const bool multi_rank = a.peer.nranks > 1 && !meta.replicated;
     // template cache for this level: as many whole fields as fit (tpl_cache_plan)
     const TplCache tc = tpl_cache_plan<C>((unsigned) kScratchBytes, cache_bytes, (meta.n + (int) gridDim.x * kLinThreads - 1) / ((int) gridDim.x * kLinThreads));
     tc_fill<C>(tc, L, meta.n, blockIdx.x, gridDim.x);
     // every histogram set starts the level zeroed; the barrier orders the zeroing before the first atomics
     for (int b = blockIdx.x * kLinThreads + tid; b < kHistSets * kHistWords; b += gridDim.x * kLinThreads) a.work.hist[b] = 0;
     grid_barrier(gs.counter, gs.epoch, gridDim.x, &ss.abort);
+    unsigned long long t_level = 0;
+    if (blockIdx.x == 0 && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_level));
+    long long prof_snap = 0;
+    if (a.prof_lvl && blockIdx.x == 0 && tid < 16) prof_snap = prof_smem()[tid];
     if (meta.n_total == 0) {                              // "you should call setData before calling computeResiduals" (template_data.cc:177)
-      if (blockIdx.x == 0 && tid == 0) { LevelStats st; st.num_iterations = 0; st.final_error = -1.0f; st.first_order_optimality = -1.0f; st.status = -3; st.num_evals = 0; a.stats[lvl] = st; }
+      if (blockIdx.x == 0 && tid == 0) { LevelStats st; st.num_iterations = 0; st.final_error = -1.0f; st.first_order_optimality = -1.0f; st.status = -3; st.num_evals = 0; st.us = 0.0f; a.stats[lvl] = st; }
       continue;
     }
 
@@ -1405,9 +1599,44 @@ __global__ void __launch_bounds__(kLinThreads, 1) k_estimate_pose(const __grid_c
         if (tid == 0) { ss.Td = a.dbg.poses[n_evals]; make_projection(L, ss.Td, ss.P); }
         __syncthreads();
       }
-      device_linearize<C>(a, lvl, ss, sh, tc, meta, scratch, gs, sel); ++n_evals;
+      float sigma; bool do_hist;
+      const double mine = device_linearize<C, BLEND>(a, lvl, ss, sh, tc, meta, scratch, gs, sel, sigma, do_hist); ++n_evals;
+      // grid totals, LinOut, solve, pose update: warp 0 (see warp0_finish); the other warps wait at the barrier
+      const bool dbg = a.dbg.n > 0;
+      bool done = false;
+      if (BP_TAIL_FIXED && n_evals > 1 && gridDim.x <= 255 && !multi_rank) {
+        if (tid < 32) {
+          double total;
+          const bool ok = fixed_exchange(mine, fa, fix_acc, gs.fxn, (int) gridDim.x, &ss.abort, total);
+          BP_PROF(PROF_SYNC4);
+          if (ok) warp0_finish(total, sigma, do_hist, first, !dbg, a, L, meta, ss, fa);
+          else if (tid == 0) ss.fx_bad = 1;
+        }
+        gs.fxn += 1;
+        __syncthreads();
+        done = !ss.fx_bad;
+      }
+      if (!done) {
+        exchange_sums(mine, a.work.ll, gs.seq, sh, blockIdx.x, gridDim.x, &ss.abort);
+        if (multi_rank) {        // rank totals -> totals over all ranks (summed in rank order by CTA 0, then handed to the other CTAs)
+          uint4* lb = a.peer.lbox + (size_t) (gs.seq & 1u) * 64 + 32;
+          if (blockIdx.x == 0) {
+            const double t = x_allreduce_f64_ordered(a.peer, gs.xseq, tid < 30 ? sh.red[0][tid] : 0.0, &ss.abort);
+            if (tid < 30) { ll_post(lb + tid, t, gs.seq); sh.red[0][tid] = t; }
+          } else {
+            if (tid < 30) sh.red[0][tid] = ll_gather<1>(lb + tid, 0, 1, gs.seq, &ss.abort);
+          }
+          __syncthreads();
+        }
+        BP_PROF(PROF_SYNC4);
+        if (tid < 32) warp0_finish(tid < 30 ? sh.red[0][tid] : 0.0, sigma, do_hist, first, !dbg, a, L, meta, ss, fa);
+        __syncthreads();
+      }
+      gs.seq += 1;
+      gs.hs = (gs.hs + 1) % kHistSets;
+      BP_PROF(PROF_FINAL);
       f_norm = ss.lin.f_norm;
-      if (a.dbg.n > 0) {
+      if (dbg) {
         if (blockIdx.x == 0 && tid == 0) a.dbg.out[n_evals - 1] = ss.lin;
         g_norm = 0.0f; status = 0x33; it = n_evals;
         __syncthreads();
@@ -1415,36 +1644,10 @@ __global__ void __launch_bounds__(kLinThreads, 1) k_estimate_pose(const __grid_c
         early = true; break;
       }
       if (first) {
-        g_norm = 0.0f; for (int k = 0; k < 6; ++k) g_norm = fmaxf(g_norm, fabsf(ss.lin.G[k]));
+        g_norm = ss.gn;
         g_tol = a.sp.gradient_tolerance * fmaxf(g_norm, sqrt_eps);
         if (g_norm < g_tol) { status = 0x32; it = 1; early = true; break; }    // :346-357
       }
-      BP_FINE(25);
-      if (tid == 0) {
-        // unpivoted LDL^T first (H is SPD and Hartley-normalised).  The pose update and the next projection matrix are
-        // computed from dp BEFORE the isApprox verdict is needed, so that the acceptance test overlaps them.
-        float dp[6], Pn[12];
-        bool ok = solve6_fast(ss.lin.H, ss.lin.G, dp);
-        M44 Tn = ss.Td;
-        apply_update(Tn, dp, meta.s, meta.c1, meta.c2, meta.c3); make_projection(L, Tn, Pn);                      // :371 / :390
-        if (!ok) {
-          ok = solve6_fp32_registers<false>(ss.lin.H, ss.lin.G, dp);              // same factorisation with Eigen's early-outs
-          if (!ok) ok = solve6_fp32_registers<true>(ss.lin.H, ss.lin.G, dp);      // Eigen's pivoted LDLT
-          if (!ok) ok = solve6_fallback(ss.lin.H, ss.lin.G, dp);                   // damped fp64 retry
-          Tn = ss.Td;
-          if (ok) { apply_update(Tn, dp, meta.s, meta.c1, meta.c2, meta.c3); make_projection(L, Tn, Pn); }
-        }
-        ss.lin.pad[0] = ok ? 1 : 0;
-        BP_FINE(26);
-#pragma unroll
-        for (int k = 0; k < 6; ++k) ss.dp[k] = dp[k];
-        if (ok) {
-          ss.Td = Tn;
-#pragma unroll
-          for (int k = 0; k < 12; ++k) ss.P[k] = Pn[k];
-        }
-      }
-      __syncthreads();
       BP_FINE(28);
       if (!ss.lin.pad[0]) {                                                    // :359-365 / gn.h:90-97
         status = 0x34; solver_error = true;
@@ -1454,9 +1657,8 @@ __global__ void __launch_bounds__(kLinThreads, 1) k_estimate_pose(const __grid_c
       if (first) { first = false; f_prev = 0.0f; dp_prev = 0.0f; }
       else if (!(it++ < a.sp.max_iterations && n_evals < a.sp.max_fun_evals)) break;   // the do-while condition (conv is false here)
       // top of the next do-while pass: testConvergence (:258-282) on the step just taken
-      float dpn = 0.0f; for (int k = 0; k < 6; ++k) dpn += ss.dp[k] * ss.dp[k];
-      dpn = sqrtf(dpn);
-      g_norm = 0.0f; for (int k = 0; k < 6; ++k) g_norm = fmaxf(g_norm, fabsf(ss.lin.G[k]));
+      const float dpn = ss.dpn;
+      g_norm = ss.gn;
       if (dpn < a.sp.parameter_tolerance || dpn < a.sp.parameter_tolerance * (sqrt_eps + dp_prev)) { status = 0x30; conv = true; }
       else if (f_norm < a.sp.function_tolerance || f_norm < a.sp.function_tolerance * (sqrt_eps + f_prev) ||
                fabsf(f_norm - f_prev) < a.sp.function_tolerance) { status = 0x31; conv = true; }
@@ -1493,10 +1695,16 @@ __global__ void __launch_bounds__(kLinThreads, 1) k_estimate_pose(const __grid_c
         a.work.valid[i] = tc_valid(tc, k);
       }
     }
-    if (ss.abort) status = -4;
+    if (ss.abort.flag || *(volatile int*) ss.abort.global_flag) status = -4;
     if (blockIdx.x == 0 && tid == 0) {
       LevelStats st; st.num_iterations = it; st.final_error = f_norm; st.first_order_optimality = g_norm; st.status = status; st.num_evals = n_evals;
+      unsigned long long t1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      st.us = 1e-3f * (float) (t1 - t_level);
       a.stats[lvl] = st;
+    }
+    if (a.prof_lvl && blockIdx.x == 0) {              // per-level share of the phase counters (thread 0 wrote them; barriers in between)
+      __syncthreads();
+      if (tid < 16) a.prof_lvl[lvl * 16 + tid] += prof_smem()[tid] - prof_snap;
     }
   }
   if (a.prof && blockIdx.x == 0) {
@@ -1504,7 +1712,7 @@ __global__ void __launch_bounds__(kLinThreads, 1) k_estimate_pose(const __grid_c
     if (tid < 64) a.prof[tid] += prof_smem()[tid];
   }
   if (blockIdx.x == 0 && tid == 0) {
-    *a.T_out = ss.T; *a.num_fun_evals = total_evals;
+    *a.T_out = ss.T; *a.num_fun_evals = total_evals; *a.aborted_out = ss.abort.flag | *(volatile int*) ss.abort.global_flag;
     *a.work.out = ss.lin;
     a.work.scale->scale = ss.scale; a.work.scale->delta = ss.delta;
   }

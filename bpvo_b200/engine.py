@@ -13,6 +13,8 @@ from . import _capi
 from .types import AlgorithmParameters, Error, OptimizerStatistics, fill_cparams
 
 FLAG_HOST_SOLVE = 1
+FLAG_NO_GRAPHS = 2
+FLAG_FAST_BLEND = 4
 
 
 def _fp(a):
@@ -58,6 +60,7 @@ class Context:
         self._lib = _capi.lib()
         self.rows, self.cols = image_size
         self.params = params
+        self.flags = int(flags)
         self._own = _borrow is None
         if _borrow is not None:
             self.h = C.c_void_p(_borrow)
@@ -225,6 +228,17 @@ class Context:
         out = (C.c_int32 * _capi.MAX_LEVELS)()
         _check(self._lib.bpvo_b200_last_level_evals(self.h, out))
         return list(out[:self.params.numPyramidLevels])
+
+    def last_level_us(self):
+        out = (C.c_float * _capi.MAX_LEVELS)()
+        _check(self._lib.bpvo_b200_last_level_us(self.h, out))
+        return list(out[:self.params.numPyramidLevels])
+
+    def level_phase_cycles(self, reset=True):
+        """{level: {phase: cycles}} of the on-device GN loop while profiling was on"""
+        buf = (C.c_longlong * (_capi.MAX_LEVELS * 16))()
+        _check(self._lib.bpvo_b200_get_level_phase_cycles(self.h, buf, int(reset)))
+        return {l: dict(zip(self.PHASES, list(buf)[l * 16:l * 16 + len(self.PHASES)])) for l in range(self.params.numPyramidLevels)}
 
     def time_linearize(self, ref, cur, level, T, iters=20, flush_l2=True) -> float:
         ms = C.c_float()

@@ -56,6 +56,11 @@ enum { BPVO_B200_KF_LARGE_TRANSLATION = 0x40, BPVO_B200_KF_LARGE_ROTATION = 0x41
 
 /* flags */
 #define BPVO_B200_FLAG_NO_GRAPHS    2  /* launch the per-frame kernel sequences one by one instead of as CUDA graphs */
+#define BPVO_B200_FLAG_FAST_BLEND   4  /* bit-planes: evaluate the 4-tap bilinear blend of the residuals with fp32 FMAs on fp64-derived
+                                          fractions instead of the reference's double expression (photo_error.cc:381-388).  |dr| <= 2e-7
+                                          (north star: 1e-5) but the residual vector is no longer bit-identical to the reference, and the
+                                          same-box A/B gained only 2 % (profiles/README.md): off by default.  Projection, Floor and validity
+                                          are fp64 in both modes; intensity always uses the double expression. */
 #define BPVO_B200_FLAG_HOST_SOLVE   1  /* estimate_pose drives the GN loop from the host (one sync per iteration)
                                           instead of the on-device loop; same results, used for parity tests */
 
@@ -267,6 +272,10 @@ int bpvo_b200_timer_start(bpvo_b200_ctx* ctx);
 int bpvo_b200_timer_stop(bpvo_b200_ctx* ctx, float* ms);
 /* linearize() evaluations per pyramid level of the last estimate_pose (numLevels ints) */
 int bpvo_b200_last_level_evals(bpvo_b200_ctx* ctx, int* evals);
+/* device time (microseconds, GPU global timer) the on-device GN loop of the last estimate_pose spent in each pyramid level */
+int bpvo_b200_last_level_us(bpvo_b200_ctx* ctx, float* us);
+/* the phase counters of get_phase_cycles split by pyramid level: [BPVO_B200_MAX_LEVELS][16] */
+int bpvo_b200_get_level_phase_cycles(bpvo_b200_ctx* ctx, long long* cycles, int reset);
 /* Parity hooks of the on-device GN loop (the kernel bpvo_b200_estimate_pose launches; no reference counterpart).
  * debug_device_linearize: `n` consecutive PoseEstimatorGN::linearize evaluations (pose_estimator_gn.h:70-81) of `level`
  * executed INSIDE that persistent kernel at the caller's poses T[0..n) (16 floats each, column-major) -- its shared-memory

@@ -5,7 +5,7 @@ mkdir -p gpurun_out
 TAG=${1:-r2a}
 nvidia-smi --query-gpu=name,memory.total,clocks.max.sm --format=csv > gpurun_out/${TAG}_env.txt
 (nproc; lscpu | grep "Model name") >> gpurun_out/${TAG}_env.txt
-timeout 1500 python -m pytest tests/test_gpu_device_loop.py -m gpu -q -x -s 2>&1 | tail -150 > gpurun_out/${TAG}_pytest_device_loop.log
+timeout 1500 python -m pytest tests/test_gpu_device_loop.py -m gpu -q -s 2>&1 | tail -150 > gpurun_out/${TAG}_pytest_device_loop.log
 timeout 300 python scripts/iter_trace.py --frames 8 > gpurun_out/${TAG}_iter_trace.json 2> gpurun_out/${TAG}_iter_trace.err
 timeout 300 python scripts/iter_trace.py --frames 4 --flags 1 > gpurun_out/${TAG}_iter_trace_hostloop.json 2> gpurun_out/${TAG}_iter_trace_hostloop.err
 timeout 300 python scripts/iter_trace.py --frames 6 --workload kitti_cfg > gpurun_out/${TAG}_iter_trace_cfg.json 2> gpurun_out/${TAG}_iter_trace_cfg.err

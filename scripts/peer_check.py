@@ -64,6 +64,20 @@ def main():
         assert same_on_all_ranks(Tp), f"{name}: ranks hold different poses"
         assert np.array_equal(out["rep"][0], Tf) and out["rep"][1] == out["full"][1], (name, "replicated levels must reproduce the single-GPU solve")
         assert abs(out["peer"][2] - out["full"][2]) < 5e-3, (name, out["peer"][2], out["full"][2])
+        # host-driven paths on a peer-mode ctx with the DEFAULT shard_min_points (every level of these scenes is replicated):
+        # linearize and the HOST_SOLVE loop must not sum the replicated levels over the ranks -- H, G, n_valid as on one GPU
+        from bpvo_b200.engine import FLAG_HOST_SOLVE
+        hs = Context(sc.K, sc.baseline, (sc.rows, sc.cols), p, device_id=local, flags=FLAG_HOST_SOLVE)
+        hs.comm_init(rank, world, uid()); hs.peer_init_distributed(dist)
+        a, b = hs.frame(), hs.frame(); a.setData(i0, d0); a.setTemplate(); b.setData(i1, d1)
+        a1, b1 = full.frame(), full.frame(); a1.setData(i0, d0); a1.setTemplate(); b1.setData(i1, d1)
+        if a.numPoints(0) == a1.numPoints(0):      # replicated (under 131072 points)
+            lh, lf = hs.linearize(a, b, 0, T0, True), full.linearize(a1, b1, 0, T0, True)
+            assert lh["n_valid"] == lf["n_valid"] and rel_err(lh["H"], lf["H"]) < 1e-6 and abs(lh["f_norm"] - lf["f_norm"]) <= 1e-6 * max(1.0, lf["f_norm"]), (name, lh, lf)
+            Th, sh_, nh = hs.estimatePose(a, b, T0)
+            assert rel_err(Th, Tf) < 1e-4, (name, "HOST_SOLVE on replicated levels", Th, Tf)
+            assert hs.getFractionOfGoodPoints(p.goodPointThreshold) <= 1.0
+        a.close(); b.close(); a1.close(); b1.close(); hs.comm_destroy(); hs.close()
         report[name] = {"evals_full": out["full"][1], "evals_nccl": out["nccl"][1], "evals_peer": out["peer"][1],
                         "pose_rel_err_vs_full": rel_err(Tp, Tf), "pose_rel_err_vs_nccl": rel_err(Tp, Tn)}
         nccl.comm_destroy(); peer.comm_destroy(); rep.comm_destroy()

@@ -48,12 +48,28 @@ def main():
     # in-kernel phase profile of the persistent solve (CTA 0 cycle counters)
     ctx.set_profiling(True)
     ctx.phase_cycles(reset=True)
+    ctx.level_phase_cycles(reset=True)
     ctx.reset_counters()
     tot_ev = 0
+    lvl_ev = [0] * p.numPyramidLevels
+    lvl_us = [0.0] * p.numPyramidLevels
     for _ in range(5):
         Tg, stats, evals = ctx.estimatePose(a, b, T)
         tot_ev += evals
+        for l, (e, u) in enumerate(zip(ctx.last_level_evals(), ctx.last_level_us())):
+            lvl_ev[l] += e; lvl_us[l] += u
     cyc = ctx.phase_cycles()
+    # the persistent (fused) solve level by level: device time per GN iteration, algorithmic bytes, fraction of the HBM peak
+    lpc = ctx.level_phase_cycles()
+    out["fused_levels"] = []
+    for l in range(p.numPyramidLevels):
+        N = a.numPoints(l); r, c = a.level_size(l)
+        B = bench.algorithmic_bytes_per_iter(N, ctx.channels, r, c)
+        us = lvl_us[l] / max(lvl_ev[l], 1)
+        tot = float(sum(lpc[l].values())) or 1.0
+        out["fused_levels"].append({"level": l, "N": N, "evals": lvl_ev[l], "us_per_gn_iter": round(us, 3), "algorithmic_bytes": B,
+                                    "gbs": B / us / 1e3 if us > 0 else 0.0, "frac": B / us / 1e3 / peak if us > 0 else 0.0,
+                                    "phase_us_per_eval": {k: round(us * v / tot, 3) for k, v in lpc[l].items()}})
     ms = ctx.counters()["ms_linearize"]
     fine = cyc.pop("_fine")
     hits, ests = cyc.pop("_bracket_hits"), cyc.pop("_scale_estimates")

@@ -11,6 +11,8 @@ from conftest import make_params, rel_err
 
 pytestmark = pytest.mark.gpu
 
+FLAG_FAST_BLEND = 4    # include/bpvo_b200.h
+
 
 def _scene(kind):
     from bpvo_b200 import synth
@@ -27,13 +29,13 @@ def _scene(kind):
     raise ValueError(kind)
 
 
-def _pair(kind, params, oracle, use_rcp=0, k0=0, k1=1, **scene_kw):
+def _pair(kind, params, oracle, use_rcp=0, k0=0, k1=1, flags=0, **scene_kw):
     """-> (scene, gpu ctx, gpu ref, gpu cur, oracle ref, oracle cur)"""
     from bpvo_b200.engine import Context
     sc = _scene(kind)
     for k, v in scene_kw.items():
         setattr(sc, k, v)
-    ctx = Context(sc.K, sc.baseline, (sc.rows, sc.cols), params)
+    ctx = Context(sc.K, sc.baseline, (sc.rows, sc.cols), params, flags=flags)
     p = ctx.params
     i0, d0 = sc.render(k0)
     i1, d1 = sc.render(k1)
@@ -97,7 +99,9 @@ def test_template_nms_radius2_and_holes(oracle):
         assert np.array_equal(gref.point_inds(l), oref.point_inds(l))
 
 
-def _cmp_linearize(ctx, gref, gcur, oref, ocur, oest, level, T, first, tol_hg):
+def _cmp_linearize(ctx, gref, gcur, oref, ocur, oest, level, T, first, tol_hg, exact=None):
+    if exact is None:
+        exact = ctx.channels == 1 or not (ctx.flags & FLAG_FAST_BLEND)
     g = ctx.linearize(gref, gcur, level, T, first)
     o = oest.linearize(oref, ocur, level, T, first)
     N = gref.numPoints(level)
@@ -113,14 +117,20 @@ def _cmp_linearize(ctx, gref, gcur, oref, ocur, oest, level, T, first, tol_hg):
     print("linearize parity:", m)
     assert m["valid_mismatch"] == 0 and g["n_valid"] == int(v_o.sum()), m
     assert m["r_err"] <= 1e-5 * max(1.0, m["r_max"]), m
+    if exact:       # fp64 blend (the default; not with BPVO_B200_FLAG_FAST_BLEND on bit-planes): the reference's bits
+        assert np.array_equal(r_g.view(np.uint32), r_o.view(np.uint32)), m
+        if ctx.params.lossFunction != 0x12:
+            assert np.float32(g["sigma"]).tobytes() == np.float32(o["sigma"]).tobytes(), m
+        assert np.array_equal(w_g.view(np.uint32), w_o.view(np.uint32)), m
     if ctx.params.lossFunction != 0x12:    # kL2: the reference estimates a scale it never uses; the engine skips it
         assert abs(g["sigma"] - o["sigma"]) <= 1e-6 * max(1.0, abs(o["sigma"])), m
     assert m["w_err"] <= 1e-5, m
     # The oracle (like the reference) accumulates C*N rank-1 terms sequentially in fp32 (error grows with C*N, ~1e-4 at
     # 2e5 terms); the engine sums per-thread fp32, then tree/fp64.  Loose bound against the oracle, tight bound against an
     # fp64 evaluation of the SAME J, r, w, valid (the engine must be the closer one).
-    assert m["H_rel"] < 5 * tol_hg, m
-    assert m["G_rel"] < 50 * tol_hg, m      # G suffers cancellation near the optimum
+    seq = 4e-9 * C * N                      # the reference's ONE sequential fp32 accumulator: 2.5 % off at 1.5e7 terms (1080p dense)
+    assert m["H_rel"] < max(5 * tol_hg, seq), m
+    assert m["G_rel"] < max(50 * tol_hg, seq), m      # G suffers cancellation near the optimum
     J = oref.jacobians(level).reshape(C * N, 6).astype(np.float64)
     wv = w_o.astype(np.float64) * np.tile(v_o, C).astype(np.float64)
     H64 = (J * wv[:, None]).T @ J
@@ -130,17 +140,22 @@ def _cmp_linearize(ctx, gref, gcur, oref, ocur, oest, level, T, first, tol_hg):
     # f_norm: the oracle accumulates sum(w r^2) sequentially in fp32 like the reference (error grows with C*N);
     # check both against an fp64 evaluation of the same (bit-identical) r, w, valid: the engine must be the closer one
     f_exact = float(np.sqrt(np.sum(w_o.astype(np.float64) * np.tile(v_o, C).astype(np.float64) * r_o.astype(np.float64) ** 2)))
-    assert abs(g["f_norm"] - f_exact) <= 2e-6 * max(1.0, f_exact), (m, f_exact)
-    assert abs(o["f_norm"] - f_exact) <= 1e-3 * max(1.0, f_exact), (m, f_exact)
+    assert abs(g["f_norm"] - f_exact) <= (2e-6 if exact else 2e-5) * max(1.0, f_exact), (m, f_exact)
+    assert abs(o["f_norm"] - f_exact) <= max(1e-3, seq) * max(1.0, f_exact), (m, f_exact)
     return g, o
 
 
+@pytest.mark.parametrize("flags", [0, FLAG_FAST_BLEND])
 @pytest.mark.parametrize("kind,desc,levels,loss", [("small", "intensity", 3, "l2"), ("small", "intensity", 3, "huber"),
                                                     ("small", "bitplanes", 3, "tukey"), ("odd", "bitplanes", 2, "huber"),
                                                     ("vga", "intensity", 4, "huber"), ("kitti", "bitplanes", 4, "tukey")])
-def test_linearize(kind, desc, levels, loss, oracle):
+def test_linearize(kind, desc, levels, loss, flags, oracle):
+    """default: the reference's fp64 blend -> r, sigma, w BIT-IDENTICAL to the oracle; BPVO_B200_FLAG_FAST_BLEND (bit-planes
+    only): fp32-FMA blend, r within 1e-5 (north star)"""
+    if desc == "intensity" and flags:
+        pytest.skip("intensity always computes the fp64 expression")
     p = make_params(desc, levels, loss)
-    sc, ctx, gref, gcur, oref, ocur = _pair(kind, p, oracle, use_rcp=0)
+    sc, ctx, gref, gcur, oref, ocur = _pair(kind, p, oracle, use_rcp=0, flags=flags)
     oest = oracle.Estimator(ctx.params)
     T = np.eye(4, dtype=np.float32)
     for l in range(levels - 1, -1, -1):
