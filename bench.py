@@ -355,6 +355,10 @@ def run_ours(args, w, rank, world, local_rank):
         dense = dense_variant_roofline(local_rank)
         hbm_bound = hbm_bound_variant(local_rank)
 
+    throughput = None
+    if rank == 0 and world == 1 and not args.no_throughput:
+        throughput = throughput_variant(sc, p, host_ptrs, local_rank, torch, args.warmup, min(args.steps, 48))
+
     sharded = None
     if world > 1 and args.workload == "kitti" and not args.no_dense:
         sharded = sharded_variant(rank, world, local_rank, dist, torch)
@@ -376,6 +380,7 @@ def run_ours(args, w, rank, world, local_rank):
             "cpu_baseline": cpu,
             "roofline_dense_variant": dense,
             "roofline_hbm_bound_variant": hbm_bound,
+            "throughput_mode": throughput,
             "sharded_1080p_dense_variant": sharded,
         }
         emit(line)
@@ -383,6 +388,66 @@ def run_ours(args, w, rank, world, local_rank):
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def throughput_variant(sc, p, host_ptrs, local_rank, torch, warmup, steps, streams_list=(2, 4)):
+    """Throughput mode beside the single-stream headline: S independent VisualOdometry streams on ONE GPU, one host thread
+    each, the on-device GN loop of every stream confined to 148 / S SMs (bpvo_b200_set_solver_ctas) so that the solves run
+    side by side.  Frames come from pinned host memory (H2D inside the timed region); wall clock between two thread
+    barriers with a device synchronize inside, i.e. frames/s of the whole GPU."""
+    import threading
+    from bpvo_b200 import VisualOdometry
+    sms = torch.cuda.get_device_properties(local_rank).multi_processor_count
+    out = []
+    for S in streams_list:
+        ctas = max(1, sms // S)
+        vos = []
+        for _ in range(S):
+            v = VisualOdometry(sc.K, sc.baseline, (sc.rows, sc.cols), p, device_id=local_rank)
+            v.ctx.set_solver_ctas(ctas)
+            v.addFrameRaw(host_ptrs[0][0], host_ptrs[0][1], want_cloud=False)
+            vos.append(v)
+        gate = threading.Barrier(S + 1)
+        evals = [0] * S
+        errs = []
+
+        def worker(i):
+            try:
+                v = vos[i]
+                for k in range(1, 1 + warmup):
+                    v.addFrameRaw(host_ptrs[k][0], host_ptrs[k][1], want_cloud=False)
+                v.ctx.synchronize()
+                gate.wait()
+                for k in range(1 + warmup, 1 + warmup + steps):
+                    evals[i] += v.addFrameRaw(host_ptrs[k][0], host_ptrs[k][1], want_cloud=False).numFunEvals
+                v.ctx.synchronize()
+            except Exception as e:      # noqa: BLE001
+                errs.append(repr(e))
+                gate.abort()
+                return
+            gate.wait()
+
+        th = [threading.Thread(target=worker, args=(i,)) for i in range(S)]
+        for t in th:
+            t.start()
+        try:
+            gate.wait()
+            t0 = time.perf_counter()
+            gate.wait()
+            dt = time.perf_counter() - t0
+        except threading.BrokenBarrierError:
+            dt = None
+        for t in th:
+            t.join()
+        for v in vos:
+            v.close()
+        if dt is None or errs:
+            out.append({"streams_per_gpu": S, "error": errs[:1]})
+            continue
+        out.append({"streams_per_gpu": S, "ctas_per_stream": ctas, "value": S * steps / dt, "unit": "frames/s",
+                    "gn_iters_per_sec": sum(evals) / dt, "ms_per_frame_per_stream": 1e3 * dt / steps,
+                    "timing": "wall clock around S host threads x K addFrame calls from pinned host buffers (H2D inside), device synchronized at both ends"})
+    return out
 
 
 def sharded_variant(rank, world, local_rank, dist, torch):
@@ -532,6 +597,7 @@ def main():
     ap.add_argument("--workload", default="kitti", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-dense", action="store_true", help="skip the dense-selection roofline variant")
+    ap.add_argument("--no-throughput", action="store_true", help="skip the several-streams-per-GPU variant")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))

@@ -94,6 +94,7 @@ def _signatures():
         "bpvo_b200_peer_init": (C.c_int, [vp, u8p]),
         "bpvo_b200_peer_set_min_points": (C.c_int, [vp, C.c_int]),
         "bpvo_b200_set_profiling": (C.c_int, [vp, C.c_int]),
+        "bpvo_b200_set_solver_ctas": (C.c_int, [vp, C.c_int]),
         "bpvo_b200_get_counters": (C.c_int, [vp, C.POINTER(CCounters)]),
         "bpvo_b200_reset_counters": (C.c_int, [vp]),
         "bpvo_b200_get_phase_cycles": (C.c_int, [vp, C.POINTER(C.c_longlong), C.c_int]),

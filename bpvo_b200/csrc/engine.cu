@@ -136,6 +136,7 @@ int bpvo_b200_create(bpvo_b200_ctx** out, const float K[9], float baseline, int 
   c->L = p->numPyramidLevels; c->baseline = baseline;
   if (getenv("BPVO_B200_NO_GRAPHS")) c->p.flags |= BPVO_B200_FLAG_NO_GRAPHS;      // A/B switches for measurements
   if (getenv("BPVO_B200_FAST_BLEND")) c->p.flags |= BPVO_B200_FLAG_FAST_BLEND;
+  if (const char* e = getenv("BPVO_B200_SOLVER_CTAS")) c->solver_ctas = atoi(e);
   // test hook: start the exchange sequence numbers close to their wrap-around so that the reset paths get exercised
   if (const char* e = getenv("BPVO_B200_SEQ_INIT")) { c->ll_seq = (unsigned) strtoul(e, nullptr, 0); c->x_seq_init = c->ll_seq; }
   c->C = (p->descriptor == BPVO_B200_BITPLANES) ? 8 : 1;
@@ -176,7 +177,7 @@ int bpvo_b200_create(bpvo_b200_ctx** out, const float K[9], float baseline, int 
   CUDA_TRY(cudaMalloc(&c->work.ticket, 4 * sizeof(unsigned)));
   CUDA_TRY(cudaMalloc(&c->work.cand, ((size_t) kMaxGrid * kCandPerCta + kOvfCap) * sizeof(float)));
   CUDA_TRY(cudaMalloc(&c->sel, sizeof(Sel)));
-  CUDA_TRY(cudaMalloc(&c->export_buf, capmax * c->C * 6 * sizeof(float)));
+  CUDA_TRY(cudaMalloc(&c->export_buf, capmax * std::max(c->C * 6, 8) * sizeof(float)));      // Jacobian export / 32-byte point records
   CUDA_TRY(cudaMemsetAsync(c->work.hist, 0, (kHistSets * kHistWords + 8 + 128) * sizeof(unsigned), c->stream));
   CUDA_TRY(cudaMemsetAsync(c->work.ticket, 0, 4 * sizeof(unsigned), c->stream));
   CUDA_TRY(cudaMemsetAsync(c->sel, 0, sizeof(Sel), c->stream));
@@ -259,6 +260,15 @@ int bpvo_b200_get_level_phase_cycles(bpvo_b200_ctx* c, long long* cycles /* [BPV
 int bpvo_b200_last_level_us(bpvo_b200_ctx* c, float* us) {
   if (!c || !us) return bp_fail(BPVO_B200_ERR_INVALID_ARG, "null argument");
   for (int l = 0; l < c->L; ++l) us[l] = c->level_us[l];
+  return BPVO_B200_OK;
+}
+// Throughput mode: the on-device GN loop of this ctx occupies only `ctas` SMs (one 256-thread CTA each; 0 = all SMs), so that
+// several independent ctxs -- one VisualOdometry stream each, driven from different host threads -- run their solves side by side
+// on one GPU (BASELINE.json configs[4] with more than one stream per GPU).  Results do not depend on the grid size beyond fp32
+// summation order (tests/test_gpu_device_loop.py runs the parity checks at 1 ... 148 CTAs).
+int bpvo_b200_set_solver_ctas(bpvo_b200_ctx* c, int ctas) {
+  if (!c || ctas < 0) return bp_fail(BPVO_B200_ERR_INVALID_ARG, "bad argument");
+  c->solver_ctas = ctas;
   return BPVO_B200_OK;
 }
 int bpvo_b200_set_profiling(bpvo_b200_ctx* c, int enable) { if (!c) return bp_fail(BPVO_B200_ERR_INVALID_ARG, "null ctx"); c->profiling = enable != 0; return BPVO_B200_OK; }
@@ -817,6 +827,7 @@ static int launch_estimate_pose_t(bpvo_b200_ctx* c, const bpvo_b200_frame* ref, 
   }
   void* args[] = {&a, &sel, &cache_bytes};
   int grid = std::min(c->sm_count, kMaxGrid);
+  if (c->solver_ctas > 0) grid = std::min(grid, c->solver_ctas);     // throughput mode: several ctxs share the SMs
   if (ov && ov->grid > 0) grid = std::min(grid, ov->grid);
   CUDA_TRY(cudaLaunchCooperativeKernel((void*) k_estimate_pose<C, BLEND>, dim3(grid), dim3(kLinThreads), args, dyn, c->stream));
   c->counters.launches++;
@@ -933,7 +944,7 @@ extern "C" int bpvo_b200_fraction_good(bpvo_b200_ctx* c, float thresh, float* fr
 
 // getPointCloudFromRefFrame (vo.cc:249-281) assembled on the device, one D2H
 extern "C" int bpvo_b200_point_cloud(bpvo_b200_ctx* c, const bpvo_b200_frame* ref, bpvo_b200_point_info* records, int* n) {
-  static_assert(sizeof(bpvo_b200_point_info) == 24 && sizeof(PointInfo) == 24, "24-byte point records");
+  static_assert(sizeof(bpvo_b200_point_info) == 32 && sizeof(PointInfo) == 32, "32-byte point records (bpvo::PointWithInfo)");
   if (!c || !ref || !n) return bp_fail(BPVO_B200_ERR_INVALID_ARG, "null argument");
   if (ref->ctx != c) return bp_fail(BPVO_B200_ERR_INVALID_ARG, "frame belongs to another ctx");
   if (!ref->has_template) return bp_fail(BPVO_B200_ERR_NO_DATA, "frame has no template");
@@ -947,7 +958,7 @@ extern "C" int bpvo_b200_point_cloud(bpvo_b200_ctx* c, const bpvo_b200_frame* re
   // sigma of the last linearize (already on the host after estimate_pose / linearize)
   const float sigma = c->h_mail->lin.sigma;
   const LevelGeom& g = c->geom[level];
-  PointInfo* d = reinterpret_cast<PointInfo*>(c->export_buf);          // capacity: capmax * C * 6 floats >= 6 floats per point
+  PointInfo* d = reinterpret_cast<PointInfo*>(c->export_buf);          // capacity: capmax * C * 6 floats and at least 8 floats per point
   if (c->C == 1) k_point_cloud<1><<<ceil_div(np, 256), 256, 0, c->stream>>>(ref->pts[level], np, ref->pyr[0], c->rows, c->cols, g.fx, g.fy, g.cx, g.cy, c->work.res, sigma, c->p.lossFunction, d);
   else k_point_cloud<8><<<ceil_div(np, 256), 256, 0, c->stream>>>(ref->pts[level], np, ref->pyr[0], c->rows, c->cols, g.fx, g.fy, g.cx, g.cy, c->work.res, sigma, c->p.lossFunction, d);
   LAUNCH_CHECK(c);

@@ -35,7 +35,7 @@ struct ImageSize { int rows = 0, cols = 0; ImageSize(int r = 0, int c = 0) : row
 typedef bpvo_b200_params AlgorithmParameters;    // POD mirror of bpvo::AlgorithmParameters
 typedef bpvo_b200_stats OptimizerStatistics;
 
-struct PointWithInfo { Point xyzw; uint8_t rgba[4]; float weight; };   // bpvo/point_cloud.h
+struct PointWithInfo { Point xyzw; uint8_t rgba[4]; float weight; uint8_t pad[8]; };   // bpvo/point_cloud.h:50-58 (32 bytes)
 struct PointCloud { std::vector<PointWithInfo> points; Matrix44 pose; };
 
 struct Result {                                  // bpvo::Result (bpvo/types.h:496-566)

@@ -167,7 +167,7 @@ class VisualOdometry::Impl {
   // getPointCloudFromRefFrame (vo.cc:249-281): weights[i], i < N, are channel 0 of the last linearize (Q7)
   std::unique_ptr<PointCloud> getPointCloudFromRefFrame() const {
     // assembled on the device (xyzw, grey level at K_l X in the full-resolution ref image, channel-0 weight): one download
-    static_assert(sizeof(PointWithInfo) == sizeof(bpvo_b200_point_info), "PointWithInfo is the 24-byte device record");
+    static_assert(sizeof(PointWithInfo) == sizeof(bpvo_b200_point_info), "PointWithInfo is the 32-byte device record");
     std::unique_ptr<PointCloud> ret(new PointCloud);
     ret->pose = Matrix44::Identity();
     int n = 0;

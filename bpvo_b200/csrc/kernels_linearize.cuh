@@ -898,7 +898,7 @@ __global__ void __launch_bounds__(256) k_export_weights(const float* __restrict_
 }
 
 // getPointCloudFromRefFrame (vo.cc:249-281) on the device: xyzw, grey level of the ref image at K_l X, channel-0 weight
-struct PointInfo { float x, y, z, w; unsigned rgba; float weight; };
+struct PointInfo { float x, y, z, w; unsigned rgba; float weight; unsigned pad[2]; };      // bpvo::PointWithInfo's 32-byte layout
 template <int C>
 __global__ void __launch_bounds__(256) k_point_cloud(const float4* __restrict__ pts, int n, const uint8_t* __restrict__ image, int rows, int cols,
                                                      float fx, float fy, float cx, float cy, const float* __restrict__ res, float sigma, int loss,
@@ -916,6 +916,7 @@ __global__ void __launch_bounds__(256) k_point_cloud(const float4* __restrict__ 
   o.x = X.x; o.y = X.y; o.z = X.z; o.w = X.w;
   o.rgba = c | (c << 8) | (c << 16) | (255u << 24);
   o.weight = robust_weight(loss, res[(size_t) i * C], __fdiv_rn(1.0f, sigma));
+  o.pad[0] = o.pad[1] = 0u;
   out[i] = o;
 }
 

@@ -190,6 +190,10 @@ class Context:
         self.peer_init(allh)
 
     # -- measurement --------------------------------------------------------------------------------
+    def set_solver_ctas(self, n: int):
+        """throughput mode: SMs the on-device GN loop of this ctx occupies (0 = all)"""
+        _check(self._lib.bpvo_b200_set_solver_ctas(self.h, int(n)))
+
     def set_profiling(self, on: bool):
         _check(self._lib.bpvo_b200_set_profiling(self.h, int(on)))
 

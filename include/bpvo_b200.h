@@ -222,11 +222,12 @@ int bpvo_b200_get_valid(bpvo_b200_ctx* ctx, uint8_t* v, size_t* count);   /* per
 /* float getFractionOfGoodPoints(float thresh)  (vo_pose_estimator.cc:101-107), counted on the device */
 int bpvo_b200_fraction_good(bpvo_b200_ctx* ctx, float thresh, float* frac);
 /* getPointCloudFromRefFrame (vo.cc:249-281) assembled on the device: per template point of `ref` at maxTestLevel one
- * 24-byte record {x, y, z, w (float), r, g, b, a (uint8), weight (float)} = bpvo::PointWithInfo without its alignment
- * padding: colour = the ref frame's full-resolution image at the projection K_l * X (bounds and truncation as
+ * 32-byte record {x, y, z, w (float), r, g, b, a (uint8), weight (float), 8 bytes of padding} = the memory layout of
+ * bpvo::PointWithInfo (bpvo/point_cloud.h:50-58: 16 + 4 + 4 bytes padded to 32, 32-byte stride), so the records can be
+ * copied straight into a PointWithInfoVector: colour = the ref frame's full-resolution image at the projection K_l * X (bounds and truncation as
  * vo.cc:269-272), weight = channel 0 of the last linearize's weights (Q7; invalid points carry 1, Q6).  One D2H of
- * 24 N bytes instead of points + weights + the whole image.  *n: in = capacity in records, out = N. */
-typedef struct { float x, y, z, w; uint8_t rgba[4]; float weight; } bpvo_b200_point_info;
+ * 32 N bytes instead of points + weights + the whole image.  *n: in = capacity in records, out = N. */
+typedef struct { float x, y, z, w; uint8_t rgba[4]; float weight; uint8_t pad[8]; } bpvo_b200_point_info;   /* 32 bytes */
 int bpvo_b200_point_cloud(bpvo_b200_ctx* ctx, const bpvo_b200_frame* ref, bpvo_b200_point_info* records, int* n);
 
 /* ---------------------------------------------------------------------------------------------
@@ -259,6 +260,9 @@ int bpvo_b200_peer_set_min_points(bpvo_b200_ctx* ctx, int min_points);
 /* ---------------------------------------------------------------------------------------------
  * measurement helpers
  * ------------------------------------------------------------------------------------------- */
+/* throughput mode: SMs (one CTA each) the on-device GN loop of this ctx uses, 0 = all.  With e.g. 4 ctxs of 37 CTAs, four
+ * independent VisualOdometry streams (one host thread each) run their solves concurrently on one GPU. */
+int bpvo_b200_set_solver_ctas(bpvo_b200_ctx* ctx, int ctas);
 int bpvo_b200_set_profiling(bpvo_b200_ctx* ctx, int enable);   /* cudaEvent pairs around each phase */
 int bpvo_b200_get_counters(bpvo_b200_ctx* ctx, bpvo_b200_counters* out);
 /* SM-cycle counters of the phases of the on-device GN loop (CTA 0), accumulated while profiling is on:

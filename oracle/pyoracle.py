@@ -484,6 +484,51 @@ def ref_lib():
     return L
 
 
+_SEAM = None
+
+
+def build_gpuseam() -> str:
+    """builds oracle/_ref/libbpvo_gpuseam.so -- the reference's own bpvo/vo.cc compiled UNCHANGED against the GPU seam of
+    integration/ (INTEGRATION.md Option A) and linked to bpvo_b200/libbpvo_b200.so -- when the reference sources are present;
+    the GPU box uses the prebuilt file.  Returns the path or '' when unavailable."""
+    so = os.path.join(_HERE, "_ref", "libbpvo_gpuseam.so")
+    ref_root = os.environ.get("BPVO_REFERENCE", "/root/reference")
+    integ = os.path.join(_HERE, "..", "integration")
+    if os.path.isdir(os.path.join(ref_root, "bpvo")) and os.path.exists(os.path.join(_HERE, "..", "bpvo_b200", "libbpvo_b200.so")):
+        deps = [os.path.join(integ, f) for f in ("vo_b200_seam.cc", "seam_test_shim.cc", os.path.join("bpvo", "vo_frame.h"),
+                                                 os.path.join("bpvo", "vo_pose_estimator.h"))] + [os.path.join(_HERE, "..", "include", "bpvo_b200.h")]
+        stale = (not os.path.exists(so)) or os.path.getmtime(so) < max(os.path.getmtime(d) for d in deps)
+        if stale:
+            subprocess.run(["make", "-C", _HERE, "-s", "gpuseam", f"REF={ref_root}"], check=True)
+    return so if os.path.exists(so) else ""
+
+
+def seam_lib():
+    """the VisualOdometry-level entry points (same names / layouts as ref_lib()'s) of libbpvo_gpuseam.so"""
+    global _SEAM
+    if _SEAM is not None:
+        return _SEAM
+    so = build_gpuseam()
+    if not so:
+        return None
+    L = C.CDLL(so)
+    fp, u8p = C.POINTER(C.c_float), C.POINTER(C.c_uint8)
+    sig = {
+        "ref_last_error": (C.c_char_p, []),
+        "ref_vo_create": (C.c_void_p, [fp, C.c_float, C.c_int, C.c_int, C.POINTER(OrcParams)]),
+        "ref_vo_destroy": (None, [C.c_void_p]),
+        "ref_vo_add_frame": (C.c_int, [C.c_void_p, u8p, fp, C.POINTER(OrcResult)]),
+        "ref_vo_num_points_at_level": (C.c_int, [C.c_void_p, C.c_int]),
+        "ref_vo_trajectory": (C.c_int, [C.c_void_p, fp, C.c_int]),
+        "ref_vo_point_cloud": (C.c_int, [C.c_void_p, fp, fp, u8p, C.c_int]),
+    }
+    for name, (res, args) in sig.items():
+        f = getattr(L, name)
+        f.restype, f.argtypes = res, args
+    _SEAM = L
+    return L
+
+
 class RefFrame:
     """the reference's own VisualOdometryFrame (compiled from /root/reference against the stand-in headers)"""
 
@@ -575,10 +620,10 @@ class RefEstimator:
 
 
 class RefVisualOdometry:
-    """the reference's own bpvo::VisualOdometry"""
+    """the reference's own bpvo::VisualOdometry (lib = seam_lib(): its vo.cc on top of the GPU seam instead of its CPU classes)"""
 
-    def __init__(self, K, baseline, image_size, params):
-        self.L = ref_lib()
+    def __init__(self, K, baseline, image_size, params, lib=None):
+        self.L = lib if lib is not None else ref_lib()
         rows, cols = image_size
         cp = make_params(params)
         self.h = self.L.ref_vo_create(_fp(_colmajor(K)), float(baseline), rows, cols, C.byref(cp))

@@ -124,7 +124,8 @@ def _cmp_linearize(ctx, gref, gcur, oref, ocur, oest, level, T, first, tol_hg, e
         assert np.array_equal(w_g.view(np.uint32), w_o.view(np.uint32)), m
     if ctx.params.lossFunction != 0x12:    # kL2: the reference estimates a scale it never uses; the engine skips it
         assert abs(g["sigma"] - o["sigma"]) <= 1e-6 * max(1.0, abs(o["sigma"])), m
-    assert m["w_err"] <= 1e-5, m
+    # (fast blend: a residual error of 2e-7 becomes a weight error of ~ 4 dr / sigma, which exceeds 1e-5 only when sigma < 0.1)
+    assert m["w_err"] <= (1e-5 if exact else max(1e-5, 8.0 * m["r_err"] / max(o["sigma"], 1e-12))), m
     # The oracle (like the reference) accumulates C*N rank-1 terms sequentially in fp32 (error grows with C*N, ~1e-4 at
     # 2e5 terms); the engine sums per-thread fp32, then tree/fp64.  Loose bound against the oracle, tight bound against an
     # fp64 evaluation of the SAME J, r, w, valid (the engine must be the closer one).
@@ -135,7 +136,9 @@ def _cmp_linearize(ctx, gref, gcur, oref, ocur, oest, level, T, first, tol_hg, e
     wv = w_o.astype(np.float64) * np.tile(v_o, C).astype(np.float64)
     H64 = (J * wv[:, None]).T @ J
     G64 = J.T @ (wv * r_o.astype(np.float64))
-    assert rel_err(g["H"], H64) < tol_hg, (m, rel_err(g["H"], H64), rel_err(o["H"], H64))
+    # (H64 is built from the ORACLE's Jacobians, i.e. with its Hartley constants from sequential fp32 sums over N points; the
+    #  engine's come from fp64 tree sums: they drift apart by ~3e-10 * N, which rescales J -- and cancels in the pose)
+    assert rel_err(g["H"], H64) < max(tol_hg, 3.5e-10 * N), (m, rel_err(g["H"], H64), rel_err(o["H"], H64))
     assert np.abs(g["G"] - G64).max() <= tol_hg * np.abs(J * (wv * np.abs(r_o))[:, None]).sum(axis=0).max(), m
     # f_norm: the oracle accumulates sum(w r^2) sequentially in fp32 like the reference (error grows with C*N);
     # check both against an fp64 evaluation of the same (bit-identical) r, w, valid: the engine must be the closer one
