@@ -390,7 +390,7 @@ def run_ours(args, w, rank, world, local_rank):
         dist.destroy_process_group()
 
 
-def throughput_variant(sc, p, host_ptrs, local_rank, torch, warmup, steps, streams_list=(2, 4)):
+def throughput_variant(sc, p, host_ptrs, local_rank, torch, warmup, steps, streams_list=(2, 4, 8)):
     """Throughput mode beside the single-stream headline: S independent VisualOdometry streams on ONE GPU, one host thread
     each, the on-device GN loop of every stream confined to 148 / S SMs (bpvo_b200_set_solver_ctas) so that the solves run
     side by side.  Frames come from pinned host memory (H2D inside the timed region); wall clock between two thread
@@ -461,6 +461,7 @@ def sharded_variant(rank, world, local_rank, dist, torch):
     i0, d0 = sc.render(0); i1, d1 = sc.render(1)
     T0 = np.eye(4, dtype=np.float32)
     out = {"workload": w["name"], "n_gpus": world}
+    poses = {}
     for mode in ("single_gpu", "sharded"):
         ctx = Context(sc.K, sc.baseline, (sc.rows, sc.cols), p, device_id=local_rank)
         if mode == "sharded":
@@ -474,17 +475,36 @@ def sharded_variant(rank, world, local_rank, dist, torch):
         ctx.set_profiling(True); ctx.reset_counters()
         dist.barrier()
         evals = 0
+        lvl_us = [0.0] * p.numPyramidLevels
+        lvl_ev = [0] * p.numPyramidLevels
         for _ in range(3):
-            T, _, n = ctx.estimatePose(a, b, T0)
+            T, stats, n = ctx.estimatePose(a, b, T0)
             evals += n
+            for l, (e, u) in enumerate(zip(ctx.last_level_evals(), ctx.last_level_us())):
+                lvl_ev[l] += e; lvl_us[l] += u
+        poses[mode] = T
         t = torch.tensor([ctx.counters()["ms_linearize"]], dtype=torch.float64, device=f"cuda:{local_rank}")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        out[mode] = {"us_per_gn_iter": 1e3 * float(t[0]) / max(evals, 1), "gn_iters": evals,
+        # correctness on the record: every rank must hold the bit-identical pose
+        tp = torch.from_numpy(np.ascontiguousarray(T)).to(f"cuda:{local_rank}")
+        ref = tp.clone(); dist.broadcast(ref, src=0)
+        same = torch.tensor([1 if torch.equal(tp, ref) else 0], device=f"cuda:{local_rank}")
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        out[mode] = {"us_per_gn_iter": 1e3 * float(t[0]) / max(evals, 1), "gn_iters": evals, "evals_per_solve": evals / 3.0,
+                     "status_per_level": [hex(s.status) for s in stats],
+                     "poses_identical_across_ranks": bool(int(same[0])),
+                     "us_per_gn_iter_per_level": [round(u / max(e, 1), 2) for u, e in zip(lvl_us, lvl_ev)],
                      "points_per_level_local": [a.numPoints(l) for l in range(p.numPyramidLevels)]}
         if mode == "sharded":
             ctx.comm_destroy()
         a.close(); b.close(); ctx.close()
+    d = np.abs(poses["sharded"].astype(np.float64) - poses["single_gpu"].astype(np.float64)).max()
+    out["pose_rel_err_vs_single_gpu"] = float(d / np.abs(poses["single_gpu"]).max())
+    gt = np.array(sc.relative_pose(0, 1))
+    out["translation_err_vs_ground_truth_m"] = float(np.abs(poses["sharded"][:3, 3] - gt[:3, 3]).max())
+    out["parity_ok"] = bool(out["pose_rel_err_vs_single_gpu"] < 1e-4 and out["sharded"]["poses_identical_across_ranks"])
     out["speedup_vs_one_gpu"] = out["single_gpu"]["us_per_gn_iter"] / out["sharded"]["us_per_gn_iter"]
+    out["sharded_efficiency"] = out["speedup_vs_one_gpu"] / world
     return out
 
 

@@ -15,13 +15,16 @@ constexpr int kHistBins = kHist1Bins + 2 * kHist2Bins + 2 * kHist3Bins;
 constexpr int kSelBins = 1024, kSelList = 256;   // bracketed median: linear bins over the bracket, short list of the two wanted bins
 constexpr int kHistWords = kHistBins + 8 + kSelBins;   // one histogram set + bookkeeping words + the bracket histogram:
 //   [kHistBins+0] max(~i) over valid points i   [+1] valid points   [+2] residuals below the bracket   [+3] residuals inside it
-//   [+4] length of the candidate overflow list   [+8 ...] kSelBins counts of the candidates by linear bin over the bracket
+//   [+4] length of the candidate overflow list   [+5] length of the short list of a sliced overflow scan
+//   [+8 ...] kSelBins counts of the candidates by linear bin over the bracket
 #ifndef BP_CAND_PER_CTA
 #define BP_CAND_PER_CTA 12
 #endif
 constexpr int kCandPerCta = BP_CAND_PER_CTA;             // bracketed median: every CTA owns a fixed region of the candidate buffer (no slot reservation) ...
-constexpr int kCtaCandCap = 1024;            // ... stages up to this many candidates in shared memory ...
-constexpr int kOvfCap = 16384;               // ... and appends what exceeds its region to a shared overflow list (wide brackets, early iterations)
+constexpr int kCtaCandCap = 2048;            // ... stages up to this many candidates in shared memory ...
+constexpr int kOvfCap = 262144;              // ... and appends what exceeds its region to a shared overflow list (wide brackets, early iterations,
+                                             //     megapixel levels: a 0.2 % bracket around the median of 1.5e7 residuals holds 3e4 of them)
+constexpr int kOvfLocalScan = 2048;          // overflow lists up to this length are scanned by every CTA; longer ones slice by slice (bracket_select)
 constexpr unsigned kCandPoison = 1u << 30;   // added to the candidate count when even that overflowed -> radix fallback
 constexpr int kScratchBytes = (kCtaCandCap + kSelList) * 4;   // dynamic-smem scratch of the bracketed select: CTA candidates | list
 constexpr int kPartialStride = 32; // doubles per block partial (21 H + 6 G + f + n_good + pad)
@@ -92,8 +95,8 @@ struct Work {
   ScaleState* scale;
   LinOut* out;
   unsigned* ticket;      // last-CTA-done counter
-  float* cand;           // [kMaxGrid][kCandPerCta] |r| values inside the median bracket, -1 = empty slot (on-device GN loop),
-                         // followed by the overflow list [kOvfCap]
+  float* cand;           // [grid][kCandPerCta] |r| values inside the median bracket, -1 = empty slot (on-device GN loop),
+                         // followed by the overflow list [kOvfCap] and the short list [kSelList] of a sliced overflow scan
 };
 
 // point-sharded multi-GPU mode with the GN loop on the device: every rank owns a mailbox in ITS memory that the peers

@@ -69,6 +69,41 @@ struct PhaseTimer {
   }
 };
 
+static int ctx_init(bpvo_b200_ctx* c, const float K[9], float baseline, int rows, int cols, const bpvo_b200_params* p);
+static int frame_init(bpvo_b200_ctx* c, bpvo_b200_frame* f);
+
+// TMA descriptors of a frame's level images (u8, pitched) and descriptors (f32 [rows][cols][8]) for bitplanes_tma_kernel.
+// cuTensorMapEncodeTiled is a driver entry point: fetched through the runtime, no link against libcuda.
+static bool encode_tensor_maps(bpvo_b200_ctx* c, bpvo_b200_frame* f) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                               const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qr;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) != cudaSuccess || qr != cudaDriverEntryPointSuccess || !fn) {
+    cudaGetLastError();
+    return false;
+  }
+  EncodeFn encode = reinterpret_cast<EncodeFn>(fn);
+  for (int l = c->p.maxTestLevel; l < c->L; ++l) {
+    const LevelGeom& g = c->geom[l];
+    {
+      const cuuint64_t dims[2] = {(cuuint64_t) g.cols, (cuuint64_t) g.rows};
+      const cuuint64_t strides[1] = {(cuuint64_t) u8_pitch(g.cols)};
+      const cuuint32_t box[2] = {(cuuint32_t) kTmInW, (cuuint32_t) kTmInH}, es[2] = {1, 1};
+      if (encode(&f->map_in[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, f->pyr[l], dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                 CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return false;
+    }
+    {
+      const cuuint64_t dims[3] = {8, (cuuint64_t) g.cols, (cuuint64_t) g.rows};
+      const cuuint64_t strides[2] = {32, (cuuint64_t) g.cols * 32};
+      const cuuint32_t box[3] = {8, (cuuint32_t) kTmTW, (cuuint32_t) kTmTH}, es[3] = {1, 1, 1};
+      if (encode(&f->map_out[l], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, f->desc[l], dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                 CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return false;
+    }
+  }
+  return true;
+}
+
 extern "C" {
 
 int bpvo_b200_version(void) { return BPVO_B200_VERSION; }
@@ -90,7 +125,8 @@ void bpvo_b200_default_params(bpvo_b200_params* p) {     // bpvo/types.cc:31-66
 
 int bpvo_b200_device_count(void) {
   int n = 0;
-  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  const cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) { cudaGetLastError(); bp_fail(BPVO_B200_ERR_CUDA, "cudaGetDeviceCount failed: %s", cudaGetErrorString(e)); return 0; }
   return n;
 }
 
@@ -132,6 +168,20 @@ int bpvo_b200_create(bpvo_b200_ctx** out, const float K[9], float baseline, int 
   CUDA_TRY(cudaSetDevice(p->device_id));
 
   bpvo_b200_ctx* c = new bpvo_b200_ctx();
+  const int rc = ctx_init(c, K, baseline, rows, cols, p);
+  if (rc != BPVO_B200_OK) {                    // release whatever was allocated before the failure (the message survives)
+    const std::string msg = g_err;
+    bpvo_b200_destroy(c);
+    g_err = msg;
+    return rc;
+  }
+  *out = c;
+  return BPVO_B200_OK;
+}
+
+}  // extern "C"
+
+static int ctx_init(bpvo_b200_ctx* c, const float K[9], float baseline, int rows, int cols, const bpvo_b200_params* p) {
   c->p = *p; c->rows = rows; c->cols = cols;
   c->L = p->numPyramidLevels; c->baseline = baseline;
   if (getenv("BPVO_B200_NO_GRAPHS")) c->p.flags |= BPVO_B200_FLAG_NO_GRAPHS;      // A/B switches for measurements
@@ -175,7 +225,7 @@ int bpvo_b200_create(bpvo_b200_ctx** out, const float K[9], float baseline, int 
   CUDA_TRY(cudaMemsetAsync(c->d_mail, 0, sizeof(Mailbox), c->stream));
   c->work.out = &c->d_mail->lin;
   CUDA_TRY(cudaMalloc(&c->work.ticket, 4 * sizeof(unsigned)));
-  CUDA_TRY(cudaMalloc(&c->work.cand, ((size_t) kMaxGrid * kCandPerCta + kOvfCap) * sizeof(float)));
+  CUDA_TRY(cudaMalloc(&c->work.cand, ((size_t) kMaxGrid * kCandPerCta + kOvfCap + kSelList) * sizeof(float)));
   CUDA_TRY(cudaMalloc(&c->sel, sizeof(Sel)));
   CUDA_TRY(cudaMalloc(&c->export_buf, capmax * std::max(c->C * 6, 8) * sizeof(float)));      // Jacobian export / 32-byte point records
   CUDA_TRY(cudaMemsetAsync(c->work.hist, 0, (kHistSets * kHistWords + 8 + 128) * sizeof(unsigned), c->stream));
@@ -185,7 +235,7 @@ int bpvo_b200_create(bpvo_b200_ctx** out, const float K[9], float baseline, int 
   // template-build scratch (sized for level maxTestLevel = the largest one built)
   const int r0 = c->geom[c->p.maxTestLevel].rows, c0 = c->geom[c->p.maxTestLevel].cols;
   CUDA_TRY(cudaMalloc(&c->flags, (size_t) r0 * c0));
-  if (c->C == 8 && p->sigmaPriorToCensusTransform > 0.0f) CUDA_TRY(cudaMalloc(&c->blur_tmp, (size_t) r0 * c0));   // pre-census blur output
+  if (c->C == 8 && p->sigmaPriorToCensusTransform > 0.0f) CUDA_TRY(cudaMalloc(&c->blur_tmp, (size_t) r0 * u8_pitch(c0)));   // pre-census blur output
   CUDA_TRY(cudaMalloc(&c->block_counts, (size_t) (ceil_div(r0 * c0, kSelPerBlock) + 1) * sizeof(int)));
   CUDA_TRY(cudaMalloc(&c->hpartials, 1024 * 4 * sizeof(double)));
   CUDA_TRY(cudaMalloc(&c->hsums, 4 * sizeof(double)));
@@ -198,23 +248,25 @@ int bpvo_b200_create(bpvo_b200_ctx** out, const float K[9], float baseline, int 
   CUDA_TRY(cudaHostAlloc(&c->stage_img, (size_t) rows * cols, cudaHostAllocDefault));
   CUDA_TRY(cudaHostAlloc(&c->stage_disp, (size_t) rows * cols * sizeof(float), cudaHostAllocDefault));
   CUDA_TRY(cudaStreamSynchronize(c->stream));
-  *out = c;
   return BPVO_B200_OK;
 }
+
+extern "C" {
 
 int bpvo_b200_destroy(bpvo_b200_ctx* c) {
   if (!c) return BPVO_B200_OK;
   cudaSetDevice(c->p.device_id);
-  cudaStreamSynchronize(c->stream);
+  if (c->stream) cudaStreamSynchronize(c->stream);
   bp_comm_destroy(c);
   cudaFree(c->work.res); cudaFree(c->work.valid); cudaFree(c->work.hist); cudaFree(c->work.ll); cudaFree(c->work.partials);
   cudaFree(c->work.scale); cudaFree(c->d_mail); cudaFree(c->work.ticket); cudaFree(c->work.cand); cudaFree(c->sel); cudaFree(c->export_buf);
   cudaFree(c->flags); cudaFree(c->blur_tmp); cudaFree(c->block_counts); cudaFree(c->hpartials); cudaFree(c->hsums);
   cudaFree(c->d_prof); cudaFree(c->d_trace); cudaFree(c->d_trace_rows);
-  cudaFreeHost(c->h_mail); cudaFreeHost(c->stage_img); cudaFreeHost(c->stage_disp);
+  if (c->h_mail) cudaFreeHost(c->h_mail); if (c->stage_img) cudaFreeHost(c->stage_img); if (c->stage_disp) cudaFreeHost(c->stage_disp);
   if (c->flush_buf) cudaFree(c->flush_buf);
-  cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->tm0); cudaEventDestroy(c->tm1); cudaEventDestroy(c->stage_free);
-  cudaStreamDestroy(c->stream);
+  for (cudaEvent_t e : {c->ev0, c->ev1, c->tm0, c->tm1, c->stage_free}) if (e) cudaEventDestroy(e);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  cudaGetLastError();
   delete c;
   return BPVO_B200_OK;
 }
@@ -281,12 +333,28 @@ int bpvo_b200_reset_counters(bpvo_b200_ctx* c) { if (!c) return bp_fail(BPVO_B20
 int bpvo_b200_frame_create(bpvo_b200_ctx* c, bpvo_b200_frame** out) {
   if (!c || !out) return bp_fail(BPVO_B200_ERR_INVALID_ARG, "null argument");
   CUDA_TRY(cudaSetDevice(c->p.device_id));
+  *out = nullptr;
   bpvo_b200_frame* f = new bpvo_b200_frame();
   f->ctx = c;
+  const int rc = frame_init(c, f);
+  if (rc != BPVO_B200_OK) {
+    const std::string msg = g_err;
+    bpvo_b200_frame_destroy(f);
+    g_err = msg;
+    return rc;
+  }
+  *out = f;
+  return BPVO_B200_OK;
+}
+
+}  // extern "C"
+
+static int frame_init(bpvo_b200_ctx* c, bpvo_b200_frame* f) {
   CUDA_TRY(cudaMalloc(&f->disp, (size_t) c->rows * c->cols * sizeof(float)));
   for (int l = 0; l < c->L; ++l) {
     const LevelGeom& g = c->geom[l];
-    CUDA_TRY(cudaMalloc(&f->pyr[l], (size_t) g.rows * g.cols));
+    CUDA_TRY(cudaMalloc(&f->pyr[l], (size_t) g.rows * u8_pitch(g.cols)));
+    CUDA_TRY(cudaMemsetAsync(f->pyr[l], 0, (size_t) g.rows * u8_pitch(g.cols), c->stream));
     if (l < c->p.maxTestLevel) continue;
     const size_t npx = (size_t) g.rows * g.cols, cap = (size_t) g.capacity;
     // one extra zero row (+ pad): the reference's cubic / Hermite footprint reaches row `rows` for yi = rows - 2
@@ -306,9 +374,11 @@ int bpvo_b200_frame_create(bpvo_b200_ctx* c, bpvo_b200_frame** out) {
   CUDA_TRY(cudaHostAlloc(&f->h_meta, kMaxLevels * sizeof(TemplateMeta), cudaHostAllocDefault));
   memset(f->h_meta, 0, kMaxLevels * sizeof(TemplateMeta));
   CUDA_TRY(cudaEventCreateWithFlags(&f->meta_ready, cudaEventDisableTiming));
-  *out = f;
+  f->tma_ok = (c->C == 8) && !getenv("BPVO_B200_NO_TMA") && encode_tensor_maps(c, f);
   return BPVO_B200_OK;
 }
+
+extern "C" {
 
 int bpvo_b200_frame_destroy(bpvo_b200_frame* f) {
   if (!f) return BPVO_B200_OK;
@@ -320,7 +390,7 @@ int bpvo_b200_frame_destroy(bpvo_b200_frame* f) {
     cudaFree(f->pyr[l]); cudaFree(f->desc[l]); cudaFree(f->saliency[l]); cudaFree(f->pts[l]);
     cudaFree(f->gx[l]); cudaFree(f->gy[l]); cudaFree(f->i0[l]); cudaFree(f->inds[l]);
   }
-  cudaFree(f->d_meta); cudaFreeHost(f->h_meta); cudaEventDestroy(f->meta_ready);
+  cudaFree(f->d_meta); if (f->h_meta) cudaFreeHost(f->h_meta); if (f->meta_ready) cudaEventDestroy(f->meta_ready);
   for (int k = 0; k < 2; ++k) if (f->graph_exec[k]) cudaGraphExecDestroy(f->graph_exec[k]);
   if (c->last_ref == f) c->last_ref = nullptr;
   delete f;
@@ -342,7 +412,7 @@ static int enqueue_descriptors(bpvo_b200_ctx* c, bpvo_b200_frame* f) {
     PhaseTimer t(c, &c->counters.ms_pyramid);
     for (int l = 1; l < c->L; ++l) {
       const LevelGeom& s = c->geom[l - 1]; const LevelGeom& d = c->geom[l];
-      pyr_down_kernel<<<dim3(ceil_div(d.cols, 32), ceil_div(d.rows, 8)), 256, 0, c->stream>>>(f->pyr[l - 1], s.rows, s.cols, f->pyr[l], d.rows, d.cols);
+      pyr_down_kernel<<<dim3(ceil_div(d.cols, 32), ceil_div(d.rows, 8)), 256, 0, c->stream>>>(f->pyr[l - 1], s.rows, s.cols, u8_pitch(s.cols), f->pyr[l], d.rows, d.cols, u8_pitch(d.cols));
       LAUNCH_CHECK(c);
     }
   }
@@ -351,7 +421,7 @@ static int enqueue_descriptors(bpvo_b200_ctx* c, bpvo_b200_frame* f) {
     for (int l = c->L - 1; l >= c->p.maxTestLevel; --l) {
       const LevelGeom& g = c->geom[l];
       if (c->C == 1) {
-        intensity_kernel<<<ceil_div(g.rows * g.cols, 256), 256, 0, c->stream>>>(f->pyr[l], f->desc[l], g.rows * g.cols);
+        intensity_kernel<<<ceil_div(g.rows * g.cols, 256), 256, 0, c->stream>>>(f->pyr[l], g.rows, g.cols, u8_pitch(g.cols), f->desc[l]);
       } else {
         float k[5]; double sum = 0; const double sg = c->p.sigmaBitPlanes > 0 ? (double) c->p.sigmaBitPlanes : 1.1;
         // cv::getGaussianKernel(5, sigma, CV_32F): exp in double -> float taps, normalised by the double sum of the float taps
@@ -361,12 +431,16 @@ static int enqueue_descriptors(bpvo_b200_ctx* c, bpvo_b200_frame* f) {
         if (c->p.sigmaPriorToCensusTransform > 0.0f) {      // census.cc:63-65: cv::GaussianBlur(3x3) on the u8 level image first
           const double sc = (double) c->p.sigmaPriorToCensusTransform, e = exp(-0.5 / (sc * sc));
           const int ka = (int) lrint(256.0 * (e / (1.0 + 2.0 * e))), kc = 256 - 2 * ka;
-          blur3_u8_kernel<<<dim3(ceil_div(g.cols, 32), ceil_div(g.rows, 8)), 256, 0, c->stream>>>(f->pyr[l], g.rows, g.cols, ka, kc, c->blur_tmp);
+          blur3_u8_kernel<<<dim3(ceil_div(g.cols, 32), ceil_div(g.rows, 8)), 256, 0, c->stream>>>(f->pyr[l], g.rows, g.cols, u8_pitch(g.cols), ka, kc, c->blur_tmp);
           LAUNCH_CHECK(c);
           census_in = c->blur_tmp;
         }
-        bitplanes_kernel<<<dim3(ceil_div(g.cols, kBpTW), ceil_div(g.rows, kBpTH)), 256, 0, c->stream>>>(
-            census_in, g.rows, g.cols, k[2], k[3], k[4], c->p.sigmaBitPlanes > 0.0f ? 1 : 0, f->desc[l]);
+        if (f->tma_ok && census_in == f->pyr[l])       // tile in / out on the TMA engine (the tensor maps describe pyr[l] and desc[l])
+          bitplanes_tma_kernel<<<dim3(ceil_div(g.cols, kTmTW), ceil_div(g.rows, kTmTH)), 256, 0, c->stream>>>(
+              f->map_in[l], f->map_out[l], g.rows, g.cols, k[2], k[3], k[4], c->p.sigmaBitPlanes > 0.0f ? 1 : 0);
+        else
+          bitplanes_kernel<<<dim3(ceil_div(g.cols, kBpTW), ceil_div(g.rows, kBpTH)), 256, 0, c->stream>>>(
+              census_in, g.rows, g.cols, u8_pitch(g.cols), k[2], k[3], k[4], c->p.sigmaBitPlanes > 0.0f ? 1 : 0, f->desc[l]);
       }
       LAUNCH_CHECK(c);
     }
@@ -389,7 +463,7 @@ int bpvo_b200_frame_set_data(bpvo_b200_frame* f, const uint8_t* image, const flo
       memcpy(c->stage_img, image, npx); memcpy(c->stage_disp, disparity, npx * sizeof(float));
       src_i = c->stage_img; src_d = c->stage_disp;
     }
-    CUDA_TRY(cudaMemcpyAsync(f->pyr[0], src_i, npx, cudaMemcpyDefault, c->stream));
+    CUDA_TRY(cudaMemcpy2DAsync(f->pyr[0], (size_t) u8_pitch(c->cols), src_i, (size_t) c->cols, (size_t) c->cols, (size_t) c->rows, cudaMemcpyDefault, c->stream));
     CUDA_TRY(cudaMemcpyAsync(f->disp, src_d, npx * sizeof(float), cudaMemcpyDefault, c->stream));
     CUDA_TRY(cudaEventRecord(c->stage_free, c->stream));
     c->counters.h2d_bytes += (int64_t) (npx * 5);
@@ -532,7 +606,7 @@ int bpvo_b200_frame_get_pyramid(const bpvo_b200_frame* f, int level, uint8_t* ou
   if (!f || level < 0 || level >= f->ctx->L) return bp_fail(BPVO_B200_ERR_INVALID_ARG, "bad frame/level");
   bpvo_b200_ctx* c = f->ctx; const LevelGeom& g = c->geom[level];
   CUDA_TRY(cudaSetDevice(c->p.device_id));
-  CUDA_TRY(cudaMemcpyAsync(out, f->pyr[level], (size_t) g.rows * g.cols, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaMemcpy2DAsync(out, (size_t) g.cols, f->pyr[level], (size_t) u8_pitch(g.cols), (size_t) g.cols, (size_t) g.rows, cudaMemcpyDeviceToHost, c->stream));
   CUDA_TRY(cudaStreamSynchronize(c->stream));
   return BPVO_B200_OK;
 }
@@ -959,8 +1033,8 @@ extern "C" int bpvo_b200_point_cloud(bpvo_b200_ctx* c, const bpvo_b200_frame* re
   const float sigma = c->h_mail->lin.sigma;
   const LevelGeom& g = c->geom[level];
   PointInfo* d = reinterpret_cast<PointInfo*>(c->export_buf);          // capacity: capmax * C * 6 floats and at least 8 floats per point
-  if (c->C == 1) k_point_cloud<1><<<ceil_div(np, 256), 256, 0, c->stream>>>(ref->pts[level], np, ref->pyr[0], c->rows, c->cols, g.fx, g.fy, g.cx, g.cy, c->work.res, sigma, c->p.lossFunction, d);
-  else k_point_cloud<8><<<ceil_div(np, 256), 256, 0, c->stream>>>(ref->pts[level], np, ref->pyr[0], c->rows, c->cols, g.fx, g.fy, g.cx, g.cy, c->work.res, sigma, c->p.lossFunction, d);
+  if (c->C == 1) k_point_cloud<1><<<ceil_div(np, 256), 256, 0, c->stream>>>(ref->pts[level], np, ref->pyr[0], c->rows, c->cols, u8_pitch(c->cols), g.fx, g.fy, g.cx, g.cy, c->work.res, sigma, c->p.lossFunction, d);
+  else k_point_cloud<8><<<ceil_div(np, 256), 256, 0, c->stream>>>(ref->pts[level], np, ref->pyr[0], c->rows, c->cols, u8_pitch(c->cols), g.fx, g.fy, g.cx, g.cy, c->work.res, sigma, c->p.lossFunction, d);
   LAUNCH_CHECK(c);
   CUDA_TRY(cudaMemcpyAsync(records, d, (size_t) np * sizeof(PointInfo), cudaMemcpyDeviceToHost, c->stream));
   CUDA_TRY(cudaStreamSynchronize(c->stream));

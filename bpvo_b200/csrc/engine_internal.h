@@ -2,6 +2,7 @@
 #pragma once
 
 #include <stdarg.h>
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include "../../include/bpvo_b200.h"
 #include "device_types.h"
@@ -79,6 +80,9 @@ struct bpvo_b200_frame {
   float* gy[bp::kMaxLevels] = {};
   float* i0[bp::kMaxLevels] = {};
   int* inds[bp::kMaxLevels] = {};
+  // TMA descriptors of pyr[l] / desc[l] for the bit-planes descriptor kernel (tma_ok: encoded successfully)
+  CUtensorMap map_in[bp::kMaxLevels], map_out[bp::kMaxLevels];
+  bool tma_ok = false;
   bp::TemplateMeta* d_meta = nullptr;
   bp::TemplateMeta* h_meta = nullptr;   // pinned mirror, valid after meta_ready
   cudaEvent_t meta_ready = nullptr;

