@@ -84,23 +84,29 @@ static bool encode_tensor_maps(bpvo_b200_ctx* c, bpvo_b200_frame* f) {
     return false;
   }
   EncodeFn encode = reinterpret_cast<EncodeFn>(fn);
+  CUtensorMap maps[2 * kMaxLevels];
+  memset(maps, 0, sizeof(maps));
   for (int l = c->p.maxTestLevel; l < c->L; ++l) {
     const LevelGeom& g = c->geom[l];
     {
       const cuuint64_t dims[2] = {(cuuint64_t) g.cols, (cuuint64_t) g.rows};
       const cuuint64_t strides[1] = {(cuuint64_t) u8_pitch(g.cols)};
       const cuuint32_t box[2] = {(cuuint32_t) kTmInW, (cuuint32_t) kTmInH}, es[2] = {1, 1};
-      if (encode(&f->map_in[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, f->pyr[l], dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+      if (encode(&maps[2 * l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, f->pyr[l], dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return false;
     }
     {
       const cuuint64_t dims[3] = {8, (cuuint64_t) g.cols, (cuuint64_t) g.rows};
       const cuuint64_t strides[2] = {32, (cuuint64_t) g.cols * 32};
       const cuuint32_t box[3] = {8, (cuuint32_t) kTmTW, (cuuint32_t) kTmTH}, es[3] = {1, 1, 1};
-      if (encode(&f->map_out[l], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, f->desc[l], dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+      if (encode(&maps[2 * l + 1], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, f->desc[l], dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return false;
     }
   }
+  // the descriptors live in global memory ([level][in, out], 64-byte aligned): written once, before any kernel reads them
+  if (cudaMalloc(&f->d_maps, sizeof(maps)) != cudaSuccess) { cudaGetLastError(); f->d_maps = nullptr; return false; }
+  if (cudaMemcpyAsync(f->d_maps, maps, sizeof(maps), cudaMemcpyHostToDevice, c->stream) != cudaSuccess ||
+      cudaStreamSynchronize(c->stream) != cudaSuccess) { cudaGetLastError(); return false; }
   return true;
 }
 
@@ -390,6 +396,7 @@ int bpvo_b200_frame_destroy(bpvo_b200_frame* f) {
     cudaFree(f->pyr[l]); cudaFree(f->desc[l]); cudaFree(f->saliency[l]); cudaFree(f->pts[l]);
     cudaFree(f->gx[l]); cudaFree(f->gy[l]); cudaFree(f->i0[l]); cudaFree(f->inds[l]);
   }
+  cudaFree(f->d_maps);
   cudaFree(f->d_meta); if (f->h_meta) cudaFreeHost(f->h_meta); if (f->meta_ready) cudaEventDestroy(f->meta_ready);
   for (int k = 0; k < 2; ++k) if (f->graph_exec[k]) cudaGraphExecDestroy(f->graph_exec[k]);
   if (c->last_ref == f) c->last_ref = nullptr;
@@ -437,7 +444,7 @@ static int enqueue_descriptors(bpvo_b200_ctx* c, bpvo_b200_frame* f) {
         }
         if (f->tma_ok && census_in == f->pyr[l])       // tile in / out on the TMA engine (the tensor maps describe pyr[l] and desc[l])
           bitplanes_tma_kernel<<<dim3(ceil_div(g.cols, kTmTW), ceil_div(g.rows, kTmTH)), 256, 0, c->stream>>>(
-              f->map_in[l], f->map_out[l], g.rows, g.cols, k[2], k[3], k[4], c->p.sigmaBitPlanes > 0.0f ? 1 : 0);
+              f->d_maps + 2 * l, f->d_maps + 2 * l + 1, g.rows, g.cols, k[2], k[3], k[4], c->p.sigmaBitPlanes > 0.0f ? 1 : 0);
         else
           bitplanes_kernel<<<dim3(ceil_div(g.cols, kBpTW), ceil_div(g.rows, kBpTH)), 256, 0, c->stream>>>(
               census_in, g.rows, g.cols, u8_pitch(g.cols), k[2], k[3], k[4], c->p.sigmaBitPlanes > 0.0f ? 1 : 0, f->desc[l]);
@@ -846,7 +853,7 @@ struct SolveOverride {
   int cache_bytes = -1;    // -1 = everything the SM has
 };
 
-template <int C, int BLEND>
+template <int C, int BLEND, bool PEER>
 static int launch_estimate_pose_t(bpvo_b200_ctx* c, const bpvo_b200_frame* ref, const bpvo_b200_frame* cur, const M44& T_init, const SolveOverride* ov) {
   SolveArgs a;
   memset(&a, 0, sizeof(a));
@@ -896,21 +903,23 @@ static int launch_estimate_pose_t(bpvo_b200_ctx* c, const bpvo_b200_frame* ref, 
   if (ov && ov->cache_bytes >= 0) cache_bytes = std::min(cache_bytes, ov->cache_bytes);
   const size_t dyn = (size_t) kScratchBytes + (size_t) cache_bytes;
   if (c->dyn_configured != dyn) {        // per ctx: the attribute is per device, and a process may drive several
-    CUDA_TRY(cudaFuncSetAttribute((const void*) k_estimate_pose<C, BLEND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) dyn));
+    CUDA_TRY(cudaFuncSetAttribute((const void*) k_estimate_pose<C, BLEND, PEER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) dyn));
     c->dyn_configured = dyn;
   }
   void* args[] = {&a, &sel, &cache_bytes};
   int grid = std::min(c->sm_count, kMaxGrid);
   if (c->solver_ctas > 0) grid = std::min(grid, c->solver_ctas);     // throughput mode: several ctxs share the SMs
   if (ov && ov->grid > 0) grid = std::min(grid, ov->grid);
-  CUDA_TRY(cudaLaunchCooperativeKernel((void*) k_estimate_pose<C, BLEND>, dim3(grid), dim3(kLinThreads), args, dyn, c->stream));
+  CUDA_TRY(cudaLaunchCooperativeKernel((void*) k_estimate_pose<C, BLEND, PEER>, dim3(grid), dim3(kLinThreads), args, dyn, c->stream));
   c->counters.launches++;
   return BPVO_B200_OK;
 }
 template <int C>
 static int launch_estimate_pose(bpvo_b200_ctx* c, const bpvo_b200_frame* ref, const bpvo_b200_frame* cur, const M44& T_init, const SolveOverride* ov = nullptr) {
-  if constexpr (C == 8) { if (c->p.flags & BPVO_B200_FLAG_FAST_BLEND) return launch_estimate_pose_t<C, 1>(c, ref, cur, T_init, ov); }
-  return launch_estimate_pose_t<C, 0>(c, ref, cur, T_init, ov);
+  // (the peer-memory instantiation carries the cross-rank exchanges; the single-GPU one is a third smaller)
+  if constexpr (C == 8) { if (c->p.flags & BPVO_B200_FLAG_FAST_BLEND) return launch_estimate_pose_t<C, 1, false>(c, ref, cur, T_init, ov); }
+  if (c->peer_mode) return launch_estimate_pose_t<C, 0, true>(c, ref, cur, T_init, ov);
+  return launch_estimate_pose_t<C, 0, false>(c, ref, cur, T_init, ov);
 }
 
 extern "C" int bpvo_b200_estimate_pose(bpvo_b200_ctx* c, const bpvo_b200_frame* ref, const bpvo_b200_frame* cur,

@@ -81,7 +81,7 @@ struct bpvo_b200_frame {
   float* i0[bp::kMaxLevels] = {};
   int* inds[bp::kMaxLevels] = {};
   // TMA descriptors of pyr[l] / desc[l] for the bit-planes descriptor kernel (tma_ok: encoded successfully)
-  CUtensorMap map_in[bp::kMaxLevels], map_out[bp::kMaxLevels];
+  CUtensorMap* d_maps = nullptr;        // device copy: [level][in, out]
   bool tma_ok = false;
   bp::TemplateMeta* d_meta = nullptr;
   bp::TemplateMeta* h_meta = nullptr;   // pinned mirror, valid after meta_ready

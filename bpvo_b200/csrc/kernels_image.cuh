@@ -186,7 +186,14 @@ constexpr int kTmTW = 64, kTmTH = 8, kTmInW = 80, kTmInH = kTmTH + 6;
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned) __cvta_generic_to_shared(p); }
 
-__global__ void __launch_bounds__(256) bitplanes_tma_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_out,
+__device__ __forceinline__ bool elect_one() {       // one lane of a converged warp (the TMA instructions want a uniform issue)
+  unsigned p;
+  asm volatile("{ .reg .pred P; elect.sync _|P, 0xffffffff; selp.u32 %0, 1, 0, P; }" : "=r"(p));
+  return p != 0;
+}
+
+// map_in / map_out: 128-byte CUtensorMap descriptors in GLOBAL memory (written once by the host at frame creation)
+__global__ void __launch_bounds__(256) bitplanes_tma_kernel(const CUtensorMap* __restrict__ map_in, const CUtensorMap* __restrict__ map_out,
                                                             int rows, int cols, float k0, float k1, float k2, int do_blur) {
   __shared__ __align__(128) uint8_t s_in[kTmInH][kTmInW];
   __shared__ __align__(128) float s_out[kTmTH][kTmTW][8];
@@ -202,10 +209,10 @@ __global__ void __launch_bounds__(256) bitplanes_tma_kernel(const __grid_constan
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  if (tid == 0) {
+  if (tid < 32 && elect_one()) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(kTmInH * kTmInW) : "memory");
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-                 ::"r"(smem_u32(&s_in[0][0])), "l"(reinterpret_cast<unsigned long long>(&map_in)), "r"(x0 - 3), "r"(y0 - 3), "r"(bar) : "memory");
+                 ::"r"(smem_u32(&s_in[0][0])), "l"(reinterpret_cast<unsigned long long>(map_in)), "r"(x0 - 3), "r"(y0 - 3), "r"(bar) : "memory");
   }
   {
     unsigned done = 0;
@@ -275,9 +282,9 @@ __global__ void __launch_bounds__(256) bitplanes_tma_kernel(const __grid_constan
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // the generic-proxy writes of s_out become visible to the TMA engine
   __syncthreads();
-  if (tid == 0) {
+  if (tid < 32 && elect_one()) {
     asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3}], [%4];"
-                 ::"l"(reinterpret_cast<unsigned long long>(&map_out)), "r"(0), "r"(x0), "r"(y0), "r"(smem_u32(&s_out[0][0][0])) : "memory");
+                 ::"l"(reinterpret_cast<unsigned long long>(map_out)), "r"(0), "r"(x0), "r"(y0), "r"(smem_u32(&s_out[0][0][0])) : "memory");
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // shared memory must outlive the engine's reads
   }

@@ -341,11 +341,16 @@ __device__ __forceinline__ void phase_residuals(const LevelTemplate& L, const Le
   const double P00 = P[0], P10 = P[1], P20 = P[2], P01 = P[3], P11 = P[4], P21 = P[5],
                P02 = P[6], P12 = P[7], P22 = P[8], P03 = P[9], P13 = P[10], P23 = P[11];
   const int cols = I.cols, rows = I.rows;
+#ifdef BP_FIXED_INTERP          /* code-size experiment: one interpolant compiled in */
+  interp = BP_FIXED_INTERP;
+#endif
   const int border_lo = (interp == 0 || interp == 1) ? 0 : 1, border_hi = (interp == 0 || interp == 1) ? 1 : 3;
   const int n_pts = m.n;
   int my_first = 0x7fffffff;
   int k = 0;
-  const bool streaming = BP_PREFETCH && tc.K > 1;      // several points per thread: look ahead (template records that are not cached, taps)
+  // look-ahead only where NOTHING of the level fits the cache (K of several dozen): on partially cached, L2-resident levels the
+  // extra instructions cost more than they hide (same-box A/B: KITTI dense level 0 32.8 -> 36.3 us with them, 1080p level 0 206.6 -> 187.8)
+  const bool streaming = BP_PREFETCH && tc.K > 1 && tc.pts == kTcNone && tc.f[TC_R] == kTcNone;
   const int stride = nblocks * kLinThreads;
   float4 Xnext = make_float4(0.0f, 0.0f, 1.0f, 1.0f);
   if (streaming) { const int i0 = first_point(block, nblocks); if (i0 < n_pts) Xnext = (tc.pts != kTcNone) ? tc_point(tc, 0) : __ldg(L.pts + i0); }
@@ -707,6 +712,9 @@ __device__ __forceinline__ bool bracket_select(const Work& W, unsigned* __restri
 }
 
 __device__ __forceinline__ float robust_weight(int loss, float r, float sigma_inv) {
+#ifdef BP_FIXED_LOSS            /* code-size experiment: one loss function compiled in */
+  loss = BP_FIXED_LOSS;
+#endif
   if (loss == 0x12) return 1.0f;
   const float x = __fmul_rn(r, sigma_inv);
   if (loss == 0x10) {                                    // huber_simd: k / max(|x|, k)
@@ -739,7 +747,7 @@ __device__ __forceinline__ double phase_reduce(const LevelTemplate& L, const Wor
   const float w_invalid_good = (1.0f > good_thr) ? (float) C : 0.0f;   // invalid entries carry weight 1 in getWeights() (Q6)
   int ks = 0;
   for (int i = first_point(block, nblocks); i < m.n; i += nblocks * kLinThreads, ++ks) {
-    if (BP_PREFETCH && tc.K > 1) {                     // whatever this level streams from global memory: two points ahead into the L2
+    if (BP_PREFETCH && tc.K > 1 && tc.pts == kTcNone && tc.f[TC_R] == kTcNone) {      // fully streaming level: two points ahead into the L2
       const int i2 = i + 2 * nblocks * kLinThreads;
       if (i2 < m.n) {
         if (tc.f[TC_GX] == kTcNone) prefetch_l2(L.gx + (size_t) i2 * C);
@@ -1370,7 +1378,7 @@ struct GridSync {
 
 // Front part of one linearize inside the persistent kernel: residuals -> exact median / scale -> weights and normal equations
 // of this CTA's points.  Returns, in thread k < 30, the CTA total of scalar k (layout of phase_reduce).
-template <int C, int BLEND>
+template <int C, int BLEND, bool PEER>
 __device__ __forceinline__ double device_linearize(const SolveArgs& a, int lvl, SolveShared& ss, LinShared& sh,
                                                    const TplCache& tc, const TemplateMeta& meta, unsigned* scratch, GridSync& gs, Sel* sel,
                                                    float& sigma_out, bool& do_hist_out) {
@@ -1398,7 +1406,7 @@ __device__ __forceinline__ double device_linearize(const SolveArgs& a, int lvl, 
     for (int b = blk * kLinThreads + tid; b < kHistWords; b += nb * kLinThreads) hprev[b] = 0;
     unsigned n = 0, ncand = 0; float lo = 0.0f, hi = 0.0f;
     bool hit = false;
-    const bool multi = a.peer.nranks > 1 && !meta.replicated;
+    const bool multi = PEER && a.peer.nranks > 1 && !meta.replicated;      // (PEER = false: the single-GPU kernel carries no cross-rank code)
     if (br.on && !multi) hit = bracket_select<C>(a.work, hset, sh, scratch, blk, nb, br, gs.counter, gs.epoch, &ss.abort, n, ncand, lo, hi);
     if (br.on && multi) {
       // CTA 0 talks to the peers (two exchanges) and hands the verdict to the other CTAs through three local words
@@ -1595,7 +1603,7 @@ __device__ __forceinline__ void warp0_finish(double total, float sigma, bool do_
   }
 }
 
-template <int C, int BLEND>
+template <int C, int BLEND, bool PEER>
 __global__ void __launch_bounds__(kLinThreads, 1) k_estimate_pose(const __grid_constant__ SolveArgs a, Sel* sel, int cache_bytes) {
   __shared__ LinShared sh;
   __shared__ SolveShared ss;
@@ -1638,7 +1646,7 @@ __global__ void __launch_bounds__(kLinThreads, 1) k_estimate_pose(const __grid_c
     float f_prev = 0.0f, g_tol = 0.0f, dp_prev = 0.0f, f_norm, g_norm;
     bool solver_error = false, early = false;
     const TemplateMeta meta = *L.meta;
-    const bool multi_rank = a.peer.nranks > 1 && !meta.replicated;
+    const bool multi_rank = PEER && a.peer.nranks > 1 && !meta.replicated;
     // template cache for this level: as many whole fields as fit (tpl_cache_plan)
     const TplCache tc = tpl_cache_plan<C>((unsigned) kScratchBytes, cache_bytes, (meta.n + (int) gridDim.x * kLinThreads - 1) / ((int) gridDim.x * kLinThreads));
     tc_fill<C>(tc, L, meta.n, blockIdx.x, gridDim.x);
@@ -1664,7 +1672,7 @@ __global__ void __launch_bounds__(kLinThreads, 1) k_estimate_pose(const __grid_c
         __syncthreads();
       }
       float sigma; bool do_hist;
-      const double mine = device_linearize<C, BLEND>(a, lvl, ss, sh, tc, meta, scratch, gs, sel, sigma, do_hist); ++n_evals;
+      const double mine = device_linearize<C, BLEND, PEER>(a, lvl, ss, sh, tc, meta, scratch, gs, sel, sigma, do_hist); ++n_evals;
       // grid totals, LinOut, solve, pose update: warp 0 (see warp0_finish); the other warps wait at the barrier
       const bool dbg = a.dbg.n > 0;
       bool done = false;
