@@ -298,6 +298,9 @@ def run_ours(args, w, rank, world, local_rank):
         ctx.reset_counters()
         ref = vo.ref_frame()
         alg_bytes, ms_lin, n_solves = 0.0, 0.0, 0
+        lvl_us = [0.0] * p.numPyramidLevels
+        lvl_ev = [0] * p.numPyramidLevels
+        lvl_bytes = [0.0] * p.numPyramidLevels
         phase = {k2: 0.0 for k2 in ("ms_upload", "ms_pyramid", "ms_descriptor", "ms_template", "ms_linearize")}
         Cch = ctx.channels
         sizes = [ref.level_size(l) for l in range(p.numPyramidLevels)]
@@ -313,8 +316,11 @@ def run_ours(args, w, rank, world, local_rank):
                 continue      # key-frames run two solves against two templates; keep the byte accounting exact by skipping them
             ms_lin += c1["ms_linearize"] - c0["ms_linearize"]
             n_solves += c1["solve_calls"] - c0["solve_calls"]
+            us = ctx.last_level_us()
             for l in range(p.numPyramidLevels):
-                alg_bytes += ev[l] * algorithmic_bytes_per_iter(npts[l], Cch, sizes[l][0], sizes[l][1])
+                b = ev[l] * algorithmic_bytes_per_iter(npts[l], Cch, sizes[l][0], sizes[l][1])
+                alg_bytes += b
+                lvl_us[l] += us[l]; lvl_ev[l] += ev[l]; lvl_bytes[l] += b
         n_solves = max(1, n_solves)
         peak, how = peaks()
         achieved = alg_bytes / (ms_lin * 1e-3) / 1e9 if ms_lin > 0 else 0.0
@@ -331,6 +337,11 @@ def run_ours(args, w, rank, world, local_rank):
                 "traffic_note": "bytes per launch from profiles/ncu_traffic.json: far BELOW the algorithmic bytes because the working set is L2-resident",
                 "peak_source": how, "ms_per_launch": ms_lin / n_solves,
                 "algorithmic_bytes_per_launch": alg_bytes / n_solves,
+                "per_level": [{"level": l, "gn_iters": lvl_ev[l], "us_per_gn_iter": lvl_us[l] / max(lvl_ev[l], 1),
+                               "achieved": lvl_bytes[l] / max(lvl_us[l], 1e-9) / 1e3, "frac": lvl_bytes[l] / max(lvl_us[l], 1e-9) / 1e3 / peak}
+                              for l in range(p.numPyramidLevels)],
+                "note": "KITTI semi-dense levels (5-30 k points, 13 MB per iteration, L2 resident) are latency / synchronisation bound, not HBM bound; "
+                        "the same kernel on HBM-bound levels: roofline_dense_variant / roofline_hbm_bound_variant (per level, in-kernel global timer)",
                 "phase_ms_per_frame": {k2: v / float(n_roof) for k2, v in phase.items()}}
         ctx.set_profiling(False)
     vo.close()
@@ -352,8 +363,9 @@ def run_ours(args, w, rank, world, local_rank):
         cpu = cpu_baseline(w, args)
     hbm_bound = None
     if rank == 0 and world == 1 and args.workload == "kitti" and not args.no_dense:
-        dense = dense_variant_roofline(local_rank)
+        dense = fused_levels_roofline("kitti_dense", local_rank)
         hbm_bound = hbm_bound_variant(local_rank)
+        hbm_bound["fused_kernel"] = fused_levels_roofline("1080p_dense", local_rank, solves=2)
 
     throughput = None
     if rank == 0 and world == 1 and not args.no_throughput:
@@ -535,40 +547,41 @@ def hbm_bound_variant(local_rank):
             "peak_source": how}
 
 
-def dense_variant_roofline(local_rank):
-    """the same persistent kernel on the DENSE selection of the same frames (nonMaxSuppRadius = -1, ~400k points at
-    level 0, 137 MB algorithmic per GN iteration): shows what the kernel does when it is bandwidth- rather than
-    latency-bound.  A handful of frames, cudaEvent time of the solve launches only."""
-    from bpvo_b200 import VisualOdometry
-    w = WORKLOADS["kitti_dense"]
+def fused_levels_roofline(workload, local_rank, solves=3):
+    """the persistent (fused) GN kernel on a dense selection, level by level: device time per GN iteration from the kernel's own
+    global-timer stamps (LevelStats.us), algorithmic bytes of SURVEY.md 8(d), fraction of the measured HBM peak.  One frame pair,
+    `solves` whole coarse-to-fine solves after a warm-up solve."""
+    from bpvo_b200.engine import Context
+    w = WORKLOADS[workload]
     sc = make_scene(w, 0xB200)
     p = make_params(w)
-    vo = VisualOdometry(sc.K, sc.baseline, (sc.rows, sc.cols), p, device_id=local_rank)
-    ctx = vo.ctx
-    frames = [sc.render(k) for k in range(6)]
-    vo.addFrame(*frames[0])
-    vo.addFrame(*frames[1])
-    ctx.set_profiling(True)
-    sizes = [vo.ref_frame().level_size(l) for l in range(p.numPyramidLevels)]
-    alg, ms, evals, solves = 0.0, 0.0, 0, 0
-    for k in range(2, 6):
-        npts = [vo.ref_frame().numPoints(l) for l in range(p.numPyramidLevels)]
-        c0 = ctx.counters()
-        r = vo.addFrame(*frames[k])
-        c1 = ctx.counters()
-        if r.isKeyFrame:
-            continue
-        ev = ctx.last_level_evals()
-        ms += c1["ms_linearize"] - c0["ms_linearize"]
-        solves += c1["solve_calls"] - c0["solve_calls"]
-        evals += sum(ev)
-        for l in range(p.numPyramidLevels):
-            alg += ev[l] * algorithmic_bytes_per_iter(npts[l], 8, sizes[l][0], sizes[l][1])
-    vo.close()
+    ctx = Context(sc.K, sc.baseline, (sc.rows, sc.cols), p, device_id=local_rank)
+    a, b = ctx.frame(), ctx.frame()
+    i0, d0 = sc.render(0); i1, d1 = sc.render(1)
+    a.setData(i0, d0); a.setTemplate(); b.setData(i1, d1)
+    T0 = np.eye(4, dtype=np.float32)
+    ctx.estimatePose(a, b, T0)
+    L = p.numPyramidLevels
+    us, ev = [0.0] * L, [0] * L
+    for _ in range(solves):
+        ctx.estimatePose(a, b, T0)
+        for l, (e, u) in enumerate(zip(ctx.last_level_evals(), ctx.last_level_us())):
+            ev[l] += e; us[l] += u
     peak, how = peaks()
-    ach = alg / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
-    return {"workload": w["name"], "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-            "peak_source": how, "gn_iters": evals, "us_per_gn_iter": 1e3 * ms / max(evals, 1), "solve_launches": solves}
+    levels = []
+    for l in range(L):
+        N = a.numPoints(l); r, c = a.level_size(l)
+        B = algorithmic_bytes_per_iter(N, ctx.channels, r, c)
+        t = us[l] / max(ev[l], 1)
+        levels.append({"level": l, "points": N, "gn_iters": ev[l], "us_per_gn_iter": t, "algorithmic_bytes_per_iter": B,
+                       "achieved": B / t / 1e3 if t > 0 else 0.0, "frac": B / t / 1e3 / peak if t > 0 else 0.0})
+    tot_b = sum(lv["algorithmic_bytes_per_iter"] * lv["gn_iters"] for lv in levels)
+    tot_us = sum(us)
+    a.close(); b.close(); ctx.close()
+    best = max(levels, key=lambda lv: lv["frac"])
+    return {"workload": w["name"], "kernel": "k_estimate_pose<8> (the fused persistent GN kernel), per pyramid level", "bound": "hbm", "peak": peak, "unit": "GB/s",
+            "peak_source": how, "levels": levels, "whole_solve": {"achieved": tot_b / tot_us / 1e3, "frac": tot_b / tot_us / 1e3 / peak, "us_per_gn_iter": tot_us / max(sum(ev), 1)},
+            "best_level": best["level"], "achieved": best["achieved"], "frac": best["frac"]}
 
 
 def cpu_baseline(w, args):

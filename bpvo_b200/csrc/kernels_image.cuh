@@ -174,15 +174,16 @@ __global__ void __launch_bounds__(256) bitplanes_kernel(const uint8_t* __restric
 // ---------------------------------------------------------------------------------------------
 // The same descriptor with the tile traffic on the TMA engine (the default; bitplanes_kernel above stays as the A/B partner,
 // BPVO_B200_NO_TMA=1):
-//   in : the (8 + 6) x (64 + 6) u8 halo tile of the level image, ONE cp.async.bulk.tensor.2d into shared memory (box 80 x 14
-//        bytes, out-of-image parts zero-filled), completion on an mbarrier -- the census then compares shared-memory bytes
-//        instead of issuing nine global byte loads per halo pixel;
+//   in : the (8 + 6) x (64 + 6) u8 halo tile of the level image, ONE cp.async.bulk.tensor.2d into shared memory, completion on
+//        an mbarrier -- the census then compares shared-memory bytes instead of issuing nine global byte loads per halo pixel.
+//        The box is 96 x 14 bytes starting at column x0 - 16: the TMA wants the box's first byte 16-byte aligned in global
+//        memory (a start at x0 - 3 raises "illegal instruction", scripts/micro/tma_probe.cu); out-of-image parts are zero-filled;
 //   out: the 8 x 64 x 8 f32 result tile (16 KB) is assembled in shared memory and leaves as ONE cp.async.bulk.tensor.3d store
 //        over the [rows][cols][8] descriptor (the TMA clips what lies outside the image: no per-thread bounds checks, full
 //        128-byte write transactions).
 // Arithmetic (census rule, tap order, roundings) is the other kernel's, bit for bit.
 // ---------------------------------------------------------------------------------------------
-constexpr int kTmTW = 64, kTmTH = 8, kTmInW = 80, kTmInH = kTmTH + 6;
+constexpr int kTmTW = 64, kTmTH = 8, kTmInW = 96, kTmInX = 16, kTmInH = kTmTH + 6;     // input box: columns [x0 - 16, x0 + 80), rows [y0 - 3, y0 + 11)
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned) __cvta_generic_to_shared(p); }
 
@@ -212,7 +213,7 @@ __global__ void __launch_bounds__(256) bitplanes_tma_kernel(const CUtensorMap* _
   if (tid < 32 && elect_one()) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(kTmInH * kTmInW) : "memory");
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-                 ::"r"(smem_u32(&s_in[0][0])), "l"(reinterpret_cast<unsigned long long>(map_in)), "r"(x0 - 3), "r"(y0 - 3), "r"(bar) : "memory");
+                 ::"r"(smem_u32(&s_in[0][0])), "l"(reinterpret_cast<unsigned long long>(map_in)), "r"(x0 - kTmInX), "r"(y0 - 3), "r"(bar) : "memory");
   }
   {
     unsigned done = 0;
@@ -223,7 +224,7 @@ __global__ void __launch_bounds__(256) bitplanes_tma_kernel(const CUtensorMap* _
   for (int i = tid; i < (kTmTH + 4) * (kTmTW + 4); i += 256) {
     const int r = i / (kTmTW + 4), c = i % (kTmTW + 4);
     const int gy = reflect101(y0 + r - 2, rows), gx = reflect101(x0 + c - 2, cols);
-    const int ly = gy - (y0 - 3), lx = gx - (x0 - 3);
+    const int ly = gy - (y0 - 3), lx = gx - (x0 - kTmInX);
     unsigned v = 0;
     // (positions whose reflection leaves the tile only feed outputs outside the image, which the TMA store clips)
     if (gy > 0 && gy < rows - 1 && gx > 0 && gx < cols - 1 && ly >= 1 && ly < kTmInH - 1 && lx >= 1 && lx < kTmInW - 1) {
