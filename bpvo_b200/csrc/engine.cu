@@ -380,7 +380,9 @@ static int frame_init(bpvo_b200_ctx* c, bpvo_b200_frame* f) {
   CUDA_TRY(cudaHostAlloc(&f->h_meta, kMaxLevels * sizeof(TemplateMeta), cudaHostAllocDefault));
   memset(f->h_meta, 0, kMaxLevels * sizeof(TemplateMeta));
   CUDA_TRY(cudaEventCreateWithFlags(&f->meta_ready, cudaEventDisableTiming));
-  f->tma_ok = (c->C == 8) && !getenv("BPVO_B200_NO_TMA") && encode_tensor_maps(c, f);
+  // TMA tile-in / tile-out variant of the bit-planes descriptor kernel: built, parity-tested, and 14 % SLOWER than the plain
+  // kernel in the same-box A/B (profiles/README.md) -- opt-in (BPVO_B200_FLAG_TMA_DESCRIPTOR or BPVO_B200_TMA=1)
+  f->tma_ok = (c->C == 8) && ((c->p.flags & BPVO_B200_FLAG_TMA_DESCRIPTOR) || getenv("BPVO_B200_TMA")) && encode_tensor_maps(c, f);
   return BPVO_B200_OK;
 }
 

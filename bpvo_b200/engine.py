@@ -15,6 +15,7 @@ from .types import AlgorithmParameters, Error, OptimizerStatistics, fill_cparams
 FLAG_HOST_SOLVE = 1
 FLAG_NO_GRAPHS = 2
 FLAG_FAST_BLEND = 4
+FLAG_TMA_DESCRIPTOR = 8
 
 
 def _fp(a):

@@ -61,6 +61,9 @@ enum { BPVO_B200_KF_LARGE_TRANSLATION = 0x40, BPVO_B200_KF_LARGE_ROTATION = 0x41
                                           (north star: 1e-5) but the residual vector is no longer bit-identical to the reference, and the
                                           same-box A/B gained only 2 % (profiles/README.md): off by default.  Projection, Floor and validity
                                           are fp64 in both modes; intensity always uses the double expression. */
+#define BPVO_B200_FLAG_TMA_DESCRIPTOR 8 /* bit-planes descriptor kernel with its tiles on the TMA engine (cp.async.bulk.tensor load of the u8 halo tile,
+                                          cp.async.bulk.tensor store of the 8 x 64 x 8 f32 result tile): same bits, 14 % slower than the default
+                                          kernel on B200 (one tile per CTA cannot hide the TMA round trips): off by default */
 #define BPVO_B200_FLAG_HOST_SOLVE   1  /* estimate_pose drives the GN loop from the host (one sync per iteration)
                                           instead of the on-device loop; same results, used for parity tests */
 

@@ -301,6 +301,58 @@ static void gaussian_blur5(const float* src, int rows, int cols, float sigma, fl
   }
 }
 
+// cv::GaussianBlur on CV_32F with an arbitrary odd kernel size (gradient_descriptor.cc:52-53 with cv::Size() -> OpenCV derives
+// ksize = cvRound(sigma * 8 + 1) | 1 for float images; imgproc.cc:166-171 imsmooth: ksize = max(5, 2 round(sigma) + 1)).
+// Same construction as gaussian_blur5: taps from cv::getGaussianKernel's formula, separable, BORDER_REFLECT_101, symmetric-tap
+// order s0 k0 + (s-1 + s1) k1 + (s-2 + s2) k2 + ..., float, no FMA.  THIRD-PARTY arithmetic: within a few ulp of cv2 4.13
+// (tests/test_oracle_cpu.py), bit-identical to the stand-in cv::GaussianBlur of oracle/refstub that oracle/_ref links.
+static void gaussian_blur_f32(const float* src, int rows, int cols, int ksize, double sigma, float* dst) {
+  if (ksize <= 0) ksize = ((int) std::lrint(sigma * 8 + 1)) | 1;
+  if (ksize == 5) { gaussian_blur5(src, rows, cols, (float) sigma, dst); return; }
+  const int half = ksize / 2;
+  std::vector<float> k(ksize);
+  { const double sx = sigma > 0 ? sigma : ((ksize - 1) * 0.5 - 1) * 0.3 + 0.8, sc = -0.5 / (sx * sx); double sum = 0;
+    for (int i = 0; i < ksize; ++i) { const double x = i - half; k[i] = (float) std::exp(sc * x * x); sum += k[i]; }
+    sum = 1.0 / sum; for (int i = 0; i < ksize; ++i) k[i] = (float) (k[i] * sum); }
+  std::vector<float> tmp((size_t) rows * cols);
+  for (int y = 0; y < rows; ++y) {
+    const float* s = src + (size_t) y * cols; float* t = tmp.data() + (size_t) y * cols;
+    for (int x = 0; x < cols; ++x) {
+      float v = s[x] * k[half];
+      for (int j = 1; j <= half; ++j) v = v + (s[reflect101(x - j, cols)] + s[reflect101(x + j, cols)]) * k[half + j];
+      t[x] = v;
+    }
+  }
+  for (int y = 0; y < rows; ++y) {
+    float* d = dst + (size_t) y * cols;
+    for (int x = 0; x < cols; ++x) {
+      float v = k[half] * tmp[(size_t) y * cols + x];
+      for (int j = 1; j <= half; ++j) v = v + k[half + j] * (tmp[(size_t) reflect101(y + j, rows) * cols + x] + tmp[(size_t) reflect101(y - j, rows) * cols + x]);
+      d[x] = v;
+    }
+  }
+}
+// imsmooth (imgproc.cc:166-171)
+static void imsmooth(const float* src, int rows, int cols, double sigma, float* dst) {
+  const int k = std::max(5, 2 * (int) std::round(sigma) + 1);
+  gaussian_blur_f32(src, rows, cols, k, sigma, dst);
+}
+// xgradient / ygradient (imgproc.h:215-266): 0.5 * central difference, one-sided 0.5 * (I1 - I0) on the first / last column / row
+static void xgradient(const float* I, int rows, int cols, float* Ix) {
+  for (int y = 0; y < rows; ++y) {
+    const float* s = I + (size_t) y * cols; float* d = Ix + (size_t) y * cols;
+    d[0] = 0.5f * (s[1] - s[0]);
+    for (int x = 1; x < cols - 1; ++x) d[x] = 0.5f * (s[x + 1] - s[x - 1]);
+    d[cols - 1] = 0.5f * (s[cols - 1] - s[cols - 2]);
+  }
+}
+static void ygradient(const float* I, int rows, int cols, float* Iy) {
+  for (int x = 0; x < cols; ++x) Iy[x] = 0.5f * (I[cols + x] - I[x]);
+  for (int y = 1; y < rows - 1; ++y)
+    for (int x = 0; x < cols; ++x) Iy[(size_t) y * cols + x] = 0.5f * (I[(size_t) (y + 1) * cols + x] - I[(size_t) (y - 1) * cols + x]);
+  for (int x = 0; x < cols; ++x) Iy[(size_t) (rows - 1) * cols + x] = 0.5f * (I[(size_t) (rows - 1) * cols + x] - I[(size_t) (rows - 2) * cols + x]);
+}
+
 // census (bpvo/census.cc:42-91, v128.h:87-120): bit k set iff neighbour_k >= centre (unsigned),
 // k: 0=NW 1=N 2=NE 3=W 4=E 5=SW 6=S 7=SE; first/last row and column are 0.  sigma>0 pre-blur
 // (census.cc:64-65, a third-party u8 3x3 GaussianBlur) is gaussian_blur3_u8() below, applied by compute_descriptor().
@@ -556,6 +608,31 @@ static void compute_descriptor(const orc_params& p, const uint8_t* img, int rows
       if (p.sigmaBitPlanes > 0.0f) {
         std::vector<float> tmp(dst, dst + n);
         gaussian_blur5(tmp.data(), rows, cols, p.sigmaBitPlanes, dst);
+      }
+    }
+  } else if (p.descriptor == ORC_INTENSITY_AND_GRADIENT) {     // GradientDescriptor::compute (gradient_descriptor.cc:42-64), sigma = sigmaPriorToCensusTransform (dense_descriptor.cc:49)
+    d.channels = 3; d.planes.resize(3 * n);
+    float* I0 = d.planes.data();
+    for (size_t i = 0; i < n; ++i) I0[i] = (float) img[i];
+    std::vector<float> sm;
+    const float* I = I0;                                       // the intensity channel stays unsmoothed
+    if (p.sigmaPriorToCensusTransform > 0.0f) { sm.resize(n); gaussian_blur_f32(I0, rows, cols, 0, (double) p.sigmaPriorToCensusTransform, sm.data()); I = sm.data(); }
+    xgradient(I, rows, cols, I0 + n);
+    ygradient(I, rows, cols, I0 + 2 * n);
+  } else if (p.descriptor == ORC_DESCRIPTOR_FIELDS) {          // DescriptorFields::compute (gradient_descriptor.cc:101-116), sigmas dfSigma1 / dfSigma2 (types.cc:36-37)
+    d.channels = 5; d.planes.resize(5 * n);
+    float* I0 = d.planes.data();
+    for (size_t i = 0; i < n; ++i) I0[i] = (float) img[i];
+    std::vector<float> sm, buf(n), tmp(n);
+    const float* I = I0;
+    if (p.dfSigma1 > 0.0f) { sm.resize(n); imsmooth(I0, rows, cols, (double) p.dfSigma1, sm.data()); I = sm.data(); }
+    for (int g = 0; g < 2; ++g) {
+      if (g == 0) xgradient(I, rows, cols, buf.data()); else ygradient(I, rows, cols, buf.data());
+      float* pos = I0 + (size_t) (1 + 2 * g) * n; float* neg = I0 + (size_t) (2 + 2 * g) * n;       // splitPosNeg :78-99
+      for (size_t i = 0; i < n; ++i) { pos[i] = buf[i] >= 0 ? buf[i] : 0.0f; neg[i] = buf[i] < 0 ? buf[i] : 0.0f; }
+      if (p.dfSigma2 > 0.0f) {
+        tmp.assign(pos, pos + n); imsmooth(tmp.data(), rows, cols, (double) p.dfSigma2, pos);
+        tmp.assign(neg, neg + n); imsmooth(tmp.data(), rows, cols, (double) p.dfSigma2, neg);
       }
     }
   } else {
@@ -1071,7 +1148,7 @@ void orc_default_params(orc_params* p) {        // bpvo/types.cc:31-66
   p->minNumPixelsForNonMaximaSuppression = 320 * 240; p->nonMaxSuppRadius = 1; p->minNumPixelsToWork = 256;
   p->minSaliency = 0.1f; p->minValidDisparity = 0.001f; p->maxValidDisparity = 512.0f;
   p->maxTestLevel = 0; p->withNormalization = 1;
-  p->use_rcp = 1; p->num_threads = 1;
+  p->use_rcp = 1; p->num_threads = 1; p->dfSigma1 = 0.75f; p->dfSigma2 = 1.75f;
 }
 
 void orc_pyr_down(const uint8_t* src, int rows, int cols, uint8_t* dst) { pyr_down(src, rows, cols, dst); }

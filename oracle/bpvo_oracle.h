@@ -27,7 +27,7 @@ extern "C" {
 
 /* enum values are the reference's (bpvo/types.h:125-166, 399-420) */
 enum { ORC_HUBER = 0x10, ORC_TUKEY = 0x11, ORC_L2 = 0x12 };
-enum { ORC_INTENSITY = 0x30, ORC_BITPLANES = 0x37 };
+enum { ORC_INTENSITY = 0x30, ORC_INTENSITY_AND_GRADIENT = 0x31, ORC_DESCRIPTOR_FIELDS = 0x32, ORC_BITPLANES = 0x37 };
 enum { ORC_CD3 = 0, ORC_CD5 = 1 };
 enum { ORC_LINEAR = 0, ORC_COSINE = 1, ORC_CUBIC = 2, ORC_CUBIC_HERMITE = 3 };
 enum { ORC_PARAM_TOL = 0x30, ORC_FUNC_TOL, ORC_GRAD_TOL, ORC_MAX_ITERS, ORC_SOLVER_ERROR };
@@ -66,6 +66,8 @@ typedef struct {
   /* oracle-only */
   int32_t use_rcp;      /* 1 = _mm_rcp_ps Jacobians as the reference (rigid_body_warp.cc:47-58) */
   int32_t num_threads;  /* 1 = reference default build (WITH_TBB off); >1 = OpenMP stand-in   */
+  float   dfSigma1;     /* DescriptorFields: smoothing before / after the gradient split (types.h, defaults 0.75 / 1.75) */
+  float   dfSigma2;
 } orc_params;
 
 typedef struct {

@@ -8,15 +8,15 @@ tail -5 gpurun_out/${TAG}_tma_sanitizer.log
 if grep -q "descriptor ok" gpurun_out/${TAG}_tma_sanitizer.log && grep -q "ERROR SUMMARY: 0 errors" gpurun_out/${TAG}_tma_sanitizer.log; then
   echo "TMA kernel clean"
 else
-  echo "TMA kernel still faulting: falling back to BPVO_B200_NO_TMA=1 for the rest"; export BPVO_B200_NO_TMA=1
+  echo "TMA kernel still faulting: falling back to for the rest"; true
 fi
 timeout 2400 python -m pytest tests -m gpu -q -rs > gpurun_out/${TAG}_pytest_gpu.log 2>&1
 timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:bitplanes -c 48 --csv --log-file gpurun_out/${TAG}_bitplanes_tma.csv \
     python bench.py --steps 4 --warmup 3 --no-cpu-baseline --no-dense --no-throughput > /dev/null 2>&1
-BPVO_B200_NO_TMA=1 timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:bitplanes -c 48 --csv --log-file gpurun_out/${TAG}_bitplanes_plain.csv \
+timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:bitplanes -c 48 --csv --log-file gpurun_out/${TAG}_bitplanes_plain.csv \
     python bench.py --steps 4 --warmup 3 --no-cpu-baseline --no-dense --no-throughput > /dev/null 2>&1
 timeout 300 python bench.py --no-cpu-baseline --no-dense --no-throughput --workload kitti_cfg > gpurun_out/${TAG}_bench_cfg_tma.json 2> gpurun_out/${TAG}_bench_cfg_tma.err
-BPVO_B200_NO_TMA=1 timeout 300 python bench.py --no-cpu-baseline --no-dense --no-throughput --workload kitti_cfg > gpurun_out/${TAG}_bench_cfg_plain.json 2> gpurun_out/${TAG}_bench_cfg_plain.err
+timeout 300 python bench.py --no-cpu-baseline --no-dense --no-throughput --workload kitti_cfg > gpurun_out/${TAG}_bench_cfg_plain.json 2> gpurun_out/${TAG}_bench_cfg_plain.err
 timeout 300 python scripts/profile_kernels.py --workload 1080p_dense > gpurun_out/${TAG}_kernels_1080p_dense.json 2> gpurun_out/${TAG}_kernels_1080p_dense.err
 timeout 300 python scripts/profile_kernels.py --workload kitti_dense > gpurun_out/${TAG}_kernels_dense.json 2> gpurun_out/${TAG}_kernels_dense.err
 grep -E "passed|failed|FAILED|^E  |SKIPPED" gpurun_out/${TAG}_pytest_gpu.log | tail -20

@@ -53,9 +53,16 @@ CASES = [("small", "intensity", 3), ("small", "bitplanes", 3), ("odd", "bitplane
          ("vga", "intensity", 4), ("kitti", "bitplanes", 4)]
 
 
+FLAG_TMA_DESCRIPTOR = 8
+
+
+@pytest.mark.parametrize("flags", [0, FLAG_TMA_DESCRIPTOR])
 @pytest.mark.parametrize("kind,desc,levels", CASES)
-def test_pyramid_and_descriptor(kind, desc, levels, oracle):
-    sc, ctx, gref, gcur, oref, ocur = _pair(kind, make_params(desc, levels), oracle)
+def test_pyramid_and_descriptor(kind, desc, levels, flags, oracle):
+    """flags = BPVO_B200_FLAG_TMA_DESCRIPTOR: the bit-planes kernel whose tiles travel on the TMA engine (same bits)"""
+    if flags and desc != "bitplanes":
+        pytest.skip("the TMA variant exists for the bit-planes descriptor")
+    sc, ctx, gref, gcur, oref, ocur = _pair(kind, make_params(desc, levels), oracle, flags=flags)
     for l in range(levels):
         assert np.array_equal(gref.pyramid(l), oref.pyramid(l)), f"pyrDown level {l} not bit-exact"
         dg, do = gref.descriptor(l), oref.descriptor(l)
