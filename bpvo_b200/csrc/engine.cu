@@ -127,6 +127,7 @@ void bpvo_b200_default_params(bpvo_b200_params* p) {     // bpvo/types.cc:31-66
   p->minSaliency = 0.1f; p->minValidDisparity = 0.001f; p->maxValidDisparity = 512.0f;
   p->maxTestLevel = 0; p->withNormalization = 1;
   p->device_id = 0; p->flags = 0;
+  p->dfSigma1 = 0.75f; p->dfSigma2 = 1.75f;
 }
 
 int bpvo_b200_device_count(void) {

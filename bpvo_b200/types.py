@@ -94,6 +94,8 @@ class AlgorithmParameters:
     maxValidDisparity: float = 512.0
     maxTestLevel: int = 0
     withNormalization: bool = True
+    dfSigma1: float = 0.75
+    dfSigma2: float = 1.75
 
     def resolved_num_levels(self, rows: int, cols: int) -> int:
         """auto pyramid depth (bpvo/vo.cc:101-104)."""
@@ -123,6 +125,7 @@ class CParams(ctypes.Structure):
         ("withNormalization", ctypes.c_int32),
         # engine options: x0 = device_id, x1 = flags (BPVO_B200_FLAG_*)
         ("x0", ctypes.c_int32), ("x1", ctypes.c_int32),
+        ("dfSigma1", ctypes.c_float), ("dfSigma2", ctypes.c_float),
     ]
 
 

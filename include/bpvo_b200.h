@@ -46,7 +46,7 @@ typedef enum {
 
 /* numeric values are the reference's (bpvo/types.h:125-166, 399-418) */
 enum { BPVO_B200_HUBER = 0x10, BPVO_B200_TUKEY = 0x11, BPVO_B200_L2 = 0x12 };
-enum { BPVO_B200_INTENSITY = 0x30, BPVO_B200_BITPLANES = 0x37 };
+enum { BPVO_B200_INTENSITY = 0x30, BPVO_B200_INTENSITY_AND_GRADIENT = 0x31, BPVO_B200_DESCRIPTOR_FIELDS = 0x32, BPVO_B200_BITPLANES = 0x37 };
 enum { BPVO_B200_CD3 = 0, BPVO_B200_CD5 = 1 };
 enum { BPVO_B200_LINEAR = 0, BPVO_B200_COSINE = 1, BPVO_B200_CUBIC = 2, BPVO_B200_CUBIC_HERMITE = 3 };   /* InterpolationType, types.h:163-169 */
 enum { BPVO_B200_PARAM_TOL = 0x30, BPVO_B200_FUNC_TOL = 0x31, BPVO_B200_GRAD_TOL = 0x32,
@@ -82,7 +82,7 @@ typedef struct {
   int32_t gradientEstimation;             /* BPVO_B200_CD3 / CD5 (template_data.cc:117-130) */
   int32_t interp;                         /* only kLinear (photo_error.cc:381-389) */
   int32_t lossFunction;
-  int32_t descriptor;                     /* kIntensity / kBitPlanes */
+  int32_t descriptor;                     /* kIntensity (1 channel), kIntensityAndGradient (3), kDescriptorFieldsFirstOrder (5), kBitPlanes (8) */
   int32_t verbosity;                      /* ignored: the engine never prints */
   float   minTranslationMagToKeyFrame;
   float   minRotationMagToKeyFrame;
@@ -99,6 +99,9 @@ typedef struct {
   /* engine options (not in the reference) */
   int32_t device_id;                      /* CUDA device ordinal */
   int32_t flags;                          /* BPVO_B200_FLAG_* */
+  /* DescriptorFields (bpvo/types.h, defaults 0.75 / 1.75 at types.cc:36-37): smoothing before / after the gradient split */
+  float   dfSigma1;
+  float   dfSigma2;
 } bpvo_b200_params;
 
 /* bpvo::OptimizerStatistics (bpvo/types.h:444-482) */

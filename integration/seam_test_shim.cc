@@ -41,6 +41,7 @@ void* ref_vo_create(const float K[9], float baseline, int rows, int cols, const 
   p.minNumPixelsToWork = q->minNumPixelsToWork; p.minSaliency = q->minSaliency;
   p.minValidDisparity = q->minValidDisparity; p.maxValidDisparity = q->maxValidDisparity;
   p.maxTestLevel = q->maxTestLevel; p.withNormalization = q->withNormalization != 0;
+  p.dfSigma1 = q->dfSigma1; p.dfSigma2 = q->dfSigma2;
   Matrix33 Km; memcpy(Km.data(), K, 9 * sizeof(float));
   std::unique_ptr<Vo> h(new Vo);
   h->vo.reset(new VisualOdometry(Km, baseline, ImageSize(rows, cols), p));

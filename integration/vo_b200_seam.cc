@@ -53,6 +53,7 @@ static bpvo_b200_params to_c_params(const AlgorithmParameters& p) {
   q.minNumPixelsToWork = p.minNumPixelsToWork; q.minSaliency = p.minSaliency;
   q.minValidDisparity = p.minValidDisparity; q.maxValidDisparity = p.maxValidDisparity;
   q.maxTestLevel = p.maxTestLevel; q.withNormalization = p.withNormalization ? 1 : 0;
+  q.dfSigma1 = p.dfSigma1; q.dfSigma2 = p.dfSigma2;
   return q;
 }
 

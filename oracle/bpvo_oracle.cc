@@ -1153,6 +1153,7 @@ void orc_default_params(orc_params* p) {        // bpvo/types.cc:31-66
 
 void orc_pyr_down(const uint8_t* src, int rows, int cols, uint8_t* dst) { pyr_down(src, rows, cols, dst); }
 void orc_gaussian_blur5(const float* src, int rows, int cols, float sigma, float* dst) { gaussian_blur5(src, rows, cols, sigma, dst); }
+void orc_gaussian_blur_f32(const float* src, int rows, int cols, int ksize, double sigma, float* dst) { gaussian_blur_f32(src, rows, cols, ksize, sigma, dst); }
 void orc_census(const uint8_t* src, int rows, int cols, uint8_t* dst) { census(src, rows, cols, dst); }
 void orc_gaussian_blur3_u8(const uint8_t* src, int rows, int cols, float sigma, uint8_t* dst) { gaussian_blur3_u8(src, rows, cols, (double) sigma, dst); }
 int orc_descriptor(const orc_params* p, const uint8_t* img, int rows, int cols, float* planes) {

@@ -94,6 +94,8 @@ void orc_default_params(orc_params* p);   /* bpvo/types.cc:31-66 */
 void orc_pyr_down(const uint8_t* src, int rows, int cols, uint8_t* dst);
 /* cv::GaussianBlur 5x5 f32 reflect-101 (bpvo/bitplanes_descriptor.cc:56) */
 void orc_gaussian_blur5(const float* src, int rows, int cols, float sigma, float* dst);
+/* cv::GaussianBlur on CV_32F with any odd kernel size; ksize <= 0: derived from sigma like cv::Size() (gradient_descriptor.cc:52-53) */
+void orc_gaussian_blur_f32(const float* src, int rows, int cols, int ksize, double sigma, float* dst);
 /* bpvo/census.cc:59-91 with sigma<=0 */
 void orc_census(const uint8_t* src, int rows, int cols, uint8_t* dst);
 void orc_gaussian_blur3_u8(const uint8_t* src, int rows, int cols, float sigma, uint8_t* dst);   /* cv::GaussianBlur 3x3 on CV_8U, cv2-4.13 fixed point */

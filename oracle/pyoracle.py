@@ -30,6 +30,7 @@ class OrcParams(C.Structure):
         ("minSaliency", C.c_float), ("minValidDisparity", C.c_float),
         ("maxValidDisparity", C.c_float), ("maxTestLevel", C.c_int32),
         ("withNormalization", C.c_int32), ("use_rcp", C.c_int32), ("num_threads", C.c_int32),
+        ("dfSigma1", C.c_float), ("dfSigma2", C.c_float),
     ]
 
 
@@ -62,6 +63,7 @@ def lib():
         "orc_default_params": (None, [C.POINTER(OrcParams)]),
         "orc_pyr_down": (None, [u8p, C.c_int, C.c_int, u8p]),
         "orc_gaussian_blur5": (None, [fp, C.c_int, C.c_int, C.c_float, fp]),
+        "orc_gaussian_blur_f32": (None, [fp, C.c_int, C.c_int, C.c_int, C.c_double, fp]),
         "orc_census": (None, [u8p, C.c_int, C.c_int, u8p]),
         "orc_gaussian_blur3_u8": (None, [u8p, C.c_int, C.c_int, C.c_float, u8p]),
         "orc_descriptor": (C.c_int, [C.POINTER(OrcParams), u8p, C.c_int, C.c_int, fp]),
@@ -141,6 +143,7 @@ def make_params(p, use_rcp: int = 1, num_threads: int = 1) -> OrcParams:
         v = getattr(p, name)
         setattr(c, name, type(getattr(c, name))(v))
     c.use_rcp, c.num_threads = int(use_rcp), int(num_threads)
+    c.dfSigma1, c.dfSigma2 = float(getattr(p, "dfSigma1", 0.75)), float(getattr(p, "dfSigma2", 1.75))
     return c
 
 
@@ -161,6 +164,14 @@ def gaussian_blur5(img, sigma):
     img = _f32(img)
     out = np.empty_like(img)
     lib().orc_gaussian_blur5(_fp(img), img.shape[0], img.shape[1], float(sigma), _fp(out))
+    return out
+
+
+def gaussian_blur_f32(img, ksize, sigma):
+    """cv::GaussianBlur on CV_32F, any odd ksize (<= 0: from sigma, like cv::Size())"""
+    img = _f32(img)
+    out = np.empty_like(img)
+    lib().orc_gaussian_blur_f32(_fp(img), img.shape[0], img.shape[1], int(ksize), float(sigma), _fp(out))
     return out
 
 

@@ -129,6 +129,7 @@ AlgorithmParameters to_params(const orc_params* q) {
   p.minNumPixelsToWork = q->minNumPixelsToWork; p.minSaliency = q->minSaliency;
   p.minValidDisparity = q->minValidDisparity; p.maxValidDisparity = q->maxValidDisparity;
   p.maxTestLevel = q->maxTestLevel; p.withNormalization = q->withNormalization != 0;
+  p.dfSigma1 = q->dfSigma1; p.dfSigma2 = q->dfSigma2;
   return p;
 }
 

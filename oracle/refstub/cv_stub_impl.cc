@@ -70,10 +70,41 @@ static void blur3_u8(const Mat& srcm, Mat& dstm, double sigma) {
   dstm = out;
 }
 
+// any odd kernel size on CV_32F (cv::Size(): ksize = cvRound(sigma * 8 + 1) | 1, as OpenCV derives it for float images):
+// same construction as the 5x5 case below -- getGaussianKernel's formula, separable, reflect-101, symmetric-tap order, no FMA
+static void blur_f32_general(const Mat& srcm, Mat& dstm, int ksize, double sigma) {
+  const int rows = srcm.rows, cols = srcm.cols, half = ksize / 2;
+  std::vector<float> k(ksize);
+  { const double sx = sigma > 0 ? sigma : ((ksize - 1) * 0.5 - 1) * 0.3 + 0.8, sc = -0.5 / (sx * sx); double sum = 0;
+    for (int i = 0; i < ksize; ++i) { const double x = i - half; k[i] = (float) std::exp(sc * x * x); sum += k[i]; }
+    sum = 1.0 / sum; for (int i = 0; i < ksize; ++i) k[i] = (float) (k[i] * sum); }
+  const float* src = srcm.ptr<float>();
+  std::vector<float> tmp((size_t) rows * cols);
+  for (int y = 0; y < rows; ++y) {
+    const float* s = src + (size_t) y * cols; float* t = tmp.data() + (size_t) y * cols;
+    for (int x = 0; x < cols; ++x) {
+      float v = s[x] * k[half];
+      for (int j = 1; j <= half; ++j) v = v + (s[reflect101(x - j, cols)] + s[reflect101(x + j, cols)]) * k[half + j];
+      t[x] = v;
+    }
+  }
+  Mat out; out.create(rows, cols, CV_32FC1);
+  float* dst = out.ptr<float>();
+  for (int y = 0; y < rows; ++y)
+    for (int x = 0; x < cols; ++x) {
+      float v = k[half] * tmp[(size_t) y * cols + x];
+      for (int j = 1; j <= half; ++j) v = v + k[half + j] * (tmp[(size_t) reflect101(y + j, rows) * cols + x] + tmp[(size_t) reflect101(y - j, rows) * cols + x]);
+      dst[(size_t) y * cols + x] = v;
+    }
+  dstm = out;
+}
+
 void GaussianBlur(const Mat& srcm, Mat& dstm, Size ksize, double sigmaX, double) {
   if ((srcm.type() & 7) == CV_8U && ksize.width == 3 && ksize.height == 3 && sigmaX > 0) { blur3_u8(srcm, dstm, sigmaX); return; }
+  if ((srcm.type() & 7) == CV_32F && ksize.width <= 0 && sigmaX > 0) ksize = Size(((int) std::lrint(sigmaX * 8 + 1)) | 1, ((int) std::lrint(sigmaX * 8 + 1)) | 1);
+  if ((srcm.type() & 7) == CV_32F && ksize.width == ksize.height && (ksize.width & 1) && ksize.width != 5) { blur_f32_general(srcm, dstm, ksize.width, sigmaX); return; }
   if ((srcm.type() & 7) != CV_32F || ksize.width != 5 || ksize.height != 5)
-    throw std::logic_error("refstub: GaussianBlur only supports 5x5 on CV_32F and 3x3 on CV_8U");
+    throw std::logic_error("refstub: GaussianBlur supports odd square kernels on CV_32F and 3x3 on CV_8U");
   const int rows = srcm.rows, cols = srcm.cols;
   float k[5];
   { const double s = sigmaX > 0 ? sigmaX : ((5 - 1) * 0.5 - 1) * 0.3 + 0.8; const double sc = -0.5 / (s * s); double sum = 0;

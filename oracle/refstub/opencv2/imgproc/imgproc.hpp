@@ -6,4 +6,5 @@ namespace cv {
 void pyrDown(const Mat& src, Mat& dst);
 void GaussianBlur(const Mat& src, Mat& dst, Size ksize, double sigmaX, double sigmaY = 0);
 inline void cvtColor(const Mat&, Mat&, int) { throw std::logic_error("refstub: cv::cvtColor is not available"); }
+inline void Laplacian(const Mat&, Mat&, int, int = 1) { throw std::logic_error("refstub: cv::Laplacian is not available"); }
 }

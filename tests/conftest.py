@@ -57,7 +57,8 @@ def oracle():
 
 def make_params(descriptor="intensity", levels=3, loss="tukey", **kw):
     from bpvo_b200.types import AlgorithmParameters, DescriptorType, LossFunctionType, VerbosityType
-    d = {"intensity": DescriptorType.kIntensity, "bitplanes": DescriptorType.kBitPlanes}[descriptor]
+    d = {"intensity": DescriptorType.kIntensity, "bitplanes": DescriptorType.kBitPlanes,
+         "gradient": DescriptorType.kIntensityAndGradient, "dfields": DescriptorType.kDescriptorFieldsFirstOrder}[descriptor]
     l = {"tukey": LossFunctionType.kTukey, "huber": LossFunctionType.kHuber, "l2": LossFunctionType.kL2}[loss]
     return AlgorithmParameters(descriptor=d, numPyramidLevels=levels, lossFunction=l, verbosity=VerbosityType.kSilent, **kw)
 

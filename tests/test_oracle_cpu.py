@@ -236,3 +236,47 @@ def test_golden_stream_fixture(oracle):
         assert np.abs(r["pose"] - g["poses"][k]).max() < 1e-4
     f = vo.ref_frame()
     assert [f.num_points(l) for l in range(3)] == list(g["npoints"])
+
+
+def test_general_gaussian_blur_and_gradient_descriptors_against_cv2(oracle):
+    """third-party arithmetic of the two extra descriptors (bpvo/gradient_descriptor.cc): cv::GaussianBlur on CV_32F with the
+    kernel size OpenCV derives from sigma (cv::Size()) or imsmooth's max(5, 2 round(sigma) + 1) -- the oracle's restatement
+    against the real OpenCV (cv2 4.13) to a few ulp of the 0..255 range; then GradientDescriptor / DescriptorFields as numpy
+    restatements of gradient_descriptor.cc:42-64, 78-116 on top of cv2's blur"""
+    cv2 = pytest.importorskip("cv2")
+    from conftest import make_params
+    rng = np.random.RandomState(5)
+    img = rng.randint(0, 256, size=(61, 83)).astype(np.uint8)
+    f = img.astype(np.float32)
+    for sigma in (0.75, 1.0, 1.2, 2.0):
+        a = oracle.gaussian_blur_f32(f, 0, sigma)
+        b = cv2.GaussianBlur(f, (0, 0), sigma, sigmaY=sigma, borderType=cv2.BORDER_REFLECT_101)
+        assert np.abs(a - b).max() <= 1e-4, sigma
+    for sigma, k in ((0.75, 5), (1.75, 5), (3.0, 7)):
+        a = oracle.gaussian_blur_f32(f, k, sigma)
+        b = cv2.GaussianBlur(f, (k, k), sigma, sigmaY=sigma, borderType=cv2.BORDER_REFLECT_101)
+        assert np.abs(a - b).max() <= 1e-4, (sigma, k)
+
+    def xgrad(I):
+        g = np.empty_like(I)
+        g[:, 0] = 0.5 * (I[:, 1] - I[:, 0]); g[:, 1:-1] = 0.5 * (I[:, 2:] - I[:, :-2]); g[:, -1] = 0.5 * (I[:, -1] - I[:, -2])
+        return g
+
+    def ygrad(I):
+        return xgrad(I.T.copy()).T.copy()
+
+    def smooth(I, s):
+        k = max(5, 2 * int(round(s)) + 1)
+        return cv2.GaussianBlur(I, (k, k), s, sigmaY=s, borderType=cv2.BORDER_REFLECT_101)
+
+    for sig in (-1.0, 1.0):
+        d = oracle.descriptor(make_params("gradient", 1, sigmaPriorToCensusTransform=sig), img)
+        I = f if sig <= 0 else cv2.GaussianBlur(f, (0, 0), sig, sigmaY=sig, borderType=cv2.BORDER_REFLECT_101)
+        assert d.shape == (3, 61, 83) and np.array_equal(d[0], f)
+        assert np.abs(d[1] - xgrad(I)).max() <= 1e-4 and np.abs(d[2] - ygrad(I)).max() <= 1e-4
+    d = oracle.descriptor(make_params("dfields", 1), img)
+    I = smooth(f, 0.75)
+    assert d.shape == (5, 61, 83) and np.array_equal(d[0], f)
+    for c, g in ((1, xgrad(I)), (3, ygrad(I))):
+        pos, neg = np.where(g >= 0, g, 0).astype(np.float32), np.where(g < 0, g, 0).astype(np.float32)
+        assert np.abs(d[c] - smooth(pos, 1.75)).max() <= 2e-4 and np.abs(d[c + 1] - smooth(neg, 1.75)).max() <= 2e-4

@@ -168,10 +168,15 @@ def _frames(kind):
 
 @pytest.mark.parametrize("kind,desc,levels,loss", [("small", "bitplanes", 3, "tukey"), ("small", "intensity", 3, "huber"),
                                                     ("odd", "bitplanes", 2, "huber"), ("odd", "intensity", 2, "l2"),
-                                                    ("vga", "intensity", 4, "huber")])
+                                                    ("vga", "intensity", 4, "huber"),
+                                                    # the reference's own bpvo/gradient_descriptor.cc: GradientDescriptor (3 channels,
+                                                    # without / with the Gaussian of cv::Size() size), DescriptorFields (5 channels)
+                                                    ("small", "gradient", 3, "huber"), ("odd", "gradient:0.75", 2, "tukey"), ("odd", "gradient:1.2", 2, "tukey"),
+                                                    ("small", "dfields", 3, "tukey"), ("odd", "dfields", 2, "huber")])
 def test_frame_and_linearize_bit_exact(oracle, ref, kind, desc, levels, loss):
     sc = _frames(kind)
-    p = make_params(desc, levels, loss)
+    desc, _, sig = desc.partition(":")
+    p = make_params(desc, levels, loss, **({"sigmaPriorToCensusTransform": float(sig)} if sig else {}))
     i0, d0 = sc.render(0); i1, d1 = sc.render(1)
     ra, rb = oracle.RefFrame(sc.K, sc.baseline, sc.rows, sc.cols, p), oracle.RefFrame(sc.K, sc.baseline, sc.rows, sc.cols, p)
     oa, ob = oracle.Frame(sc.K, sc.baseline, sc.rows, sc.cols, p, use_rcp=1), oracle.Frame(sc.K, sc.baseline, sc.rows, sc.cols, p, use_rcp=1)
