@@ -36,6 +36,13 @@ constexpr int kLLGroup = BP_LL_GROUP;      // CTAs per group of the two-level fl
 constexpr int kMaxGrid = 1024;     // upper bound of CTAs of the persistent kernel (sizes the exchange mailboxes)
 constexpr int kLinThreads = 256;   // threads per CTA of the linearize phases (1 CTA per SM; measured: 128 -> 14.7, 256 -> 12.4, 512 -> 13.5 us / GN iteration)
 
+// Channel-interleaved arrays (descriptor [rows][cols][S], template fields and residuals [N][S]) store S = kStride<C> floats per
+// pixel / point: 1, 4 (C = 3: intensity + gradient), 8 (C = 5: descriptor fields, C = 8: bit-planes), so that a record is one or
+// two aligned 16-byte loads whatever C; the padding channels are zero and never enter a sum.
+template <int C> constexpr int kStride = (C == 1) ? 1 : ((C <= 4) ? 4 : 8);
+
+__host__ __device__ inline int channel_stride(int C) { return (C == 1) ? 1 : ((C <= 4) ? 4 : 8); }
+
 // Per-level template ("TemplateData", bpvo/template_data.h) in the device layout:
 //   pts   [N]      float4 (X, Y, Z, 1)                                  (reference: _points)
 //   gx    [N][C]   fx * Ix of every channel, point-major                (reference: folded into _jacobians)

@@ -51,6 +51,16 @@ int bp_fail(int code, const char* fmt, ...) {
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// channel-count dispatch: CC is a compile-time constant inside the statement (1 intensity, 3 intensity + gradient,
+// 5 descriptor fields, 8 bit-planes)
+#define BP_SWITCH_C(CH, ...)                                     \
+  switch (CH) {                                                  \
+    case 1: { constexpr int CC = 1; __VA_ARGS__; } break;        \
+    case 3: { constexpr int CC = 3; __VA_ARGS__; } break;        \
+    case 5: { constexpr int CC = 5; __VA_ARGS__; } break;        \
+    default: { constexpr int CC = 8; __VA_ARGS__; } break;       \
+  }
+
 // -------------------------------------------------------------------------------------------------
 // phase timers (cudaEvent pairs, only when profiling is on)
 // -------------------------------------------------------------------------------------------------
@@ -155,8 +165,13 @@ int bpvo_b200_create(bpvo_b200_ctx** out, const float K[9], float baseline, int 
   if (p->maxTestLevel < 0 || p->maxTestLevel >= p->numPyramidLevels)
     return bp_fail(BPVO_B200_ERR_INVALID_ARG, "invalid maxTestLevel");                       // dense_descriptor_pyramid.cc:38
   if (rows < 16 || cols < 24) return bp_fail(BPVO_B200_ERR_INVALID_ARG, "image too small");
-  if (p->descriptor != BPVO_B200_INTENSITY && p->descriptor != BPVO_B200_BITPLANES)
-    return bp_fail(BPVO_B200_ERR_UNSUPPORTED, "DescriptorType 0x%x is not on the accelerated path (Intensity, BitPlanes only)", p->descriptor);
+  if (p->descriptor != BPVO_B200_INTENSITY && p->descriptor != BPVO_B200_BITPLANES && p->descriptor != BPVO_B200_INTENSITY_AND_GRADIENT &&
+      p->descriptor != BPVO_B200_DESCRIPTOR_FIELDS)
+    return bp_fail(BPVO_B200_ERR_UNSUPPORTED, "DescriptorType 0x%x is not on the accelerated path (Intensity, IntensityAndGradient, DescriptorFieldsFirstOrder, BitPlanes)", p->descriptor);
+  if (p->descriptor == BPVO_B200_INTENSITY_AND_GRADIENT && p->sigmaPriorToCensusTransform > 4.0f)
+    return bp_fail(BPVO_B200_ERR_UNSUPPORTED, "GradientDescriptor: sigma > 4 needs a Gaussian of more than 33 taps");
+  if (p->descriptor == BPVO_B200_DESCRIPTOR_FIELDS && (p->dfSigma1 > 16.0f || p->dfSigma2 > 16.0f))
+    return bp_fail(BPVO_B200_ERR_UNSUPPORTED, "DescriptorFields: sigma > 16 needs a Gaussian of more than 33 taps");
   if (p->interp != BPVO_B200_LINEAR && p->interp != BPVO_B200_COSINE && p->interp != BPVO_B200_CUBIC && p->interp != BPVO_B200_CUBIC_HERMITE)
     return bp_fail(BPVO_B200_ERR_INVALID_ARG, "unknown InterpolationType");
   if (p->lossFunction != BPVO_B200_HUBER && p->lossFunction != BPVO_B200_TUKEY && p->lossFunction != BPVO_B200_L2)
@@ -196,7 +211,8 @@ static int ctx_init(bpvo_b200_ctx* c, const float K[9], float baseline, int rows
   if (const char* e = getenv("BPVO_B200_SOLVER_CTAS")) c->solver_ctas = atoi(e);
   // test hook: start the exchange sequence numbers close to their wrap-around so that the reset paths get exercised
   if (const char* e = getenv("BPVO_B200_SEQ_INIT")) { c->ll_seq = (unsigned) strtoul(e, nullptr, 0); c->x_seq_init = c->ll_seq; }
-  c->C = (p->descriptor == BPVO_B200_BITPLANES) ? 8 : 1;
+  c->C = (p->descriptor == BPVO_B200_BITPLANES) ? 8 : (p->descriptor == BPVO_B200_DESCRIPTOR_FIELDS) ? 5 : (p->descriptor == BPVO_B200_INTENSITY_AND_GRADIENT) ? 3 : 1;
+  c->CS = channel_stride(c->C);
   memcpy(c->K, K, sizeof(c->K));
   cudaDeviceProp prop;
   CUDA_TRY(cudaGetDeviceProperties(&prop, p->device_id));
@@ -221,7 +237,7 @@ static int ctx_init(bpvo_b200_ctx* c, const float K[9], float baseline, int rows
   const size_t cap0 = (size_t) c->geom[c->p.maxTestLevel].capacity;
   size_t capmax = 0; for (int l = c->p.maxTestLevel; l < c->L; ++l) capmax = std::max(capmax, (size_t) c->geom[l].capacity);
   (void) cap0;
-  CUDA_TRY(cudaMalloc(&c->work.res, capmax * c->C * sizeof(float)));
+  CUDA_TRY(cudaMalloc(&c->work.res, capmax * c->CS * sizeof(float)));
   CUDA_TRY(cudaMalloc(&c->work.valid, capmax));
   CUDA_TRY(cudaMalloc(&c->work.hist, (kHistSets * kHistWords + 8 + 128) * sizeof(unsigned)));
   CUDA_TRY(cudaMalloc(&c->work.ll, (size_t) 4 * kMaxGrid * 32 * sizeof(uint4)));
@@ -234,7 +250,7 @@ static int ctx_init(bpvo_b200_ctx* c, const float K[9], float baseline, int rows
   CUDA_TRY(cudaMalloc(&c->work.ticket, 4 * sizeof(unsigned)));
   CUDA_TRY(cudaMalloc(&c->work.cand, ((size_t) kMaxGrid * kCandPerCta + kOvfCap + kSelList) * sizeof(float)));
   CUDA_TRY(cudaMalloc(&c->sel, sizeof(Sel)));
-  CUDA_TRY(cudaMalloc(&c->export_buf, capmax * std::max(c->C * 6, 8) * sizeof(float)));      // Jacobian export / 32-byte point records
+  CUDA_TRY(cudaMalloc(&c->export_buf, capmax * std::max(c->C * 7, 8) * sizeof(float)));      // Jacobian export / 32-byte point records
   CUDA_TRY(cudaMemsetAsync(c->work.hist, 0, (kHistSets * kHistWords + 8 + 128) * sizeof(unsigned), c->stream));
   CUDA_TRY(cudaMemsetAsync(c->work.ticket, 0, 4 * sizeof(unsigned), c->stream));
   CUDA_TRY(cudaMemsetAsync(c->sel, 0, sizeof(Sel), c->stream));
@@ -243,6 +259,8 @@ static int ctx_init(bpvo_b200_ctx* c, const float K[9], float baseline, int rows
   const int r0 = c->geom[c->p.maxTestLevel].rows, c0 = c->geom[c->p.maxTestLevel].cols;
   CUDA_TRY(cudaMalloc(&c->flags, (size_t) r0 * c0));
   if (c->C == 8 && p->sigmaPriorToCensusTransform > 0.0f) CUDA_TRY(cudaMalloc(&c->blur_tmp, (size_t) r0 * u8_pitch(c0)));   // pre-census blur output
+  if (c->C == 3 || c->C == 5)        // f32 scratch planes of the gradient-based descriptors
+    for (int k = 0; k < 5; ++k) CUDA_TRY(cudaMalloc(&c->plane[k], (size_t) r0 * c0 * sizeof(float)));
   CUDA_TRY(cudaMalloc(&c->block_counts, (size_t) (ceil_div(r0 * c0, kSelPerBlock) + 1) * sizeof(int)));
   CUDA_TRY(cudaMalloc(&c->hpartials, 1024 * 4 * sizeof(double)));
   CUDA_TRY(cudaMalloc(&c->hsums, 4 * sizeof(double)));
@@ -267,6 +285,7 @@ int bpvo_b200_destroy(bpvo_b200_ctx* c) {
   bp_comm_destroy(c);
   cudaFree(c->work.res); cudaFree(c->work.valid); cudaFree(c->work.hist); cudaFree(c->work.ll); cudaFree(c->work.partials);
   cudaFree(c->work.scale); cudaFree(c->d_mail); cudaFree(c->work.ticket); cudaFree(c->work.cand); cudaFree(c->sel); cudaFree(c->export_buf);
+  for (int k = 0; k < 5; ++k) cudaFree(c->plane[k]);
   cudaFree(c->flags); cudaFree(c->blur_tmp); cudaFree(c->block_counts); cudaFree(c->hpartials); cudaFree(c->hsums);
   cudaFree(c->d_prof); cudaFree(c->d_trace); cudaFree(c->d_trace_rows);
   if (c->h_mail) cudaFreeHost(c->h_mail); if (c->stage_img) cudaFreeHost(c->stage_img); if (c->stage_disp) cudaFreeHost(c->stage_disp);
@@ -366,14 +385,14 @@ static int frame_init(bpvo_b200_ctx* c, bpvo_b200_frame* f) {
     const size_t npx = (size_t) g.rows * g.cols, cap = (size_t) g.capacity;
     // one extra zero row (+ pad): the reference's cubic / Hermite footprint reaches row `rows` for yi = rows - 2
     // (photo_error.cc:358 bounds y by rows - 1 only) and reads past its buffer there; the engine reads zeros instead
-    const size_t desc_elems = (npx + (size_t) g.cols + 4) * c->C;
+    const size_t desc_elems = (npx + (size_t) g.cols + 4) * c->CS;
     CUDA_TRY(cudaMalloc(&f->desc[l], desc_elems * sizeof(float)));
     CUDA_TRY(cudaMemsetAsync(f->desc[l], 0, desc_elems * sizeof(float), c->stream));
     CUDA_TRY(cudaMalloc(&f->saliency[l], npx * sizeof(float)));
     CUDA_TRY(cudaMalloc(&f->pts[l], cap * sizeof(float4)));
-    CUDA_TRY(cudaMalloc(&f->gx[l], cap * c->C * sizeof(float)));
-    CUDA_TRY(cudaMalloc(&f->gy[l], cap * c->C * sizeof(float)));
-    CUDA_TRY(cudaMalloc(&f->i0[l], cap * c->C * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&f->gx[l], cap * c->CS * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&f->gy[l], cap * c->CS * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&f->i0[l], cap * c->CS * sizeof(float)));
     CUDA_TRY(cudaMalloc(&f->inds[l], cap * sizeof(int)));
   }
   CUDA_TRY(cudaMalloc(&f->d_meta, kMaxLevels * sizeof(TemplateMeta)));
@@ -416,6 +435,60 @@ static bool is_dma_able(const void* p) {
 
 static int run_as_graph(bpvo_b200_ctx* c, bpvo_b200_frame* f, int which, int (*enqueue)(bpvo_b200_ctx*, bpvo_b200_frame*));
 
+// cv::getGaussianKernel(ksize, sigma, CV_32F): exp in double -> float taps, normalised by the double sum of the float taps
+static BlurTaps gaussian_taps(int ksize, double sigma) {
+  BlurTaps t; memset(&t, 0, sizeof(t));
+  const int half = ksize / 2;
+  t.half = half;
+  float k[33]; double sum = 0;
+  const double sx = sigma > 0 ? sigma : ((ksize - 1) * 0.5 - 1) * 0.3 + 0.8, sc = -0.5 / (sx * sx);
+  for (int i = 0; i < ksize; ++i) { const double x = i - half; k[i] = (float) exp(sc * x * x); sum += k[i]; }
+  sum = 1.0 / sum;
+  for (int j = 0; j <= half; ++j) t.k[j] = (float) (k[half + j] * sum);
+  return t;
+}
+static int enqueue_blur(bpvo_b200_ctx* c, const float* src, int rows, int cols, const BlurTaps& t, float* scratch, float* dst, int dst_stride, int dst_off) {
+  const int nb = ceil_div(rows * cols, 256);
+  blur_row_kernel<<<nb, 256, 0, c->stream>>>(src, rows, cols, t, scratch); LAUNCH_CHECK(c);
+  blur_col_kernel<<<nb, 256, 0, c->stream>>>(scratch, rows, cols, t, dst, dst_stride, dst_off); LAUNCH_CHECK(c);
+  return BPVO_B200_OK;
+}
+// GradientDescriptor::compute / DescriptorFields::compute (gradient_descriptor.cc:42-64, 101-116) of one pyramid level
+static int enqueue_gradient_descriptor(bpvo_b200_ctx* c, bpvo_b200_frame* f, int l) {
+  const LevelGeom& g = c->geom[l];
+  const int npx = g.rows * g.cols, nb = ceil_div(npx, 256), pitch = u8_pitch(g.cols);
+  float* A = c->plane[0]; float* Is = c->plane[1]; float* P = c->plane[2]; float* N = c->plane[3]; float* scratch = c->plane[4];
+  u8_to_f32_kernel<<<nb, 256, 0, c->stream>>>(f->pyr[l], g.rows, g.cols, pitch, A); LAUNCH_CHECK(c);
+  int rc;
+  if (c->C == 3) {
+    const float sg = c->p.sigmaPriorToCensusTransform;         // dense_descriptor.cc:49
+    const float* src = A;
+    if (sg > 0.0f) {                                            // cv::GaussianBlur(.., cv::Size(), sigma): ksize = cvRound(sigma * 8 + 1) | 1
+      const int ksize = ((int) lrint((double) sg * 8 + 1)) | 1;
+      if ((rc = enqueue_blur(c, A, g.rows, g.cols, gaussian_taps(ksize, (double) sg), scratch, Is, 1, 0))) return rc;
+      src = Is;
+    }
+    gradient_descriptor_kernel<<<nb, 256, 0, c->stream>>>(f->pyr[l], g.rows, g.cols, pitch, src, f->desc[l]); LAUNCH_CHECK(c);
+    return BPVO_B200_OK;
+  }
+  auto smooth_taps = [](float sigma) { const int k = std::max(5, 2 * (int) round((double) sigma) + 1); return gaussian_taps(k, (double) sigma); };   // imsmooth
+  const float* src = A;
+  if (c->p.dfSigma1 > 0.0f) { if ((rc = enqueue_blur(c, A, g.rows, g.cols, smooth_taps(c->p.dfSigma1), scratch, Is, 1, 0))) return rc; src = Is; }
+  dfields_base_kernel<<<nb, 256, 0, c->stream>>>(f->pyr[l], g.rows, g.cols, pitch, f->desc[l]); LAUNCH_CHECK(c);
+  for (int dir = 0; dir < 2; ++dir) {
+    split_gradient_kernel<<<nb, 256, 0, c->stream>>>(src, g.rows, g.cols, dir, P, N); LAUNCH_CHECK(c);
+    if (c->p.dfSigma2 > 0.0f) {
+      const BlurTaps t = smooth_taps(c->p.dfSigma2);
+      if ((rc = enqueue_blur(c, P, g.rows, g.cols, t, scratch, f->desc[l], 8, 1 + 2 * dir))) return rc;
+      if ((rc = enqueue_blur(c, N, g.rows, g.cols, t, scratch, f->desc[l], 8, 2 + 2 * dir))) return rc;
+    } else {
+      plane_to_channel_kernel<<<nb, 256, 0, c->stream>>>(P, npx, f->desc[l], 8, 1 + 2 * dir); LAUNCH_CHECK(c);
+      plane_to_channel_kernel<<<nb, 256, 0, c->stream>>>(N, npx, f->desc[l], 8, 2 + 2 * dir); LAUNCH_CHECK(c);
+    }
+  }
+  return BPVO_B200_OK;
+}
+
 // the kernel sequence of setData: DenseDescriptorPyramid::init (dense_descriptor_pyramid.cc:67-78)
 static int enqueue_descriptors(bpvo_b200_ctx* c, bpvo_b200_frame* f) {
   {
@@ -432,6 +505,10 @@ static int enqueue_descriptors(bpvo_b200_ctx* c, bpvo_b200_frame* f) {
       const LevelGeom& g = c->geom[l];
       if (c->C == 1) {
         intensity_kernel<<<ceil_div(g.rows * g.cols, 256), 256, 0, c->stream>>>(f->pyr[l], g.rows, g.cols, u8_pitch(g.cols), f->desc[l]);
+      } else if (c->C == 3 || c->C == 5) {
+        int rc = enqueue_gradient_descriptor(c, f, l);
+        if (rc) return rc;
+        continue;
       } else {
         float k[5]; double sum = 0; const double sg = c->p.sigmaBitPlanes > 0 ? (double) c->p.sigmaBitPlanes : 1.1;
         // cv::getGaussianKernel(5, sigma, CV_32F): exp in double -> float taps, normalised by the double sum of the float taps
@@ -497,8 +574,7 @@ static int enqueue_template(bpvo_b200_ctx* c, bpvo_b200_frame* f) {
   for (int l = c->L - 1; l >= c->p.maxTestLevel; --l) {
     const LevelGeom& g = c->geom[l];
     const int npx = g.rows * g.cols;
-    if (c->C == 1) saliency_kernel<1><<<ceil_div(npx, 256), 256, 0, c->stream>>>(f->desc[l], g.rows, g.cols, f->saliency[l]);
-    else saliency_kernel<8><<<ceil_div(npx, 256), 256, 0, c->stream>>>(f->desc[l], g.rows, g.cols, f->saliency[l]);
+    BP_SWITCH_C(c->C, saliency_kernel<CC><<<ceil_div(npx, 256), 256, 0, c->stream>>>(f->desc[l], g.rows, g.cols, f->saliency[l]));
     LAUNCH_CHECK(c);
     SelectArgs sa;
     sa.S = f->saliency[l]; sa.D = f->disp; sa.rows = g.rows; sa.cols = g.cols; sa.Dcols = c->cols; sa.level = l;
@@ -522,10 +598,9 @@ static int enqueue_template(bpvo_b200_ctx* c, bpvo_b200_frame* f) {
       set_identity_normalization_kernel<<<1, 1, 0, c->stream>>>(f->d_meta + l);
       LAUNCH_CHECK(c);
     }
-    const int rb = std::max(1, std::min(ceil_div(g.capacity * c->C, 256), c->sm_count * 8));
+    const int rb = std::max(1, std::min(ceil_div(g.capacity * c->CS, 256), c->sm_count * 8));
     const int cd5 = c->p.gradientEstimation == BPVO_B200_CD5;
-    if (c->C == 1) template_records_kernel<1><<<rb, 256, 0, c->stream>>>(f->desc[l], g.cols, f->inds[l], f->d_meta + l, g.fx, g.fy, cd5, f->gx[l], f->gy[l], f->i0[l]);
-    else template_records_kernel<8><<<rb, 256, 0, c->stream>>>(f->desc[l], g.cols, f->inds[l], f->d_meta + l, g.fx, g.fy, cd5, f->gx[l], f->gy[l], f->i0[l]);
+    BP_SWITCH_C(c->C, template_records_kernel<CC><<<rb, 256, 0, c->stream>>>(f->desc[l], g.cols, f->inds[l], f->d_meta + l, g.fx, g.fy, cd5, f->gx[l], f->gy[l], f->i0[l]));
     LAUNCH_CHECK(c);
   }
   CUDA_TRY(cudaMemcpyAsync(f->h_meta, f->d_meta, kMaxLevels * sizeof(TemplateMeta), cudaMemcpyDeviceToHost, c->stream));
@@ -627,7 +702,7 @@ int bpvo_b200_frame_get_descriptor(const bpvo_b200_frame* f, int level, float* p
   const int npx = g.rows * g.cols;
   float* tmp = nullptr;
   CUDA_TRY(cudaMalloc(&tmp, (size_t) npx * c->C * sizeof(float)));
-  deinterleave_kernel<<<ceil_div(npx, 256), 256, 0, c->stream>>>(f->desc[level], npx, c->C, tmp);
+  deinterleave_kernel<<<ceil_div(npx, 256), 256, 0, c->stream>>>(f->desc[level], npx, c->C, c->CS, tmp);
   cudaError_t e = cudaMemcpyAsync(planes, tmp, (size_t) npx * c->C * sizeof(float), cudaMemcpyDeviceToHost, c->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
   cudaFree(tmp);
@@ -655,8 +730,7 @@ static int export_template(const bpvo_b200_frame* f, int level, float* pixels_ou
   CUDA_TRY(cudaMalloc(&tmp, (size_t) n * c->C * 7 * sizeof(float)));
   float* dJ = tmp; float* dP = tmp + (size_t) n * c->C * 6;
   LevelTemplate t = make_level_template(f, level);
-  if (c->C == 1) export_template_kernel<1><<<ceil_div(n, 256), 256, 0, c->stream>>>(t, dP, dJ);
-  else export_template_kernel<8><<<ceil_div(n * 8, 256), 256, 0, c->stream>>>(t, dP, dJ);
+  BP_SWITCH_C(c->C, export_template_kernel<CC><<<ceil_div(n * CC, 256), 256, 0, c->stream>>>(t, dP, dJ));
   cudaError_t e = cudaSuccess;
   if (pixels_out) e = cudaMemcpyAsync(pixels_out, dP, (size_t) n * c->C * sizeof(float), cudaMemcpyDeviceToHost, c->stream);
   if (e == cudaSuccess && J_out) e = cudaMemcpyAsync(J_out, dJ, (size_t) n * c->C * 6 * sizeof(float), cudaMemcpyDeviceToHost, c->stream);
@@ -787,7 +861,7 @@ extern "C" int bpvo_b200_linearize(bpvo_b200_ctx* c, const bpvo_b200_frame* ref,
     PhaseTimer t(c, &c->counters.ms_linearize);
     if (first_call_of_level) { k_reset_scale<<<1, 1, 0, c->stream>>>(c->work.scale); LAUNCH_CHECK(c); }
     M44 Tm; memcpy(Tm.m, T, sizeof(Tm.m));
-    rc = (c->C == 1) ? launch_linearize<1>(c, ref, cur, level, Tm) : launch_linearize<8>(c, ref, cur, level, Tm);
+    BP_SWITCH_C(c->C, rc = launch_linearize<CC>(c, ref, cur, level, Tm));
     if (rc) return rc;
   }
   CUDA_TRY(cudaMemcpyAsync(&c->h_mail->lin, c->work.out, sizeof(LinOut), cudaMemcpyDeviceToHost, c->stream));
@@ -943,7 +1017,7 @@ extern "C" int bpvo_b200_estimate_pose(bpvo_b200_ctx* c, const bpvo_b200_frame* 
   } else {
     {
       PhaseTimer t(c, &c->counters.ms_linearize);
-      rc = (c->C == 1) ? launch_estimate_pose<1>(c, ref, cur, T) : launch_estimate_pose<8>(c, ref, cur, T);
+      BP_SWITCH_C(c->C, rc = launch_estimate_pose<CC>(c, ref, cur, T));
       if (rc) return rc;
     }
     Mailbox* mb = c->h_mail;
@@ -986,8 +1060,7 @@ static int export_last(bpvo_b200_ctx* c, float* w, float* r, size_t* count) {
   const float sigma = c->h_mail->lin.sigma;
   float* dw = w ? c->export_buf : nullptr;
   float* dr = r ? c->export_buf + (size_t) n * c->C : nullptr;
-  if (c->C == 1) k_export_weights<1><<<ceil_div(n, 256), 256, 0, c->stream>>>(c->work.res, n, sigma, c->p.lossFunction, dw, dr);
-  else k_export_weights<8><<<ceil_div(n * 8, 256), 256, 0, c->stream>>>(c->work.res, n, sigma, c->p.lossFunction, dw, dr);
+  BP_SWITCH_C(c->C, k_export_weights<CC><<<ceil_div(n * CC, 256), 256, 0, c->stream>>>(c->work.res, n, sigma, c->p.lossFunction, dw, dr));
   LAUNCH_CHECK(c);
   if (w) CUDA_TRY(cudaMemcpyAsync(w, dw, ncopy * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
   if (r) CUDA_TRY(cudaMemcpyAsync(r, dr, ncopy * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
@@ -1045,8 +1118,7 @@ extern "C" int bpvo_b200_point_cloud(bpvo_b200_ctx* c, const bpvo_b200_frame* re
   const float sigma = c->h_mail->lin.sigma;
   const LevelGeom& g = c->geom[level];
   PointInfo* d = reinterpret_cast<PointInfo*>(c->export_buf);          // capacity: capmax * C * 6 floats and at least 8 floats per point
-  if (c->C == 1) k_point_cloud<1><<<ceil_div(np, 256), 256, 0, c->stream>>>(ref->pts[level], np, ref->pyr[0], c->rows, c->cols, u8_pitch(c->cols), g.fx, g.fy, g.cx, g.cy, c->work.res, sigma, c->p.lossFunction, d);
-  else k_point_cloud<8><<<ceil_div(np, 256), 256, 0, c->stream>>>(ref->pts[level], np, ref->pyr[0], c->rows, c->cols, u8_pitch(c->cols), g.fx, g.fy, g.cx, g.cy, c->work.res, sigma, c->p.lossFunction, d);
+  BP_SWITCH_C(c->C, k_point_cloud<CC><<<ceil_div(np, 256), 256, 0, c->stream>>>(ref->pts[level], np, ref->pyr[0], c->rows, c->cols, u8_pitch(c->cols), g.fx, g.fy, g.cx, g.cy, c->work.res, sigma, c->p.lossFunction, d));
   LAUNCH_CHECK(c);
   CUDA_TRY(cudaMemcpyAsync(records, d, (size_t) np * sizeof(PointInfo), cudaMemcpyDeviceToHost, c->stream));
   CUDA_TRY(cudaStreamSynchronize(c->stream));
@@ -1073,7 +1145,7 @@ extern "C" int bpvo_b200_debug_device_linearize(bpvo_b200_ctx* c, const bpvo_b20
     ov.dbg.poses = d_poses; ov.dbg.out = d_out; ov.dbg.n = n; ov.dbg.level = level;
     ov.grid = grid_ctas; ov.cache_bytes = cache_bytes;
     M44 T0; memcpy(T0.m, T, sizeof(T0.m));
-    rc = (c->C == 1) ? launch_estimate_pose<1>(c, ref, cur, T0, &ov) : launch_estimate_pose<8>(c, ref, cur, T0, &ov);
+    BP_SWITCH_C(c->C, rc = launch_estimate_pose<CC>(c, ref, cur, T0, &ov));
     if (rc == BPVO_B200_OK) {
       e = cudaMemcpyAsync(out, d_out, (size_t) n * sizeof(LinOut), cudaMemcpyDeviceToHost, c->stream);
       if (e == cudaSuccess) e = cudaMemcpyAsync(c->h_mail, c->d_mail, sizeof(Mailbox), cudaMemcpyDeviceToHost, c->stream);
@@ -1119,9 +1191,9 @@ extern "C" int bpvo_b200_debug_get_trace(bpvo_b200_ctx* c, float* rows, int max_
 
 // host evaluation of the persistent kernel's per-level shared-memory plan (tests / documentation)
 extern "C" int bpvo_b200_debug_cache_plan(int channels, int cache_bytes, int slots_needed, unsigned out[8]) {
-  if (!out || (channels != 1 && channels != 8)) return bp_fail(BPVO_B200_ERR_INVALID_ARG, "bad argument");
-  const TplCache t = (channels == 8) ? tpl_cache_plan<8>((unsigned) kScratchBytes, cache_bytes, slots_needed)
-                                     : tpl_cache_plan<1>((unsigned) kScratchBytes, cache_bytes, slots_needed);
+  if (!out || (channels != 1 && channels != 3 && channels != 5 && channels != 8)) return bp_fail(BPVO_B200_ERR_INVALID_ARG, "bad argument");
+  TplCache t = tpl_cache_off();
+  BP_SWITCH_C(channels, t = tpl_cache_plan<CC>((unsigned) kScratchBytes, cache_bytes, slots_needed));
   out[0] = t.pts; out[1] = t.f[TC_I0]; out[2] = t.f[TC_GX]; out[3] = t.f[TC_GY]; out[4] = t.f[TC_R]; out[5] = t.valid;
   out[6] = (unsigned) t.K; out[7] = (unsigned) kScratchBytes;
   return BPVO_B200_OK;
@@ -1141,7 +1213,7 @@ extern "C" int bpvo_b200_time_linearize(bpvo_b200_ctx* c, const bpvo_b200_frame*
     if (flush_l2) CUDA_TRY(cudaMemsetAsync(c->flush_buf, i & 0xff, flush_bytes, c->stream));
     k_reset_scale<<<1, 1, 0, c->stream>>>(c->work.scale);
     CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
-    rc = (c->C == 1) ? launch_linearize<1>(c, ref, cur, level, Tm) : launch_linearize<8>(c, ref, cur, level, Tm);
+    BP_SWITCH_C(c->C, rc = launch_linearize<CC>(c, ref, cur, level, Tm));
     if (rc) return rc;
     CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
     CUDA_TRY(cudaEventSynchronize(c->ev1));

@@ -30,7 +30,8 @@ struct bpvo_b200_frame;
 
 struct bpvo_b200_ctx {
   bpvo_b200_params p;
-  int rows = 0, cols = 0, L = 0, C = 1;
+  int rows = 0, cols = 0, L = 0, C = 1, CS = 1;     // C channels, stored with a stride of CS floats (device_types.h: kStride)
+  float* plane[5] = {};                              // f32 scratch planes of the gradient-based descriptors
   float K[9]; float baseline = 0;
   LevelGeom geom[bp::kMaxLevels];
   int sm_count = 0; bool coop = false; int smem_optin = 0;

@@ -291,11 +291,86 @@ __global__ void __launch_bounds__(256) bitplanes_tma_kernel(const CUtensorMap* _
   }
 }
 
-// interleaved [rows][cols][C] -> planar C x rows x cols (parity dumps only)
-__global__ void __launch_bounds__(256) deinterleave_kernel(const float* __restrict__ src, int n, int C, float* __restrict__ dst) {
+// ---------------------------------------------------------------------------------------------
+// The two gradient-based descriptors (bpvo/gradient_descriptor.cc), interleaved like the others:
+//   GradientDescriptor  (kIntensityAndGradient, 3 channels, stride 4): I, Ix, Iy -- gradients of the image smoothed with a
+//                        Gaussian whose size OpenCV derives from sigma (cv::Size()) when sigma > 0, the intensity unsmoothed (:42-64)
+//   DescriptorFields    (kDescriptorFieldsFirstOrder, 5 channels, stride 8): I, then the positive and the negative part of Ix
+//                        and of Iy of the sigma1-smoothed image, each smoothed with sigma2 (imsmooth, imgproc.cc:166-171) (:78-116)
+// Small multi-pass kernels over f32 planes (key-frame / per-frame work of a few MB; the alignment kernels dominate).  Arithmetic
+// follows the oracle operation for operation (explicit roundings, OpenCV's symmetric tap order), so results are bit-identical.
+// ---------------------------------------------------------------------------------------------
+struct BlurTaps { int half; float k[17]; };      // k[0] centre tap, k[j] the taps at distance j (kernel size 2 half + 1 <= 33)
+
+__global__ void __launch_bounds__(256) u8_to_f32_kernel(const uint8_t* __restrict__ src, int rows, int cols, int spitch, float* __restrict__ dst) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < rows * cols) { const int y = i / cols, x = i - y * cols; dst[i] = (float) src[(size_t) y * spitch + x]; }
+}
+__global__ void __launch_bounds__(256) blur_row_kernel(const float* __restrict__ src, int rows, int cols, BlurTaps t, float* __restrict__ dst) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * cols) return;
+  const int y = i / cols, x = i - y * cols;
+  const float* s = src + (size_t) y * cols;
+  float v = __fmul_rn(__ldg(s + x), t.k[0]);
+  for (int j = 1; j <= t.half; ++j) v = __fadd_rn(v, __fmul_rn(__fadd_rn(__ldg(s + reflect101(x - j, cols)), __ldg(s + reflect101(x + j, cols))), t.k[j]));
+  dst[i] = v;
+}
+// column pass; the result goes to dst[i * dst_stride + dst_off] (a plane: stride 1, or one channel of an interleaved descriptor)
+__global__ void __launch_bounds__(256) blur_col_kernel(const float* __restrict__ src, int rows, int cols, BlurTaps t, float* __restrict__ dst, int dst_stride, int dst_off) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * cols) return;
+  const int y = i / cols, x = i - y * cols;
+  float v = __fmul_rn(t.k[0], __ldg(src + i));
+  for (int j = 1; j <= t.half; ++j)
+    v = __fadd_rn(v, __fmul_rn(t.k[j], __fadd_rn(__ldg(src + (size_t) reflect101(y + j, rows) * cols + x), __ldg(src + (size_t) reflect101(y - j, rows) * cols + x))));
+  dst[(size_t) i * dst_stride + dst_off] = v;
+}
+// xgradient / ygradient of imgproc.h:215-266: 0.5 (I[+1] - I[-1]), one-sided 0.5 (I1 - I0) on the first / last column (row)
+__device__ __forceinline__ float grad_x(const float* __restrict__ I, int cols, int y, int x) {
+  const float* s = I + (size_t) y * cols;
+  const int a = (x == 0) ? 0 : x - 1, b = (x == cols - 1) ? cols - 1 : x + 1;
+  return __fmul_rn(0.5f, __fsub_rn(__ldg(s + b), __ldg(s + a)));
+}
+__device__ __forceinline__ float grad_y(const float* __restrict__ I, int rows, int cols, int y, int x) {
+  const int a = (y == 0) ? 0 : y - 1, b = (y == rows - 1) ? rows - 1 : y + 1;
+  return __fmul_rn(0.5f, __fsub_rn(__ldg(I + (size_t) b * cols + x), __ldg(I + (size_t) a * cols + x)));
+}
+// GradientDescriptor: out[p] = {f32(u8), Ix, Iy, 0}; Is = the plane the gradients are taken from
+__global__ void __launch_bounds__(256) gradient_descriptor_kernel(const uint8_t* __restrict__ img, int rows, int cols, int spitch,
+                                                                  const float* __restrict__ Is, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * cols) return;
+  const int y = i / cols, x = i - y * cols;
+  reinterpret_cast<float4*>(out)[i] = make_float4((float) img[(size_t) y * spitch + x], grad_x(Is, cols, y, x), grad_y(Is, rows, cols, y, x), 0.0f);
+}
+// DescriptorFields, step 1: positive / negative part of one gradient direction of Is -> two planes (splitPosNeg :78-99)
+__global__ void __launch_bounds__(256) split_gradient_kernel(const float* __restrict__ Is, int rows, int cols, int dir, float* __restrict__ pos, float* __restrict__ neg) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * cols) return;
+  const int y = i / cols, x = i - y * cols;
+  const float g = dir ? grad_y(Is, rows, cols, y, x) : grad_x(Is, cols, y, x);
+  pos[i] = (g >= 0.0f) ? g : 0.0f;
+  neg[i] = (g < 0.0f) ? g : 0.0f;
+}
+// a plane into one channel of an interleaved descriptor (sigma2 <= 0: no smoothing)
+__global__ void __launch_bounds__(256) plane_to_channel_kernel(const float* __restrict__ src, int n, float* __restrict__ dst, int dst_stride, int dst_off) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[(size_t) i * dst_stride + dst_off] = src[i];
+}
+// DescriptorFields: channel 0 = f32(u8), padding channels 5..7 = 0
+__global__ void __launch_bounds__(256) dfields_base_kernel(const uint8_t* __restrict__ img, int rows, int cols, int spitch, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * cols) return;
+  const int y = i / cols, x = i - y * cols;
+  float* o = out + (size_t) i * 8;
+  o[0] = (float) img[(size_t) y * spitch + x]; o[5] = 0.0f; o[6] = 0.0f; o[7] = 0.0f;
+}
+
+// interleaved [rows][cols][stride] -> planar C x rows x cols (parity dumps only)
+__global__ void __launch_bounds__(256) deinterleave_kernel(const float* __restrict__ src, int n, int C, int stride, float* __restrict__ dst) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  for (int c = 0; c < C; ++c) dst[(size_t) c * n + i] = src[(size_t) i * C + c];
+  for (int c = 0; c < C; ++c) dst[(size_t) c * n + i] = src[(size_t) i * stride + c];
 }
 
 }  // namespace bp

@@ -50,29 +50,33 @@ __device__ __forceinline__ void prefetch_l2(const void* p) {
 #endif
 }
 
-template <int C> struct VecC;
-template <> struct VecC<8> {
-  float v[8];
+template <int C> struct VecC {
+  float v[C];
+  static_assert(C == 1 || C == 3 || C == 5 || C == 8, "channel counts of the supported descriptors");
+  __device__ __forceinline__ void set(const float4& a, const float4& b) {
+#pragma unroll
+    for (int c = 0; c < C; ++c) v[c] = (c == 0) ? a.x : (c == 1) ? a.y : (c == 2) ? a.z : (c == 3) ? a.w : (c == 4) ? b.x : (c == 5) ? b.y : (c == 6) ? b.z : b.w;
+  }
   __device__ __forceinline__ void load(const float* __restrict__ p) {
+    if (C == 1) { v[0] = __ldg(p); return; }
     const float4 a = __ldg(reinterpret_cast<const float4*>(p));
-    const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
-    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    const float4 b = (C > 4) ? __ldg(reinterpret_cast<const float4*>(p) + 1) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    set(a, b);
   }
   __device__ __forceinline__ void load_plain(const float* p) {   // data written earlier in the same kernel
+    if (C == 1) { v[0] = *p; return; }
     const float4 a = *reinterpret_cast<const float4*>(p);
-    const float4 b = *(reinterpret_cast<const float4*>(p) + 1);
-    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    const float4 b = (C > 4) ? *(reinterpret_cast<const float4*>(p) + 1) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    set(a, b);
   }
   __device__ __forceinline__ void store(float* p) const {
-    reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
-    reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+    if (C == 1) { *p = v[0]; return; }
+    float w[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) w[c] = (c < C) ? v[c < C ? c : 0] : 0.0f;
+    reinterpret_cast<float4*>(p)[0] = make_float4(w[0], w[1], w[2], w[3]);
+    if (C > 4) reinterpret_cast<float4*>(p)[1] = make_float4(w[4], w[5], w[6], w[7]);
   }
-};
-template <> struct VecC<1> {
-  float v[1];
-  __device__ __forceinline__ void load(const float* __restrict__ p) { v[0] = __ldg(p); }
-  __device__ __forceinline__ void load_plain(const float* p) { v[0] = *p; }
-  __device__ __forceinline__ void store(float* p) const { *p = v[0]; }
 };
 
 // Shared-memory copy of the template records (and residuals) of the points THIS CTA's threads own.  The on-device GN
@@ -136,9 +140,9 @@ template <int C> __device__ __forceinline__ void tc_fill(const TplCache& tc, con
   for (int i = first_point(block, nblocks); i < n && k < tc.K; i += nblocks * kLinThreads, ++k) {
     if (tc.pts != kTcNone) tc_point(tc, k) = __ldg(L.pts + i);
     VecC<C> v;
-    if (tc.f[TC_I0] != kTcNone) { v.load(L.i0 + (size_t) i * C); tc_put<C>(tc, k, TC_I0, v); }
-    if (tc.f[TC_GX] != kTcNone) { v.load(L.gx + (size_t) i * C); tc_put<C>(tc, k, TC_GX, v); }
-    if (tc.f[TC_GY] != kTcNone) { v.load(L.gy + (size_t) i * C); tc_put<C>(tc, k, TC_GY, v); }
+    if (tc.f[TC_I0] != kTcNone) { v.load(L.i0 + (size_t) i * kStride<C>); tc_put<C>(tc, k, TC_I0, v); }
+    if (tc.f[TC_GX] != kTcNone) { v.load(L.gx + (size_t) i * kStride<C>); tc_put<C>(tc, k, TC_GX, v); }
+    if (tc.f[TC_GY] != kTcNone) { v.load(L.gy + (size_t) i * kStride<C>); tc_put<C>(tc, k, TC_GY, v); }
   }
 }
 
@@ -281,11 +285,11 @@ __device__ __noinline__ void sample_nonlinear(int interp, const float* __restric
   if (interp == 1) {                                     // kCosine: 2 x 2 footprint at (xi, yi)
     float Cx[2], Cy[2];
     coeffs_cosine(xf, Cx); coeffs_cosine(yf, Cy);
-    const float* p1 = desc + ((size_t) yi * cols + xi) * C;
-    const float* p2 = p1 + (size_t) cols * C;
+    const float* p1 = desc + ((size_t) yi * cols + xi) * kStride<C>;
+    const float* p2 = p1 + (size_t) cols * kStride<C>;
     for (int c = 0; c < C; ++c) {
-      const float d1 = __fadd_rn(__fmul_rn(__ldg(p1 + c), Cx[0]), __fmul_rn(__ldg(p1 + C + c), Cx[1]));
-      const float d2 = __fadd_rn(__fmul_rn(__ldg(p2 + c), Cx[0]), __fmul_rn(__ldg(p2 + C + c), Cx[1]));
+      const float d1 = __fadd_rn(__fmul_rn(__ldg(p1 + c), Cx[0]), __fmul_rn(__ldg(p1 + kStride<C> + c), Cx[1]));
+      const float d2 = __fadd_rn(__fmul_rn(__ldg(p2 + c), Cx[0]), __fmul_rn(__ldg(p2 + kStride<C> + c), Cx[1]));
       r[c] = __fsub_rn(__fadd_rn(__fmul_rn(Cy[0], d1), __fmul_rn(Cy[1], d2)), i0[c]);
     }
   } else if (interp == 2) {                              // kCubic: rows yi-1 .. yi+2, columns xi .. xi+3
@@ -294,8 +298,8 @@ __device__ __noinline__ void sample_nonlinear(int interp, const float* __restric
     for (int c = 0; c < C; ++c) {
       float Iw = 0.0f;
       for (int k = 0; k < 4; ++k) {
-        const float* p = desc + ((size_t) (yi - 1 + k) * cols + xi) * C + c;
-        const float d = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(__ldg(p), Cx[0]), __fmul_rn(__ldg(p + C), Cx[1])), __fmul_rn(__ldg(p + 2 * C), Cx[2])), __fmul_rn(__ldg(p + 3 * C), Cx[3]));
+        const float* p = desc + ((size_t) (yi - 1 + k) * cols + xi) * kStride<C> + c;
+        const float d = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(__ldg(p), Cx[0]), __fmul_rn(__ldg(p + kStride<C>), Cx[1])), __fmul_rn(__ldg(p + 2 * kStride<C>), Cx[2])), __fmul_rn(__ldg(p + 3 * kStride<C>), Cx[3]));
         Iw = (k == 0) ? __fmul_rn(Cy[0], d) : __fadd_rn(Iw, __fmul_rn(Cy[k], d));
       }
       r[c] = __fsub_rn(Iw, i0[c]);
@@ -304,8 +308,8 @@ __device__ __noinline__ void sample_nonlinear(int interp, const float* __restric
     for (int c = 0; c < C; ++c) {
       float V[4];
       for (int k = 0; k < 4; ++k) {
-        const float* p = desc + ((size_t) (yi - 1 + k) * cols + xi) * C + c;
-        V[k] = hermite1(__ldg(p), __ldg(p + C), __ldg(p + 2 * C), __ldg(p + 3 * C), xf);
+        const float* p = desc + ((size_t) (yi - 1 + k) * cols + xi) * kStride<C> + c;
+        V[k] = hermite1(__ldg(p), __ldg(p + kStride<C>), __ldg(p + 2 * kStride<C>), __ldg(p + 3 * kStride<C>), xf);
       }
       r[c] = __fsub_rn(hermite1(V[0], V[1], V[2], V[3], yf), i0[c]);
     }
@@ -359,7 +363,7 @@ __device__ __forceinline__ void phase_residuals(const LevelTemplate& L, const Le
     if (streaming) {
       X = Xnext;
       const int i1 = i + stride, i2 = i + 2 * stride;
-      if (i2 < n_pts) { if (tc.pts == kTcNone) prefetch_l2(L.pts + i2); if (tc.f[TC_I0] == kTcNone) prefetch_l2(L.i0 + (size_t) i2 * C); }
+      if (i2 < n_pts) { if (tc.pts == kTcNone) prefetch_l2(L.pts + i2); if (tc.f[TC_I0] == kTcNone) prefetch_l2(L.i0 + (size_t) i2 * kStride<C>); }
       if (i1 < n_pts) {
         Xnext = (tc.pts != kTcNone) ? tc_point(tc, k + 1) : __ldg(L.pts + i1);
         // fp32 estimate of the next point's projection, only to prefetch its taps (a wrong guess costs nothing but the prefetch)
@@ -367,8 +371,8 @@ __device__ __forceinline__ void phase_residuals(const LevelTemplate& L, const Le
         const float iw = __frcp_rn(h2);
         const float uu = (P[0] * Xnext.x + P[3] * Xnext.y + P[6] * Xnext.z + P[9]) * iw, vv = (P[1] * Xnext.x + P[4] * Xnext.y + P[7] * Xnext.z + P[10]) * iw;
         if (uu >= 0.0f && vv >= 0.0f && uu < (float) (cols - 1) && vv < (float) (rows - 1)) {
-          const float* tp = I.desc + ((size_t) (int) vv * cols + (int) uu) * C;
-          prefetch_l2(tp); prefetch_l2(tp + C); prefetch_l2(tp + (size_t) cols * C); prefetch_l2(tp + (size_t) cols * C + C);
+          const float* tp = I.desc + ((size_t) (int) vv * cols + (int) uu) * kStride<C>;
+          prefetch_l2(tp); prefetch_l2(tp + kStride<C>); prefetch_l2(tp + (size_t) cols * kStride<C>); prefetch_l2(tp + (size_t) cols * kStride<C> + kStride<C>);
         }
       }
     } else {
@@ -392,11 +396,11 @@ __device__ __forceinline__ void phase_residuals(const LevelTemplate& L, const Le
       const double xf = __dsub_rn(u, (double) xi), yf = __dsub_rn(v, (double) yi);
       const double wx = __dsub_rn(1.0, xf), wy = __dsub_rn(1.0, yf);
       VecC<C> i0;
-      if (tc.f[TC_I0] != kTcNone) tc_get<C>(tc, k, TC_I0, i0); else i0.load(L.i0 + (size_t) i * C);
+      if (tc.f[TC_I0] != kTcNone) tc_get<C>(tc, k, TC_I0, i0); else i0.load(L.i0 + (size_t) i * kStride<C>);
       if (interp == 0) {
-        const float* tap = I.desc + ((size_t) yi * cols + xi) * C;
+        const float* tap = I.desc + ((size_t) yi * cols + xi) * kStride<C>;
         VecC<C> t00, t01, t10, t11;
-        t00.load(tap); t01.load(tap + C); t10.load(tap + (size_t) cols * C); t11.load(tap + (size_t) cols * C + C);
+        t00.load(tap); t01.load(tap + kStride<C>); t10.load(tap + (size_t) cols * kStride<C>); t11.load(tap + (size_t) cols * kStride<C> + kStride<C>);
         if (BLEND == 1 && C == 8) {
           const float xf32 = (float) xf, yf32 = (float) yf, wx32 = (float) wx, wy32 = (float) wy;
 #pragma unroll
@@ -448,7 +452,7 @@ __device__ __forceinline__ void phase_residuals(const LevelTemplate& L, const Le
     }
     // residuals / valid flags stay in shared memory while the level is cached (C = 8: written back once, after the last
     // iteration of the finest level); C = 1 keeps the global copy for the n < 3 median rule of finish_scale()
-    if (!(tc.f[TC_R] != kTcNone && C == 8)) { r.store(W.res + (size_t) i * C); W.valid[i] = ok ? 1 : 0; }
+    if (!(tc.f[TC_R] != kTcNone && C != 1)) { r.store(W.res + (size_t) i * kStride<C>); W.valid[i] = ok ? 1 : 0; }
     if (tc.f[TC_R] != kTcNone) { tc_put<C>(tc, k, TC_R, r); tc_valid(tc, k) = ok ? 1 : 0; }
   }
   BP_FINE(17);
@@ -504,7 +508,7 @@ __device__ __forceinline__ void phase_hist1(const Work& W, unsigned* __restrict_
   for (int i = first_point(block, nblocks); i < m.n; i += nblocks * kLinThreads, ++k) {
     if (!((tc.f[TC_R] != kTcNone) ? tc_valid(tc, k) : W.valid[i])) continue;
     VecC<C> r;
-    if (tc.f[TC_R] != kTcNone) tc_get<C>(tc, k, TC_R, r); else r.load_plain(W.res + (size_t) i * C);
+    if (tc.f[TC_R] != kTcNone) tc_get<C>(tc, k, TC_R, r); else r.load_plain(W.res + (size_t) i * kStride<C>);
 #pragma unroll
     for (int c = 0; c < C; ++c) atomicAdd(&sh.hist[__float_as_uint(fabsf(r.v[c])) >> 20], 1u);
   }
@@ -553,7 +557,7 @@ __device__ __forceinline__ void phase_select(const LevelTemplate& L, const Work&
   for (int i = first_point(block, nblocks); i < n_pts; i += nblocks * kLinThreads, ++k) {
     if (!((tc.f[TC_R] != kTcNone) ? tc_valid(tc, k) : W.valid[i])) continue;
     VecC<C> r;
-    if (tc.f[TC_R] != kTcNone) tc_get<C>(tc, k, TC_R, r); else r.load_plain(W.res + (size_t) i * C);
+    if (tc.f[TC_R] != kTcNone) tc_get<C>(tc, k, TC_R, r); else r.load_plain(W.res + (size_t) i * kStride<C>);
 #pragma unroll
     for (int c = 0; c < C; ++c) {
       const unsigned bits = __float_as_uint(fabsf(r.v[c]));
@@ -585,7 +589,7 @@ __device__ __forceinline__ float finish_scale(const Work& W, const unsigned* __r
   if (n == 0) {
     med = 0.0f;
   } else if (n < 3) {
-    med = fabsf(W.res[(size_t) (~hset[kHistBins]) * C]);         // data[0]: channel 0 of the first valid point
+    med = fabsf(W.res[(size_t) (~hset[kHistBins]) * kStride<C>]);         // data[0]: channel 0 of the first valid point
     lo = hi = med;
   } else {
     const unsigned* hist3 = hset + kHist1Bins + 2 * kHist2Bins;
@@ -750,9 +754,9 @@ __device__ __forceinline__ double phase_reduce(const LevelTemplate& L, const Wor
     if (BP_PREFETCH && tc.K > 1 && tc.pts == kTcNone && tc.f[TC_R] == kTcNone) {      // fully streaming level: two points ahead into the L2
       const int i2 = i + 2 * nblocks * kLinThreads;
       if (i2 < m.n) {
-        if (tc.f[TC_GX] == kTcNone) prefetch_l2(L.gx + (size_t) i2 * C);
-        if (tc.f[TC_GY] == kTcNone) prefetch_l2(L.gy + (size_t) i2 * C);
-        if (tc.f[TC_R] == kTcNone) { prefetch_l2(W.res + (size_t) i2 * C); if ((threadIdx.x & 31) == 0) prefetch_l2(W.valid + i2); }
+        if (tc.f[TC_GX] == kTcNone) prefetch_l2(L.gx + (size_t) i2 * kStride<C>);
+        if (tc.f[TC_GY] == kTcNone) prefetch_l2(L.gy + (size_t) i2 * kStride<C>);
+        if (tc.f[TC_R] == kTcNone) { prefetch_l2(W.res + (size_t) i2 * kStride<C>); if ((threadIdx.x & 31) == 0) prefetch_l2(W.valid + i2); }
         if (tc.pts == kTcNone) prefetch_l2(L.pts + i2);
       }
     }
@@ -761,9 +765,9 @@ __device__ __forceinline__ double phase_reduce(const LevelTemplate& L, const Wor
     VecC<C> r, gx, gy;
     // (this order -- gx, gy, then r -- and per-field tests measured fastest in same-box A/B runs; a separate straight-line
     //  path for the all-cached case, or r first, cost 1-3 %: the kernel sits at the register limit and ptxas is touchy)
-    if (tc.f[TC_GX] != kTcNone) tc_get<C>(tc, ks, TC_GX, gx); else gx.load(L.gx + (size_t) i * C);
-    if (tc.f[TC_GY] != kTcNone) tc_get<C>(tc, ks, TC_GY, gy); else gy.load(L.gy + (size_t) i * C);
-    if (tc.f[TC_R] != kTcNone) tc_get<C>(tc, ks, TC_R, r); else r.load_plain(W.res + (size_t) i * C);
+    if (tc.f[TC_GX] != kTcNone) tc_get<C>(tc, ks, TC_GX, gx); else gx.load(L.gx + (size_t) i * kStride<C>);
+    if (tc.f[TC_GY] != kTcNone) tc_get<C>(tc, ks, TC_GY, gy); else gy.load(L.gy + (size_t) i * kStride<C>);
+    if (tc.f[TC_R] != kTcNone) tc_get<C>(tc, ks, TC_R, r); else r.load_plain(W.res + (size_t) i * kStride<C>);
     float sxx = 0, sxy = 0, syy = 0, bx = 0, by = 0, e = 0, good = 0;
 #pragma unroll
     for (int c = 0; c < C; ++c) {
@@ -963,7 +967,7 @@ __global__ void __launch_bounds__(256) k_export_weights(const float* __restrict_
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n * C) return;
   const int i = t / C, c = t - i * C;
-  const float r = res[t];
+  const float r = res[(size_t) i * kStride<C> + c];
   if (w_out) w_out[(size_t) c * n + i] = robust_weight(loss, r, __fdiv_rn(1.0f, sigma));
   if (r_out) r_out[(size_t) c * n + i] = r;
 }
@@ -986,7 +990,7 @@ __global__ void __launch_bounds__(256) k_point_cloud(const float4* __restrict__ 
   PointInfo o;
   o.x = X.x; o.y = X.y; o.z = X.z; o.w = X.w;
   o.rgba = c | (c << 8) | (c << 16) | (255u << 24);
-  o.weight = robust_weight(loss, res[(size_t) i * C], __fdiv_rn(1.0f, sigma));
+  o.weight = robust_weight(loss, res[(size_t) i * kStride<C>], __fdiv_rn(1.0f, sigma));
   o.pad[0] = o.pad[1] = 0u;
   out[i] = o;
 }
@@ -1759,11 +1763,11 @@ __global__ void __launch_bounds__(kLinThreads, 1) k_estimate_pose(const __grid_c
     }
     total_evals += n_evals;
     // residuals / valid flags of the last linearize of the finest level go back to global memory for getWeights() & co.
-    if (tc.f[TC_R] != kTcNone && C == 8 && (lvl == a.sp.max_test_level || a.dbg.n > 0)) {
+    if (tc.f[TC_R] != kTcNone && C != 1 && (lvl == a.sp.max_test_level || a.dbg.n > 0)) {
       int k = 0;
       for (int i = first_point(blockIdx.x, gridDim.x); i < meta.n; i += gridDim.x * kLinThreads, ++k) {
         VecC<C> r; tc_get<C>(tc, k, TC_R, r);
-        r.store(a.work.res + (size_t) i * C);
+        r.store(a.work.res + (size_t) i * kStride<C>);
         a.work.valid[i] = tc_valid(tc, k);
       }
     }

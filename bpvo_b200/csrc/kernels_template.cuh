@@ -19,7 +19,7 @@ namespace bp {
 
 // descriptor value of channel c at linear pixel p (interleaved layout)
 template <int C> __device__ __forceinline__ float dval(const float* __restrict__ d, int p, int c) {
-  return __ldg(d + (size_t) p * C + c);
+  return __ldg(d + (size_t) p * kStride<C> + c);
 }
 
 // gradientAbsMag at linear pixel p of channel c: abs(I[p-1]-I[p+1]) + abs(I[p-cols]-I[p+cols]).
@@ -287,8 +287,10 @@ __global__ void __launch_bounds__(256) template_records_kernel(const float* __re
                                                                float* __restrict__ gx, float* __restrict__ gy, float* __restrict__ i0) {
   const int n = meta->n;
   // grid-stride: the grid is capped (n is only known on the device)
-  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n * C; t += gridDim.x * blockDim.x) {
-    const int i = t / C, c = t - i * C;
+  constexpr int S = kStride<C>;            // the padding channels of a record are written as zeros
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n * S; t += gridDim.x * blockDim.x) {
+    const int i = t / S, c = t - i * S;
+    if (c >= C) { i0[t] = 0.0f; gx[t] = 0.0f; gy[t] = 0.0f; continue; }
     const int p = inds[i];
     const float v0 = dval<C>(desc, p, c);
     float ix, iy;
@@ -320,8 +322,9 @@ __global__ void __launch_bounds__(256) export_template_kernel(LevelTemplate L, f
   const int n = L.meta->n;
   if (t >= n * C) return;
   const int i = t / C, c = t - i * C;
+  const size_t rec = (size_t) i * kStride<C> + c;
   const float4 p = L.pts[i];
-  const float Ix = L.gx[t], Iy = L.gy[t];
+  const float Ix = L.gx[rec], Iy = L.gy[rec];
   const float x = p.x, y = p.y, z = p.z, z2 = __fmul_rn(z, z);
   const float xy = __fadd_rn(__fmul_rn(x, Ix), __fmul_rn(y, Iy));
   float* j = J + ((size_t) c * n + i) * 6;
@@ -338,7 +341,7 @@ __global__ void __launch_bounds__(256) export_template_kernel(LevelTemplate L, f
   j[4] = __fdiv_rn(Iy, zs);
   const float s_i = (float) (1.0 / (double) m.s);
   j[5] = -__fdiv_rn(__fmul_rn(s_i, xy), z2);
-  pixels[(size_t) c * n + i] = L.i0[t];
+  pixels[(size_t) c * n + i] = L.i0[rec];
 }
 
 }  // namespace bp

@@ -76,7 +76,7 @@ class Context:
     @property
     def channels(self):
         from .types import DescriptorType
-        return 8 if self.params.descriptor == DescriptorType.kBitPlanes else 1
+        return {DescriptorType.kBitPlanes: 8, DescriptorType.kDescriptorFieldsFirstOrder: 5, DescriptorType.kIntensityAndGradient: 3}.get(self.params.descriptor, 1)
 
     def close(self):
         if getattr(self, "_own", False) and self.h:

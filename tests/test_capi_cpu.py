@@ -39,7 +39,7 @@ def test_default_params_are_the_reference_defaults():
     assert (c.numPyramidLevels, c.sigmaBitPlanes, c.maxIterations, c.lossFunction, c.descriptor) == (-1, 0.5, 50, 0x11, 0x30)
     assert (c.minNumPixelsForNonMaximaSuppression, c.nonMaxSuppRadius, c.withNormalization) == (76800, 1, 1)
     assert abs(c.parameterTolerance - 1e-7) < 1e-12 and abs(c.minSaliency - 0.1) < 1e-7
-    assert C.sizeof(CParams) == 28 * 4
+    assert C.sizeof(CParams) == 30 * 4      # 26 reference fields + device_id, flags + dfSigma1, dfSigma2
 
 
 def test_auto_pyramid_levels_rule():

@@ -69,6 +69,8 @@ def _check_device_vs_fine(ctx, gref, gcur, level, poses, grid_ctas=0, cache_byte
     ("vga", "intensity", 4, "huber", {}),
     ("kitti", "bitplanes", 4, "tukey", {}),                         # the headline workload (semi-dense)
     ("kitti", "bitplanes", 4, "tukey", {"nonMaxSuppRadius": -1}),   # dense: 11 cache slots per thread at level 0
+    ("small", "gradient", 3, "huber", {}),                          # 3 channels, record stride 4
+    ("vga", "dfields", 3, "tukey", {}),                             # 5 channels, record stride 8
     ("small", "bitplanes", 3, "tukey", {"_flags": 4}),              # BPVO_B200_FLAG_FAST_BLEND: the fp32-FMA blend instantiation
     ("kitti", "bitplanes", 4, "tukey", {"_flags": 4}),
 ])

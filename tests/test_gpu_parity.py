@@ -50,7 +50,9 @@ def _pair(kind, params, oracle, use_rcp=0, k0=0, k1=1, flags=0, **scene_kw):
 
 
 CASES = [("small", "intensity", 3), ("small", "bitplanes", 3), ("odd", "bitplanes", 2), ("odd", "intensity", 2),
-         ("vga", "intensity", 4), ("kitti", "bitplanes", 4)]
+         ("vga", "intensity", 4), ("kitti", "bitplanes", 4),
+         # the gradient-based descriptors (bpvo/gradient_descriptor.cc): 3 and 5 channels
+         ("small", "gradient", 3), ("odd", "gradient", 2), ("small", "dfields", 3), ("odd", "dfields", 2), ("vga", "dfields", 3)]
 
 
 FLAG_TMA_DESCRIPTOR = 8
@@ -108,7 +110,7 @@ def test_template_nms_radius2_and_holes(oracle):
 
 def _cmp_linearize(ctx, gref, gcur, oref, ocur, oest, level, T, first, tol_hg, exact=None):
     if exact is None:
-        exact = ctx.channels == 1 or not (ctx.flags & FLAG_FAST_BLEND)
+        exact = ctx.channels != 8 or not (ctx.flags & FLAG_FAST_BLEND)
     g = ctx.linearize(gref, gcur, level, T, first)
     o = oest.linearize(oref, ocur, level, T, first)
     N = gref.numPoints(level)
@@ -158,12 +160,14 @@ def _cmp_linearize(ctx, gref, gcur, oref, ocur, oest, level, T, first, tol_hg, e
 @pytest.mark.parametrize("flags", [0, FLAG_FAST_BLEND])
 @pytest.mark.parametrize("kind,desc,levels,loss", [("small", "intensity", 3, "l2"), ("small", "intensity", 3, "huber"),
                                                     ("small", "bitplanes", 3, "tukey"), ("odd", "bitplanes", 2, "huber"),
-                                                    ("vga", "intensity", 4, "huber"), ("kitti", "bitplanes", 4, "tukey")])
+                                                    ("vga", "intensity", 4, "huber"), ("kitti", "bitplanes", 4, "tukey"),
+                                                    ("small", "gradient", 3, "huber"), ("odd", "gradient", 2, "tukey"),
+                                                    ("small", "dfields", 3, "tukey"), ("vga", "dfields", 3, "huber")])
 def test_linearize(kind, desc, levels, loss, flags, oracle):
     """default: the reference's fp64 blend -> r, sigma, w BIT-IDENTICAL to the oracle; BPVO_B200_FLAG_FAST_BLEND (bit-planes
     only): fp32-FMA blend, r within 1e-5 (north star)"""
-    if desc == "intensity" and flags:
-        pytest.skip("intensity always computes the fp64 expression")
+    if desc != "bitplanes" and flags:
+        pytest.skip("only bit-planes has the fp32 blend; the other descriptors always compute the fp64 expression")
     p = make_params(desc, levels, loss)
     sc, ctx, gref, gcur, oref, ocur = _pair(kind, p, oracle, use_rcp=0, flags=flags)
     oest = oracle.Estimator(ctx.params)
@@ -247,7 +251,8 @@ def test_linearize_pose_pushes_points_out(oracle):
 
 
 @pytest.mark.parametrize("kind,desc,levels,loss", [("small", "intensity", 3, "huber"), ("small", "bitplanes", 3, "tukey"),
-                                                    ("vga", "intensity", 4, "huber"), ("kitti", "bitplanes", 4, "tukey")])
+                                                    ("vga", "intensity", 4, "huber"), ("kitti", "bitplanes", 4, "tukey"),
+                                                    ("vga", "gradient", 4, "huber"), ("vga", "dfields", 4, "tukey")])
 def test_estimate_pose(kind, desc, levels, loss, oracle):
     from bpvo_b200.engine import Context, FLAG_HOST_SOLVE
     p = make_params(desc, levels, loss)
@@ -272,7 +277,8 @@ def test_estimate_pose(kind, desc, levels, loss, oracle):
 
 
 @pytest.mark.parametrize("kind,desc,levels,loss,nframes", [("small", "bitplanes", 3, "tukey", 8), ("vga", "intensity", 4, "huber", 6),
-                                                            ("kitti", "bitplanes", 4, "tukey", 6)])
+                                                            ("kitti", "bitplanes", 4, "tukey", 6), ("vga", "dfields", 4, "tukey", 5),
+                                                            ("vga", "gradient", 4, "huber", 5)])
 def test_vo_stream(kind, desc, levels, loss, nframes, oracle):
     """whole addFrame state machine (key-framing, re-estimation, trajectory, point cloud) vs the oracle"""
     from bpvo_b200 import VisualOdometry
