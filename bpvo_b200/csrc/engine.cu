@@ -930,7 +930,7 @@ struct SolveOverride {
   int cache_bytes = -1;    // -1 = everything the SM has
 };
 
-template <int C, int BLEND, bool PEER>
+template <int C, int BLEND, bool PEER, int FIX>
 static int launch_estimate_pose_t(bpvo_b200_ctx* c, const bpvo_b200_frame* ref, const bpvo_b200_frame* cur, const M44& T_init, const SolveOverride* ov) {
   SolveArgs a;
   memset(&a, 0, sizeof(a));
@@ -980,23 +980,30 @@ static int launch_estimate_pose_t(bpvo_b200_ctx* c, const bpvo_b200_frame* ref, 
   if (ov && ov->cache_bytes >= 0) cache_bytes = std::min(cache_bytes, ov->cache_bytes);
   const size_t dyn = (size_t) kScratchBytes + (size_t) cache_bytes;
   if (c->dyn_configured != dyn) {        // per ctx: the attribute is per device, and a process may drive several
-    CUDA_TRY(cudaFuncSetAttribute((const void*) k_estimate_pose<C, BLEND, PEER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) dyn));
+    CUDA_TRY(cudaFuncSetAttribute((const void*) k_estimate_pose<C, BLEND, PEER, FIX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) dyn));
     c->dyn_configured = dyn;
   }
   void* args[] = {&a, &sel, &cache_bytes};
   int grid = std::min(c->sm_count, kMaxGrid);
   if (c->solver_ctas > 0) grid = std::min(grid, c->solver_ctas);     // throughput mode: several ctxs share the SMs
   if (ov && ov->grid > 0) grid = std::min(grid, ov->grid);
-  CUDA_TRY(cudaLaunchCooperativeKernel((void*) k_estimate_pose<C, BLEND, PEER>, dim3(grid), dim3(kLinThreads), args, dyn, c->stream));
+  CUDA_TRY(cudaLaunchCooperativeKernel((void*) k_estimate_pose<C, BLEND, PEER, FIX>, dim3(grid), dim3(kLinThreads), args, dyn, c->stream));
   c->counters.launches++;
   return BPVO_B200_OK;
 }
 template <int C>
 static int launch_estimate_pose(bpvo_b200_ctx* c, const bpvo_b200_frame* ref, const bpvo_b200_frame* cur, const M44& T_init, const SolveOverride* ov = nullptr) {
   // (the peer-memory instantiation carries the cross-rank exchanges; the single-GPU one is a third smaller)
-  if constexpr (C == 8) { if (c->p.flags & BPVO_B200_FLAG_FAST_BLEND) return launch_estimate_pose_t<C, 1, false>(c, ref, cur, T_init, ov); }
-  if (c->peer_mode) return launch_estimate_pose_t<C, 0, true>(c, ref, cur, T_init, ov);
-  return launch_estimate_pose_t<C, 0, false>(c, ref, cur, T_init, ov);
+  if constexpr (C == 8) {
+    if (c->p.flags & BPVO_B200_FLAG_FAST_BLEND) return launch_estimate_pose_t<C, 1, false, 0>(c, ref, cur, T_init, ov);
+    // the bit-planes workloads' hot configurations with the loss function and the linear interpolant compiled in
+    if (!c->peer_mode && c->p.interp == BPVO_B200_LINEAR && !getenv("BPVO_B200_GENERIC_KERNEL")) {
+      if (c->p.lossFunction == BPVO_B200_TUKEY) return launch_estimate_pose_t<C, 0, false, BPVO_B200_TUKEY>(c, ref, cur, T_init, ov);
+      if (c->p.lossFunction == BPVO_B200_HUBER) return launch_estimate_pose_t<C, 0, false, BPVO_B200_HUBER>(c, ref, cur, T_init, ov);
+    }
+  }
+  if (c->peer_mode) return launch_estimate_pose_t<C, 0, true, 0>(c, ref, cur, T_init, ov);
+  return launch_estimate_pose_t<C, 0, false, 0>(c, ref, cur, T_init, ov);
 }
 
 extern "C" int bpvo_b200_estimate_pose(bpvo_b200_ctx* c, const bpvo_b200_frame* ref, const bpvo_b200_frame* cur,
