@@ -28,7 +28,9 @@ constexpr int kOvfLocalScan = 2048;          // overflow lists up to this length
 constexpr unsigned kCandPoison = 1u << 30;   // added to the candidate count when even that overflowed -> radix fallback
 constexpr int kScratchBytes = (kCtaCandCap + kSelList) * 4;   // dynamic-smem scratch of the bracketed select: CTA candidates | list
 constexpr int kPartialStride = 32; // doubles per block partial (21 H + 6 G + f + n_good + pad)
-constexpr int kHistSets = 3;       // histogram sets of the on-device loop (triple-buffered: a set is zeroed one real barrier before its next use)
+constexpr int kHistSets = 4;       // histogram sets of the on-device loop: a set is zeroed two GN iterations (>= two grid-wide exchanges) before its next use
+constexpr int kMsgWords = 8;       // 16-byte flag-in-data words of a CTA's median message: {valid points, below} {candidates, c0} {c1, c2} ... {c11, c12}
+constexpr int kMsgCand = 2 * kMsgWords - 3;   // candidates a message carries (13)
 #ifndef BP_LL_GROUP
 #define BP_LL_GROUP 24        /* same-box A/B over 8 / 12 / 16 / 24 / 37 / 74 / 148: 24 is the fastest (by 0.4 % over 12) */
 #endif
@@ -102,6 +104,7 @@ struct Work {
   ScaleState* scale;
   LinOut* out;
   unsigned* ticket;      // last-CTA-done counter
+  uint4* msg;            // [2][kMaxGrid][kMsgWords] median messages of the CTAs (flag-in-data, double-buffered by sequence parity)
   float* cand;           // [grid][kCandPerCta] |r| values inside the median bracket, -1 = empty slot (on-device GN loop),
                          // followed by the overflow list [kOvfCap] and the short list [kSelList] of a sliced overflow scan
 };

@@ -242,6 +242,8 @@ static int ctx_init(bpvo_b200_ctx* c, const float K[9], float baseline, int rows
   CUDA_TRY(cudaMalloc(&c->work.hist, (kHistSets * kHistWords + 8 + 128) * sizeof(unsigned)));
   CUDA_TRY(cudaMalloc(&c->work.ll, (size_t) 4 * kMaxGrid * 32 * sizeof(uint4)));
   CUDA_TRY(cudaMemsetAsync(c->work.ll, 0, (size_t) 4 * kMaxGrid * 32 * sizeof(uint4), c->stream));
+  CUDA_TRY(cudaMalloc(&c->work.msg, (size_t) 2 * kMaxGrid * kMsgWords * sizeof(uint4)));
+  CUDA_TRY(cudaMemsetAsync(c->work.msg, 0, (size_t) 2 * kMaxGrid * kMsgWords * sizeof(uint4), c->stream));
   CUDA_TRY(cudaMalloc(&c->work.partials, (size_t) 1024 * kPartialStride * sizeof(double)));
   CUDA_TRY(cudaMalloc(&c->work.scale, sizeof(ScaleState)));
   CUDA_TRY(cudaMalloc(&c->d_mail, sizeof(Mailbox)));
@@ -283,7 +285,7 @@ int bpvo_b200_destroy(bpvo_b200_ctx* c) {
   cudaSetDevice(c->p.device_id);
   if (c->stream) cudaStreamSynchronize(c->stream);
   bp_comm_destroy(c);
-  cudaFree(c->work.res); cudaFree(c->work.valid); cudaFree(c->work.hist); cudaFree(c->work.ll); cudaFree(c->work.partials);
+  cudaFree(c->work.res); cudaFree(c->work.valid); cudaFree(c->work.hist); cudaFree(c->work.ll); cudaFree(c->work.msg); cudaFree(c->work.partials);
   cudaFree(c->work.scale); cudaFree(c->d_mail); cudaFree(c->work.ticket); cudaFree(c->work.cand); cudaFree(c->sel); cudaFree(c->export_buf);
   for (int k = 0; k < 5; ++k) cudaFree(c->plane[k]);
   cudaFree(c->flags); cudaFree(c->blur_tmp); cudaFree(c->block_counts); cudaFree(c->hpartials); cudaFree(c->hsums);
@@ -955,6 +957,7 @@ static int launch_estimate_pose_t(bpvo_b200_ctx* c, const bpvo_b200_frame* ref, 
   const unsigned seq_span = (unsigned) (c->L * (std::min(c->p.maxIterations + 2, 1200) + 2) + 2) + (unsigned) (ov ? ov->dbg.n : 0);
   if (c->ll_seq == 0 || c->ll_seq > 0xffffffffu - seq_span) {
     CUDA_TRY(cudaMemsetAsync(c->work.ll, 0, (size_t) 4 * kMaxGrid * 32 * sizeof(uint4), c->stream));
+    CUDA_TRY(cudaMemsetAsync(c->work.msg, 0, (size_t) 2 * kMaxGrid * kMsgWords * sizeof(uint4), c->stream));
     c->ll_seq = 1;
   }
   a.seq_base = c->ll_seq; c->ll_seq += seq_span;

@@ -44,6 +44,9 @@ __device__ __forceinline__ int first_point(int block, int nblocks) {
 #ifndef BP_PREFETCH
 #define BP_PREFETCH 1
 #endif
+#ifndef BP_MSG_SELECT
+#define BP_MSG_SELECT 1       /* persistent kernel: median candidates as flag-in-data messages instead of grid barrier + global lists (message_select) */
+#endif
 __device__ __forceinline__ void prefetch_l2(const void* p) {
 #if BP_PREFETCH
   asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
@@ -333,7 +336,8 @@ __device__ __forceinline__ int sel_bin(float v, float lo, float inv_w) { return 
 template <int C, int BLEND>
 __device__ __forceinline__ void phase_residuals(const LevelTemplate& L, const LevelImage& I, const float* P, const Work& W,
                                                 unsigned* __restrict__ hist1, bool do_hist, Bracket br, const TplCache& tc,
-                                                const TemplateMeta& m, unsigned* scratch, LinShared& sh, int block, int nblocks, int interp = 0) {
+                                                const TemplateMeta& m, unsigned* scratch, LinShared& sh, int block, int nblocks, int interp = 0,
+                                                unsigned msg_seq = 0) {
   const int tid = threadIdx.x;
   const bool do_hist1 = do_hist && !br.on;   // with a bracket the level-1 histogram is only built (phase_hist1) if the bracket misses
   if (do_hist1) { for (int b = tid; b < kHist1Bins; b += kLinThreads) sh.hist[b] = 0; }
@@ -476,6 +480,18 @@ __device__ __forceinline__ void phase_residuals(const LevelTemplate& L, const Le
     }
     if (br.on) {
       const unsigned nc = sh.found[6];
+      if (msg_seq && tid < kMsgWords) {       // the same facts as ONE self-validating 128-byte message (persistent kernel: no barrier needed to read it)
+        unsigned lo, hi;
+        if (tid == 0) { lo = sh.found[4]; hi = sh.found[5]; }
+        else if (tid == 1) { lo = nc; hi = (nc > 0u && nc <= (unsigned) kMsgCand) ? __float_as_uint(cta_cand[0]) : 0xbf800000u; }
+        else {
+          const unsigned i0 = 2u * tid - 3u, i1 = 2u * tid - 2u;
+          lo = (i0 < nc && nc <= (unsigned) kMsgCand) ? __float_as_uint(cta_cand[i0]) : 0xbf800000u;      // -1.0f = empty
+          hi = (i1 < nc && nc <= (unsigned) kMsgCand) ? __float_as_uint(cta_cand[i1]) : 0xbf800000u;
+        }
+        asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(W.msg + ((size_t) (msg_seq & 1u) * kMaxGrid + block) * kMsgWords + tid),
+                     "r"(lo), "r"(msg_seq), "r"(hi), "r"(msg_seq) : "memory");
+      }
       if (tid < kCandPerCta)                  // this CTA's region of the candidate buffer: values, then -1 = empty
         W.cand[(size_t) block * kCandPerCta + tid] = ((unsigned) tid < nc) ? cta_cand[tid] : -1.0f;
       if (nc > (unsigned) kCandPerCta && nc <= (unsigned) kCtaCandCap) {       // rare (wide bracket): the rest goes to the shared overflow list
@@ -604,6 +620,7 @@ __device__ __forceinline__ float finish_scale(const Work& W, const unsigned* __r
 
 struct AbortCtl;
 __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& epoch, unsigned nblocks, AbortCtl* abort_flag);
+__device__ __forceinline__ bool wait_expired(unsigned& spins, AbortCtl* ac);
 
 // Bracketed exact median (on-device loop): P1 counted the valid residuals below the bracket and left the ones inside it
 // in the per-CTA regions of W.cand.  If both middle ranks fall inside and no region overflowed, the two order statistics
@@ -710,6 +727,100 @@ __device__ __forceinline__ bool bracket_select(const Work& W, unsigned* __restri
   BP_FINE(38);
   lo_out = __uint_as_float(sh.found[6]); hi_out = __uint_as_float(sh.found[7]);
   return true;
+}
+
+// The usual way to the exact median in the persistent kernel: NO grid barrier.  Every CTA posted, at the end of P1, one 128-byte
+// flag-in-data message {valid points, residuals below the bracket, candidates inside it, up to 13 candidate values}; every CTA polls
+// all messages (one L2 round trip once the last CTA has posted: data and "ready" arrive together), sums the counters, bins the
+// candidates into a shared-memory histogram over the bracket and ranks the few values of the two wanted bins -- the same pair of
+// order statistics as bracket_select / the radix select.  Verdicts (identical in every CTA: same messages):
+//   1 = hit (lo / hi valid);  2 = the bracket missed the middle ranks -> radix select;
+//   0 = some CTA had more candidates than a message holds (wide bracket) -> grid barrier + bracket_select on the global lists.
+constexpr int kMsgPre = (148 * kMsgWords + kLinThreads - 1) / kLinThreads;       // message words a thread holds in registers (grids <= 148 CTAs)
+template <int C>
+__device__ __forceinline__ int message_select(const Work& W, unsigned seq, LinShared& sh, unsigned* scratch, int nblocks, const Bracket& br, AbortCtl* abort_flag,
+                                              unsigned& n_out, unsigned& ncand_out, float& lo_out, float& hi_out) {
+  const int tid = threadIdx.x;
+  const uint4* base = W.msg + (size_t) (seq & 1u) * kMaxGrid * kMsgWords;
+  const int total = nblocks * kMsgWords;
+  unsigned plo[kMsgPre], phi[kMsgPre];
+  bool ok[kMsgPre]; bool all = true;
+#pragma unroll
+  for (int q = 0; q < kMsgPre; ++q) { ok[q] = tid + q * kLinThreads >= total; plo[q] = phi[q] = 0xbf800000u; all = all && ok[q]; }
+  for (int b = tid; b < kSelBins; b += kLinThreads) sh.hist[b] = 0;              // histogram of the candidates over the bracket (shared memory)
+  if (tid < 4) sh.found[tid] = 0;                                                 // [0] valid points [1] below [2] candidates [3] overflowing CTAs  (P1's tail still reads [4..7])
+  unsigned spins = 0;
+  while (!all) {
+    all = true;
+#pragma unroll
+    for (int q = 0; q < kMsgPre; ++q) {
+      if (!ok[q]) {
+        unsigned x, f0, y, f1;
+        asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(x), "=r"(f0), "=r"(y), "=r"(f1) : "l"(base + tid + q * kLinThreads) : "memory");
+        if (f0 == seq && f1 == seq) { ok[q] = true; plo[q] = x; phi[q] = y; }
+      }
+      all = all && ok[q];
+    }
+    if (!all && wait_expired(spins, abort_flag)) break;
+  }
+  __syncthreads();                                                                // histogram zeroed, counters zeroed
+#pragma unroll
+  for (int q = 0; q < kMsgPre; ++q) {
+    const int j = tid + q * kLinThreads;
+    if (j >= total) continue;
+    const int k = j & (kMsgWords - 1);
+    if (k == 0) { atomicAdd(&sh.found[0], plo[q]); atomicAdd(&sh.found[1], phi[q]); }
+    else {
+      if (k == 1) { atomicAdd(&sh.found[2], plo[q]); if (plo[q] > (unsigned) kMsgCand) atomicAdd(&sh.found[3], 1u); }
+      else { const float v = __uint_as_float(plo[q]); if (v >= 0.0f) atomicAdd(&sh.hist[sel_bin(v, br.lo, br.inv_w)], 1u); }
+      const float v = __uint_as_float(phi[q]); if (v >= 0.0f) atomicAdd(&sh.hist[sel_bin(v, br.lo, br.inv_w)], 1u);
+    }
+  }
+  __syncthreads();
+  const unsigned n = sh.found[0] * (unsigned) C, below = sh.found[1], ncand = sh.found[2], nover = sh.found[3];
+  n_out = n; ncand_out = ncand;
+  if (nover != 0u) return 0;
+  if (n < 3) return 2;
+  const unsigned t_hi = n / 2, t_lo = (n % 2 == 0) ? t_hi - 1 : t_hi;
+  if (below > t_lo || t_hi >= below + ncand) return 2;
+  const unsigned ra = t_lo - below, rb = t_hi - below;
+  unsigned bin_a, rem_a, bin_b, rem_b, tot;
+  {
+    unsigned loc[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) loc[k] = sh.hist[tid * 4 + k];
+    block_find2_regs<4>(loc, ra, rb, sh, bin_a, rem_a, bin_b, rem_b, tot);        // resets sh.found[0..7]
+  }
+  float* list = reinterpret_cast<float*>(scratch + kCtaCandCap);   // [kSelList]
+#pragma unroll
+  for (int q = 0; q < kMsgPre; ++q) {
+    const int j = tid + q * kLinThreads;
+    if (j >= total || (j & (kMsgWords - 1)) == 0) continue;
+    if ((j & (kMsgWords - 1)) != 1) {
+      const float v = __uint_as_float(plo[q]);
+      if (v >= 0.0f) { const unsigned b = (unsigned) sel_bin(v, br.lo, br.inv_w); if (b == bin_a || b == bin_b) { const unsigned slot = atomicAdd(&sh.found[4], 1u); if (slot < (unsigned) kSelList) list[slot] = v; } }
+    }
+    const float v = __uint_as_float(phi[q]);
+    if (v >= 0.0f) { const unsigned b = (unsigned) sel_bin(v, br.lo, br.inv_w); if (b == bin_a || b == bin_b) { const unsigned slot = atomicAdd(&sh.found[4], 1u); if (slot < (unsigned) kSelList) list[slot] = v; } }
+  }
+  __syncthreads();
+  const unsigned nl = sh.found[4];
+  if (nl > (unsigned) kSelList) return 2;           // pathological pile-up of equal values: let the radix select handle it
+  if (tid < (int) nl) {
+    const float v = list[tid];
+    const unsigned bj = (unsigned) sel_bin(v, br.lo, br.inv_w);
+    unsigned rank = 0;
+    for (unsigned j = 0; j < nl; ++j) {
+      const float u = list[j];
+      const unsigned bu = (unsigned) sel_bin(u, br.lo, br.inv_w);
+      rank += (bu == bj && (u < v || (u == v && j < (unsigned) tid))) ? 1u : 0u;
+    }
+    if (bj == bin_a && rank == rem_a) sh.found[6] = __float_as_uint(v);
+    if (bj == bin_b && rank == rem_b) sh.found[7] = __float_as_uint(v);
+  }
+  __syncthreads();
+  lo_out = __uint_as_float(sh.found[6]); hi_out = __uint_as_float(sh.found[7]);
+  return 1;
 }
 
 __device__ __forceinline__ float robust_weight(int loss, float r, float sigma_inv) {
@@ -1398,37 +1509,45 @@ __device__ __forceinline__ double device_linearize(const SolveArgs& a, int lvl, 
   br.on = do_hist && ss.br_on;
   br.lo = ss.br_lo * (1.0f - ss.br_rel); br.hi = ss.br_hi * (1.0f + ss.br_rel);
   br.inv_w = (br.hi > br.lo) ? (float) kSelBins / (br.hi - br.lo) : 0.0f;
-  phase_residuals<C, BLEND>(L, I, ss.P, a.work, hset, do_hist, br, tc, meta, scratch, sh, blk, nb, interp);
+  const bool multi = PEER && a.peer.nranks > 1 && !meta.replicated;      // (PEER = false: the single-GPU kernel carries no cross-rank code)
+  const bool use_msg = BP_MSG_SELECT && br.on && !multi && nb <= 148;    // the median facts travel as flag-in-data messages: no grid barrier
+  phase_residuals<C, BLEND>(L, I, ss.P, a.work, hset, do_hist, br, tc, meta, scratch, sh, blk, nb, interp, use_msg ? gs.seq : 0u);
   BP_PROF(PROF_P1);
   float sigma = ss.scale;
   if (do_hist) {
-    grid_barrier(gs.counter, gs.epoch, nb, &ss.abort);
-    BP_PROF(PROF_SYNC1);
-    BP_FINE(32);
-    for (int b = blk * kLinThreads + tid; b < kHistWords; b += nb * kLinThreads) hprev[b] = 0;
     unsigned n = 0, ncand = 0; float lo = 0.0f, hi = 0.0f;
     bool hit = false;
-    const bool multi = PEER && a.peer.nranks > 1 && !meta.replicated;      // (PEER = false: the single-GPU kernel carries no cross-rank code)
-    if (br.on && !multi) hit = bracket_select<C>(a.work, hset, sh, scratch, blk, nb, br, gs.counter, gs.epoch, &ss.abort, n, ncand, lo, hi);
-    if (br.on && multi) {
-      // CTA 0 talks to the peers (two exchanges) and hands the verdict to the other CTAs through three local words
-      uint4* lb = a.peer.lbox + (size_t) (gs.seq & 1u) * 64;
-      if (blk == 0) {
-        hit = bracket_select_xrank<C>(a.peer, gs.xseq, a.work, hset, sh, scratch, nb, br, &ss.abort, n, ncand, lo, hi);
-        if (tid == 0) {
-          ll_post(lb + 0, __longlong_as_double((long long) (((unsigned long long) n << 32) | (hit ? 1u : 0u))), gs.seq);
-          ll_post(lb + 1, __longlong_as_double((long long) (((unsigned long long) __float_as_uint(hi) << 32) | __float_as_uint(lo))), gs.seq);
-          ll_post(lb + 2, __longlong_as_double((long long) (unsigned long long) ncand), gs.seq);
+    int verdict = 0;
+    if (use_msg) verdict = message_select<C>(a.work, gs.seq, sh, scratch, nb, br, &ss.abort, n, ncand, lo, hi);
+    if (verdict == 1) hit = true;
+    if (verdict == 0) {                 // first evaluation of a level, multi-rank level, or a bracket too wide for the messages: barrier + global lists
+      grid_barrier(gs.counter, gs.epoch, nb, &ss.abort);
+      BP_PROF(PROF_SYNC1);
+      BP_FINE(32);
+      if (br.on && !multi) hit = bracket_select<C>(a.work, hset, sh, scratch, blk, nb, br, gs.counter, gs.epoch, &ss.abort, n, ncand, lo, hi);
+      if (br.on && multi) {
+        // CTA 0 talks to the peers (two exchanges) and hands the verdict to the other CTAs through three local words
+        uint4* lb = a.peer.lbox + (size_t) (gs.seq & 1u) * 64;
+        if (blk == 0) {
+          hit = bracket_select_xrank<C>(a.peer, gs.xseq, a.work, hset, sh, scratch, nb, br, &ss.abort, n, ncand, lo, hi);
+          if (tid == 0) {
+            ll_post(lb + 0, __longlong_as_double((long long) (((unsigned long long) n << 32) | (hit ? 1u : 0u))), gs.seq);
+            ll_post(lb + 1, __longlong_as_double((long long) (((unsigned long long) __float_as_uint(hi) << 32) | __float_as_uint(lo))), gs.seq);
+            ll_post(lb + 2, __longlong_as_double((long long) (unsigned long long) ncand), gs.seq);
+          }
+        } else {
+          if (tid < 3) sh.xch[0][tid] = ll_gather<1>(lb + tid, 0, 1, gs.seq, &ss.abort);
+          __syncthreads();
+          const unsigned long long w0 = (unsigned long long) __double_as_longlong(sh.xch[0][0]), w1 = (unsigned long long) __double_as_longlong(sh.xch[0][1]),
+                                   w2 = (unsigned long long) __double_as_longlong(sh.xch[0][2]);
+          hit = (w0 & 1u) != 0; n = (unsigned) (w0 >> 32); lo = __uint_as_float((unsigned) w1); hi = __uint_as_float((unsigned) (w1 >> 32)); ncand = (unsigned) w2;
+          __syncthreads();
         }
-      } else {
-        if (tid < 3) sh.xch[0][tid] = ll_gather<1>(lb + tid, 0, 1, gs.seq, &ss.abort);
-        __syncthreads();
-        const unsigned long long w0 = (unsigned long long) __double_as_longlong(sh.xch[0][0]), w1 = (unsigned long long) __double_as_longlong(sh.xch[0][1]),
-                                 w2 = (unsigned long long) __double_as_longlong(sh.xch[0][2]);
-        hit = (w0 & 1u) != 0; n = (unsigned) (w0 >> 32); lo = __uint_as_float((unsigned) w1); hi = __uint_as_float((unsigned) (w1 >> 32)); ncand = (unsigned) w2;
-        __syncthreads();
       }
     }
+    // the set of the linearize before this one: every CTA has long finished with it (two exchanges ago); it is next used three
+    // GN iterations from now
+    for (int b = blk * kLinThreads + tid; b < kHistWords; b += nb * kLinThreads) hprev[b] = 0;
     if (hit) {
       const float med = (n % 2 != 0) ? hi : (float) ((double) __fadd_rn(lo, hi) / 2.0);
       sigma = scale_from_median(n, med);
@@ -1494,6 +1613,7 @@ __device__ __forceinline__ double device_linearize(const SolveArgs& a, int lvl, 
 #ifndef BP_TAIL_FIXED
 #define BP_TAIL_FIXED 1
 #endif
+
 constexpr int kFixBits = 46;
 struct FixAcc {                  // lives in the registers of warp 0, lane k = scalar k
   unsigned long long prev[2];    // complete value of this lane's word of either set after its last use
