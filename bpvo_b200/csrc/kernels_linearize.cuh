@@ -44,8 +44,11 @@ __device__ __forceinline__ int first_point(int block, int nblocks) {
 #ifndef BP_PREFETCH
 #define BP_PREFETCH 1
 #endif
+// BP_MSG_SELECT = 1: the median candidates travel as per-CTA flag-in-data messages (message_select) instead of grid barrier + global
+// lists.  Built, parity-green -- and 8 % SLOWER in the same-box A/B (profiles/README.md): a bracket usually holds 1-2.5 k candidates,
+// so some CTA nearly always has more than the 13 a 128-byte message carries and the iteration pays the message round AND the barrier.
 #ifndef BP_MSG_SELECT
-#define BP_MSG_SELECT 1       /* persistent kernel: median candidates as flag-in-data messages instead of grid barrier + global lists (message_select) */
+#define BP_MSG_SELECT 0
 #endif
 __device__ __forceinline__ void prefetch_l2(const void* p) {
 #if BP_PREFETCH
