@@ -371,6 +371,10 @@ def run_ours(args, w, rank, world, local_rank):
     if rank == 0 and world == 1 and not args.no_throughput:
         throughput = throughput_variant(sc, p, host_ptrs, local_rank, torch, args.warmup, min(args.steps, 48))
 
+    stereo = None
+    if rank == 0 and world == 1 and args.workload == "kitti" and not args.no_stereo:
+        stereo = stereo_variant(sc, p, local_rank, torch, args)
+
     sharded = None
     if world > 1 and args.workload == "kitti" and not args.no_dense:
         sharded = sharded_variant(rank, world, local_rank, dist, torch)
@@ -394,12 +398,95 @@ def run_ours(args, w, rank, world, local_rank):
             "roofline_hbm_bound_variant": hbm_bound,
             "throughput_mode": throughput,
             "sharded_1080p_dense_variant": sharded,
+            "upstream_stereo_variant": stereo,
         }
         emit(line)
     pin_img.free(); pin_dsp.free()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def stereo_variant(sc, p, local_rank, torch, args, pairs=24):
+    """SURVEY 8(f) N4, beside the headline: the disparity producer in front of the path (OpenCV StereoBM with conf/kitti.cfg's
+    settings: BlockMatching, SADWindowSize 9, 128 disparities) on the GPU, and image PAIRS -> poses through addStereoFrame.
+    CPU side: the oracle port on all host threads, and cv2's own StereoBM (the library the reference calls) when importable."""
+    import time
+    from bpvo_b200 import VisualOdometry
+    from bpvo_b200.engine import PinnedBuffer
+    from bpvo_b200.stereo import StereoAlgorithm
+    nd, wsz = 128, 9
+    npx = sc.rows * sc.cols
+    n = pairs + 4
+    pinL = PinnedBuffer((n, sc.rows, sc.cols), np.uint8); pinR = PinnedBuffer((n, sc.rows, sc.cols), np.uint8)
+    pinD = PinnedBuffer((sc.rows, sc.cols), np.float32)
+    for k in range(n):
+        pinL.array[k] = sc.render(k)[0]; pinR.array[k] = sc.render_right(k)
+    st = StereoAlgorithm((sc.rows, sc.cols), device_id=local_rank, numberOfDisparities=nd, SADWindowSize=wsz)
+    dL = torch.from_numpy(pinL.array).cuda(local_rank); dR = torch.from_numpy(pinR.array).cuda(local_rank)
+    dD = torch.empty((sc.rows, sc.cols), dtype=torch.float32, device=dL.device)
+    torch.cuda.synchronize()
+    kern_ms = []
+    for k in range(n):                                 # resident in HBM, result stays in HBM: device time of the three kernels
+        st.run_raw(dL[k].data_ptr(), dR[k].data_ptr(), dD.data_ptr())
+        if k >= 4:
+            kern_ms.append(st.last_kernel_ms())
+    t0 = time.perf_counter()
+    for k in range(4, n):                              # pinned host buffers in, pinned host disparity map out
+        st.run_raw(pinL.ptr + k * npx, pinR.ptr + k * npx, pinD.ptr)
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / pairs
+    d_gpu = pinD.array.copy()
+    valid = float((d_gpu >= 0).mean())
+    truth = sc.render(n - 1)[1]
+    err = float(np.abs(d_gpu - truth)[d_gpu >= 0].mean())
+    # pairs -> poses
+    vo = VisualOdometry(sc.K, sc.baseline, (sc.rows, sc.cols), p, device_id=local_rank)
+    for k in range(4):
+        vo._lib.bpvo_b200_vo_add_stereo_frame(vo.h, st.h, pinL.ptr + k * npx, pinR.ptr + k * npx, __import__("ctypes").byref(vo._res))
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    evals = 0
+    for k in range(4, n):
+        rc = vo._lib.bpvo_b200_vo_add_stereo_frame(vo.h, st.h, pinL.ptr + k * npx, pinR.ptr + k * npx, __import__("ctypes").byref(vo._res))
+        assert rc == 0
+        evals += vo._res.numFunEvals
+    pipe_ms = (time.perf_counter() - t0) * 1e3 / pairs
+    vo.close()
+    # CPU: oracle port (OpenMP over rows), and cv2 itself if it is there
+    from oracle import pyoracle as po
+    L0, R0 = pinL.array[n - 1], pinR.array[n - 1]
+    t0 = time.perf_counter(); reps = 3
+    for _ in range(reps):
+        want16, wantf = po.stereo_bm(L0, R0, nd, wsz)
+    cpu_ms = (time.perf_counter() - t0) * 1e3 / reps
+    cv2_ms, cv2_threads, cv2_equal = None, None, None
+    try:
+        import cv2
+        bm = cv2.StereoBM_create(nd, wsz)
+        bm.compute(L0, R0)
+        t0 = time.perf_counter()
+        for _ in range(10):
+            ref16 = bm.compute(L0, R0)
+        cv2_ms = (time.perf_counter() - t0) * 1e3 / 10
+        cv2_threads = cv2.getNumThreads()
+        cv2_equal = bool(np.array_equal(ref16, want16))
+    except Exception:       # noqa: BLE001
+        pass
+    st.close(); pinL.free(); pinR.free(); pinD.free()
+    k_ms = float(np.median(kern_ms))
+    peak, how = peaks()
+    alg_bytes = 2.0 * npx + 4.0 * npx                        # two u8 images in, the f32 map out
+    cells = (sc.rows - wsz + 1) * (sc.cols - nd + 1 - wsz + 1) * nd
+    return {"what": "OpenCV StereoBM (conf/kitti.cfg: BlockMatching, SADWindowSize 9, numberOfDisparities 128) + pairs -> poses; bit-exact vs the oracle in tests/test_gpu_stereo.py",
+            "pairs_per_sec_resident": 1e3 / k_ms, "kernel_ms_per_pair": k_ms, "kernels_per_pair": 3,
+            "pairs_per_sec_e2e_pinned_host": 1e3 / e2e_ms, "h2d_bytes_per_pair": 2 * npx, "d2h_bytes_per_pair": 4 * npx,
+            "identical_to_oracle": bool(np.array_equal(d_gpu, wantf)), "valid_fraction": valid, "mean_abs_error_vs_rendered_disparity_px": err,
+            "pairs_to_poses": {"frames_per_sec": 1e3 / pipe_ms, "ms_per_frame": pipe_ms, "gn_iters_per_frame": evals / float(pairs),
+                               "note": "bpvo_b200_vo_add_stereo_frame from pinned host pairs: block matching + addFrame, disparity never leaves the device"},
+            "roofline": {"bound": "alu / shared-memory loads (integer SAD), not hbm", "algorithmic_bytes": alg_bytes, "hbm_frac": alg_bytes / (k_ms * 1e-3) / 1e9 / peak,
+                         "window_sad_cells": cells, "giga_cells_per_sec": cells / (k_ms * 1e-3) / 1e9, "peak_source": how},
+            "cpu_baseline": {"oracle_port_ms": cpu_ms, "oracle_threads": os.cpu_count(), "cv2_ms": cv2_ms, "cv2_threads": cv2_threads, "cv2_identical_to_oracle": cv2_equal,
+                             "kind": "port (+ the third-party library itself when importable)"}}
 
 
 def throughput_variant(sc, p, host_ptrs, local_rank, torch, warmup, steps, streams_list=(2, 4, 8)):
@@ -631,6 +718,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-dense", action="store_true", help="skip the dense-selection roofline variant")
     ap.add_argument("--no-throughput", action="store_true", help="skip the several-streams-per-GPU variant")
+    ap.add_argument("--no-stereo", action="store_true", help="skip the upstream-stereo (image pairs) variant")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))

@@ -9,7 +9,7 @@ from .types import (AlgorithmParameters, DescriptorType, Error, GradientEstimati
 
 __all__ = ["AlgorithmParameters", "DescriptorType", "Error", "GradientEstimationType", "InterpolationType",
            "KeyFramingReason", "LossFunctionType", "OptimizerStatistics", "PointCloud", "PoseEstimationStatus",
-           "Result", "VerbosityType", "VisualOdometry", "Context", "Frame"]
+           "Result", "VerbosityType", "VisualOdometry", "Context", "Frame", "StereoAlgorithm"]
 
 
 def __getattr__(name):
@@ -17,6 +17,9 @@ def __getattr__(name):
     if name == "VisualOdometry":
         from .vo import VisualOdometry
         return VisualOdometry
+    if name == "StereoAlgorithm":
+        from .stereo import StereoAlgorithm
+        return StereoAlgorithm
     if name in ("Context", "Frame", "PinnedBuffer"):
         from . import engine
         return getattr(engine, name)

@@ -37,6 +37,12 @@ class CCounters(C.Structure):
                 ("launches", C.c_int64), ("linearize_calls", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64), ("solve_calls", C.c_int64)]
 
 
+class CStereoParams(C.Structure):          # bpvo_b200_stereo_params: the CvStereoBMState fields utils/stereo_algorithm.cc:67-85 sets
+    _fields_ = [(n, C.c_int32) for n in ("numberOfDisparities", "SADWindowSize", "minDisparity", "preFilterType", "preFilterSize",
+                                         "preFilterCap", "textureThreshold", "uniquenessRatio", "speckleWindowSize", "speckleRange",
+                                         "trySmallerWindows", "disp12MaxDiff", "device_id")]
+
+
 # name -> (restype, argtypes); exactly the symbols include/bpvo_b200.h declares
 def _signatures():
     vp, fp, u8p, ip = C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_uint8), C.POINTER(C.c_int32)
@@ -107,6 +113,15 @@ def _signatures():
         "bpvo_b200_host_alloc": (C.c_void_p, [C.c_size_t]),
         "bpvo_b200_host_free": (None, [C.c_void_p]),
         "bpvo_b200_time_linearize": (C.c_int, [vp, vp, vp, C.c_int, fp, C.c_int, C.c_int, fp]),
+        "bpvo_b200_stereo_default_params": (None, [C.POINTER(CStereoParams)]),
+        "bpvo_b200_stereo_create": (C.c_int, [C.POINTER(vp), C.c_int, C.c_int, C.POINTER(CStereoParams)]),
+        "bpvo_b200_stereo_destroy": (C.c_int, [vp]),
+        "bpvo_b200_stereo_run": (C.c_int, [vp, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+        "bpvo_b200_stereo_invalid_value": (C.c_float, [vp]),
+        "bpvo_b200_stereo_get_prefiltered": (C.c_int, [vp, C.c_void_p, C.c_void_p]),
+        "bpvo_b200_stereo_last_kernel_ms": (C.c_int, [vp, fp]),
+        "bpvo_b200_stereo_launches": (C.c_longlong, [vp]),
+        "bpvo_b200_vo_add_stereo_frame": (C.c_int, [vp, vp, C.c_void_p, C.c_void_p, C.POINTER(CResult)]),
     }
 
 

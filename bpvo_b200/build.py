@@ -10,7 +10,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libbpvo_b200.so")
-SOURCES = ["engine.cu", "comm.cu", os.path.join("host", "vo_shim.cpp")]
+SOURCES = ["engine.cu", "comm.cu", "stereo.cu", os.path.join("host", "vo_shim.cpp")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 

@@ -47,6 +47,9 @@ __device__ __forceinline__ int first_point(int block, int nblocks) {
 // BP_MSG_SELECT = 1: the median candidates travel as per-CTA flag-in-data messages (message_select) instead of grid barrier + global
 // lists.  Built, parity-green -- and 8 % SLOWER in the same-box A/B (profiles/README.md): a bracket usually holds 1-2.5 k candidates,
 // so some CTA nearly always has more than the 13 a 128-byte message carries and the iteration pays the message round AND the barrier.
+#ifndef BP_BRACKET_THREAD
+#define BP_BRACKET_THREAD (kLinThreads - 1)      // 0 = the round-2a arrangement: thread 0, followed by a CTA barrier (A/B)
+#endif
 #ifndef BP_MSG_SELECT
 #define BP_MSG_SELECT 0
 #endif
@@ -1574,7 +1577,9 @@ __device__ __forceinline__ double device_linearize(const SolveArgs& a, int lvl, 
     }
     // Next bracket, centred on this median (every CTA computes the same).  Half-width: at least twice the distance
     // the median just moved; otherwise sized from the measured candidate density so that ~500 values fall inside.
-    if (tid == 0) {
+    // Off the critical path: done by the LAST thread (its warp owns the fewest points in P4) and not followed by a barrier
+    // of its own -- the state is next read at the top of the next linearize, with P4's and the exchange's barriers in between.
+    if (tid == BP_BRACKET_THREAD) {
       const float mid_new = 0.5f * (lo + hi), mid_old = 0.5f * (ss.br_lo + ss.br_hi);
       float rel = 0.06f;           // first bracket of a level: wide (the median still moves by percents), the overflow list absorbs it
       if (ss.br_on && mid_new > 0.0f) {
@@ -1588,7 +1593,7 @@ __device__ __forceinline__ double device_linearize(const SolveArgs& a, int lvl, 
       if (hit) ss.lin.pad[1] = 3;
       if (a.prof && blk == 0) { long long* sp = prof_smem(); sp[12] += hit ? 1 : 0; sp[13] += 1; sp[14] += (br.on && !hit && ncand >= kCandPoison) ? 1 : 0; sp[15] += (br.on && !hit && ncand < kCandPoison) ? 1 : 0; }
     }
-    __syncthreads();
+    if (BP_BRACKET_THREAD == 0) __syncthreads();
     BP_FINE(39);
   }   // else: P4 reads only what the SAME thread wrote in P1, no grid-wide dependency
   const double mine = phase_reduce<C>(L, a.work, sigma, loss, a.sp.good_threshold, tc, meta, sh, blk, nb, false);

@@ -119,7 +119,17 @@ class Scene:
     def render(self, k: int):
         """-> (image u8 [rows, cols], disparity f32 [rows, cols]) of frame k."""
         W = self.cam_to_world(k)
+        return self._render_from(W[:3, :3], W[:3, 3], k)
+
+    def render_right(self, k: int):
+        """-> image u8 of the RIGHT camera of the rig at frame k (same orientation, centre one baseline along the camera's
+        x axis): with render(k)[0] the rectified pair a stereo matcher turns into render(k)[1] (upstream stereo)."""
+        W = self.cam_to_world(k)
         R, t = W[:3, :3], W[:3, 3]
+        tr = np.array([t[0] + R[0, 0] * self.baseline, t[1] + R[1, 0] * self.baseline, t[2] + R[2, 0] * self.baseline])
+        return self._render_from(R, tr, k)[0]
+
+    def _render_from(self, R, t, k: int):
         n = np.asarray(self.plane_n, dtype=np.float64)
         n = n / np.sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2])
         d0 = n[2] * self.plane_depth

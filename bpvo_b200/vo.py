@@ -55,10 +55,13 @@ class VisualOdometry:
             raise ValueError("image / disparity size mismatch")
         return self.addFrameRaw(image.ctypes.data, disparity.ctypes.data)
 
-    def addFrameRaw(self, image_ptr: int, disparity_ptr: int, want_cloud: bool = True) -> Result:
+    def addFrameRaw(self, image_ptr: int, disparity_ptr: int, want_cloud: bool = True, _stereo=None) -> Result:
         """same, from raw host addresses (e.g. PinnedBuffer.ptr): no numpy work in the timed path"""
         r = self._res
-        _check(self._lib.bpvo_b200_vo_add_frame(self.h, image_ptr, disparity_ptr, C.byref(r)))
+        if _stereo is not None:
+            _check(self._lib.bpvo_b200_vo_add_stereo_frame(self.h, _stereo[0].h, image_ptr, _stereo[1], C.byref(r)))
+        else:
+            _check(self._lib.bpvo_b200_vo_add_frame(self.h, image_ptr, disparity_ptr, C.byref(r)))
         out = Result()
         out.pose = _from_colmajor(r.pose, 4)
         out.isKeyFrame = bool(r.isKeyFrame)
@@ -75,6 +78,14 @@ class VisualOdometry:
             _check(self._lib.bpvo_b200_vo_point_cloud(self.h, _fp(xyzw), _fp(w), g.ctypes.data_as(C.POINTER(C.c_uint8)), n, C.byref(cnt)))
             out.pointCloud = PointCloud(xyzw, w, g, self.trajectory()[-1])
         return out
+
+    def addStereoFrame(self, stereo, left, right, want_cloud: bool = True) -> Result:
+        """image pair in, pose out: `stereo` (bpvo_b200.stereo.StereoAlgorithm) produces the disparity map on the device and
+        addFrame consumes it there (what utils/dataset.cc:133 + VisualOdometry::addFrame do on the host)"""
+        left = np.ascontiguousarray(left, dtype=np.uint8); right = np.ascontiguousarray(right, dtype=np.uint8)
+        if left.shape != (self.rows, self.cols) or right.shape != left.shape:
+            raise ValueError("image size mismatch")
+        return self.addFrameRaw(left.ctypes.data, 0, want_cloud, _stereo=(stereo, right.ctypes.data))
 
     def numPointsAtLevel(self, level: int = -1) -> int:
         n = C.c_int32()

@@ -315,6 +315,51 @@ void  bpvo_b200_host_free(void* p);
 int bpvo_b200_time_linearize(bpvo_b200_ctx* ctx, const bpvo_b200_frame* ref, const bpvo_b200_frame* cur, int level,
                              const float T[16], int iters, int flush_l2, float* ms_per_iter);
 
+/* =============================================================================================
+ * Upstream stereo: the disparity producer in front of the path.
+ * Replaces bpvo::StereoAlgorithm (utils/stereo_algorithm.h:14-37) for its default algorithm "BlockMatching":
+ * utils/stereo_algorithm.cc:67-85 fills OpenCV's CvStereoBMState from the config file (the fields below, same names and
+ * defaults), :99-111 runs cvFindStereoCorrespondenceBM and converts CV_16S -> CV_32F with 1/16.  Results are bit-identical to
+ * OpenCV's StereoBM (pinned against cv2 4.13, see oracle/stereo_oracle.cc).  Not accelerated, rejected at creation with
+ * BPVO_B200_ERR_UNSUPPORTED: the NORMALIZED_RESPONSE pre-filter, minDisparity > 0, speckle filtering, the left-right check
+ * (none of them is used by the reference's configurations), SADWindowSize > 31, numberOfDisparities > 256; the other
+ * algorithms of StereoAlgorithm (SGBM, and the GPL-gated SGM / RSGM) stay on the CPU.
+ * ============================================================================================= */
+enum { BPVO_B200_STEREO_BM_NORMALIZED_RESPONSE = 0, BPVO_B200_STEREO_BM_XSOBEL = 1 };   /* CV_STEREO_BM_* */
+typedef struct bpvo_b200_stereo bpvo_b200_stereo;
+typedef struct {
+  int32_t numberOfDisparities;   /* no default: "must be provided" (stereo_algorithm.cc:75); multiple of 16 */
+  int32_t SADWindowSize;         /* 15 */
+  int32_t minDisparity;          /* 0 */
+  int32_t preFilterType;         /* CV_STEREO_BM_XSOBEL */
+  int32_t preFilterSize;         /* 9 (unused by XSOBEL) */
+  int32_t preFilterCap;          /* 31 */
+  int32_t textureThreshold;      /* 10 */
+  int32_t uniquenessRatio;       /* 15 */
+  int32_t speckleWindowSize;     /* 0 */
+  int32_t speckleRange;          /* 0 */
+  int32_t trySmallerWindows;     /* read from the config (conf/kitti.cfg:13) and ignored, as OpenCV ignores it */
+  int32_t disp12MaxDiff;         /* -1 */
+  int32_t device_id;
+} bpvo_b200_stereo_params;
+void bpvo_b200_stereo_default_params(bpvo_b200_stereo_params* p);
+/* StereoAlgorithm::StereoAlgorithm (stereo_algorithm.cc:156-160); OpenCV's argument checks with OpenCV's messages */
+int bpvo_b200_stereo_create(bpvo_b200_stereo** out, int rows, int cols, const bpvo_b200_stereo_params* p);
+int bpvo_b200_stereo_destroy(bpvo_b200_stereo* s);
+/* StereoAlgorithm::run (stereo_algorithm.cc:163-166).  left / right: rows x cols u8, row-major, host or device memory.
+ * dmap: rows x cols f32 disparities in pixels (invalid = minDisparity - 1); disp16: OpenCV's CV_16S map (4 fractional bits);
+ * host or device memory, either may be NULL.  Returns when the results are in place. */
+int bpvo_b200_stereo_run(bpvo_b200_stereo* s, const uint8_t* left, const uint8_t* right, float* dmap, int16_t* disp16);
+/* StereoAlgorithm::getInvalidValue (stereo_algorithm.cc:168) */
+float bpvo_b200_stereo_invalid_value(const bpvo_b200_stereo* s);
+/* parity dump: the XSOBEL pre-filtered pair of the last run (rows x cols u8 each, host memory, either may be NULL) */
+int bpvo_b200_stereo_get_prefiltered(bpvo_b200_stereo* s, uint8_t* left, uint8_t* right);
+/* device time of the last run's kernels (CUDA events on the object's stream); kernels launched so far */
+int bpvo_b200_stereo_last_kernel_ms(bpvo_b200_stereo* s, float* ms);
+long long bpvo_b200_stereo_launches(const bpvo_b200_stereo* s);
+/* image pair in, pose out (utils/dataset.cc:133 feeding VisualOdometry::addFrame): the disparity map stays on the device */
+int bpvo_b200_vo_add_stereo_frame(bpvo_b200_vo* vo, bpvo_b200_stereo* s, const uint8_t* left, const uint8_t* right, bpvo_b200_result* result);
+
 #ifdef __cplusplus
 }
 #endif

@@ -161,6 +161,20 @@ int  orc_vo_trajectory(const orc_vo*, float* poses /* 16 per pose */, int max_po
 int  orc_vo_point_cloud(const orc_vo*, float* xyzw, float* weights, uint8_t* gray, int max_points);
 const char* orc_last_error(void);
 
+/* ---- the disparity producer in front of the path: OpenCV's StereoBM as utils/stereo_algorithm.cc:67-111
+ *      configures and calls it; restated in stereo_oracle.cc, pinned bit-exact against cv2 4.13 ---- */
+typedef struct {
+  int numberOfDisparities;   /* multiple of 16 */
+  int SADWindowSize;         /* odd, >= 5 */
+  int minDisparity;          /* <= 0 */
+  int preFilterCap;          /* 1..63 (XSOBEL pre-filter) */
+  int textureThreshold;
+  int uniquenessRatio;
+} orc_stereo_params;
+void orc_stereo_prefilter_xsobel(const uint8_t* src, int rows, int cols, int cap, uint8_t* dst);
+/* disp16: CV_16S fixed point (4 fractional bits), disp_f32 (may be NULL): disp16 / 16 as StereoAlgorithm::run returns it */
+int orc_stereo_bm(const uint8_t* left, const uint8_t* right, int rows, int cols, const orc_stereo_params* p, int16_t* disp16, float* disp_f32);
+
 #ifdef __cplusplus
 }
 #endif

@@ -45,10 +45,15 @@ class OrcResult(C.Structure):
                 ("numPointCloud", C.c_int32)]
 
 
+class OrcStereoParams(C.Structure):
+    _fields_ = [("numberOfDisparities", C.c_int), ("SADWindowSize", C.c_int), ("minDisparity", C.c_int),
+                ("preFilterCap", C.c_int), ("textureThreshold", C.c_int), ("uniquenessRatio", C.c_int)]
+
+
 def build(force: bool = False) -> str:
     so = os.path.join(_HERE, "liboracle.so")
-    src = os.path.join(_HERE, "bpvo_oracle.cc")
-    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, f) for f in ("bpvo_oracle.cc", "stereo_oracle.cc", "bpvo_oracle.h")]
+    if force or not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(s) for s in srcs):
         subprocess.run(["make", "-C", _HERE, "-s", "-B", "liboracle.so"], check=True)
     return so
 
@@ -106,6 +111,8 @@ def lib():
         "orc_vo_trajectory": (C.c_int, [vp, fp, C.c_int]),
         "orc_vo_point_cloud": (C.c_int, [vp, fp, fp, u8p, C.c_int]),
         "orc_last_error": (C.c_char_p, []),
+        "orc_stereo_prefilter_xsobel": (None, [u8p, C.c_int, C.c_int, C.c_int, u8p]),
+        "orc_stereo_bm": (C.c_int, [u8p, u8p, C.c_int, C.c_int, C.POINTER(OrcStereoParams), C.POINTER(C.c_int16), fp]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)
@@ -672,3 +679,24 @@ class RefVisualOdometry:
         xyzw = np.zeros((n, 4), np.float32); w = np.zeros(n, np.float32); g = np.zeros(n, np.uint8)
         self.L.ref_vo_point_cloud(self.h, _fp(xyzw), _fp(w), _u8(g), n)
         return xyzw, w, g
+
+
+def stereo_prefilter_xsobel(img, cap=31):
+    img = np.ascontiguousarray(img, np.uint8)
+    out = np.empty_like(img)
+    lib().orc_stereo_prefilter_xsobel(_u8(img), img.shape[0], img.shape[1], int(cap), _u8(out))
+    return out
+
+
+def stereo_bm(left, right, numberOfDisparities, SADWindowSize=15, minDisparity=0, preFilterCap=31, textureThreshold=10,
+              uniquenessRatio=15):
+    """OpenCV StereoBM as the reference configures it (utils/stereo_algorithm.cc:67-111) -> (int16 fixed point, float32 = /16)."""
+    left = np.ascontiguousarray(left, np.uint8); right = np.ascontiguousarray(right, np.uint8)
+    assert left.shape == right.shape and left.ndim == 2
+    sp = OrcStereoParams(int(numberOfDisparities), int(SADWindowSize), int(minDisparity), int(preFilterCap), int(textureThreshold),
+                         int(uniquenessRatio))
+    d16 = np.empty(left.shape, np.int16); df = np.empty(left.shape, np.float32)
+    rc = lib().orc_stereo_bm(_u8(left), _u8(right), left.shape[0], left.shape[1], C.byref(sp), d16.ctypes.data_as(C.POINTER(C.c_int16)), _fp(df))
+    if rc != 0:
+        raise ValueError("orc_stereo_bm: unsupported parameters")
+    return d16, df

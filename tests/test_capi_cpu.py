@@ -157,3 +157,27 @@ def test_shared_memory_plan_of_the_device_loop():
         for need in range(0, 60):
             for b in (0, 4096, 50000, budget):
                 check(ch, b, need)
+
+
+def test_stereo_params_mirror_the_reference_defaults():
+    """bpvo_b200_stereo_params = the CvStereoBMState fields utils/stereo_algorithm.cc:67-85 sets, with OpenCV's defaults"""
+    from bpvo_b200 import _capi
+    p = _capi.CStereoParams()
+    assert C.sizeof(p) == 13 * 4
+    _capi.lib().bpvo_b200_stereo_default_params(C.byref(p))
+    assert (p.preFilterType, p.preFilterSize, p.preFilterCap, p.SADWindowSize, p.minDisparity, p.numberOfDisparities) == (1, 9, 31, 15, 0, 0)
+    assert (p.textureThreshold, p.uniquenessRatio, p.speckleWindowSize, p.speckleRange, p.trySmallerWindows, p.disp12MaxDiff) == (10, 15, 0, 0, 0, -1)
+
+
+@pytest.mark.skipif(HAS_GPU, reason="checks the no-device behaviour")
+def test_stereo_create_fails_loudly_without_a_device():
+    from bpvo_b200 import Error
+    from bpvo_b200.stereo import StereoAlgorithm
+    with pytest.raises(Error, match="no CUDA device"):
+        StereoAlgorithm((64, 128), numberOfDisparities=16)
+    with pytest.raises(Error, match="numberOfDisparities"):
+        StereoAlgorithm((64, 128))                                        # "must be provided" (stereo_algorithm.cc:75)
+    with pytest.raises(Error, match="divisble by 16"):
+        StereoAlgorithm((64, 128), numberOfDisparities=20)                # OpenCV's own check and message
+    with pytest.raises(Error, match="accelerated path"):
+        StereoAlgorithm((64, 128), numberOfDisparities=16, StereoAlgorithm="SGBM")

@@ -280,3 +280,70 @@ def test_general_gaussian_blur_and_gradient_descriptors_against_cv2(oracle):
     for c, g in ((1, xgrad(I)), (3, ygrad(I))):
         pos, neg = np.where(g >= 0, g, 0).astype(np.float32), np.where(g < 0, g, 0).astype(np.float32)
         assert np.abs(d[c] - smooth(pos, 1.75)).max() <= 2e-4 and np.abs(d[c + 1] - smooth(neg, 1.75)).max() <= 2e-4
+
+
+# ---- upstream stereo: OpenCV's StereoBM as utils/stereo_algorithm.cc:67-111 configures and runs it ----
+def _stereo_golden():
+    g = np.load(os.path.join(GOLD, "stereo_bm.npz"))
+    for i in range(int(g["n"])):
+        nd, wsz, mind, cap, tex, uniq = (int(v) for v in g[f"params_{i}"])
+        yield i, g[f"left_{i}"], g[f"right_{i}"], dict(numberOfDisparities=nd, SADWindowSize=wsz, minDisparity=mind, preFilterCap=cap,
+                                                         textureThreshold=tex, uniquenessRatio=uniq), g[f"disp16_{i}"]
+
+
+def test_stereo_bm_matches_cv2_golden(oracle):
+    """cvFindStereoCorrespondenceBM (third-party; utils/stereo_algorithm.cc:107): the oracle's restatement is bit-exact against
+    cv2 4.13 on the committed vectors (shifted noise, the synthetic rig, pure noise, a texture-less half, negative minDisparity)"""
+    n = 0
+    for i, left, right, kw, want in _stereo_golden():
+        d16, df = oracle.stereo_bm(left, right, **kw)
+        assert np.array_equal(d16, want), f"case {i}: {int((d16 != want).sum())} pixels differ"
+        assert np.array_equal(df, want.astype(np.float32) / 16.0)        # convertTo(CV_32FC1, 1/16), stereo_algorithm.cc:110
+        n += 1
+    assert n >= 8
+
+
+def test_stereo_bm_matches_cv2_live(oracle):
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(5)
+    for trial in range(10):
+        nd = int(rng.choice([16, 32, 64])); wsz = int(rng.choice([5, 9, 15, 21]))
+        H = int(rng.integers(wsz + 8, 80)); W = int(rng.integers(nd + wsz + 8, nd + wsz + 100))
+        mind = int(rng.choice([0, 0, -7, -nd])); tex = int(rng.choice([0, 10, 500])); uniq = int(rng.choice([0, 15, 30])); cap = int(rng.choice([5, 31, 63]))
+        base = cv2.GaussianBlur(rng.integers(0, 256, (H, W + 2 * nd)).astype(np.uint8), (0, 0), 1.2)
+        s = int(rng.integers(0, nd))
+        left = base[:, nd:nd + W].copy(); right = base[:, nd + s:nd + s + W].copy()
+        bm = cv2.StereoBM_create(nd, wsz)
+        bm.setMinDisparity(mind); bm.setTextureThreshold(tex); bm.setUniquenessRatio(uniq); bm.setPreFilterCap(cap)
+        d16, _ = oracle.stereo_bm(left, right, nd, wsz, mind, cap, tex, uniq)
+        assert np.array_equal(d16, bm.compute(left, right)), (trial, H, W, nd, wsz, mind, tex, uniq, cap)
+
+
+def test_stereo_bm_properties(oracle):
+    """what the definition implies whatever the data: the border is filtered, a pure shift is recovered exactly, a
+    texture-less image is filtered everywhere, unsupported parameters are refused"""
+    from bpvo_b200.synth import scene_small
+    rng = np.random.default_rng(9)
+    nd, wsz, s = 32, 9, 11
+    base = rng.integers(0, 256, (40, 200)).astype(np.uint8)
+    left = base[:, 40:160].copy(); right = base[:, 40 + s:160 + s].copy()
+    d16, df = oracle.stereo_bm(left, right, nd, wsz)
+    inv = -16
+    w2 = wsz // 2
+    assert (d16[:w2] == inv).all() and (d16[-w2:] == inv).all() and (d16[:, :nd - 1 + w2] == inv).all() and (d16[:, -w2:] == inv).all()
+    core = d16[w2:-w2, nd - 1 + w2:-w2]
+    assert (np.abs(core.astype(int) - s * 16) <= 8).all()                # SAD 0 at the true shift; the sub-pixel step moves it by at most half a pixel
+    flat = np.full((40, 120), 90, np.uint8)
+    assert (oracle.stereo_bm(flat, flat, nd, wsz)[0] == inv).all()       # texture sum 0 < 10
+    with pytest.raises(ValueError):
+        oracle.stereo_bm(left, right, 30, wsz)                           # not a multiple of 16
+    with pytest.raises(ValueError):
+        oracle.stereo_bm(left, right, nd, 8)                             # even window
+    with pytest.raises(ValueError):
+        oracle.stereo_bm(left, right, nd, wsz, minDisparity=2)           # OpenCV writes out of bounds there: not restated
+    # the synthetic rig: the right camera sits one baseline along x, so block matching recovers the rendered disparity
+    sc = scene_small(rows=96, cols=160, seed=3); sc.baseline = 0.5
+    L, D = sc.render(0); R = sc.render_right(0)
+    d16, df = oracle.stereo_bm(L, R, 48, 9)
+    ok = d16 >= 0
+    assert ok.mean() > 0.4 and np.abs(df[ok] - D[ok]).mean() < 0.25
