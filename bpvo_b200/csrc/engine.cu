@@ -547,10 +547,11 @@ int bpvo_b200_frame_set_data(bpvo_b200_frame* f, const uint8_t* image, const flo
   {
     PhaseTimer t(c, &c->counters.ms_upload);
     const uint8_t* src_i = image; const float* src_d = disparity;
-    if (!(is_dma_able(image) && is_dma_able(disparity))) {
+    const bool stage_i = !is_dma_able(image), stage_d = !is_dma_able(disparity);      // each on its own: the disparity map may live on the device (upstream stereo) while the image is pageable
+    if (stage_i || stage_d) {
       CUDA_TRY(cudaEventSynchronize(c->stage_free));
-      memcpy(c->stage_img, image, npx); memcpy(c->stage_disp, disparity, npx * sizeof(float));
-      src_i = c->stage_img; src_d = c->stage_disp;
+      if (stage_i) { memcpy(c->stage_img, image, npx); src_i = c->stage_img; }
+      if (stage_d) { memcpy(c->stage_disp, disparity, npx * sizeof(float)); src_d = c->stage_disp; }
     }
     CUDA_TRY(cudaMemcpy2DAsync(f->pyr[0], (size_t) u8_pitch(c->cols), src_i, (size_t) c->cols, (size_t) c->cols, (size_t) c->rows, cudaMemcpyDefault, c->stream));
     CUDA_TRY(cudaMemcpyAsync(f->disp, src_d, npx * sizeof(float), cudaMemcpyDefault, c->stream));
