@@ -8,14 +8,17 @@
 //                    uniqueness tests, parabola-like sub-pixel step in 1/16 px, filtered value (minDisparity - 1) elsewhere
 // (definitions: oracle/stereo_oracle.cc header; parity: tests/test_gpu_stereo.py against the oracle and cv2-4.13 golden vectors).
 //
-// k_bm_match layout: one CTA = a 32-column x 32-row tile, blockDim = (32 columns, ndisp / 16 disparity groups); the pre-filtered
-// left / right tiles (+ window halo, + ndisp - 1 columns of the right image) are staged in shared memory once.  A thread owns one
-// column and 16 disparities: it marches down the rows keeping the 16 window SADs in registers (add the entering row's horizontal
-// sums, subtract the leaving row's), and the per-pixel decisions (arg-min over all groups, uniqueness, the two neighbours of the
-// minimum) go through three small shared-memory arrays, double-buffered so that a row costs two CTA barriers.
+// Layout: one CTA = a 32-column x 16-row tile, blockDim = (32 columns, ndisp / 16 disparity groups); the pre-filtered left / right
+// tiles (+ window halo, + ndisp - 1 columns of the right image) are staged in shared memory once.  A thread owns one column and 16
+// disparities: it marches down the rows keeping the 16 window SADs in registers (add the entering row's horizontal sums,
+// subtract the leaving row's), and the per-pixel decisions (arg-min over all groups, uniqueness, the two neighbours of the
+// minimum) go through small shared-memory arrays, double-buffered by row parity so that a row costs two CTA barriers.
+// k_bm_match_fast<NW> (minDisparity == 0, the reference's setting) packs four window columns per VABSDIFF4.U8.ACC instruction;
+// k_bm_match (any minDisparity <= 0, where the right-image column is clamped per window column) works byte by byte.
 // No atomics, no global scratch: traffic = the two u8 images in, the disparity map out.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 #include <string>
 
@@ -30,7 +33,8 @@ namespace {
       return bp_fail(BPVO_B200_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
   } while (0)
 
-constexpr int kTX = 32, kTY = 32, kDG = 16;      // tile columns / rows, disparities per thread
+constexpr int kTX = 32, kDG = 16;                // tile columns, disparities per thread
+constexpr int kMaxTileRows = 32;
 constexpr int kMaxWsz = 31, kMaxDisp = 256;
 
 __global__ void __launch_bounds__(256) k_bm_prefilter(const uint8_t* __restrict__ src0, const uint8_t* __restrict__ src1,
@@ -62,93 +66,214 @@ struct BmArgs {
   int ndisp, wsz, mindisp, cap, tex, uniq;
   int xmin, xmax, ymin, ymax;      // valid region (xmax already cut at cols + minDisparity)
   int m;                           // lofs - rofs = ndisp - 1 + minDisparity: right column = left column - m + d
+  int ty;                          // output rows per tile
+  int LWp, RWp;                    // shared-memory row strides of the left / right tile (multiples of 4)
   int16_t* d16; float* df;         // either may be null
 };
 
-// horizontal window sums of one tile row into the 16 running SADs (SIGN = +1 entering row, -1 leaving row)
+// |a.b0 - b.b0| + ... + |a.b3 - b.b3| + c in ONE instruction (VABSDIFF4.U8.ACC)
+__device__ __forceinline__ unsigned vsad4(unsigned a, unsigned b, unsigned c) {
+  unsigned d;
+  asm("vabsdiff4.u32.u32.u32.add %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+
+struct BmShared { uint8_t* Lt; uint8_t* Rt; unsigned* keys; int* sads; int* flag; int sstride; };
+
+// shared-memory plan (host and device): [left tile][right tile][keys 2 x ng x 32][SADs 32 x (ndisp + 4)][flags 2 x 32]
+__host__ __device__ inline size_t bm_smem_plan(int ty, int wsz, int LWp, int RWp, int ndisp, size_t off[5]) {
+  size_t o = 0;
+  off[0] = o; o += (size_t) (ty + wsz - 1) * LWp;
+  off[1] = o; o += (size_t) (ty + wsz - 1) * RWp;
+  o = (o + 15) & ~(size_t) 15;
+  off[2] = o; o += (size_t) 2 * (ndisp / kDG) * kTX * 4;
+  off[3] = o; o += (size_t) kTX * (ndisp + 4) * 4;
+  off[4] = o; o += (size_t) 2 * kTX * 4;
+  return o;
+}
+
+// stage the pre-filtered tiles: one warp per row, no divisions; columns past the image repeat the last one (never used by a
+// valid pixel)
+__device__ __forceinline__ void bm_stage(const BmArgs& a, const BmShared& s, int X0, int y0, int trows, int lane, int g, int ng) {
+  const int w2 = a.wsz / 2, rc0 = X0 - a.m - w2;
+  for (int r = g; r < trows; r += ng) {
+    const uint8_t* srcL = a.PL + (size_t) (y0 - w2 + r) * a.cols;
+    const uint8_t* srcR = a.PR + (size_t) (y0 - w2 + r) * a.cols;
+    for (int c = lane; c < a.LWp; c += kTX) s.Lt[r * a.LWp + c] = srcL[min(X0 - w2 + c, a.cols - 1)];
+    for (int c = lane; c < a.RWp; c += kTX) s.Rt[r * a.RWp + c] = srcR[min(max(rc0 + c, 0), a.cols - 1)];
+  }
+  if (g == 0) { s.flag[lane] = 0; s.flag[kTX + lane] = 0; }
+}
+
+// The per-pixel decisions of one output row, given this thread's 16 window SADs: first minimum over all disparity groups,
+// texture and uniqueness tests, sub-pixel step.  Two CTA barriers; keys / flags are double-buffered by row parity.
+__device__ __forceinline__ void bm_decide(const BmArgs& a, const BmShared& s, const int (&sad)[kDG], int tsum, int buf, int lane, int g, int ng,
+                                          int X, int y) {
+  unsigned key = 0xffffffffu;                              // (SAD << 8) | internal d: the minimum is the FIRST smallest SAD
+#pragma unroll
+  for (int k = 0; k < kDG; ++k) key = min(key, ((unsigned) sad[k] << 8) | (unsigned) (g * kDG + k));
+  s.keys[(buf * ng + g) * kTX + lane] = key;
+  __syncthreads();
+  // every SAD of the pixel goes to shared memory for the two neighbours of the minimum: written BETWEEN the two barriers (the
+  // previous row's reader, a g == 0 thread, is past its reads once it has arrived at the barrier above)
+  int4* mine = reinterpret_cast<int4*>(s.sads + lane * s.sstride + g * kDG);          // row stride ndisp + 4 ints: conflict-free 128-bit stores
+#pragma unroll
+  for (int q = 0; q < kDG / 4; ++q) mine[q] = make_int4(sad[4 * q], sad[4 * q + 1], sad[4 * q + 2], sad[4 * q + 3]);
+  unsigned best = 0xffffffffu;
+  for (int q = 0; q < ng; ++q) best = min(best, s.keys[(buf * ng + q) * kTX + lane]);
+  const int mind = (int) (best & 255u), minsad = (int) (best >> 8);
+  if (a.uniq > 0) {
+    const int thresh = minsad + (minsad * a.uniq / 100);
+    bool viol = false;
+#pragma unroll
+    for (int k = 0; k < kDG; ++k) viol = viol || ((unsigned) (g * kDG + k - (mind - 1)) > 2u && sad[k] <= thresh);       // d outside [mind-1, mind+1]
+    if (viol) s.flag[buf * kTX + lane] = 1;
+  }
+  if (g == 0) s.flag[(buf ^ 1) * kTX + lane] = 0;          // the other buffer: read by the previous row's last step, set again by the next row
+  __syncthreads();
+  if (g == 0 && X < a.xmax) {
+    int16_t out = (int16_t) ((a.mindisp - 1) * 16);
+    if (tsum >= a.tex && !s.flag[buf * kTX + lane]) {
+      const int dp = (mind + 1 < a.ndisp) ? mind + 1 : a.ndisp - 2, dn = (mind > 0) ? mind - 1 : 1;      // neighbours, mirrored at the ends
+      const int p = s.sads[lane * s.sstride + dp], n = s.sads[lane * s.sstride + dn];
+      const int den = p + n - 2 * minsad + abs(p - n);
+      out = (int16_t) (((a.ndisp - mind - 1 + a.mindisp) * 256 + (den != 0 ? (p - n) * 256 / den : 0) + 15) >> 4);
+    }
+    const size_t o = (size_t) y * a.cols + X;
+    if (a.d16) a.d16[o] = out;
+    if (a.df) a.df[o] = (float) out * 0.0625f;
+  }
+}
+
+__device__ __forceinline__ BmShared bm_shared(const BmArgs& a, unsigned char* smem) {
+  size_t off[5];
+  bm_smem_plan(a.ty, a.wsz, a.LWp, a.RWp, a.ndisp, off);
+  BmShared s;
+  s.Lt = smem + off[0]; s.Rt = smem + off[1]; s.keys = reinterpret_cast<unsigned*>(smem + off[2]);
+  s.sads = reinterpret_cast<int*>(smem + off[3]); s.flag = reinterpret_cast<int*>(smem + off[4]); s.sstride = a.ndisp + 4;
+  return s;
+}
+
+// ---- generic matcher: any window, any minDisparity <= 0 (the right-image column is clamped per window column) ----
 template <int SIGN>
 __device__ __forceinline__ void bm_row(const uint8_t* __restrict__ lrow, const uint8_t* __restrict__ rrow, int wsz, int rb0, int rb_max, int cap,
                                        int (&sad)[kDG], int& tsum) {
   for (int dx = 0; dx < wsz; ++dx) {
-    const int lv = lrow[dx];
-    tsum += SIGN * abs(lv - cap);
+    const unsigned lv = lrow[dx];
     const uint8_t* r = rrow + min(rb0 + dx, rb_max);
+    if (SIGN > 0) {
+      tsum = (int) __usad(lv, (unsigned) cap, (unsigned) tsum);
 #pragma unroll
-    for (int k = 0; k < kDG; ++k) sad[k] += SIGN * abs(lv - (int) r[k]);
+      for (int k = 0; k < kDG; ++k) sad[k] = (int) __usad(lv, (unsigned) r[k], (unsigned) sad[k]);
+    } else {
+      tsum -= (int) __usad(lv, (unsigned) cap, 0u);
+#pragma unroll
+      for (int k = 0; k < kDG; ++k) sad[k] -= (int) __usad(lv, (unsigned) r[k], 0u);
+    }
   }
 }
 
 __global__ void __launch_bounds__(kTX * (kMaxDisp / kDG)) k_bm_match(const BmArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
-  const int lane = threadIdx.x, g = threadIdx.y, ng = blockDim.y, tid = g * kTX + lane, nthreads = ng * kTX;
+  const int lane = threadIdx.x, g = threadIdx.y, ng = blockDim.y;
   const int w2 = a.wsz / 2;
-  const int X0 = a.xmin + blockIdx.x * kTX, y0 = a.ymin + blockIdx.y * kTY;
-  const int ty = min(kTY, a.ymax - y0);                   // output rows of this tile
+  const int X0 = a.xmin + blockIdx.x * kTX, y0 = a.ymin + blockIdx.y * a.ty;
+  const int ty = min(a.ty, a.ymax - y0);                  // output rows of this tile
   const int trows = ty + a.wsz - 1;                       // staged rows: y0 - w2 .. y0 + ty - 1 + w2 (all inside the image)
-  const int LW = kTX + a.wsz - 1, RW = kTX + a.wsz - 1 + a.ndisp - 1;
-  const int rc0 = X0 - a.m - w2;                          // first staged column of the right image (>= 0)
-  uint8_t* Lt = smem;
-  uint8_t* Rt = Lt + (size_t) (kTY + a.wsz - 1) * LW;
-  unsigned* keys = reinterpret_cast<unsigned*>(smem + (((size_t) (kTY + a.wsz - 1) * (LW + RW) + 15) & ~(size_t) 15));        // [2][ng][32]
-  int* pn = reinterpret_cast<int*>(keys + 2 * ng * kTX);                                                                      // [2][2][32]
-  int* flag = pn + 2 * 2 * kTX;                                                                                               // [2][32]
-  for (int i = tid; i < trows * LW; i += nthreads) {
-    const int r = i / LW, c = i - r * LW;
-    Lt[i] = a.PL[(size_t) (y0 - w2 + r) * a.cols + min(X0 - w2 + c, a.cols - 1)];
-  }
-  for (int i = tid; i < trows * RW; i += nthreads) {
-    const int r = i / RW, c = i - r * RW;
-    Rt[i] = a.PR[(size_t) (y0 - w2 + r) * a.cols + min(rc0 + c, a.cols - 1)];
-  }
-  if (tid < 2 * kTX) flag[tid] = 0;
+  const int rc0 = X0 - a.m - w2;                          // first staged column of the right image
+  const BmShared s = bm_shared(a, smem);
+  bm_stage(a, s, X0, y0, trows, lane, g, ng);
   __syncthreads();
-
   const int X = X0 + lane;
   // right-image base column of window column dx: min(X - m - w2 + dx, cols - ndisp) (+ d), relative to the staged tile
-  const int rb0 = X - a.m - w2 - rc0 + g * kDG, rb_max = a.cols - a.ndisp - rc0 + g * kDG;
+  const int rb0 = lane + g * kDG, rb_max = a.cols - a.ndisp - rc0 + g * kDG;
   int sad[kDG], tsum = 0;
 #pragma unroll
   for (int k = 0; k < kDG; ++k) sad[k] = 0;
-  for (int r = 0; r < a.wsz; ++r) bm_row<1>(Lt + (size_t) r * LW + lane, Rt + (size_t) r * RW, a.wsz, rb0, rb_max, a.cap, sad, tsum);
-  const int16_t filtered = (int16_t) ((a.mindisp - 1) * 16);
+  for (int r = 0; r < a.wsz; ++r) bm_row<1>(s.Lt + (size_t) r * a.LWp + lane, s.Rt + (size_t) r * a.RWp, a.wsz, rb0, rb_max, a.cap, sad, tsum);
   for (int yy = 0; yy < ty; ++yy) {
     if (yy > 0) {
-      bm_row<1>(Lt + (size_t) (yy + a.wsz - 1) * LW + lane, Rt + (size_t) (yy + a.wsz - 1) * RW, a.wsz, rb0, rb_max, a.cap, sad, tsum);
-      bm_row<-1>(Lt + (size_t) (yy - 1) * LW + lane, Rt + (size_t) (yy - 1) * RW, a.wsz, rb0, rb_max, a.cap, sad, tsum);
+      bm_row<1>(s.Lt + (size_t) (yy + a.wsz - 1) * a.LWp + lane, s.Rt + (size_t) (yy + a.wsz - 1) * a.RWp, a.wsz, rb0, rb_max, a.cap, sad, tsum);
+      bm_row<-1>(s.Lt + (size_t) (yy - 1) * a.LWp + lane, s.Rt + (size_t) (yy - 1) * a.RWp, a.wsz, rb0, rb_max, a.cap, sad, tsum);
     }
-    const int buf = yy & 1;
-    unsigned key = 0xffffffffu;                            // (SAD << 8) | internal d: the minimum is the FIRST smallest SAD
+    bm_decide(a, s, sad, tsum, yy & 1, lane, g, ng, X, y0 + yy);
+  }
+}
+
+// ---- fast matcher (minDisparity == 0: no clamping inside the valid region): four window columns per instruction ----
+// A window row of the left image is NW packed words (bytes past the window masked to zero); for disparity index k the matching
+// right-image bytes are the same row shifted by k bytes: every 4-byte window at every byte offset of a (16 + 4 NW)-byte
+// register strip, cut out with funnel shifts.  One VABSDIFF4.U8.ACC then adds four absolute differences to a SAD:
+// per thread and tile row NW + 1 + NW + 5 aligned 32-bit shared-memory loads and ~22 NW + 20 instructions for 16 disparities
+// (the byte-wise version: 17 loads and ~35 instructions per window COLUMN).  Entering and leaving rows accumulate separately
+// (the instruction only adds); SAD = entered - left.
+template <int NW>
+__device__ __forceinline__ void bm_row_fast(const uint8_t* __restrict__ lrow_w, const uint8_t* __restrict__ rrow_w, unsigned sh, unsigned tail,
+                                            unsigned capw, unsigned (&acc)[kDG], unsigned& tacc) {
+  const unsigned* lw = reinterpret_cast<const unsigned*>(lrow_w);
+  const unsigned* rw = reinterpret_cast<const unsigned*>(rrow_w);
+  unsigned La[NW + 1], Ra[NW + 5];
 #pragma unroll
-    for (int k = 0; k < kDG; ++k) key = min(key, ((unsigned) sad[k] << 8) | (unsigned) (g * kDG + k));
-    keys[(buf * ng + g) * kTX + lane] = key;
-    __syncthreads();
-    unsigned best = 0xffffffffu;
-    for (int q = 0; q < ng; ++q) best = min(best, keys[(buf * ng + q) * kTX + lane]);
-    const int mind = (int) (best & 255u), minsad = (int) (best >> 8);
-    const int thresh = minsad + (minsad * a.uniq / 100);
-    const int dp = (mind + 1 < a.ndisp) ? mind + 1 : a.ndisp - 2, dn = (mind > 0) ? mind - 1 : 1;      // neighbours, mirrored at the ends
-    bool viol = false;
+  for (int i = 0; i < NW + 1; ++i) La[i] = lw[i];
 #pragma unroll
-    for (int k = 0; k < kDG; ++k) {
-      const int d = g * kDG + k;
-      viol = viol || ((d < mind - 1 || d > mind + 1) && sad[k] <= thresh);
-      if (d == dp) pn[(buf * 2 + 0) * kTX + lane] = sad[k];
-      if (d == dn) pn[(buf * 2 + 1) * kTX + lane] = sad[k];
+  for (int i = 0; i < NW + 5; ++i) Ra[i] = rw[i];
+  unsigned Lw[NW], Bw[NW + 4];
+#pragma unroll
+  for (int i = 0; i < NW; ++i) Lw[i] = __funnelshift_r(La[i], La[i + 1], sh);
+  Lw[NW - 1] &= tail;
+#pragma unroll
+  for (int i = 0; i < NW + 4; ++i) Bw[i] = __funnelshift_r(Ra[i], Ra[i + 1], sh);
+#pragma unroll
+  for (int j = 0; j < NW; ++j) tacc = vsad4(Lw[j], (j == NW - 1) ? (capw & tail) : capw, tacc);
+#pragma unroll
+  for (int k = 0; k < kDG; ++k) {
+#pragma unroll
+    for (int j = 0; j < NW; ++j) {
+      const int o = k + 4 * j;
+      unsigned W = (o % 4 == 0) ? Bw[o / 4] : __funnelshift_r(Bw[o / 4], Bw[o / 4 + 1], 8 * (o % 4));
+      if (j == NW - 1) W &= tail;
+      acc[k] = vsad4(W, Lw[j], acc[k]);
     }
-    if (a.uniq > 0 && viol) flag[buf * kTX + lane] = 1;
-    if (g == 0) flag[(buf ^ 1) * kTX + lane] = 0;          // the other buffer: read by the previous row's last step, set again by the next row
-    __syncthreads();
-    if (g == 0 && X < a.xmax) {
-      int16_t out = filtered;
-      if (tsum >= a.tex && !flag[buf * kTX + lane]) {
-        const int p = pn[(buf * 2 + 0) * kTX + lane], n = pn[(buf * 2 + 1) * kTX + lane];
-        const int den = p + n - 2 * minsad + abs(p - n);
-        out = (int16_t) (((a.ndisp - mind - 1 + a.mindisp) * 256 + (den != 0 ? (p - n) * 256 / den : 0) + 15) >> 4);
-      }
-      const size_t o = (size_t) (y0 + yy) * a.cols + X;
-      if (a.d16) a.d16[o] = out;
-      if (a.df) a.df[o] = (float) out * 0.0625f;
+  }
+}
+
+template <int NW>
+__global__ void __launch_bounds__(kTX * (kMaxDisp / kDG)) k_bm_match_fast(const BmArgs a) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int lane = threadIdx.x, g = threadIdx.y, ng = blockDim.y;
+  const int X0 = a.xmin + blockIdx.x * kTX, y0 = a.ymin + blockIdx.y * a.ty;
+  const int ty = min(a.ty, a.ymax - y0);
+  const int trows = ty + a.wsz - 1;
+  const BmShared s = bm_shared(a, smem);
+  bm_stage(a, s, X0, y0, trows, lane, g, ng);
+  __syncthreads();
+  const int X = X0 + lane;
+  const unsigned sh = 8u * (unsigned) (lane & 3);                                  // byte offset of this thread's strips inside their aligned words
+  const unsigned tail = 0xffffffffu >> (8 * (4 * NW - a.wsz));                    // keeps the window bytes of the last word
+  const unsigned capw = (unsigned) a.cap * 0x01010101u;
+  const uint8_t* lbase = s.Lt + (lane & ~3);
+  const uint8_t* rbase = s.Rt + (lane & ~3) + g * kDG;
+  unsigned accp[kDG], accm[kDG], tp = 0, tm = 0;
+#pragma unroll
+  for (int k = 0; k < kDG; ++k) { accp[k] = 0; accm[k] = 0; }
+  for (int r = 0; r < a.wsz; ++r) bm_row_fast<NW>(lbase + (size_t) r * a.LWp, rbase + (size_t) r * a.RWp, sh, tail, capw, accp, tp);
+  for (int yy = 0; yy < ty; ++yy) {
+    if (yy > 0) {
+      bm_row_fast<NW>(lbase + (size_t) (yy + a.wsz - 1) * a.LWp, rbase + (size_t) (yy + a.wsz - 1) * a.RWp, sh, tail, capw, accp, tp);
+      bm_row_fast<NW>(lbase + (size_t) (yy - 1) * a.LWp, rbase + (size_t) (yy - 1) * a.RWp, sh, tail, capw, accm, tm);
     }
+    int sad[kDG];
+#pragma unroll
+    for (int k = 0; k < kDG; ++k) sad[k] = (int) (accp[k] - accm[k]);
+    bm_decide(a, s, sad, (int) (tp - tm), yy & 1, lane, g, ng, X, y0 + yy);
+  }
+}
+
+typedef void (*BmKernel)(const BmArgs);
+static BmKernel pick_fast(int nw) {
+  switch (nw) {
+    case 2: return k_bm_match_fast<2>; case 3: return k_bm_match_fast<3>; case 4: return k_bm_match_fast<4>; case 5: return k_bm_match_fast<5>;
+    case 6: return k_bm_match_fast<6>; case 7: return k_bm_match_fast<7>; default: return k_bm_match_fast<8>;
   }
 }
 
@@ -168,6 +293,8 @@ struct bpvo_b200_stereo {
   uint8_t* d_in[2] = {}; uint8_t* d_pre[2] = {};
   int16_t* d_d16 = nullptr; float* d_df = nullptr;
   size_t smem = 0;
+  int ty = 16, LWp = 0, RWp = 0;
+  BmKernel kernel = nullptr;
   long long launches = 0;
 };
 
@@ -216,9 +343,16 @@ int bpvo_b200_stereo_create(bpvo_b200_stereo** out, int rows, int cols, const bp
   for (int k = 0; k < 2 && e == cudaSuccess; ++k) { e = cudaMalloc(&s->d_in[k], n); if (e == cudaSuccess) e = cudaMalloc(&s->d_pre[k], n); }
   if (e == cudaSuccess) e = cudaMalloc(&s->d_d16, n * sizeof(int16_t));
   if (e == cudaSuccess) e = cudaMalloc(&s->d_df, n * sizeof(float));
-  const int LW = kTX + p->SADWindowSize - 1, RW = LW + p->numberOfDisparities - 1, ng = p->numberOfDisparities / kDG;
-  s->smem = (((size_t) (kTY + p->SADWindowSize - 1) * (LW + RW) + 15) & ~(size_t) 15) + (size_t) (2 * ng * kTX + 2 * 2 * kTX + 2 * kTX) * 4;
-  if (e == cudaSuccess && s->smem > 48 * 1024) e = cudaFuncSetAttribute(k_bm_match, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) s->smem);
+  // tile plan: 32 columns x `ty` rows per CTA; row strides cover the aligned 32-bit strips the fast matcher loads
+  const int nw = (p->SADWindowSize + 3) / 4, ng = p->numberOfDisparities / kDG;
+  s->LWp = kTX + 4 * nw; s->RWp = kDG * ng + 4 * nw + kTX;
+  s->ty = 16;
+  if (const char* ev = getenv("BPVO_B200_STEREO_TILE_ROWS")) { const int v = atoi(ev); if (v >= 1 && v <= kMaxTileRows) s->ty = v; }
+  const bool generic = p->minDisparity != 0 || (getenv("BPVO_B200_STEREO_GENERIC") && atoi(getenv("BPVO_B200_STEREO_GENERIC")) != 0);
+  s->kernel = generic ? k_bm_match : pick_fast(nw);
+  size_t off[5];
+  s->smem = bm_smem_plan(s->ty, p->SADWindowSize, s->LWp, s->RWp, p->numberOfDisparities, off);
+  if (e == cudaSuccess && s->smem > 48 * 1024) e = cudaFuncSetAttribute(reinterpret_cast<const void*>(s->kernel), cudaFuncAttributeMaxDynamicSharedMemorySize, (int) s->smem);
   if (e != cudaSuccess) {
     bpvo_b200_stereo_destroy(s);
     return bp_fail(BPVO_B200_ERR_CUDA, "stereo_create: %s", cudaGetErrorString(e));
@@ -270,10 +404,11 @@ int bpvo_b200_stereo_run(bpvo_b200_stereo* s, const uint8_t* left, const uint8_t
   a.xmax = cols - w2 < cols + a.mindisp ? cols - w2 : cols + a.mindisp;
   a.ymin = w2; a.ymax = rows - w2;
   a.d16 = d16; a.df = df;
+  a.ty = s->ty; a.LWp = s->LWp; a.RWp = s->RWp;
   const int lofs = maxD > 0 ? maxD : 0, rofs = maxD < 0 ? -maxD : 0, width1 = cols - rofs - a.ndisp + 1;
   if (a.xmax > a.xmin && a.ymax > a.ymin && lofs < cols && rofs < cols && width1 >= 1) {
-    const dim3 grid((a.xmax - a.xmin + kTX - 1) / kTX, (a.ymax - a.ymin + kTY - 1) / kTY), block(kTX, a.ndisp / kDG);
-    k_bm_match<<<grid, block, s->smem, s->stream>>>(a);
+    const dim3 grid((a.xmax - a.xmin + kTX - 1) / kTX, (a.ymax - a.ymin + a.ty - 1) / a.ty), block(kTX, a.ndisp / kDG);
+    s->kernel<<<grid, block, s->smem, s->stream>>>(a);
     s->launches += 1;
   }
   ST_TRY(cudaGetLastError());
