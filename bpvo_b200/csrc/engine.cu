@@ -983,9 +983,13 @@ static int launch_estimate_pose_t(bpvo_b200_ctx* c, const bpvo_b200_frame* ref, 
   cache_bytes = std::max(0, cache_bytes);
   if (ov && ov->cache_bytes >= 0) cache_bytes = std::min(cache_bytes, ov->cache_bytes);
   const size_t dyn = (size_t) kScratchBytes + (size_t) cache_bytes;
-  if (c->dyn_configured != dyn) {        // per ctx: the attribute is per device, and a process may drive several
-    CUDA_TRY(cudaFuncSetAttribute((const void*) k_estimate_pose<C, BLEND, PEER, FIX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) dyn));
-    c->dyn_configured = dyn;
+  {                                      // the attribute is per kernel instantiation and per device (a process may drive several of either)
+    static size_t configured[64] = {};   // (benign if two host threads race here: at worst the call is repeated)
+    const int dev = c->p.device_id & 63;
+    if (configured[dev] != dyn) {
+      CUDA_TRY(cudaFuncSetAttribute((const void*) k_estimate_pose<C, BLEND, PEER, FIX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) dyn));
+      configured[dev] = dyn;
+    }
   }
   void* args[] = {&a, &sel, &cache_bytes};
   int grid = std::min(c->sm_count, kMaxGrid);
@@ -1002,7 +1006,24 @@ static int launch_estimate_pose(bpvo_b200_ctx* c, const bpvo_b200_frame* ref, co
     if (c->p.flags & BPVO_B200_FLAG_FAST_BLEND) return launch_estimate_pose_t<C, 1, false, 0>(c, ref, cur, T_init, ov);
     // the bit-planes workloads' hot configurations with the loss function and the linear interpolant compiled in
     if (!c->peer_mode && c->p.interp == BPVO_B200_LINEAR && !getenv("BPVO_B200_GENERIC_KERNEL")) {
-      if (c->p.lossFunction == BPVO_B200_TUKEY) return launch_estimate_pose_t<C, 0, false, BPVO_B200_TUKEY>(c, ref, cur, T_init, ov);
+      if (c->p.lossFunction == BPVO_B200_TUKEY) {
+        // finest level too large for the shared-memory cache (1080p dense: 48 points per thread): the instantiation that keeps
+        // two points per thread in flight in the residual phase.  Decided from the template header when it is already on the
+        // host (never waits for it); results are bit-identical either way.
+        bool streams = false;
+        if (!getenv("BPVO_B200_NO_STREAM2") && cudaEventQuery(ref->meta_ready) == cudaSuccess) {
+          int grid = std::min(c->sm_count, kMaxGrid);
+          if (c->solver_ctas > 0) grid = std::min(grid, c->solver_ctas);
+          const int n = ref->h_meta[c->p.maxTestLevel].n;
+          const int cache_bytes = std::max(0, ((c->smem_optin - 24 * 1024 - kScratchBytes) / 1024) * 1024);
+          const TplCache plan = tpl_cache_plan<C>((unsigned) kScratchBytes, cache_bytes, (n + grid * kLinThreads - 1) / (grid * kLinThreads));
+          streams = plan.K > 1 && plan.pts == kTcNone && plan.f[TC_R] == kTcNone;
+        } else {
+          cudaGetLastError();
+        }
+        if (streams) return launch_estimate_pose_t<C, 0, false, BPVO_B200_TUKEY | 0x100>(c, ref, cur, T_init, ov);
+        return launch_estimate_pose_t<C, 0, false, BPVO_B200_TUKEY>(c, ref, cur, T_init, ov);
+      }
       if (c->p.lossFunction == BPVO_B200_HUBER) return launch_estimate_pose_t<C, 0, false, BPVO_B200_HUBER>(c, ref, cur, T_init, ov);
     }
   }

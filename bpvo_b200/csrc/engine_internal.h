@@ -51,7 +51,6 @@ struct bpvo_b200_ctx {
   void* flush_buf = nullptr;
   const bpvo_b200_frame* last_ref = nullptr; int last_level = 0;
   bool profiling = false;
-  size_t dyn_configured = 0;     // dynamic shared memory the persistent kernel was last configured for on this device
   int solver_ctas = 0;           // CTAs (= SMs) of the persistent solve; 0 = all (bpvo_b200_set_solver_ctas, throughput mode)
   unsigned ll_seq = 0;           // next sequence number of the persistent kernel's exchanges
   bpvo_b200_counters counters{};

@@ -339,7 +339,11 @@ __device__ __forceinline__ int sel_bin(float v, float lo, float inv_w) { return 
 //   1  projection, Floor and validity stay fp64 (same taps, same valid flags as the reference), the fractions are rounded to fp32
 //      once and the 4-tap blend runs as fp32 FMAs: |r - r_reference| <= 2e-7 on [0, 1] data against the north star's 1e-5.
 // C = 1 (intensity, values up to 255) always takes the fp64 expression: 5 conversions per point, nothing to gain.
-template <int C, int BLEND>
+// NB: points a thread has in flight on fully streaming levels (nothing of the level fits the shared-memory cache).  2 = the
+// loop handles two points per pass -- both projections, then all eight tap loads and both I0 loads, then both blends: twice the
+// bytes in flight per thread on levels where the phase is bound by memory latency at 8 warps per SM (1080p dense level 0).
+// The arithmetic per point is the same expression sequence: results are bit-identical to NB = 1.
+template <int C, int BLEND, int NB = 1>
 __device__ __forceinline__ void phase_residuals(const LevelTemplate& L, const LevelImage& I, const float* P, const Work& W,
                                                 unsigned* __restrict__ hist1, bool do_hist, Bracket br, const TplCache& tc,
                                                 const TemplateMeta& m, unsigned* scratch, LinShared& sh, int block, int nblocks, int interp = 0,
@@ -364,8 +368,116 @@ __device__ __forceinline__ void phase_residuals(const LevelTemplate& L, const Le
   const bool streaming = BP_PREFETCH && tc.K > 1 && tc.pts == kTcNone && tc.f[TC_R] == kTcNone;
   const int stride = nblocks * kLinThreads;
   float4 Xnext = make_float4(0.0f, 0.0f, 1.0f, 1.0f);
-  if (streaming) { const int i0 = first_point(block, nblocks); if (i0 < n_pts) Xnext = (tc.pts != kTcNone) ? tc_point(tc, 0) : __ldg(L.pts + i0); }
-  for (int i = first_point(block, nblocks); i < n_pts; i += stride, ++k) {
+  int i_start = first_point(block, nblocks);
+  if (NB == 2 && streaming && interp == 0) {
+    // ---- two points per pass (see NB above); the tail (at most one point) and every other case take the loop below ----
+    auto project = [&](const float4& X, int& xi, int& yi, double& xf, double& yf) -> bool {
+      const double X0 = X.x, X1 = X.y, X2 = X.z, X3 = X.w;
+      const double h0 = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(P00, X0), __dmul_rn(P01, X1)), __dmul_rn(P02, X2)), __dmul_rn(P03, X3));
+      const double h1 = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(P10, X0), __dmul_rn(P11, X1)), __dmul_rn(P12, X2)), __dmul_rn(P13, X3));
+      const double h2 = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(P20, X0), __dmul_rn(P21, X1)), __dmul_rn(P22, X2)), __dmul_rn(P23, X3));
+      const double w = __ddiv_rn(1.0, h2);
+      const double u = __dmul_rn(w, h0), v = __dmul_rn(w, h1);
+      bool ok = isfinite(u) && isfinite(v) && fabs(u) < 1e9 && fabs(v) < 1e9;
+      xi = 0; yi = 0; xf = 0.0; yf = 0.0;
+      if (ok) {
+        xi = (int) u; xi -= (xi > u);
+        yi = (int) v; yi -= (yi > v);
+        ok = xi >= border_lo && xi < cols - border_hi && yi >= border_lo && yi < rows - 1;
+        xf = __dsub_rn(u, (double) xi); yf = __dsub_rn(v, (double) yi);
+      }
+      return ok;
+    };
+    auto prefetch_taps = [&](const float4& X) {      // fp32 estimate of a later point's projection, only to pull its taps into the L2
+      const float h2 = P[2] * X.x + P[5] * X.y + P[8] * X.z + P[11];
+      const float iw = __frcp_rn(h2);
+      const float uu = (P[0] * X.x + P[3] * X.y + P[6] * X.z + P[9]) * iw, vv = (P[1] * X.x + P[4] * X.y + P[7] * X.z + P[10]) * iw;
+      if (uu >= 0.0f && vv >= 0.0f && uu < (float) (cols - 1) && vv < (float) (rows - 1)) {
+        const float* tp = I.desc + ((size_t) (int) vv * cols + (int) uu) * kStride<C>;
+        prefetch_l2(tp); prefetch_l2(tp + kStride<C>); prefetch_l2(tp + (size_t) cols * kStride<C>); prefetch_l2(tp + (size_t) cols * kStride<C> + kStride<C>);
+      }
+    };
+    int i = i_start;
+    float4 Xa = make_float4(0.0f, 0.0f, 1.0f, 1.0f), Xb = Xa;
+    if (i + stride < n_pts) { Xa = __ldg(L.pts + i); Xb = __ldg(L.pts + i + stride); }
+    for (; i + stride < n_pts; i += 2 * stride, k += 2) {
+      const int ia = i, ib = i + stride, ja = i + 2 * stride, jb = i + 3 * stride;
+      const float4 Xa0 = Xa, Xb0 = Xb;
+      if (jb < n_pts) {                       // next pass: its points into registers now, its taps and I0 into the L2
+        Xa = __ldg(L.pts + ja); Xb = __ldg(L.pts + jb);
+        prefetch_l2(L.i0 + (size_t) ja * kStride<C>); prefetch_l2(L.i0 + (size_t) jb * kStride<C>);
+        const int fa = i + 4 * stride, fb = i + 5 * stride;
+        if (fb < n_pts) { prefetch_l2(L.pts + fa); prefetch_l2(L.pts + fb); }
+      }
+      int xia, yia, xib, yib; double xfa, yfa, xfb, yfb;
+      const bool oka = project(Xa0, xia, yia, xfa, yfa), okb = project(Xb0, xib, yib, xfb, yfb);
+      VecC<C> ta[4], tb[4], i0a, i0b;
+      if (oka) {
+        const float* tap = I.desc + ((size_t) yia * cols + xia) * kStride<C>;
+        ta[0].load(tap); ta[1].load(tap + kStride<C>); ta[2].load(tap + (size_t) cols * kStride<C>); ta[3].load(tap + (size_t) cols * kStride<C> + kStride<C>);
+        i0a.load(L.i0 + (size_t) ia * kStride<C>);
+      }
+      if (okb) {
+        const float* tap = I.desc + ((size_t) yib * cols + xib) * kStride<C>;
+        tb[0].load(tap); tb[1].load(tap + kStride<C>); tb[2].load(tap + (size_t) cols * kStride<C>); tb[3].load(tap + (size_t) cols * kStride<C> + kStride<C>);
+        i0b.load(L.i0 + (size_t) ib * kStride<C>);
+      }
+      if (jb < n_pts) { prefetch_taps(Xa); prefetch_taps(Xb); }
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const bool ok = h ? okb : oka;
+        const int ii = h ? ib : ia;
+        const double xf = h ? xfb : xfa, yf = h ? yfb : yfa;
+        VecC<C> r;
+        if (ok) {
+          const double wx = __dsub_rn(1.0, xf), wy = __dsub_rn(1.0, yf);
+#pragma unroll
+          for (int c = 0; c < C; ++c) {
+            const float t00 = h ? tb[0].v[c] : ta[0].v[c], t01 = h ? tb[1].v[c] : ta[1].v[c], t10 = h ? tb[2].v[c] : ta[2].v[c], t11 = h ? tb[3].v[c] : ta[3].v[c];
+            const float i0v = h ? i0b.v[c] : i0a.v[c];
+            if (BLEND == 1 && C == 8) {
+              const float xf32 = (float) xf, yf32 = (float) yf, wx32 = (float) wx, wy32 = (float) wy;
+              const float top = fmaf(t01, xf32, t00 * wx32);
+              const float bot = fmaf(t11, xf32, t10 * wx32);
+              r.v[c] = fmaf(yf32, bot, wy32 * top) - i0v;
+            } else {
+              const double top = __dadd_rn(__dmul_rn((double) t00, wx), __dmul_rn((double) t01, xf));
+              const double bot = __dadd_rn(__dmul_rn((double) t10, wx), __dmul_rn((double) t11, xf));
+              const double Iw = __dadd_rn(__dmul_rn(wy, top), __dmul_rn(yf, bot));
+              r.v[c] = (float) __dsub_rn(Iw, (double) i0v);
+            }
+          }
+          if (do_hist) {
+            if (do_hist1) {
+#pragma unroll
+              for (int c = 0; c < C; ++c) atomicAdd(&sh.hist[__float_as_uint(fabsf(r.v[c])) >> 20], 1u);
+            }
+            my_first = min(my_first, ii);
+            ++cnt_valid;
+            if (br.on) {
+#pragma unroll
+              for (int c = 0; c < C; ++c) {
+                const float av = fabsf(r.v[c]);
+                cnt_below += (av < br.lo) ? 1u : 0u;
+                if (av >= br.lo && av <= br.hi) {
+                  const unsigned slot = atomicAdd(&sh.found[6], 1u);
+                  if (slot < (unsigned) kCtaCandCap) cta_cand[slot] = av;
+                  atomicAdd(hist1 + kHistBins + 8 + sel_bin(av, br.lo, br.inv_w), 1u);
+                }
+              }
+            }
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < C; ++c) r.v[c] = 0.0f;
+        }
+        r.store(W.res + (size_t) ii * kStride<C>); W.valid[ii] = ok ? 1 : 0;      // streaming level: residuals live in global memory
+      }
+    }
+    i_start = i;
+  }
+  if (streaming) { const int i0 = i_start; if (i0 < n_pts) Xnext = (tc.pts != kTcNone) ? tc_point(tc, k) : __ldg(L.pts + i0); }
+  for (int i = i_start; i < n_pts; i += stride, ++k) {
     float4 X;
     if (streaming) {
       X = Xnext;
@@ -1507,7 +1619,7 @@ __device__ __forceinline__ double device_linearize(const SolveArgs& a, int lvl, 
   // the set of the PREVIOUS linearize: zeroed after this iteration's barrier, next used two iterations from now, i.e.
   // with the next iteration's barrier in between (all sets are zero at the start of a level)
   unsigned* hprev = a.work.hist + (size_t) ((gs.hs + kHistSets - 1) % kHistSets) * kHistWords;
-  const int loss = FIX ? FIX : a.sp.loss, interp = FIX ? 0 : a.sp.interp;
+  const int loss = FIX ? (FIX & 0xff) : a.sp.loss, interp = FIX ? 0 : a.sp.interp;      // FIX bit 8: two points in flight on streaming levels (phase_residuals NB)
   const bool do_hist = (loss != 0x12) && (ss.delta > 1e-6f);      // ss.P was set by thread 0 together with the pose
   if (tid == 0) ss.lin.pad[1] = do_hist ? 1 : 0;                       // diagnosis: 0 = scale kept, 1 = radix select, 3 = bracketed select
   BP_PROF(PROF_OTHER);
@@ -1517,7 +1629,7 @@ __device__ __forceinline__ double device_linearize(const SolveArgs& a, int lvl, 
   br.inv_w = (br.hi > br.lo) ? (float) kSelBins / (br.hi - br.lo) : 0.0f;
   const bool multi = PEER && a.peer.nranks > 1 && !meta.replicated;      // (PEER = false: the single-GPU kernel carries no cross-rank code)
   const bool use_msg = BP_MSG_SELECT && br.on && !multi && nb <= 148;    // the median facts travel as flag-in-data messages: no grid barrier
-  phase_residuals<C, BLEND>(L, I, ss.P, a.work, hset, do_hist, br, tc, meta, scratch, sh, blk, nb, interp, use_msg ? gs.seq : 0u);
+  phase_residuals<C, BLEND, (FIX & 0x100) ? 2 : 1>(L, I, ss.P, a.work, hset, do_hist, br, tc, meta, scratch, sh, blk, nb, interp, use_msg ? gs.seq : 0u);
   BP_PROF(PROF_P1);
   float sigma = ss.scale;
   if (do_hist) {

@@ -8,7 +8,7 @@
 //                    uniqueness tests, parabola-like sub-pixel step in 1/16 px, filtered value (minDisparity - 1) elsewhere
 // (definitions: oracle/stereo_oracle.cc header; parity: tests/test_gpu_stereo.py against the oracle and cv2-4.13 golden vectors).
 //
-// Layout: one CTA = a 32-column x 16-row tile, blockDim = (32 columns, ndisp / 16 disparity groups); the pre-filtered left / right
+// Layout: one CTA = a 32-column x 32-row tile, blockDim = (32 columns, ndisp / 16 disparity groups); the pre-filtered left / right
 // tiles (+ window halo, + ndisp - 1 columns of the right image) are staged in shared memory once.  A thread owns one column and 16
 // disparities: it marches down the rows keeping the 16 window SADs in registers (add the entering row's horizontal sums,
 // subtract the leaving row's), and the per-pixel decisions (arg-min over all groups, uniqueness, the two neighbours of the
@@ -293,7 +293,7 @@ struct bpvo_b200_stereo {
   uint8_t* d_in[2] = {}; uint8_t* d_pre[2] = {};
   int16_t* d_d16 = nullptr; float* d_df = nullptr;
   size_t smem = 0;
-  int ty = 16, LWp = 0, RWp = 0;
+  int ty = 32, LWp = 0, RWp = 0;
   BmKernel kernel = nullptr;
   long long launches = 0;
 };
@@ -346,7 +346,7 @@ int bpvo_b200_stereo_create(bpvo_b200_stereo** out, int rows, int cols, const bp
   // tile plan: 32 columns x `ty` rows per CTA; row strides cover the aligned 32-bit strips the fast matcher loads
   const int nw = (p->SADWindowSize + 3) / 4, ng = p->numberOfDisparities / kDG;
   s->LWp = kTX + 4 * nw; s->RWp = kDG * ng + 4 * nw + kTX;
-  s->ty = 16;
+  s->ty = 32;
   if (const char* ev = getenv("BPVO_B200_STEREO_TILE_ROWS")) { const int v = atoi(ev); if (v >= 1 && v <= kMaxTileRows) s->ty = v; }
   const bool generic = p->minDisparity != 0 || (getenv("BPVO_B200_STEREO_GENERIC") && atoi(getenv("BPVO_B200_STEREO_GENERIC")) != 0);
   s->kernel = generic ? k_bm_match : pick_fast(nw);
