@@ -962,7 +962,9 @@ __device__ __forceinline__ float robust_weight(int loss, float r, float sigma_in
 // ---------------------------------------------------------------------------------------------
 // Returns, in thread k < 30, the CTA total of scalar k.  write_partials: also store it to W.partials (+ fence) for the
 // last-CTA fold of the host-driven kernels; the persistent kernel exchanges the totals itself (exchange_sums).
-template <int C>
+// NB = 2: on fully streaming levels two points per pass (all eight loads first, then the two accumulations in the usual order:
+// the sums are bit-identical to NB = 1); see phase_residuals.
+template <int C, int NB = 1>
 __device__ __forceinline__ double phase_reduce(const LevelTemplate& L, const Work& W, float sigma, int loss, float good_thr,
                                                const TplCache& tc, const TemplateMeta& m, LinShared& sh, int block, int nblocks, bool write_partials = true) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -973,7 +975,58 @@ __device__ __forceinline__ double phase_reduce(const LevelTemplate& L, const Wor
   const float is = 1.0f / m.s;
   const float w_invalid_good = (1.0f > good_thr) ? (float) C : 0.0f;   // invalid entries carry weight 1 in getWeights() (Q6)
   int ks = 0;
-  for (int i = first_point(block, nblocks); i < m.n; i += nblocks * kLinThreads, ++ks) {
+  int i_start = first_point(block, nblocks);
+  if (NB == 2 && BP_PREFETCH && tc.K > 1 && tc.pts == kTcNone && tc.f[TC_R] == kTcNone) {
+    const int stride = nblocks * kLinThreads;
+    auto accumulate = [&](const float4& X, const VecC<C>& r, const VecC<C>& gx, const VecC<C>& gy) {
+      float sxx = 0, sxy = 0, syy = 0, bx = 0, by = 0, e = 0, good = 0;
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const float w = robust_weight(loss, r.v[c], sigma_inv);
+        const float wr = w * r.v[c];
+        const float wgx = w * gx.v[c], wgy = w * gy.v[c];
+        sxx += wgx * gx.v[c]; sxy += wgx * gy.v[c]; syy += wgy * gy.v[c];
+        bx += wr * gx.v[c]; by += wr * gy.v[c]; e += wr * r.v[c];
+        good += (w > good_thr) ? 1.0f : 0.0f;
+      }
+      const float iz = 1.0f / X.z, iz2 = iz * iz;
+      const float xc = X.x - m.c1, yc = X.y - m.c2, zc = (X.z - m.c3) * iz;
+      float A[6], B[6];
+      A[0] = -X.x * yc * iz2;        B[0] = -X.y * yc * iz2 - zc;
+      A[1] = X.x * xc * iz2 + zc;    B[1] = X.y * xc * iz2;
+      A[2] = -yc * iz;               B[2] = xc * iz;
+      A[3] = iz * is;                B[3] = 0.0f;
+      A[4] = 0.0f;                   B[4] = iz * is;
+      A[5] = -X.x * iz2 * is;        B[5] = -X.y * iz2 * is;
+      int k = 0;
+#pragma unroll
+      for (int a = 0; a < 6; ++a) {
+        const float pa = sxx * A[a] + sxy * B[a], qa = sxy * A[a] + syy * B[a];
+#pragma unroll
+        for (int b = a; b < 6; ++b) acc[k++] += pa * A[b] + qa * B[b];
+      }
+#pragma unroll
+      for (int a = 0; a < 6; ++a) acc[21 + a] += bx * A[a] + by * B[a];
+      acc[27] += e; acc[28] += good; acc[29] += 1.0f;
+    };
+    int i = i_start;
+    for (; i + stride < m.n; i += 2 * stride, ks += 2) {
+      const int ia = i, ib = i + stride, ja = i + 4 * stride, jb = i + 5 * stride;
+      if (jb < m.n) {                         // two passes ahead into the L2
+        prefetch_l2(L.gx + (size_t) ja * kStride<C>); prefetch_l2(L.gy + (size_t) ja * kStride<C>); prefetch_l2(W.res + (size_t) ja * kStride<C>); prefetch_l2(L.pts + ja);
+        prefetch_l2(L.gx + (size_t) jb * kStride<C>); prefetch_l2(L.gy + (size_t) jb * kStride<C>); prefetch_l2(W.res + (size_t) jb * kStride<C>); prefetch_l2(L.pts + jb);
+        if ((threadIdx.x & 31) == 0) { prefetch_l2(W.valid + ja); prefetch_l2(W.valid + jb); }
+      }
+      const bool va = W.valid[ia] != 0, vb = W.valid[ib] != 0;
+      float4 Xa, Xb; VecC<C> ra, gxa, gya, rb, gxb, gyb;
+      if (va) { Xa = __ldg(L.pts + ia); gxa.load(L.gx + (size_t) ia * kStride<C>); gya.load(L.gy + (size_t) ia * kStride<C>); ra.load_plain(W.res + (size_t) ia * kStride<C>); }
+      if (vb) { Xb = __ldg(L.pts + ib); gxb.load(L.gx + (size_t) ib * kStride<C>); gyb.load(L.gy + (size_t) ib * kStride<C>); rb.load_plain(W.res + (size_t) ib * kStride<C>); }
+      if (va) accumulate(Xa, ra, gxa, gya); else acc[28] += w_invalid_good;
+      if (vb) accumulate(Xb, rb, gxb, gyb); else acc[28] += w_invalid_good;
+    }
+    i_start = i;
+  }
+  for (int i = i_start; i < m.n; i += nblocks * kLinThreads, ++ks) {
     if (BP_PREFETCH && tc.K > 1 && tc.pts == kTcNone && tc.f[TC_R] == kTcNone) {      // fully streaming level: two points ahead into the L2
       const int i2 = i + 2 * nblocks * kLinThreads;
       if (i2 < m.n) {
@@ -1603,6 +1656,20 @@ struct GridSync {
   int hs;              // histogram set of the next linearize (cycles through kHistSets)
 };
 
+// The two-points-in-flight variants of the streaming levels as out-of-line functions: their register allocation (two sets of
+// taps / gradients in flight) stays out of the persistent kernel's, which sits at the 255-register limit, and the call costs one
+// save / restore per phase, not per point.
+template <int C, int BLEND>
+__device__ __noinline__ void phase_residuals_stream2(const LevelTemplate& L, const LevelImage& I, const float* P, const Work& W, unsigned* hist1, bool do_hist,
+                                                     const Bracket& br, const TplCache& tc, const TemplateMeta& m, unsigned* scratch, LinShared& sh, int block, int nblocks) {
+  phase_residuals<C, BLEND, 2>(L, I, P, W, hist1, do_hist, br, tc, m, scratch, sh, block, nblocks, 0, 0u);
+}
+template <int C>
+__device__ __noinline__ double phase_reduce_stream2(const LevelTemplate& L, const Work& W, float sigma, int loss, float good_thr, const TplCache& tc,
+                                                    const TemplateMeta& m, LinShared& sh, int block, int nblocks) {
+  return phase_reduce<C, 2>(L, W, sigma, loss, good_thr, tc, m, sh, block, nblocks, false);
+}
+
 // Front part of one linearize inside the persistent kernel: residuals -> exact median / scale -> weights and normal equations
 // of this CTA's points.  Returns, in thread k < 30, the CTA total of scalar k (layout of phase_reduce).
 // FIX: 0 = loss function and interpolant are run-time parameters; 0x10 / 0x11 / 0x12 = that RobustFunction with linear interpolation
@@ -1629,7 +1696,9 @@ __device__ __forceinline__ double device_linearize(const SolveArgs& a, int lvl, 
   br.inv_w = (br.hi > br.lo) ? (float) kSelBins / (br.hi - br.lo) : 0.0f;
   const bool multi = PEER && a.peer.nranks > 1 && !meta.replicated;      // (PEER = false: the single-GPU kernel carries no cross-rank code)
   const bool use_msg = BP_MSG_SELECT && br.on && !multi && nb <= 148;    // the median facts travel as flag-in-data messages: no grid barrier
-  phase_residuals<C, BLEND, (FIX & 0x100) ? 2 : 1>(L, I, ss.P, a.work, hset, do_hist, br, tc, meta, scratch, sh, blk, nb, interp, use_msg ? gs.seq : 0u);
+  const bool stream2 = (FIX & 0x100) && BP_PREFETCH && tc.K > 1 && tc.pts == kTcNone && tc.f[TC_R] == kTcNone;      // level-uniform
+  if (stream2) phase_residuals_stream2<C, BLEND>(L, I, ss.P, a.work, hset, do_hist, br, tc, meta, scratch, sh, blk, nb);
+  else phase_residuals<C, BLEND>(L, I, ss.P, a.work, hset, do_hist, br, tc, meta, scratch, sh, blk, nb, interp, use_msg ? gs.seq : 0u);
   BP_PROF(PROF_P1);
   float sigma = ss.scale;
   if (do_hist) {
@@ -1708,7 +1777,8 @@ __device__ __forceinline__ double device_linearize(const SolveArgs& a, int lvl, 
     if (BP_BRACKET_THREAD == 0) __syncthreads();
     BP_FINE(39);
   }   // else: P4 reads only what the SAME thread wrote in P1, no grid-wide dependency
-  const double mine = phase_reduce<C>(L, a.work, sigma, loss, a.sp.good_threshold, tc, meta, sh, blk, nb, false);
+  const double mine = stream2 ? phase_reduce_stream2<C>(L, a.work, sigma, loss, a.sp.good_threshold, tc, meta, sh, blk, nb)
+                              : phase_reduce<C>(L, a.work, sigma, loss, a.sp.good_threshold, tc, meta, sh, blk, nb, false);
   BP_PROF(PROF_P4);
   sigma_out = sigma; do_hist_out = do_hist;
   return mine;
