@@ -1658,15 +1658,16 @@ struct GridSync {
 
 // The two-points-in-flight variants of the streaming levels as out-of-line functions: their register allocation (two sets of
 // taps / gradients in flight) stays out of the persistent kernel's, which sits at the 255-register limit, and the call costs one
-// save / restore per phase, not per point.
+// save / restore per phase, not per point.  Every structure goes in BY VALUE: a reference would force the caller's copy into
+// local memory for the whole kernel (measured: every level 35 % slower).
 template <int C, int BLEND>
-__device__ __noinline__ void phase_residuals_stream2(const LevelTemplate& L, const LevelImage& I, const float* P, const Work& W, unsigned* hist1, bool do_hist,
-                                                     const Bracket& br, const TplCache& tc, const TemplateMeta& m, unsigned* scratch, LinShared& sh, int block, int nblocks) {
+__device__ __noinline__ void phase_residuals_stream2(const LevelTemplate L, const LevelImage I, const float* P, const Work W, unsigned* hist1, bool do_hist,
+                                                     const Bracket br, const TplCache tc, const TemplateMeta m, unsigned* scratch, LinShared& sh, int block, int nblocks) {
   phase_residuals<C, BLEND, 2>(L, I, P, W, hist1, do_hist, br, tc, m, scratch, sh, block, nblocks, 0, 0u);
 }
 template <int C>
-__device__ __noinline__ double phase_reduce_stream2(const LevelTemplate& L, const Work& W, float sigma, int loss, float good_thr, const TplCache& tc,
-                                                    const TemplateMeta& m, LinShared& sh, int block, int nblocks) {
+__device__ __noinline__ double phase_reduce_stream2(const LevelTemplate L, const Work W, float sigma, int loss, float good_thr, const TplCache tc,
+                                                    const TemplateMeta m, LinShared& sh, int block, int nblocks) {
   return phase_reduce<C, 2>(L, W, sigma, loss, good_thr, tc, m, sh, block, nblocks, false);
 }
 
