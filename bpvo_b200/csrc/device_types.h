@@ -170,6 +170,8 @@ struct SolveArgs {
   int* aborted_out;      // receives the rank-wide abort word (an in-kernel wait expired)
   long long* prof;       // optional: per-phase cycle counters of CTA 0 (nullptr = off)
   long long* prof_lvl;   // optional: the same, split by pyramid level [kMaxLevels][16]
+  int lvl_first, lvl_last;   // pyramid levels this launch walks, coarse to fine (normally num_levels - 1 .. max_test_level)
+  int chain;             // 1 = second launch of a solve split by level: the start pose is *T_out, the evaluation count adds to *num_fun_evals
   unsigned seq_base;     // first sequence number of this launch's exchanges (monotonic across launches of a ctx)
   unsigned long long timeout_ns;   // every in-kernel wait gives up this long after the launch started (AbortCtl)
   PeerArgs peer;

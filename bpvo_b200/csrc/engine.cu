@@ -934,9 +934,11 @@ struct SolveOverride {
 };
 
 template <int C, int BLEND, bool PEER, int FIX>
-static int launch_estimate_pose_t(bpvo_b200_ctx* c, const bpvo_b200_frame* ref, const bpvo_b200_frame* cur, const M44& T_init, const SolveOverride* ov) {
+static int launch_estimate_pose_t(bpvo_b200_ctx* c, const bpvo_b200_frame* ref, const bpvo_b200_frame* cur, const M44& T_init, const SolveOverride* ov,
+                                  int lvl_first = -1, int lvl_last = -1, int chain = 0) {
   SolveArgs a;
   memset(&a, 0, sizeof(a));
+  a.lvl_first = lvl_first >= 0 ? lvl_first : c->L - 1; a.lvl_last = lvl_last >= 0 ? lvl_last : c->p.maxTestLevel; a.chain = chain;
   if (ov) a.dbg = ov->dbg;
   if (c->d_trace && !(ov && ov->dbg.n > 0)) { a.dbg.trace = c->d_trace; a.dbg.trace_cap = kTraceRows; a.dbg.trace_rows = c->d_trace_rows; }
   for (int l = c->p.maxTestLevel; l < c->L; ++l) {
@@ -1021,7 +1023,20 @@ static int launch_estimate_pose(bpvo_b200_ctx* c, const bpvo_b200_frame* ref, co
         } else {
           cudaGetLastError();
         }
-        if (streams) return launch_estimate_pose_t<C, 0, false, BPVO_B200_TUKEY | 0x100>(c, ref, cur, T_init, ov);
+        if (streams) {
+          // the solve split by level: the cached levels in the usual kernel, then the streaming level in its own instantiation,
+          // which starts from the pose the first launch left on the device
+          const int fine = c->p.maxTestLevel;
+          if (ov && ov->dbg.n > 0)           // parity hook (one level): the kernel that level would run in
+            return ov->dbg.level == fine ? launch_estimate_pose_t<C, 0, false, BPVO_B200_TUKEY | 0x100>(c, ref, cur, T_init, ov)
+                                         : launch_estimate_pose_t<C, 0, false, BPVO_B200_TUKEY>(c, ref, cur, T_init, ov);
+          if (c->L - 1 > fine) {
+            const int rc = launch_estimate_pose_t<C, 0, false, BPVO_B200_TUKEY>(c, ref, cur, T_init, ov, c->L - 1, fine + 1, 0);
+            if (rc != BPVO_B200_OK) return rc;
+            return launch_estimate_pose_t<C, 0, false, BPVO_B200_TUKEY | 0x100>(c, ref, cur, T_init, ov, fine, fine, 1);
+          }
+          return launch_estimate_pose_t<C, 0, false, BPVO_B200_TUKEY | 0x100>(c, ref, cur, T_init, ov);
+        }
         return launch_estimate_pose_t<C, 0, false, BPVO_B200_TUKEY>(c, ref, cur, T_init, ov);
       }
       if (c->p.lossFunction == BPVO_B200_HUBER) return launch_estimate_pose_t<C, 0, false, BPVO_B200_HUBER>(c, ref, cur, T_init, ov);

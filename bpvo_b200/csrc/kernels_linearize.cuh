@@ -1656,15 +1656,12 @@ struct GridSync {
   int hs;              // histogram set of the next linearize (cycles through kHistSets)
 };
 
-// The two-points-in-flight variants of the streaming levels as out-of-line functions: their register allocation (two sets of
-// taps / gradients in flight) stays out of the persistent kernel's, which sits at the 255-register limit, and the call costs one
-// save / restore per phase, not per point.  Every structure goes in BY VALUE: a reference would force the caller's copy into
-// local memory for the whole kernel (measured: every level 35 % slower).
-template <int C, int BLEND>
-__device__ __noinline__ void phase_residuals_stream2(const LevelTemplate L, const LevelImage I, const float* P, const Work W, unsigned* hist1, bool do_hist,
-                                                     const Bracket br, const TplCache tc, const TemplateMeta m, unsigned* scratch, LinShared& sh, int block, int nblocks) {
-  phase_residuals<C, BLEND, 2>(L, I, P, W, hist1, do_hist, br, tc, m, scratch, sh, block, nblocks, 0, 0u);
-}
+// The two-points-in-flight reduce phase of the streaming levels as an out-of-line function: its register allocation (30
+// accumulators + two sets of gradients / residuals in flight) stays out of the persistent kernel's, which sits at the 255-register
+// limit, and the call costs one save / restore per phase, not per point.  Every structure goes in BY VALUE: a reference would force
+// the caller's copy into local memory for the whole kernel.  Even so a kernel containing the call runs its CACHED levels a third
+// slower (the long-lived state is spilled around the call site): the instantiation that carries it (FIX bit 8) is only ever
+// launched for the streaming level itself -- the host splits the solve by level (SolveArgs::chain).
 template <int C>
 __device__ __noinline__ double phase_reduce_stream2(const LevelTemplate L, const Work W, float sigma, int loss, float good_thr, const TplCache tc,
                                                     const TemplateMeta m, LinShared& sh, int block, int nblocks) {
@@ -1698,8 +1695,7 @@ __device__ __forceinline__ double device_linearize(const SolveArgs& a, int lvl, 
   const bool multi = PEER && a.peer.nranks > 1 && !meta.replicated;      // (PEER = false: the single-GPU kernel carries no cross-rank code)
   const bool use_msg = BP_MSG_SELECT && br.on && !multi && nb <= 148;    // the median facts travel as flag-in-data messages: no grid barrier
   const bool stream2 = (FIX & 0x100) && BP_PREFETCH && tc.K > 1 && tc.pts == kTcNone && tc.f[TC_R] == kTcNone;      // level-uniform
-  if (stream2) phase_residuals_stream2<C, BLEND>(L, I, ss.P, a.work, hset, do_hist, br, tc, meta, scratch, sh, blk, nb);
-  else phase_residuals<C, BLEND>(L, I, ss.P, a.work, hset, do_hist, br, tc, meta, scratch, sh, blk, nb, interp, use_msg ? gs.seq : 0u);
+  phase_residuals<C, BLEND, (FIX & 0x100) ? 2 : 1>(L, I, ss.P, a.work, hset, do_hist, br, tc, meta, scratch, sh, blk, nb, interp, use_msg ? gs.seq : 0u);
   BP_PROF(PROF_P1);
   float sigma = ss.scale;
   if (do_hist) {
@@ -1940,13 +1936,13 @@ __global__ void __launch_bounds__(kLinThreads, 1) k_estimate_pose(const __grid_c
     BP_FINE_INIT(a.prof);
   }
   if (tid == 0) {
-    ss.T = a.T_init; ss.fx_bad = 0; ss.dpn = 0.0f; ss.gn = 0.0f;
+    ss.T = a.chain ? *a.T_out : a.T_init; ss.fx_bad = 0; ss.dpn = 0.0f; ss.gn = 0.0f;
     unsigned long long t0; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
     ss.abort.flag = 0; ss.abort.deadline = t0 + a.timeout_ns; ss.abort.global_flag = reinterpret_cast<int*>(gs.counter + 1);
   }
   __syncthreads();
   const float sqrt_eps = sqrtf(FLT_EPSILON);
-  for (int lvl = a.sp.num_levels - 1; lvl >= a.sp.max_test_level; --lvl) {
+  for (int lvl = a.lvl_first; lvl >= a.lvl_last; --lvl) {
     if (a.dbg.n > 0 && lvl != a.dbg.level) continue;                           // parity hook: one level only
     const LevelTemplate& L = a.tmpl[lvl];
     // PoseEstimatorBase::run (pose_estimator_base.h:324-407); all control flow below is CTA-uniform AND grid-uniform
@@ -2097,7 +2093,8 @@ __global__ void __launch_bounds__(kLinThreads, 1) k_estimate_pose(const __grid_c
     if (tid < 64) a.prof[tid] += prof_smem()[tid];
   }
   if (blockIdx.x == 0 && tid == 0) {
-    *a.T_out = ss.T; *a.num_fun_evals = total_evals; *a.aborted_out = ss.abort.flag | *(volatile int*) ss.abort.global_flag;
+    *a.T_out = ss.T; *a.num_fun_evals = total_evals + (a.chain ? *a.num_fun_evals : 0);
+    *a.aborted_out = ss.abort.flag | *(volatile int*) ss.abort.global_flag | (a.chain ? *a.aborted_out : 0);
     *a.work.out = ss.lin;
     a.work.scale->scale = ss.scale; a.work.scale->delta = ss.delta;
   }
