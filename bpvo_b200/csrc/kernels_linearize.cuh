@@ -628,21 +628,55 @@ __device__ __forceinline__ void phase_residuals(const LevelTemplate& L, const Le
   BP_FINE(19);
 }
 
+// One pass over this CTA's residuals for the select phases.  Residuals in the shared-memory cache: one point per step.
+// Residuals in global memory (streaming levels, host-driven kernels): FOUR points per step, flags and vectors loaded before any
+// is used -- at 8 warps per SM a one-load-per-step loop is bound by memory latency (1080p dense level 0: ~110 us per pass
+// against ~15 us of bandwidth time).  f(r) sees the residual vector of every valid point; the order does not matter (counting).
+// (MLP = 1 keeps the one-point loop everywhere: the persistent kernel of the cached workloads sits at the register limit.)
+template <int C, int MLP, class F>
+__device__ __forceinline__ void for_each_valid_residual(const Work& W, const TplCache& tc, int n_pts, int block, int nblocks, F&& f) {
+  const int stride = nblocks * kLinThreads;
+  if (MLP == 1) {
+    int k = 0;
+    for (int i = first_point(block, nblocks); i < n_pts; i += stride, ++k) {
+      if (!((tc.f[TC_R] != kTcNone) ? tc_valid(tc, k) : W.valid[i])) continue;
+      VecC<C> r;
+      if (tc.f[TC_R] != kTcNone) tc_get<C>(tc, k, TC_R, r); else r.load_plain(W.res + (size_t) i * kStride<C>);
+      f(r);
+    }
+    return;
+  }
+  if (tc.f[TC_R] != kTcNone) {
+    int k = 0;
+    for (int i = first_point(block, nblocks); i < n_pts; i += stride, ++k) {
+      if (!tc_valid(tc, k)) continue;
+      VecC<C> r; tc_get<C>(tc, k, TC_R, r);
+      f(r);
+    }
+    return;
+  }
+  for (int i = first_point(block, nblocks); i < n_pts; i += 4 * stride) {
+    bool v[4]; VecC<C> r[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { const int j = i + q * stride; v[q] = j < n_pts && W.valid[j] != 0; }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) if (v[q]) r[q].load_plain(W.res + (size_t) (i + q * stride) * kStride<C>);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) if (v[q]) f(r[q]);
+  }
+}
+
 // level-1 histogram of |r| as a separate pass (on-device loop, only after a bracket miss)
-template <int C>
+template <int C, int MLP = 1>
 __device__ __forceinline__ void phase_hist1(const Work& W, unsigned* __restrict__ hist1, const TplCache& tc, const TemplateMeta& m,
                                             LinShared& sh, int block, int nblocks) {
   const int tid = threadIdx.x;
   for (int b = tid; b < kHist1Bins; b += kLinThreads) sh.hist[b] = 0;
   __syncthreads();
-  int k = 0;
-  for (int i = first_point(block, nblocks); i < m.n; i += nblocks * kLinThreads, ++k) {
-    if (!((tc.f[TC_R] != kTcNone) ? tc_valid(tc, k) : W.valid[i])) continue;
-    VecC<C> r;
-    if (tc.f[TC_R] != kTcNone) tc_get<C>(tc, k, TC_R, r); else r.load_plain(W.res + (size_t) i * kStride<C>);
+  for_each_valid_residual<C, MLP>(W, tc, m.n, block, nblocks, [&](const VecC<C>& r) {
 #pragma unroll
     for (int c = 0; c < C; ++c) atomicAdd(&sh.hist[__float_as_uint(fabsf(r.v[c])) >> 20], 1u);
-  }
+  });
   __syncthreads();
   for (int b = tid; b < kHist1Bins; b += kLinThreads) { const unsigned v = sh.hist[b]; if (v) atomicAdd(hist1 + b, v); }
 }
@@ -651,7 +685,7 @@ __device__ __forceinline__ void phase_hist1(const Work& W, unsigned* __restrict_
 // P2 / P3: refine the radix select by 11 then 9 more bits.  level == 2: input hist1, output hist2 sets;
 // level == 3: input hist2 sets, output hist3 sets.  slot 0 = rank n/2-1 ("lo"), slot 1 = rank n/2 ("hi").
 // ---------------------------------------------------------------------------------------------
-template <int C, int LEVEL>
+template <int C, int LEVEL, int MLP = 1>
 __device__ __forceinline__ void phase_select(const LevelTemplate& L, const Work& W, unsigned* __restrict__ hset, Sel* __restrict__ sel,
                                              const TplCache& tc, const TemplateMeta& m, LinShared& sh, int block, int nblocks) {
   const int tid = threadIdx.x;
@@ -683,12 +717,7 @@ __device__ __forceinline__ void phase_select(const LevelTemplate& L, const Work&
   __syncthreads();
   constexpr int SHIFT_MATCH = (LEVEL == 2) ? 20 : 9;
   constexpr int SHIFT_BIN = (LEVEL == 2) ? 9 : 0;
-  const int n_pts = m.n;
-  int k = 0;
-  for (int i = first_point(block, nblocks); i < n_pts; i += nblocks * kLinThreads, ++k) {
-    if (!((tc.f[TC_R] != kTcNone) ? tc_valid(tc, k) : W.valid[i])) continue;
-    VecC<C> r;
-    if (tc.f[TC_R] != kTcNone) tc_get<C>(tc, k, TC_R, r); else r.load_plain(W.res + (size_t) i * kStride<C>);
+  for_each_valid_residual<C, MLP>(W, tc, m.n, block, nblocks, [&](const VecC<C>& r) {
 #pragma unroll
     for (int c = 0; c < C; ++c) {
       const unsigned bits = __float_as_uint(fabsf(r.v[c]));
@@ -696,7 +725,7 @@ __device__ __forceinline__ void phase_select(const LevelTemplate& L, const Work&
       if (pre == pa) atomicAdd(&sh.hist[bin], 1u);
       if (pre == pb) atomicAdd(&sh.hist[NBOUT + bin], 1u);
     }
-  }
+  });
   __syncthreads();
   unsigned* out = (LEVEL == 2) ? hist2 : hist3;
   for (int b = tid; b < 2 * NBOUT; b += kLinThreads) { const unsigned v = sh.hist[b]; if (v) atomicAdd(out + b, v); }
@@ -1176,7 +1205,7 @@ template <int C, int LEVEL> __global__ void __launch_bounds__(kLinThreads, 1) k_
   __shared__ LinShared sh;
   const bool do_hist = (a.loss != 0x12) && (a.work.scale->delta > 1e-6f);
   if (!do_hist) return;
-  phase_select<C, LEVEL>(a.tmpl, a.work, a.hset, a.sel, tpl_cache_off(), *a.tmpl.meta, sh, blockIdx.x, gridDim.x);
+  phase_select<C, LEVEL, 4>(a.tmpl, a.work, a.hset, a.sel, tpl_cache_off(), *a.tmpl.meta, sh, blockIdx.x, gridDim.x);
 }
 // point-sharded mode: the last CTA leaves this rank's 30 fp64 sums in a.sums (all-reduced by the host over NCCL),
 // k_finalize_sums then builds the LinOut every rank sees identically.
@@ -1694,6 +1723,7 @@ __device__ __forceinline__ double device_linearize(const SolveArgs& a, int lvl, 
   br.inv_w = (br.hi > br.lo) ? (float) kSelBins / (br.hi - br.lo) : 0.0f;
   const bool multi = PEER && a.peer.nranks > 1 && !meta.replicated;      // (PEER = false: the single-GPU kernel carries no cross-rank code)
   const bool use_msg = BP_MSG_SELECT && br.on && !multi && nb <= 148;    // the median facts travel as flag-in-data messages: no grid barrier
+  constexpr int SEL_MLP = (FIX & 0x100) ? 4 : 1;      // loads in flight per thread in the select passes over global residuals
   const bool stream2 = (FIX & 0x100) && BP_PREFETCH && tc.K > 1 && tc.pts == kTcNone && tc.f[TC_R] == kTcNone;      // level-uniform
   phase_residuals<C, BLEND, (FIX & 0x100) ? 2 : 1>(L, I, ss.P, a.work, hset, do_hist, br, tc, meta, scratch, sh, blk, nb, interp, use_msg ? gs.seq : 0u);
   BP_PROF(PROF_P1);
@@ -1737,14 +1767,14 @@ __device__ __forceinline__ double device_linearize(const SolveArgs& a, int lvl, 
       sigma = scale_from_median(n, med);
       BP_PROF(PROF_SCALE);
     } else {
-      if (br.on) { phase_hist1<C>(a.work, hset, tc, meta, sh, blk, nb); grid_barrier(gs.counter, gs.epoch, nb, &ss.abort); }   // bracket missed: build the histogram now
+      if (br.on) { phase_hist1<C, SEL_MLP>(a.work, hset, tc, meta, sh, blk, nb); grid_barrier(gs.counter, gs.epoch, nb, &ss.abort); }   // bracket missed: build the histogram now
       if (multi) xrank_hist_allreduce(a.peer, gs.xseq, hset, kHist1Bins, sh, gs.counter, gs.epoch, nb, &ss.abort);
-      phase_select<C, 2>(L, a.work, hset, sel, tc, meta, sh, blk, nb);
+      phase_select<C, 2, SEL_MLP>(L, a.work, hset, sel, tc, meta, sh, blk, nb);
       BP_PROF(PROF_P2);
       grid_barrier(gs.counter, gs.epoch, nb, &ss.abort);
       if (multi) xrank_hist_allreduce(a.peer, gs.xseq, hset + kHist1Bins, 2 * kHist2Bins, sh, gs.counter, gs.epoch, nb, &ss.abort);
       BP_PROF(PROF_SYNC2);
-      phase_select<C, 3>(L, a.work, hset, sel, tc, meta, sh, blk, nb);
+      phase_select<C, 3, SEL_MLP>(L, a.work, hset, sel, tc, meta, sh, blk, nb);
       BP_PROF(PROF_P3);
       grid_barrier(gs.counter, gs.epoch, nb, &ss.abort);
       if (multi) xrank_hist_allreduce(a.peer, gs.xseq, hset + kHist1Bins + 2 * kHist2Bins, 2 * kHist3Bins, sh, gs.counter, gs.epoch, nb, &ss.abort);
