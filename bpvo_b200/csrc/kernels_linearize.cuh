@@ -1723,7 +1723,7 @@ __device__ __forceinline__ double device_linearize(const SolveArgs& a, int lvl, 
   br.inv_w = (br.hi > br.lo) ? (float) kSelBins / (br.hi - br.lo) : 0.0f;
   const bool multi = PEER && a.peer.nranks > 1 && !meta.replicated;      // (PEER = false: the single-GPU kernel carries no cross-rank code)
   const bool use_msg = BP_MSG_SELECT && br.on && !multi && nb <= 148;    // the median facts travel as flag-in-data messages: no grid barrier
-  constexpr int SEL_MLP = (FIX & 0x100) ? 4 : 1;      // loads in flight per thread in the select passes over global residuals
+  constexpr int SEL_MLP = 1;      // loads in flight per thread in the select passes (4 was measured SLOWER inside this kernel, even in the streaming instantiation: 14.6 -> 21.4 us; the host-driven k_select gains 3 % from it)
   const bool stream2 = (FIX & 0x100) && BP_PREFETCH && tc.K > 1 && tc.pts == kTcNone && tc.f[TC_R] == kTcNone;      // level-uniform
   phase_residuals<C, BLEND, (FIX & 0x100) ? 2 : 1>(L, I, ss.P, a.work, hset, do_hist, br, tc, meta, scratch, sh, blk, nb, interp, use_msg ? gs.seq : 0u);
   BP_PROF(PROF_P1);
