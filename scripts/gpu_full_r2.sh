@@ -20,9 +20,9 @@ timeout 300 python scripts/profile_stereo.py kitti > gpurun_out/${TAG}_stereo_ki
 timeout 300 python scripts/profile_stereo.py 1080p > gpurun_out/${TAG}_stereo_1080p.json 2>> gpurun_out/${TAG}_stereo.err
 BPVO_B200_NO_STREAM2=1 timeout 300 python scripts/profile_kernels.py --workload 1080p_dense > gpurun_out/${TAG}_kernels_1080p_dense_one_launch.json 2> gpurun_out/${TAG}_kernels_1080p_dense_one_launch.err
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file gpurun_out/${TAG}_launches.csv \
-    python bench.py --steps 6 --warmup 3 --no-cpu-baseline --no-dense --no-throughput > gpurun_out/${TAG}_ncu_bench.log 2>&1
+    python bench.py --steps 6 --warmup 3 --no-cpu-baseline --no-dense --no-throughput --no-stereo > gpurun_out/${TAG}_ncu_bench.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_estimate_pose -s 3 -c 1 -o gpurun_out/${TAG}_k_estimate_pose \
-    python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-dense --no-throughput > gpurun_out/${TAG}_ncu_full.log 2>&1
+    python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-dense --no-throughput --no-stereo > gpurun_out/${TAG}_ncu_full.log 2>&1
 ncu -i gpurun_out/${TAG}_k_estimate_pose.ncu-rep --page details > gpurun_out/${TAG}_k_estimate_pose_details.txt 2>&1
 ncu -i gpurun_out/${TAG}_k_estimate_pose.ncu-rep --page raw --csv > gpurun_out/${TAG}_k_estimate_pose_raw.csv 2>&1
 # the fused kernel where it is HBM bound: one solve of the dense 1080p workload (all five levels in the one launch)
