@@ -348,7 +348,8 @@ int bpvo_b200_stereo_create(bpvo_b200_stereo** out, int rows, int cols, const bp
 int bpvo_b200_stereo_destroy(bpvo_b200_stereo* s);
 /* StereoAlgorithm::run (stereo_algorithm.cc:163-166).  left / right: rows x cols u8, row-major, host or device memory.
  * dmap: rows x cols f32 disparities in pixels (invalid = minDisparity - 1); disp16: OpenCV's CV_16S map (4 fractional bits);
- * host or device memory, either may be NULL.  Returns when the results are in place. */
+ * host or device memory, either may be NULL.  Returns when the results are in place.  The work runs on the object's own
+ * stream: device-resident inputs must be complete when the call is made (synchronize the producing stream first). */
 int bpvo_b200_stereo_run(bpvo_b200_stereo* s, const uint8_t* left, const uint8_t* right, float* dmap, int16_t* disp16);
 /* StereoAlgorithm::getInvalidValue (stereo_algorithm.cc:168) */
 float bpvo_b200_stereo_invalid_value(const bpvo_b200_stereo* s);
