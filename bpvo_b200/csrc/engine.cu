@@ -1016,8 +1016,10 @@ static int launch_estimate_pose(bpvo_b200_ctx* c, const bpvo_b200_frame* ref, co
         if (!getenv("BPVO_B200_NO_STREAM2") && cudaEventQuery(ref->meta_ready) == cudaSuccess) {
           int grid = std::min(c->sm_count, kMaxGrid);
           if (c->solver_ctas > 0) grid = std::min(grid, c->solver_ctas);
+          if (ov && ov->grid > 0) grid = std::min(grid, ov->grid);
           const int n = ref->h_meta[c->p.maxTestLevel].n;
-          const int cache_bytes = std::max(0, ((c->smem_optin - 24 * 1024 - kScratchBytes) / 1024) * 1024);
+          int cache_bytes = std::max(0, ((c->smem_optin - 24 * 1024 - kScratchBytes) / 1024) * 1024);
+          if (ov && ov->cache_bytes >= 0) cache_bytes = std::min(cache_bytes, ov->cache_bytes);      // (the parity hook can force streaming at small sizes)
           const TplCache plan = tpl_cache_plan<C>((unsigned) kScratchBytes, cache_bytes, (n + grid * kLinThreads - 1) / (grid * kLinThreads));
           streams = plan.K > 1 && plan.pts == kTcNone && plan.f[TC_R] == kTcNone;
         } else {

@@ -109,6 +109,29 @@ def test_device_linearize_1080p_dense_level0(oracle):
     _cmp_linearize(ctx, gref, gcur, oref, ocur, oest, 0, poses[0], True, 3e-4)
 
 
+def test_split_solve_equals_one_launch(oracle, monkeypatch):
+    """dense 1080p: the finest level does not fit the shared-memory cache, so the solve is split by level -- the cached levels in
+    the usual kernel, level 0 in the instantiation with two points per thread in flight, chained through the pose on the device.
+    Same arithmetic per point, same summation order: pose, statistics and evaluation counts are IDENTICAL to the one-launch
+    solve (BPVO_B200_NO_STREAM2), and so are the residuals / weights left behind by the last evaluation"""
+    p = make_params("bitplanes", 5, "tukey", nonMaxSuppRadius=-1)
+    sc, ctx, gref, gcur, oref, ocur = _pair("1080p", p, oracle)
+    T0 = np.eye(4, dtype=np.float32)
+    launches0 = ctx.counters()["launches"]
+    Ta, sa, na = ctx.estimatePose(gref, gcur, T0)
+    ra, wa, eva = np.array(ctx.getResiduals()), np.array(ctx.getWeights()), ctx.last_level_evals()
+    launches_split = ctx.counters()["launches"] - launches0
+    monkeypatch.setenv("BPVO_B200_NO_STREAM2", "1")
+    Tb, sb, nb = ctx.estimatePose(gref, gcur, T0)
+    rb, wb, evb = np.array(ctx.getResiduals()), np.array(ctx.getWeights()), ctx.last_level_evals()
+    launches_one = ctx.counters()["launches"] - launches0 - launches_split
+    assert launches_split == launches_one + 1                        # one more (cooperative) launch, nothing else
+    assert np.array_equal(Ta, Tb) and na == nb and list(eva) == list(evb)
+    for l in range(5):
+        assert (sa[l].numIterations, sa[l].status, sa[l].finalError) == (sb[l].numIterations, sb[l].status, sb[l].finalError), l
+    assert np.array_equal(ra, rb) and np.array_equal(wa, wb)
+
+
 def _oracle_vs_gpu_solve(kind, p, oracle, pose_tol=1e-4):
     sc, ctx, gref, gcur, oref, ocur = _pair(kind, p, oracle, use_rcp=1)
     oest = oracle.Estimator(ctx.params)
