@@ -446,7 +446,11 @@ int bpvo_b200_vo_add_stereo_frame(bpvo_b200_vo* vo, bpvo_b200_stereo* s, const u
   if (!vo || !s) return bp_fail(BPVO_B200_ERR_INVALID_ARG, "null argument");
   const int rc = bpvo_b200_stereo_run(s, left, right, s->d_df, nullptr);
   if (rc != BPVO_B200_OK) return rc;
-  return bpvo_b200_vo_add_frame(vo, left, s->d_df, result);
+  // the left image is on the device already (staged by the run above unless the caller's pointer was a device pointer): addFrame
+  // takes that copy, one upload per image instead of two.  Both calls return with their streams drained, so the staging buffer is
+  // free again before the next pair overwrites it.
+  const uint8_t* left_dev = device_readable(left) ? left : s->d_in[0];
+  return bpvo_b200_vo_add_frame(vo, left_dev, s->d_df, result);
 }
 
 }  // extern "C"
