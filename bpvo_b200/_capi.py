@@ -118,6 +118,7 @@ def _signatures():
         "bpvo_b200_stereo_destroy": (C.c_int, [vp]),
         "bpvo_b200_stereo_run": (C.c_int, [vp, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
         "bpvo_b200_stereo_invalid_value": (C.c_float, [vp]),
+        "bpvo_b200_stereo_filtered_value": (C.c_float, [vp]),
         "bpvo_b200_stereo_get_prefiltered": (C.c_int, [vp, C.c_void_p, C.c_void_p]),
         "bpvo_b200_stereo_last_kernel_ms": (C.c_int, [vp, fp]),
         "bpvo_b200_stereo_launches": (C.c_longlong, [vp]),

@@ -11,6 +11,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 #include <string>
 #include <vector>
 
@@ -986,11 +987,11 @@ static int launch_estimate_pose_t(bpvo_b200_ctx* c, const bpvo_b200_frame* ref, 
   if (ov && ov->cache_bytes >= 0) cache_bytes = std::min(cache_bytes, ov->cache_bytes);
   const size_t dyn = (size_t) kScratchBytes + (size_t) cache_bytes;
   {                                      // the attribute is per kernel instantiation and per device (a process may drive several of either)
-    static size_t configured[64] = {};   // (benign if two host threads race here: at worst the call is repeated)
+    static std::atomic<size_t> configured[64];      // (two host threads may both make the call: harmless)
     const int dev = c->p.device_id & 63;
-    if (configured[dev] != dyn) {
+    if (configured[dev].load(std::memory_order_relaxed) != dyn) {
       CUDA_TRY(cudaFuncSetAttribute((const void*) k_estimate_pose<C, BLEND, PEER, FIX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) dyn));
-      configured[dev] = dyn;
+      configured[dev].store(dyn, std::memory_order_relaxed);
     }
   }
   void* args[] = {&a, &sel, &cache_bytes};

@@ -29,7 +29,8 @@ class StereoAlgorithm {
   void run(const uint8_t* left, const uint8_t* right, float* dmap) {
     if (bpvo_b200_stereo_run(_s, left, right, dmap, nullptr) != BPVO_B200_OK) throw Error(bpvo_b200_last_error());
   }
-  float getInvalidValue() const { return bpvo_b200_stereo_invalid_value(_s); }
+  float getInvalidValue() const { return bpvo_b200_stereo_invalid_value(_s); }      // the reference's short(minDisparity - 1) / 16.0f
+  float filteredValue() const { return bpvo_b200_stereo_filtered_value(_s); }       // what invalid pixels hold in dmap: minDisparity - 1
   ImageSize imageSize() const { return _size; }
   bpvo_b200_stereo* handle() const { return _s; }
 

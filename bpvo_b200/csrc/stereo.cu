@@ -419,8 +419,11 @@ int bpvo_b200_stereo_run(bpvo_b200_stereo* s, const uint8_t* left, const uint8_t
   return BPVO_B200_OK;
 }
 
-// StereoAlgorithm::getInvalidValue (utils/stereo_algorithm.cc:138-146, 168)
-float bpvo_b200_stereo_invalid_value(const bpvo_b200_stereo* s) { return s ? (float) (int16_t) (s->p.minDisparity - 1) * 16.0f / 16.0f : -1.0f; }
+// StereoAlgorithm::getInvalidValue (utils/stereo_algorithm.cc:138-146, 168): short(minDisparity - 1) / 16.0f, as the reference
+// computes it -- which is NOT the value invalid pixels carry in the map (the reference divides the already descaled marker by 16
+// once more: -0.0625 for minDisparity 0).  The marker itself: bpvo_b200_stereo_filtered_value = minDisparity - 1.
+float bpvo_b200_stereo_invalid_value(const bpvo_b200_stereo* s) { return s ? (float) (int16_t) (s->p.minDisparity - 1) / 16.0f : -0.0625f; }
+float bpvo_b200_stereo_filtered_value(const bpvo_b200_stereo* s) { return s ? (float) (s->p.minDisparity - 1) : -1.0f; }
 
 // the XSOBEL pre-filtered pair of the last run (parity dump): rows x cols u8 each, host pointers
 int bpvo_b200_stereo_get_prefiltered(bpvo_b200_stereo* s, uint8_t* left, uint8_t* right) {

@@ -65,7 +65,13 @@ class StereoAlgorithm:
         _check(self._lib.bpvo_b200_stereo_run(self.h, left_ptr, right_ptr, dmap_ptr or None, disp16_ptr or None))
 
     def getInvalidValue(self) -> float:
+        """float getInvalidValue() const, with the reference's arithmetic (stereo_algorithm.cc:138-146): short(minDisparity - 1) / 16,
+        i.e. -0.0625 by default -- NOT what invalid pixels hold in the map; that is filteredValue()"""
         return float(self._lib.bpvo_b200_stereo_invalid_value(self.h))
+
+    def filteredValue(self) -> float:
+        """the value invalid pixels carry in the disparity map: minDisparity - 1"""
+        return float(self._lib.bpvo_b200_stereo_filtered_value(self.h))
 
     def prefiltered(self):
         a = np.empty((self.rows, self.cols), np.uint8); b = np.empty_like(a)

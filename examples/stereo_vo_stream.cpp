@@ -38,7 +38,7 @@ int main(int argc, char** argv) {
       stereo.run(left.data(), right.data(), dmap.data());
       bpvo_b200::Result r = vo.addFrame(left.data(), dmap.data());
       double sum = 0; size_t invalid = 0;
-      for (float d : dmap) { if (d == stereo.getInvalidValue()) ++invalid; else sum += d; }
+      for (float d : dmap) { if (d == stereo.filteredValue()) ++invalid; else sum += d; }
       std::printf("%d %d %.17g %zu", (int) r.isKeyFrame, r.numFunEvals, sum, invalid);
       for (int i = 0; i < 16; ++i) std::printf(" %a", r.pose.data()[i]);
       std::printf("\n");

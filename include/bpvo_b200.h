@@ -351,8 +351,10 @@ int bpvo_b200_stereo_destroy(bpvo_b200_stereo* s);
  * host or device memory, either may be NULL.  Returns when the results are in place.  The work runs on the object's own
  * stream: device-resident inputs must be complete when the call is made (synchronize the producing stream first). */
 int bpvo_b200_stereo_run(bpvo_b200_stereo* s, const uint8_t* left, const uint8_t* right, float* dmap, int16_t* disp16);
-/* StereoAlgorithm::getInvalidValue (stereo_algorithm.cc:168) */
+/* StereoAlgorithm::getInvalidValue (stereo_algorithm.cc:138-146, 168) with the reference's arithmetic: short(minDisparity - 1) / 16.0f
+ * (-0.0625 for minDisparity 0) -- not the value invalid pixels carry in dmap, which is filtered_value = minDisparity - 1 */
 float bpvo_b200_stereo_invalid_value(const bpvo_b200_stereo* s);
+float bpvo_b200_stereo_filtered_value(const bpvo_b200_stereo* s);
 /* parity dump: the XSOBEL pre-filtered pair of the last run (rows x cols u8 each, host memory, either may be NULL) */
 int bpvo_b200_stereo_get_prefiltered(bpvo_b200_stereo* s, uint8_t* left, uint8_t* right);
 /* device time of the last run's kernels (CUDA events on the object's stream); kernels launched so far */

@@ -43,7 +43,7 @@ def test_matches_cv2_golden_vectors():
         dmap, d16 = st.run(left, right, want_fixed_point=True)
         assert np.array_equal(d16, want), f"case {i}: {int((d16 != want).sum())} pixels differ from cv2"
         assert np.array_equal(dmap, want.astype(np.float32) / 16.0)
-        assert st.getInvalidValue() == float(mind - 1)
+        assert st.filteredValue() == float(mind - 1) and st.getInvalidValue() == float(mind - 1) / 16.0      # (the reference's getInvalidValue quirk)
         st.close()
 
 
