@@ -35,6 +35,16 @@ int bp_fail(int code, const char* fmt, ...) {
   return code;
 }
 
+cudaError_t bp_join_copies(bpvo_b200_ctx* c) {
+  if (!c->disp_pending) return cudaSuccess;
+  c->disp_pending = false;
+  return cudaStreamWaitEvent(c->stream, c->disp_done, 0);
+}
+cudaError_t bp_sync_stream(bpvo_b200_ctx* c) {
+  const cudaError_t e = bp_join_copies(c);
+  return e != cudaSuccess ? e : cudaStreamSynchronize(c->stream);
+}
+
 #define CUDA_TRY(expr)                                                                         \
   do {                                                                                         \
     cudaError_t _e = (expr);                                                                   \
@@ -117,7 +127,7 @@ static bool encode_tensor_maps(bpvo_b200_ctx* c, bpvo_b200_frame* f) {
   // the descriptors live in global memory ([level][in, out], 64-byte aligned): written once, before any kernel reads them
   if (cudaMalloc(&f->d_maps, sizeof(maps)) != cudaSuccess) { cudaGetLastError(); f->d_maps = nullptr; return false; }
   if (cudaMemcpyAsync(f->d_maps, maps, sizeof(maps), cudaMemcpyHostToDevice, c->stream) != cudaSuccess ||
-      cudaStreamSynchronize(c->stream) != cudaSuccess) { cudaGetLastError(); return false; }
+      bp_sync_stream(c) != cudaSuccess) { cudaGetLastError(); return false; }
   return true;
 }
 
@@ -235,6 +245,9 @@ static int ctx_init(bpvo_b200_ctx* c, const float K[9], float baseline, int rows
   CUDA_TRY(cudaEventCreate(&c->ev0)); CUDA_TRY(cudaEventCreate(&c->ev1));
   CUDA_TRY(cudaEventCreate(&c->tm0)); CUDA_TRY(cudaEventCreate(&c->tm1));
   CUDA_TRY(cudaEventCreateWithFlags(&c->stage_free, cudaEventDisableTiming));
+  CUDA_TRY(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  CUDA_TRY(cudaEventCreateWithFlags(&c->disp_done, cudaEventDisableTiming)); CUDA_TRY(cudaEventCreateWithFlags(&c->order_ev, cudaEventDisableTiming));
+  CUDA_TRY(cudaEventRecord(c->disp_done, c->copy_stream));
   const size_t cap0 = (size_t) c->geom[c->p.maxTestLevel].capacity;
   size_t capmax = 0; for (int l = c->p.maxTestLevel; l < c->L; ++l) capmax = std::max(capmax, (size_t) c->geom[l].capacity);
   (void) cap0;
@@ -275,7 +288,7 @@ static int ctx_init(bpvo_b200_ctx* c, const float K[9], float baseline, int rows
   memset(c->h_mail, 0, sizeof(Mailbox));
   CUDA_TRY(cudaHostAlloc(&c->stage_img, (size_t) rows * cols, cudaHostAllocDefault));
   CUDA_TRY(cudaHostAlloc(&c->stage_disp, (size_t) rows * cols * sizeof(float), cudaHostAllocDefault));
-  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  CUDA_TRY(bp_sync_stream(c));
   return BPVO_B200_OK;
 }
 
@@ -284,7 +297,7 @@ extern "C" {
 int bpvo_b200_destroy(bpvo_b200_ctx* c) {
   if (!c) return BPVO_B200_OK;
   cudaSetDevice(c->p.device_id);
-  if (c->stream) cudaStreamSynchronize(c->stream);
+  if (c->stream) bp_sync_stream(c);
   bp_comm_destroy(c);
   cudaFree(c->work.res); cudaFree(c->work.valid); cudaFree(c->work.hist); cudaFree(c->work.ll); cudaFree(c->work.msg); cudaFree(c->work.partials);
   cudaFree(c->work.scale); cudaFree(c->d_mail); cudaFree(c->work.ticket); cudaFree(c->work.cand); cudaFree(c->sel); cudaFree(c->export_buf);
@@ -293,7 +306,8 @@ int bpvo_b200_destroy(bpvo_b200_ctx* c) {
   cudaFree(c->d_prof); cudaFree(c->d_trace); cudaFree(c->d_trace_rows);
   if (c->h_mail) cudaFreeHost(c->h_mail); if (c->stage_img) cudaFreeHost(c->stage_img); if (c->stage_disp) cudaFreeHost(c->stage_disp);
   if (c->flush_buf) cudaFree(c->flush_buf);
-  for (cudaEvent_t e : {c->ev0, c->ev1, c->tm0, c->tm1, c->stage_free}) if (e) cudaEventDestroy(e);
+  if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
+  for (cudaEvent_t e : {c->ev0, c->ev1, c->tm0, c->tm1, c->stage_free, c->disp_done, c->order_ev}) if (e) cudaEventDestroy(e);
   if (c->stream) cudaStreamDestroy(c->stream);
   cudaGetLastError();
   delete c;
@@ -302,7 +316,7 @@ int bpvo_b200_destroy(bpvo_b200_ctx* c) {
 
 int bpvo_b200_synchronize(bpvo_b200_ctx* c) {
   if (!c) return bp_fail(BPVO_B200_ERR_INVALID_ARG, "null ctx");
-  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  CUDA_TRY(bp_sync_stream(c));
   return BPVO_B200_OK;
 }
 int bpvo_b200_timer_start(bpvo_b200_ctx* c) {
@@ -325,7 +339,7 @@ int bpvo_b200_last_level_evals(bpvo_b200_ctx* c, int* evals) {
 int bpvo_b200_get_phase_cycles(bpvo_b200_ctx* c, long long cycles[64], int reset) {
   if (!c || !cycles) return bp_fail(BPVO_B200_ERR_INVALID_ARG, "null argument");
   CUDA_TRY(cudaSetDevice(c->p.device_id));
-  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  CUDA_TRY(bp_sync_stream(c));
   CUDA_TRY(cudaMemcpy(cycles, c->d_prof, 64 * sizeof(long long), cudaMemcpyDeviceToHost));
   if (reset) CUDA_TRY(cudaMemset(c->d_prof, 0, 64 * sizeof(long long)));
   return BPVO_B200_OK;
@@ -333,7 +347,7 @@ int bpvo_b200_get_phase_cycles(bpvo_b200_ctx* c, long long cycles[64], int reset
 int bpvo_b200_get_level_phase_cycles(bpvo_b200_ctx* c, long long* cycles /* [BPVO_B200_MAX_LEVELS][16] */, int reset) {
   if (!c || !cycles) return bp_fail(BPVO_B200_ERR_INVALID_ARG, "null argument");
   CUDA_TRY(cudaSetDevice(c->p.device_id));
-  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  CUDA_TRY(bp_sync_stream(c));
   CUDA_TRY(cudaMemcpy(cycles, c->d_prof + 64, kMaxLevels * 16 * sizeof(long long), cudaMemcpyDeviceToHost));
   if (reset) CUDA_TRY(cudaMemset(c->d_prof + 64, 0, kMaxLevels * 16 * sizeof(long long)));
   return BPVO_B200_OK;
@@ -415,7 +429,7 @@ int bpvo_b200_frame_destroy(bpvo_b200_frame* f) {
   if (!f) return BPVO_B200_OK;
   bpvo_b200_ctx* c = f->ctx;
   cudaSetDevice(c->p.device_id);
-  cudaStreamSynchronize(c->stream);
+  bp_sync_stream(c);
   cudaFree(f->disp);
   for (int l = 0; l < c->L; ++l) {
     cudaFree(f->pyr[l]); cudaFree(f->desc[l]); cudaFree(f->saliency[l]); cudaFree(f->pts[l]);
@@ -551,12 +565,19 @@ int bpvo_b200_frame_set_data(bpvo_b200_frame* f, const uint8_t* image, const flo
     const bool stage_i = !is_dma_able(image), stage_d = !is_dma_able(disparity);      // each on its own: the disparity map may live on the device (upstream stereo) while the image is pageable
     if (stage_i || stage_d) {
       CUDA_TRY(cudaEventSynchronize(c->stage_free));
+      CUDA_TRY(cudaEventSynchronize(c->disp_done));
       if (stage_i) { memcpy(c->stage_img, image, npx); src_i = c->stage_img; }
       if (stage_d) { memcpy(c->stage_disp, disparity, npx * sizeof(float)); src_d = c->stage_disp; }
     }
     CUDA_TRY(cudaMemcpy2DAsync(f->pyr[0], (size_t) u8_pitch(c->cols), src_i, (size_t) c->cols, (size_t) c->cols, (size_t) c->rows, cudaMemcpyDefault, c->stream));
-    CUDA_TRY(cudaMemcpyAsync(f->disp, src_d, npx * sizeof(float), cudaMemcpyDefault, c->stream));
     CUDA_TRY(cudaEventRecord(c->stage_free, c->stream));
+    // the disparity map: on the copy stream, behind everything `stream` holds so far (an earlier template build of this frame
+    // object may still read the buffer), beside everything enqueued from here on
+    CUDA_TRY(cudaEventRecord(c->order_ev, c->stream));
+    CUDA_TRY(cudaStreamWaitEvent(c->copy_stream, c->order_ev, 0));
+    CUDA_TRY(cudaMemcpyAsync(f->disp, src_d, npx * sizeof(float), cudaMemcpyDefault, c->copy_stream));
+    CUDA_TRY(cudaEventRecord(c->disp_done, c->copy_stream));
+    c->disp_pending = true;
     c->counters.h2d_bytes += (int64_t) (npx * 5);
   }
   int rc = run_as_graph(c, f, 0, enqueue_descriptors);
@@ -648,6 +669,7 @@ int bpvo_b200_frame_set_template(bpvo_b200_frame* f) {
   bpvo_b200_ctx* c = f->ctx;
   CUDA_TRY(cudaSetDevice(c->p.device_id));
   PhaseTimer t(c, &c->counters.ms_template);
+  CUDA_TRY(bp_join_copies(c));                      // the selection reads the disparity map
   int rc = run_as_graph(c, f, 1, enqueue_template);
   if (rc) return rc;
   CUDA_TRY(cudaEventRecord(f->meta_ready, c->stream));
@@ -687,7 +709,7 @@ int bpvo_b200_frame_get_points(const bpvo_b200_frame* f, int level, float* xyzw)
   bpvo_b200_ctx* c = f->ctx;
   CUDA_TRY(cudaSetDevice(c->p.device_id));
   CUDA_TRY(cudaMemcpyAsync(xyzw, f->pts[level], (size_t) f->h_meta[level].n * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
-  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  CUDA_TRY(bp_sync_stream(c));
   c->counters.d2h_bytes += (int64_t) f->h_meta[level].n * 16;
   return BPVO_B200_OK;
 }
@@ -696,7 +718,7 @@ int bpvo_b200_frame_get_pyramid(const bpvo_b200_frame* f, int level, uint8_t* ou
   bpvo_b200_ctx* c = f->ctx; const LevelGeom& g = c->geom[level];
   CUDA_TRY(cudaSetDevice(c->p.device_id));
   CUDA_TRY(cudaMemcpy2DAsync(out, (size_t) g.cols, f->pyr[level], (size_t) u8_pitch(g.cols), (size_t) g.cols, (size_t) g.rows, cudaMemcpyDeviceToHost, c->stream));
-  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  CUDA_TRY(bp_sync_stream(c));
   return BPVO_B200_OK;
 }
 int bpvo_b200_frame_get_descriptor(const bpvo_b200_frame* f, int level, float* planes, int* channels) {
@@ -708,7 +730,7 @@ int bpvo_b200_frame_get_descriptor(const bpvo_b200_frame* f, int level, float* p
   CUDA_TRY(cudaMalloc(&tmp, (size_t) npx * c->C * sizeof(float)));
   deinterleave_kernel<<<ceil_div(npx, 256), 256, 0, c->stream>>>(f->desc[level], npx, c->C, c->CS, tmp);
   cudaError_t e = cudaMemcpyAsync(planes, tmp, (size_t) npx * c->C * sizeof(float), cudaMemcpyDeviceToHost, c->stream);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  if (e == cudaSuccess) e = bp_sync_stream(c);
   cudaFree(tmp);
   if (e != cudaSuccess) return bp_fail(BPVO_B200_ERR_CUDA, "descriptor download failed: %s", cudaGetErrorString(e));
   if (channels) *channels = c->C;
@@ -719,7 +741,7 @@ int bpvo_b200_frame_get_saliency(const bpvo_b200_frame* f, int level, float* out
   bpvo_b200_ctx* c = f->ctx; const LevelGeom& g = c->geom[level];
   CUDA_TRY(cudaSetDevice(c->p.device_id));
   CUDA_TRY(cudaMemcpyAsync(out, f->saliency[level], (size_t) g.rows * g.cols * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
-  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  CUDA_TRY(bp_sync_stream(c));
   return BPVO_B200_OK;
 }
 static int export_template(const bpvo_b200_frame* f, int level, float* pixels_out, float* J_out) {
@@ -738,7 +760,7 @@ static int export_template(const bpvo_b200_frame* f, int level, float* pixels_ou
   cudaError_t e = cudaSuccess;
   if (pixels_out) e = cudaMemcpyAsync(pixels_out, dP, (size_t) n * c->C * sizeof(float), cudaMemcpyDeviceToHost, c->stream);
   if (e == cudaSuccess && J_out) e = cudaMemcpyAsync(J_out, dJ, (size_t) n * c->C * 6 * sizeof(float), cudaMemcpyDeviceToHost, c->stream);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  if (e == cudaSuccess) e = bp_sync_stream(c);
   cudaFree(tmp);
   if (e != cudaSuccess) return bp_fail(BPVO_B200_ERR_CUDA, "template export failed: %s", cudaGetErrorString(e));
   return BPVO_B200_OK;
@@ -752,7 +774,7 @@ int bpvo_b200_frame_get_point_inds(const bpvo_b200_frame* f, int level, int32_t*
   bpvo_b200_ctx* c = f->ctx;
   CUDA_TRY(cudaSetDevice(c->p.device_id));
   CUDA_TRY(cudaMemcpyAsync(out, f->inds[level], (size_t) f->h_meta[level].n * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  CUDA_TRY(bp_sync_stream(c));
   return BPVO_B200_OK;
 }
 int bpvo_b200_frame_get_normalization(const bpvo_b200_frame* f, int level, float Tn[16]) {
@@ -869,7 +891,7 @@ extern "C" int bpvo_b200_linearize(bpvo_b200_ctx* c, const bpvo_b200_frame* ref,
     if (rc) return rc;
   }
   CUDA_TRY(cudaMemcpyAsync(&c->h_mail->lin, c->work.out, sizeof(LinOut), cudaMemcpyDeviceToHost, c->stream));
-  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  CUDA_TRY(bp_sync_stream(c));
   c->counters.d2h_bytes += sizeof(LinOut);
   const LinOut& o = c->h_mail->lin;
   if (H) memcpy(H, o.H, sizeof(o.H));
@@ -1072,7 +1094,7 @@ extern "C" int bpvo_b200_estimate_pose(bpvo_b200_ctx* c, const bpvo_b200_frame* 
     }
     Mailbox* mb = c->h_mail;
     CUDA_TRY(cudaMemcpyAsync(mb, c->d_mail, sizeof(Mailbox), cudaMemcpyDeviceToHost, c->stream));      // pose, statistics, LinOut: one D2H
-    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    CUDA_TRY(bp_sync_stream(c));
     c->counters.d2h_bytes += sizeof(Mailbox);
     if (mb->aborted) return bp_fail(BPVO_B200_ERR_CUDA, "on-device GN loop: a grid barrier / exchange timed out");
     T = mb->T; evals = mb->evals;
@@ -1106,7 +1128,7 @@ static int export_last(bpvo_b200_ctx* c, float* w, float* r, size_t* count) {
   CUDA_TRY(cudaSetDevice(c->p.device_id));
   // sigma of the last linearize
   CUDA_TRY(cudaMemcpyAsync(&c->h_mail->lin, c->work.out, sizeof(LinOut), cudaMemcpyDeviceToHost, c->stream));
-  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  CUDA_TRY(bp_sync_stream(c));
   const float sigma = c->h_mail->lin.sigma;
   float* dw = w ? c->export_buf : nullptr;
   float* dr = r ? c->export_buf + (size_t) n * c->C : nullptr;
@@ -1114,7 +1136,7 @@ static int export_last(bpvo_b200_ctx* c, float* w, float* r, size_t* count) {
   LAUNCH_CHECK(c);
   if (w) CUDA_TRY(cudaMemcpyAsync(w, dw, ncopy * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
   if (r) CUDA_TRY(cudaMemcpyAsync(r, dr, ncopy * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
-  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  CUDA_TRY(bp_sync_stream(c));
   c->counters.d2h_bytes += (int64_t) (ncopy * sizeof(float) * ((w ? 1 : 0) + (r ? 1 : 0)));
   return BPVO_B200_OK;
 }
@@ -1128,7 +1150,7 @@ extern "C" int bpvo_b200_get_valid(bpvo_b200_ctx* c, uint8_t* v, size_t* count) 
   if (!v || *count == 0) return BPVO_B200_OK;
   CUDA_TRY(cudaSetDevice(c->p.device_id));
   CUDA_TRY(cudaMemcpyAsync(v, c->work.valid, *count, cudaMemcpyDeviceToHost, c->stream));
-  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  CUDA_TRY(bp_sync_stream(c));
   return BPVO_B200_OK;
 }
 
@@ -1171,7 +1193,7 @@ extern "C" int bpvo_b200_point_cloud(bpvo_b200_ctx* c, const bpvo_b200_frame* re
   BP_SWITCH_C(c->C, k_point_cloud<CC><<<ceil_div(np, 256), 256, 0, c->stream>>>(ref->pts[level], np, ref->pyr[0], c->rows, c->cols, u8_pitch(c->cols), g.fx, g.fy, g.cx, g.cy, c->work.res, sigma, c->p.lossFunction, d));
   LAUNCH_CHECK(c);
   CUDA_TRY(cudaMemcpyAsync(records, d, (size_t) np * sizeof(PointInfo), cudaMemcpyDeviceToHost, c->stream));
-  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  CUDA_TRY(bp_sync_stream(c));
   c->counters.d2h_bytes += (int64_t) np * sizeof(PointInfo);
   return BPVO_B200_OK;
 }
@@ -1201,7 +1223,7 @@ extern "C" int bpvo_b200_debug_device_linearize(bpvo_b200_ctx* c, const bpvo_b20
       if (e == cudaSuccess) e = cudaMemcpyAsync(c->h_mail, c->d_mail, sizeof(Mailbox), cudaMemcpyDeviceToHost, c->stream);
     }
   }
-  cudaError_t e2 = cudaStreamSynchronize(c->stream);
+  cudaError_t e2 = bp_sync_stream(c);
   cudaFree(d_poses); cudaFree(d_out);
   if (rc) return rc;
   if (e != cudaSuccess || e2 != cudaSuccess) return bp_fail(BPVO_B200_ERR_CUDA, "debug_device_linearize failed: %s", cudaGetErrorString(e != cudaSuccess ? e : e2));
@@ -1215,7 +1237,7 @@ extern "C" int bpvo_b200_debug_device_linearize(bpvo_b200_ctx* c, const bpvo_b20
 extern "C" int bpvo_b200_debug_set_trace(bpvo_b200_ctx* c, int enable) {
   if (!c) return bp_fail(BPVO_B200_ERR_INVALID_ARG, "null ctx");
   CUDA_TRY(cudaSetDevice(c->p.device_id));
-  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  CUDA_TRY(bp_sync_stream(c));
   if (enable && !c->d_trace) {
     CUDA_TRY(cudaMalloc(&c->d_trace, (size_t) kTraceRows * kTraceCols * sizeof(float)));
     CUDA_TRY(cudaMalloc(&c->d_trace_rows, sizeof(int)));
@@ -1229,7 +1251,7 @@ extern "C" int bpvo_b200_debug_get_trace(bpvo_b200_ctx* c, float* rows, int max_
   *n_rows = 0;
   if (!c->d_trace) return BPVO_B200_OK;
   CUDA_TRY(cudaSetDevice(c->p.device_id));
-  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  CUDA_TRY(bp_sync_stream(c));
   int n = 0;
   CUDA_TRY(cudaMemcpy(&n, c->d_trace_rows, sizeof(int), cudaMemcpyDeviceToHost));
   n = std::min(n, kTraceRows);

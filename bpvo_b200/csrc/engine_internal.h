@@ -36,6 +36,12 @@ struct bpvo_b200_ctx {
   LevelGeom geom[bp::kMaxLevels];
   int sm_count = 0; bool coop = false; int smem_optin = 0;
   cudaStream_t stream = nullptr;
+  // the disparity map of a frame is not needed before a template is built from it (key-frames only): its upload runs on a second
+  // stream, beside the pyramid / descriptor kernels and the solve of the frame.  Every consumer and every host-side wait on
+  // `stream` first makes `stream` wait for `disp_done` (bp_join_copies / bp_sync_stream).
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t disp_done = nullptr, order_ev = nullptr;
+  bool disp_pending = false;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, stage_free = nullptr, tm0 = nullptr, tm1 = nullptr;
   int level_evals[bp::kMaxLevels] = {}; float level_us[bp::kMaxLevels] = {};
   bp::Work work{};
@@ -93,6 +99,8 @@ struct bpvo_b200_frame {
 };
 
 int bp_fail(int code, const char* fmt, ...);
+cudaError_t bp_join_copies(bpvo_b200_ctx* c);      // `stream` waits for the pending disparity upload (no host wait)
+cudaError_t bp_sync_stream(bpvo_b200_ctx* c);      // bp_join_copies + cudaStreamSynchronize(stream)
 int bp_hartley(bpvo_b200_ctx* c, bpvo_b200_frame* f, int level);
 int bp_comm_destroy(bpvo_b200_ctx* c);
 int bp_comm_allreduce_u32(bpvo_b200_ctx* c, unsigned* buf, size_t count);
